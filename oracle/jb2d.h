@@ -107,9 +107,12 @@ inline float distanceSquared(const Vec2& a, const Vec2& b) {
     return dot(c, c);
 }
 inline float distance(const Vec2& a, const Vec2& b) { return (a - b).length(); }
-inline float clampf(float a, float lo, float hi) { return std::max(lo, std::min(a, hi)); }
-inline Vec2 vmin(const Vec2& a, const Vec2& b) { return Vec2(std::min(a.x, b.x), std::min(a.y, b.y)); }
-inline Vec2 vmax(const Vec2& a, const Vec2& b) { return Vec2(std::max(a.x, b.x), std::max(a.y, b.y)); }
+// MathUtils.min / max / clamp (JBox2D): a < b ? a : b, a > b ? a : b, max(lo, min(a, hi))
+inline float minf(float a, float b) { return a < b ? a : b; }
+inline float maxf(float a, float b) { return a > b ? a : b; }
+inline float clampf(float a, float lo, float hi) { return maxf(lo, minf(a, hi)); }
+inline Vec2 vmin(const Vec2& a, const Vec2& b) { return Vec2(minf(a.x, b.x), minf(a.y, b.y)); }
+inline Vec2 vmax(const Vec2& a, const Vec2& b) { return Vec2(maxf(a.x, b.x), maxf(a.y, b.y)); }
 
 struct Mat22 {
     Vec2 col1, col2;
@@ -1018,7 +1021,7 @@ inline void timeOfImpact(int* outState, float* outT, const DistanceProxy* proxyA
     sweepA.normalize();
     sweepB.normalize();
     float totalRadius = proxyA->radius + proxyB->radius;
-    float target = std::max(kLinearSlop, totalRadius - 3.0f * kLinearSlop);
+    float target = maxf(kLinearSlop, totalRadius - 3.0f * kLinearSlop);
     float tolerance = 0.25f * kLinearSlop;
     float t1 = 0.0f;
     const int k_maxIterations = 20;
@@ -1291,6 +1294,7 @@ struct World {
     std::vector<Body*> allBodies;    // creation order (ownership)
     // statistics of the last step (reported by the oracle API)
     int lastPositionIterations = 0, lastToiEvents = 0, lastIslands = 0;
+    std::vector<uint32_t> lastOrder;   // (proxyA << 16 | proxyB) of every solved contact, in Gauss-Seidel order, island after island
 
     World() { tr.lut = sw.sincosLut; }
     void setSwitches(const Switches& s) {
@@ -1507,6 +1511,8 @@ struct World {
                 }
             }
         }
+        for (int i = 0; i < contactCountI; ++i)
+            lastOrder.push_back(((uint32_t)contacts[i]->fixtureA->proxyId << 16) | (uint32_t)contacts[i]->fixtureB->proxyId);
         // ContactSolver constructor
         std::vector<ContactConstraint> cons(contactCountI);
         for (int i = 0; i < contactCountI; ++i) {
@@ -1654,7 +1660,7 @@ struct World {
                 Vec2 dv = vB + cross(wB, ccp->rB) - vA - cross(wA, ccp->rA);
                 float vn = dot(dv, normal);
                 float lambda = -ccp->normalMass * (vn - ccp->velocityBias);
-                float newImpulse = std::max(ccp->normalImpulse + lambda, 0.0f);
+                float newImpulse = maxf(ccp->normalImpulse + lambda, 0.0f);
                 lambda = newImpulse - ccp->normalImpulse;
                 Vec2 P = lambda * normal;
                 vA -= invMassA * P;
@@ -1778,7 +1784,7 @@ struct World {
                 float separation;
                 positionManifold(c->type, c->localNormal, c->localPoint, c->points[j].localPoint, c->radius, bodyA, bodyB, &normal, &point, &separation);
                 Vec2 rA = point - bodyA->sweep.c, rB = point - bodyB->sweep.c;
-                minSeparation = std::min(minSeparation, separation);
+                minSeparation = minf(minSeparation, separation);
                 float C = clampf(baumgarte * (separation + kLinearSlop), -kMaxLinearCorrection, 0.0f);
                 float rnA = cross(rA, normal), rnB = cross(rB, normal);
                 float K = invMassA + invMassB + invIA * rnA * rnA + invIB * rnB * rnB;
@@ -1804,6 +1810,7 @@ struct World {
         std::vector<Contact*> islandContacts;
         lastPositionIterations = 0;
         lastIslands = 0;
+        lastOrder.clear();
         for (Body* seed = bodyList; seed; seed = seed->next) {
             if (seed->islandFlag) continue;
             if (seed->type == STATIC_BODY) continue;
@@ -1910,7 +1917,7 @@ struct World {
                     float separation;
                     positionManifold(m->type, m->localNormal, m->localPoint, m->points[j].localPoint, radius, bodyA, bodyB, &normal, &point, &separation);
                     Vec2 rA = point - bodyA->sweep.c, rB = point - bodyB->sweep.c;
-                    minSeparation = std::min(minSeparation, separation);
+                    minSeparation = minf(minSeparation, separation);
                     float C = clampf(k_toiBaumgarte * (separation + kLinearSlop), -kMaxLinearCorrection, 0.0f);
                     float rnA = cross(rA, normal), rnB = cross(rB, normal);
                     float K = invMassA + invMassB + invIA * rnA * rnA + invIB * rnB * rnB;

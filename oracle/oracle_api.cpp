@@ -497,6 +497,14 @@ int orc_step_info(orc_batch* b, int arena, int32_t* out) {
     return PS_OK;
 }
 
+// Gauss-Seidel order of the last World.step: contact keys island after island; returns the count
+int orc_solve_order(orc_batch* b, int arena, uint32_t* out, int cap) {
+    jb::World& w = *b->arenas[arena]->world;
+    int n = (int)w.lastOrder.size();
+    for (int i = 0; i < n && i < cap; i++) out[i] = w.lastOrder[i];
+    return n;
+}
+
 // Narrow-phase unit entry: manifold of two proxies of arena 0 at explicit transforms (x, y, angle).
 // out: [0]=pointCount [1]=type [2..3]=localNormal [4..5]=localPoint [6..7]=p0.local [8..9]=p1.local [10]=id0 [11]=id1
 int orc_manifold(orc_batch* b, int proxyA, float ax, float ay, float aa, int proxyB, float bx, float by, float ba, float* out) {

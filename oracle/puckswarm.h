@@ -1228,6 +1228,12 @@ struct Arena {
         for (int k = 0; k < cfg.n_puck_types; k++)
             for (int i = 0; i < nPucksPerType; i++) createPuck(k, -w / 2, w / 2);
         for (int i = 0; i < cfg.n_robots; i++) createRobot(i < cfg.n_informed_robots);
+        // Canonical transform: JBox2D keeps the creation transform (position = BodyDef.position) until the first
+        // synchronizeTransform, which recomputes position = c - R * localCenter and may move a robot's origin by one
+        // ulp. The state exchange format carries (c, a) only, so the oracle adopts the recomputed transform right
+        // after construction (fixture AABBs and the first pair search above still use the creation transform).
+        for (jb::Body* b = world->bodyList; b; b = b->next)
+            if (b->type == jb::DYNAMIC_BODY) b->synchronizeTransform();
     }
     // sensors.PointSensor.pointSense (src/sensors/PointSensor.java:85-114)
     uint8_t pointSense(const jb::Body* robotBody, const Vec2& posWrtBody) const {

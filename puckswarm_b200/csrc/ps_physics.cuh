@@ -1,0 +1,1099 @@
+// puckswarm_b200 -- one JBox2D World.step(dt, velIters, posIters) of one arena, executed by one CTA.
+//
+// Replaces, for the PuckSwarm scene, org.jbox2d.dynamics.World.step as called from
+// src/arena/RunOffline.java:94: ContactManager.collide, World.solve (islands by
+// DFS, Island.solve, ContactSolver), Body.synchronizeFixtures + ContactManager.findNewContacts,
+// World.solveTOI, clearForces. Results are meant to be bit-identical to the sequential reference:
+//   * the contact cache is an array in creation order (JBox2D's world / per-body contact lists are that
+//     order reversed), compacted stably, new pairs appended in sorted proxy-id order;
+//   * islands and the Gauss-Seidel order inside them come from the same stack DFS (newest body first,
+//     newest contact edge first) followed by Island.solve's static-last swap partition;
+//   * islands are independent, so each island is solved by its own thread while the parallel phases
+//     (narrow phase, constraint setup, integration, fixture sync, pair search, TOI per body) use the CTA.
+#pragma once
+#include "ps_ctx.cuh"
+#include "ps_toi.cuh"
+
+namespace ps {
+
+struct PhysCfg {
+    Dims d;
+    int MC;          // contact cache capacity per arena
+    int MT;          // touching-contact capacity per arena
+    int MPAIR;       // new-pair buffer capacity (power of two)
+    int MW;          // capacity of the wall-contact list
+    int velIters, posIters, toiEnabled;
+    float dt;
+    float damp;      // clamp(1 - dt * 10, 0, 1): linear and angular damping factor of pucks and robots
+};
+
+// One touching contact of the current step: ContactConstraint + what the position solver needs.
+struct TC {
+    int bodyA, bodyB;     // dynamic body index, -1 = wall
+    int ci;               // index in the contact cache
+    int type;             // manifold type
+    int solverPoints;     // ContactConstraint.pointCount (may drop to 1 by the condition-number test)
+    int manifoldPoints;
+    V2 normal, localNormal, localPoint;
+    float radius;
+    V2 lp[2], rA[2], rB[2];
+    float nMass[2], tMass[2], nImp[2], tImp[2];
+    float k11, k12, k22, m11, m12, m22;   // K and normalMass = K^-1 (both symmetric)
+    uint32_t key;         // (proxyA << 16) | proxyB
+};
+
+// Per-arena persistent state in global memory (layout = ps_state_view of one arena).
+struct ArenaState {
+    float* body;          // [6][NB] c.x c.y a v.x v.y w
+    float* senseAabb;     // [4][NB]
+    float* fat;           // [4][NP]
+    uint32_t* ckey;       // [MC]
+    uint32_t* cinfo;      // [MC]
+    float* cimp;          // [MC][4]
+    int* nContacts;
+    float* invDt0;
+    int* errorFlags;
+};
+
+// Per-CTA working memory. Pointers may refer to shared or global memory.
+struct PhysWork {
+    float *cx, *cy, *a, *vx, *vy, *w, *c0x, *c0y, *a0;   // [NB]
+    float *rpx, *rpy, *rc, *rs;                          // [R] robot transform (pucks: position = c, R unused)
+    float *r0px, *r0py, *r0c, *r0s;                      // [R] robot transform at the start of the step (xf1)
+    float *fx, *fy, *tq;                                 // [R] force / torque accumulators
+    int* adjOff;                                         // [NB + 1]
+    int* adjFill;                                        // [NB]
+    uint16_t* adj;                                       // [2 * MT] touching contacts per body, newest first
+    uint16_t* order;                                     // [MT] Gauss-Seidel order, island after island
+    int* islandStart;                                    // [NB + 1]
+    uint16_t* stack;                                     // [NB]
+    uint8_t* bodyFlag;                                   // [NB]
+    uint8_t* tcFlag;                                     // [MT]
+    uint8_t* moved;                                      // [NP]
+    float* bodyFat;                                      // [4][NB] union of the body's fat AABBs
+    int* movedList;                                      // [NP]
+    float* fatOld;                                       // [4][NP] fat AABB before this step's moveProxy
+    uint32_t* pairs;                                     // [MPAIR]
+    int* wallList;                                       // [MW] cached contacts with the wall
+    TC* tc;                                              // [MT]
+    int* counters;                                       // [8]: 0 nTouching, 1 nIslands, 2 nMoved, 3 nPairs, 4 nWall, 5 scratch
+    int* stats;                                          // [8] per-step diagnostics: 0 max position iterations, 1 TOI events, 2 islands
+};
+
+enum { ERR_CONTACT_CAP = 1, ERR_LM_CAP = 2, ERR_TOUCH_CAP = 4, ERR_PAIR_CAP = 8 };
+
+struct PhysEnv {
+    const Scene* scene;
+    Trig trig;
+    PhysCfg cfg;
+};
+
+PS_HD bool isRobot(const Dims& d, int b) { return b >= d.P; }
+
+PS_HD Xf bodyXf(const PhysEnv& e, const PhysWork& wk, int b) {
+    Xf T;
+    if (b < 0) {
+        T = e.scene->wallXf;
+    } else if (b < e.cfg.d.P) {
+        T.px = wk.cx[b];
+        T.py = wk.cy[b];
+        T.c = 1.0f;
+        T.s = 0.0f;
+    } else {
+        int r = b - e.cfg.d.P;
+        T.px = wk.rpx[r];
+        T.py = wk.rpy[r];
+        T.c = wk.rc[r];
+        T.s = wk.rs[r];
+    }
+    return T;
+}
+PS_HD Xf bodyXf0(const PhysEnv& e, const PhysWork& wk, int b) {
+    Xf T;
+    if (b < e.cfg.d.P) {
+        T.px = wk.c0x[b];
+        T.py = wk.c0y[b];
+        T.c = 1.0f;
+        T.s = 0.0f;
+    } else {
+        int r = b - e.cfg.d.P;
+        T.px = wk.r0px[r];
+        T.py = wk.r0py[r];
+        T.c = wk.r0c[r];
+        T.s = wk.r0s[r];
+    }
+    return T;
+}
+// Body.synchronizeTransform (only robots carry a rotation that anything reads)
+PS_HD void syncBodyXf(const PhysEnv& e, const PhysWork& wk, int b) {
+    if (b >= e.cfg.d.P) {
+        int r = b - e.cfg.d.P;
+        Xf T = makeXf(e.trig, wk.cx[b], wk.cy[b], wk.a[b], e.scene->robot.lcx, e.scene->robot.lcy);
+        wk.rpx[r] = T.px;
+        wk.rpy[r] = T.py;
+        wk.rc[r] = T.c;
+        wk.rs[r] = T.s;
+    }
+}
+PS_HD const BodyConst& bodyConst(const PhysEnv& e, int b) { return b < e.cfg.d.P ? e.scene->puck : e.scene->robot; }
+
+PS_HD Aabb loadAabb(const float* base, int n, int i) {
+    Aabb a;
+    a.lx = base[i];
+    a.ly = base[n + i];
+    a.ux = base[2 * n + i];
+    a.uy = base[3 * n + i];
+    return a;
+}
+PS_HD void storeAabb(float* base, int n, int i, const Aabb& a) {
+    base[i] = a.lx;
+    base[n + i] = a.ly;
+    base[2 * n + i] = a.ux;
+    base[3 * n + i] = a.uy;
+}
+PS_HD Aabb proxyFat(const PhysEnv& e, const ArenaState& st, int proxy) {
+    if (proxy < kWallFixtures) return e.scene->wallFat[proxy];
+    return loadAabb(st.fat, e.cfg.d.NP, proxy - kWallFixtures);
+}
+
+// Contact.update: evaluate the manifold at the current transforms and carry the impulses of points whose id survived.
+PS_HD void updateContact(const PhysEnv& e, const PhysWork& wk, const ArenaState& st, int ci, Manifold& m, float* imp /*[4]*/) {
+    uint32_t key = st.ckey[ci];
+    int pa = (int)(key >> 16), pb = (int)(key & 0xFFFFu);
+    const Shape& sA = e.scene->shapes[proxyShape(e.cfg.d, pa)];
+    const Shape& sB = e.scene->shapes[proxyShape(e.cfg.d, pb)];
+    Xf xfA = bodyXf(e, wk, proxyBody(e.cfg.d, pa)), xfB = bodyXf(e, wk, proxyBody(e.cfg.d, pb));
+    evaluateManifold(m, sA, xfA, sB, xfB);
+    uint32_t oldInfo = st.cinfo[ci];
+    int oldCount = (int)(oldInfo & 3u);
+    float o[4];
+    o[0] = st.cimp[4 * ci + 0];
+    o[1] = st.cimp[4 * ci + 1];
+    o[2] = st.cimp[4 * ci + 2];
+    o[3] = st.cimp[4 * ci + 3];
+    uint32_t info = (uint32_t)m.pointCount;
+    imp[0] = imp[1] = imp[2] = imp[3] = 0.0f;
+    for (int i = 0; i < m.pointCount; ++i) {
+        uint32_t id2 = m.id[i];
+        info |= id2 << (8 + 8 * i);
+        for (int j = 0; j < oldCount; ++j) {
+            uint32_t id1 = (oldInfo >> (8 + 8 * j)) & 0xFFu;
+            if (id1 == id2) {
+                imp[2 * i] = o[2 * j];
+                imp[2 * i + 1] = o[2 * j + 1];
+                break;
+            }
+        }
+    }
+    st.cinfo[ci] = info;
+    st.cimp[4 * ci + 0] = imp[0];
+    st.cimp[4 * ci + 1] = imp[1];
+    st.cimp[4 * ci + 2] = imp[2];
+    st.cimp[4 * ci + 3] = imp[3];
+}
+
+// ContactSolver constructor for one touching contact
+PS_HD void initConstraint(const PhysEnv& e, const PhysWork& wk, TC& c, const Manifold& m, int pa, int pb, const float* imp, float dtRatio) {
+    const Dims& d = e.cfg.d;
+    int bA = proxyBody(d, pa), bB = proxyBody(d, pb);
+    const Shape& sA = e.scene->shapes[proxyShape(d, pa)];
+    const Shape& sB = e.scene->shapes[proxyShape(d, pb)];
+    Xf xfA = bodyXf(e, wk, bA), xfB = bodyXf(e, wk, bB);
+    float invMassA = 0, invIA = 0, invMassB = 0, invIB = 0;
+    V2 cA = mk(0, 0), cB = mk(0, 0);
+    if (bA >= 0) {
+        const BodyConst& k = bodyConst(e, bA);
+        invMassA = k.invMass;
+        invIA = k.invI;
+        cA = mk(wk.cx[bA], wk.cy[bA]);
+    }
+    if (bB >= 0) {
+        const BodyConst& k = bodyConst(e, bB);
+        invMassB = k.invMass;
+        invIB = k.invI;
+        cB = mk(wk.cx[bB], wk.cy[bB]);
+    }
+    c.bodyA = bA;
+    c.bodyB = bB;
+    c.key = ((uint32_t)pa << 16) | (uint32_t)pb;
+    c.type = m.type;
+    c.manifoldPoints = m.pointCount;
+    c.solverPoints = m.pointCount;
+    c.localNormal = m.localNormal;
+    c.localPoint = m.localPoint;
+    c.radius = sA.radius + sB.radius;
+    V2 pts[2];
+    worldManifold(m, xfA, sA.radius, xfB, sB.radius, c.normal, pts);
+    for (int j = 0; j < m.pointCount; ++j) {
+        c.nImp[j] = dtRatio * imp[2 * j];
+        c.tImp[j] = dtRatio * imp[2 * j + 1];
+        c.lp[j] = m.p[j];
+        c.rA[j] = pts[j] - cA;
+        c.rB[j] = pts[j] - cB;
+        float rnA = cross(c.rA[j], c.normal), rnB = cross(c.rB[j], c.normal);
+        rnA *= rnA;
+        rnB *= rnB;
+        float kNormal = invMassA + invMassB + invIA * rnA + invIB * rnB;
+        c.nMass[j] = 1.0f / kNormal;
+        V2 tangent = crossVS(c.normal, 1.0f);
+        float rtA = cross(c.rA[j], tangent), rtB = cross(c.rB[j], tangent);
+        rtA *= rtA;
+        rtB *= rtB;
+        float kTangent = invMassA + invMassB + invIA * rtA + invIB * rtB;
+        c.tMass[j] = 1.0f / kTangent;
+        // velocityBias = -restitution * vRel with restitution 0 everywhere: always (+-)0, never changes vn - bias
+    }
+    if (m.pointCount == 2) {
+        float rn1A = cross(c.rA[0], c.normal), rn1B = cross(c.rB[0], c.normal);
+        float rn2A = cross(c.rA[1], c.normal), rn2B = cross(c.rB[1], c.normal);
+        float k11 = invMassA + invMassB + invIA * rn1A * rn1A + invIB * rn1B * rn1B;
+        float k22 = invMassA + invMassB + invIA * rn2A * rn2A + invIB * rn2B * rn2B;
+        float k12 = invMassA + invMassB + invIA * rn1A * rn2A + invIB * rn1B * rn2B;
+        if (k11 * k11 < 100.0f * (k11 * k22 - k12 * k12)) {
+            c.k11 = k11;
+            c.k12 = k12;
+            c.k22 = k22;
+            // Mat22.getInverse of [[k11 k12][k12 k22]]
+            float det = k11 * k22 - k12 * k12;
+            if (det != 0.0f) det = 1.0f / det;
+            c.m11 = det * k22;
+            c.m12 = -det * k12;
+            c.m22 = det * k11;
+        } else {
+            c.solverPoints = 1;
+        }
+    }
+}
+
+struct BodyVel {
+    V2 v;
+    float w, invMass, invI;
+};
+PS_HD BodyVel loadVel(const PhysEnv& e, const PhysWork& wk, int b) {
+    BodyVel r;
+    if (b < 0) {
+        r.v = mk(0, 0);
+        r.w = 0;
+        r.invMass = 0;
+        r.invI = 0;
+    } else {
+        const BodyConst& k = bodyConst(e, b);
+        r.v = mk(wk.vx[b], wk.vy[b]);
+        r.w = wk.w[b];
+        r.invMass = k.invMass;
+        r.invI = k.invI;
+    }
+    return r;
+}
+PS_HD void storeVel(const PhysWork& wk, int b, const BodyVel& r) {
+    if (b >= 0) {
+        wk.vx[b] = r.v.x;
+        wk.vy[b] = r.v.y;
+        wk.w[b] = r.w;
+    }
+}
+
+// ContactSolver.warmStart for one constraint
+PS_HD void warmStartOne(const PhysEnv& e, const PhysWork& wk, const TC& c) {
+    BodyVel A = loadVel(e, wk, c.bodyA), B = loadVel(e, wk, c.bodyB);
+    V2 normal = c.normal, tangent = crossVS(normal, 1.0f);
+    for (int j = 0; j < c.solverPoints; ++j) {
+        V2 P = c.nImp[j] * normal + c.tImp[j] * tangent;
+        A.w -= A.invI * cross(c.rA[j], P);
+        A.v = A.v - A.invMass * P;
+        B.w += B.invI * cross(c.rB[j], P);
+        B.v = B.v + B.invMass * P;
+    }
+    storeVel(wk, c.bodyA, A);
+    storeVel(wk, c.bodyB, B);
+}
+
+// ContactSolver.solveVelocityConstraints for one constraint (friction first, then normal / block solver)
+PS_HD void solveVelocityOne(const PhysEnv& e, const PhysWork& wk, TC& c) {
+    BodyVel A = loadVel(e, wk, c.bodyA), B = loadVel(e, wk, c.bodyB);
+    V2 vA = A.v, vB = B.v;
+    float wA = A.w, wB = B.w;
+    float invMassA = A.invMass, invIA = A.invI, invMassB = B.invMass, invIB = B.invI;
+    V2 normal = c.normal, tangent = crossVS(normal, 1.0f);
+    float friction = e.scene->friction;
+    for (int j = 0; j < c.solverPoints; ++j) {
+        V2 dv = vB + crossSV(wB, c.rB[j]) - vA - crossSV(wA, c.rA[j]);
+        float vt = dot(dv, tangent);
+        float lambda = c.tMass[j] * (-vt);
+        float maxFriction = friction * c.nImp[j];
+        float newImpulse = clampf(c.tImp[j] + lambda, -maxFriction, maxFriction);
+        lambda = newImpulse - c.tImp[j];
+        V2 P = lambda * tangent;
+        vA = vA - invMassA * P;
+        wA -= invIA * cross(c.rA[j], P);
+        vB = vB + invMassB * P;
+        wB += invIB * cross(c.rB[j], P);
+        c.tImp[j] = newImpulse;
+    }
+    if (c.solverPoints == 1) {
+        V2 dv = vB + crossSV(wB, c.rB[0]) - vA - crossSV(wA, c.rA[0]);
+        float vn = dot(dv, normal);
+        float lambda = -c.nMass[0] * (vn - 0.0f);
+        float newImpulse = fmaxf_(c.nImp[0] + lambda, 0.0f);
+        lambda = newImpulse - c.nImp[0];
+        V2 P = lambda * normal;
+        vA = vA - invMassA * P;
+        wA -= invIA * cross(c.rA[0], P);
+        vB = vB + invMassB * P;
+        wB += invIB * cross(c.rB[0], P);
+        c.nImp[0] = newImpulse;
+    } else {
+        V2 a = mk(c.nImp[0], c.nImp[1]);
+        V2 dv1 = vB + crossSV(wB, c.rB[0]) - vA - crossSV(wA, c.rA[0]);
+        V2 dv2 = vB + crossSV(wB, c.rB[1]) - vA - crossSV(wA, c.rA[1]);
+        float vn1 = dot(dv1, normal), vn2 = dot(dv2, normal);
+        V2 b = mk(vn1 - 0.0f, vn2 - 0.0f);
+        // b -= K * a
+        b = b - mk(c.k11 * a.x + c.k12 * a.y, c.k12 * a.x + c.k22 * a.y);
+        V2 x;
+        bool ok = false;
+        // case 1: both points active, x = -K^-1 b
+        V2 mb = mk(c.m11 * b.x + c.m12 * b.y, c.m12 * b.x + c.m22 * b.y);
+        x = -mb;
+        if (x.x >= 0.0f && x.y >= 0.0f) ok = true;
+        if (!ok) {   // case 2: point 1 active
+            x.x = -c.nMass[0] * b.x;
+            x.y = 0.0f;
+            vn2 = c.k12 * x.x + b.y;
+            if (x.x >= 0.0f && vn2 >= 0.0f) ok = true;
+        }
+        if (!ok) {   // case 3: point 2 active
+            x.x = 0.0f;
+            x.y = -c.nMass[1] * b.y;
+            vn1 = c.k12 * x.y + b.x;
+            if (x.y >= 0.0f && vn1 >= 0.0f) ok = true;
+        }
+        if (!ok) {   // case 4: none active
+            x.x = 0.0f;
+            x.y = 0.0f;
+            if (b.x >= 0.0f && b.y >= 0.0f) ok = true;
+        }
+        if (ok) {
+            V2 dd = x - a;
+            V2 P1 = dd.x * normal, P2 = dd.y * normal;
+            vA = vA - invMassA * (P1 + P2);
+            wA -= invIA * (cross(c.rA[0], P1) + cross(c.rA[1], P2));
+            vB = vB + invMassB * (P1 + P2);
+            wB += invIB * (cross(c.rB[0], P1) + cross(c.rB[1], P2));
+            c.nImp[0] = x.x;
+            c.nImp[1] = x.y;
+        }
+    }
+    A.v = vA;
+    A.w = wA;
+    B.v = vB;
+    B.w = wB;
+    storeVel(wk, c.bodyA, A);
+    storeVel(wk, c.bodyB, B);
+}
+
+// One position-correction of one manifold point; massA/massB let the TOI solver freeze one side.
+// Returns the separation it saw.
+PS_HD float correctPoint(const PhysEnv& e, const PhysWork& wk, int bA, int bB, int type, V2 localNormal, V2 localPoint, V2 pointLocal,
+                         float radius, float baumgarte, float invMassA, float invIA, float invMassB, float invIB) {
+    Xf xfA = bodyXf(e, wk, bA), xfB = bodyXf(e, wk, bB);
+    V2 normal, point;
+    float separation;
+    positionManifold(type, localNormal, localPoint, pointLocal, radius, xfA, xfB, normal, point, separation);
+    V2 cA = bA >= 0 ? mk(wk.cx[bA], wk.cy[bA]) : mk(0, 0);
+    V2 cB = bB >= 0 ? mk(wk.cx[bB], wk.cy[bB]) : mk(0, 0);
+    V2 rA = point - cA, rB = point - cB;
+    float C = clampf(baumgarte * (separation + kLinearSlop), -kMaxLinearCorrection, 0.0f);
+    float rnA = cross(rA, normal), rnB = cross(rB, normal);
+    float K = invMassA + invMassB + invIA * rnA * rnA + invIB * rnB * rnB;
+    float impulse = K > 0.0f ? -C / K : 0.0f;
+    V2 P = impulse * normal;
+    if (bA >= 0) {
+        V2 nc = cA - invMassA * P;
+        wk.cx[bA] = nc.x;
+        wk.cy[bA] = nc.y;
+        wk.a[bA] -= invIA * cross(rA, P);
+        syncBodyXf(e, wk, bA);
+    }
+    if (bB >= 0) {
+        V2 nc = cB + invMassB * P;
+        wk.cx[bB] = nc.x;
+        wk.cy[bB] = nc.y;
+        wk.a[bB] += invIB * cross(rB, P);
+        syncBodyXf(e, wk, bB);
+    }
+    return separation;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Phase A: load state into working memory, apply the robots' commands (Robot.move, src/arena/Robot.java:175-182)
+template <class Ctx>
+PS_HD void physLoad(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaState& st, const float* cmdFwd, const float* cmdTorque) {
+    const Dims& d = e.cfg.d;
+    int NB = d.NB;
+    PS_FOR(b, NB) {
+        wk.cx[b] = st.body[0 * NB + b];
+        wk.cy[b] = st.body[1 * NB + b];
+        wk.a[b] = st.body[2 * NB + b];
+        wk.vx[b] = st.body[3 * NB + b];
+        wk.vy[b] = st.body[4 * NB + b];
+        wk.w[b] = st.body[5 * NB + b];
+        syncBodyXf(e, wk, b);
+        if (b >= d.P) {
+            int r = b - d.P;
+            Xf T = bodyXf(e, wk, b);
+            // f = getWorldVector((forwards, 0)); p = getWorldPoint(localCenter); applyForce(f, p); applyTorque(t)
+            V2 f = mulR(T, mk(cmdFwd[r], 0.0f));
+            V2 p = mulX(T, mk(e.scene->robot.lcx, e.scene->robot.lcy));
+            float fx = 0.0f, fy = 0.0f, tq = 0.0f;
+            fx += f.x;
+            fy += f.y;
+            tq += cross(p - mk(wk.cx[b], wk.cy[b]), f);
+            tq += cmdTorque[r];
+            wk.fx[r] = fx;
+            wk.fy[r] = fy;
+            wk.tq[r] = tq;
+        }
+    }
+    if (ctx.tid() == 0) {
+        for (int i = 0; i < 8; i++) wk.counters[i] = 0;
+        wk.stats[0] = wk.stats[1] = wk.stats[2] = 0;
+    }
+    ctx.sync();
+}
+
+// Phase B: ContactManager.collide -- destroy contacts whose fat AABBs separated, re-evaluate the others, compact the
+// cache stably, and set up the solver constraint of every touching contact.
+template <class Ctx>
+PS_HD void physCollide(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaState& st, float dtRatio) {
+    const Dims& d = e.cfg.d;
+    int n = *st.nContacts;
+    int nKeep = 0, nTouch = 0;
+    int nRound = roundUpThreads(ctx, n);
+    for (int base = 0; base < nRound; base += ctx.nthreads()) {
+        int i = base + ctx.tid();
+        bool keep = false, touching = false;
+        uint32_t key = 0, info = 0;
+        float imp[4] = {0, 0, 0, 0};
+        Manifold m;
+        m.pointCount = 0;
+        if (i < n) {
+            key = st.ckey[i];
+            int pa = (int)(key >> 16), pb = (int)(key & 0xFFFFu);
+            keep = aabbOverlap(proxyFat(e, st, pa), proxyFat(e, st, pb));
+            if (keep) {
+                updateContact(e, wk, st, i, m, imp);
+                info = st.cinfo[i];
+                touching = m.pointCount > 0;
+            }
+        }
+        int totalKeep, totalTouch;
+        int posKeep = nKeep + ctx.exscanFlag(keep, totalKeep);
+        int posTouch = nTouch + ctx.exscanFlag(touching, totalTouch);
+        // (the scans contain barriers: every read of this chunk is done before any write below)
+        if (keep) {
+            st.ckey[posKeep] = key;
+            st.cinfo[posKeep] = info;
+            st.cimp[4 * posKeep + 0] = imp[0];
+            st.cimp[4 * posKeep + 1] = imp[1];
+            st.cimp[4 * posKeep + 2] = imp[2];
+            st.cimp[4 * posKeep + 3] = imp[3];
+            if (touching) {
+                if (posTouch < e.cfg.MT) {
+                    TC c;
+                    c.ci = posKeep;
+                    initConstraint(e, wk, c, m, (int)(key >> 16), (int)(key & 0xFFFFu), imp, dtRatio);
+                    wk.tc[posTouch] = c;
+                } else {
+                    *st.errorFlags |= ERR_TOUCH_CAP;
+                }
+            }
+        }
+        nKeep += totalKeep;
+        nTouch += totalTouch;
+        ctx.sync();
+    }
+    if (nTouch > e.cfg.MT) nTouch = e.cfg.MT;
+    if (ctx.tid() == 0) {
+        *st.nContacts = nKeep;
+        wk.counters[0] = nTouch;
+    }
+    ctx.sync();
+}
+
+// Phase C: World.solve -- contact graph, islands by DFS, integrate velocities.
+template <class Ctx>
+PS_HD void physIslands(Ctx& ctx, const PhysEnv& e, const PhysWork& wk) {
+    const Dims& d = e.cfg.d;
+    int NB = d.NB;
+    int nT = wk.counters[0];
+    PS_FOR(b, NB + 1) {
+        wk.adjOff[b] = 0;
+        if (b < NB) {
+            wk.adjFill[b] = 0;
+            wk.bodyFlag[b] = 0;
+        }
+    }
+    PS_FOR(t, nT) wk.tcFlag[t] = 0;
+    ctx.sync();
+    // degree of every dynamic body in the touching-contact graph
+    PS_FOR(t, nT) {
+        int bA = wk.tc[t].bodyA, bB = wk.tc[t].bodyB;
+        if (bA >= 0) ctx.atomicAddI(&wk.adjOff[bA + 1], 1);
+        if (bB >= 0) ctx.atomicAddI(&wk.adjOff[bB + 1], 1);
+    }
+    ctx.sync();
+    // exclusive prefix over bodies (adjOff[b + 1] currently holds deg(b))
+    {
+        int carry = 0;
+        int nRound = roundUpThreads(ctx, NB);
+        for (int base = 0; base < nRound; base += ctx.nthreads()) {
+            int b = base + ctx.tid();
+            int deg = b < NB ? wk.adjOff[b + 1] : 0;
+            int total;
+            int off = carry + ctx.exscanInt(deg, total);
+            ctx.sync();
+            if (b < NB) wk.adjOff[b + 1] = off + deg;
+            carry += total;
+            ctx.sync();
+        }
+    }
+    // fill, then order every body's list newest contact first (= JBox2D's per-body contact edge list)
+    PS_FOR(t, nT) {
+        int bA = wk.tc[t].bodyA, bB = wk.tc[t].bodyB;
+        if (bA >= 0) wk.adj[wk.adjOff[bA] + ctx.atomicAddI(&wk.adjFill[bA], 1)] = (uint16_t)t;
+        if (bB >= 0) wk.adj[wk.adjOff[bB] + ctx.atomicAddI(&wk.adjFill[bB], 1)] = (uint16_t)t;
+    }
+    ctx.sync();
+    PS_FOR(b, NB) {
+        int lo = wk.adjOff[b], hi = wk.adjOff[b + 1];
+        for (int i = lo + 1; i < hi; ++i) {   // insertion sort, descending
+            uint16_t v = wk.adj[i];
+            int j = i - 1;
+            while (j >= lo && wk.adj[j] < v) {
+                wk.adj[j + 1] = wk.adj[j];
+                --j;
+            }
+            wk.adj[j + 1] = v;
+        }
+    }
+    // integrate velocities (Island.solve step 1) -- independent of the island structure
+    PS_FOR(b, NB) {
+        const BodyConst& k = bodyConst(e, b);
+        float fx = 0.0f, fy = 0.0f, tq = 0.0f;
+        if (b >= d.P) {
+            fx = wk.fx[b - d.P];
+            fy = wk.fy[b - d.P];
+            tq = wk.tq[b - d.P];
+        }
+        float dt = e.cfg.dt;
+        // v += dt * (gravity + invMass * force), gravity = (0, 0)
+        float vx = wk.vx[b] + dt * (0.0f + k.invMass * fx);
+        float vy = wk.vy[b] + dt * (0.0f + k.invMass * fy);
+        float w = wk.w[b] + dt * k.invI * tq;
+        wk.vx[b] = vx * e.cfg.damp;
+        wk.vy[b] = vy * e.cfg.damp;
+        wk.w[b] = w * e.cfg.damp;
+    }
+    ctx.sync();
+    // stack DFS: seeds in body-list order (newest body first), edges newest first; only islands with contacts are recorded
+    if (ctx.tid() == 0) {
+        int nIsl = 0, ordN = 0;
+        for (int seed = NB - 1; seed >= 0; --seed) {
+            if (wk.bodyFlag[seed]) continue;
+            wk.bodyFlag[seed] = 1;
+            if (wk.adjOff[seed] == wk.adjOff[seed + 1]) continue;
+            int start = ordN;
+            wk.islandStart[nIsl] = start;
+            int sp = 0;
+            wk.stack[sp++] = (uint16_t)seed;
+            while (sp > 0) {
+                int b = wk.stack[--sp];
+                for (int i = wk.adjOff[b]; i < wk.adjOff[b + 1]; ++i) {
+                    int t = wk.adj[i];
+                    if (wk.tcFlag[t]) continue;
+                    wk.tcFlag[t] = 1;
+                    wk.order[ordN++] = (uint16_t)t;
+                    int bA = wk.tc[t].bodyA, bB = wk.tc[t].bodyB;
+                    int other = bA == b ? bB : bA;
+                    if (other < 0) continue;   // the wall is static: part of the island, never expanded
+                    if (wk.bodyFlag[other]) continue;
+                    wk.stack[sp++] = (uint16_t)other;
+                    wk.bodyFlag[other] = 1;
+                }
+            }
+            // Island.solve: contacts between two non-static bodies first (swap partition)
+            int i1 = start - 1;
+            for (int i2 = start; i2 < ordN; ++i2) {
+                int t = wk.order[i2];
+                bool nonStatic = wk.tc[t].bodyA >= 0 && wk.tc[t].bodyB >= 0;
+                if (nonStatic) {
+                    ++i1;
+                    uint16_t tmp = wk.order[i1];
+                    wk.order[i1] = wk.order[i2];
+                    wk.order[i2] = tmp;
+                }
+            }
+            ++nIsl;
+        }
+        wk.islandStart[nIsl] = ordN;
+        wk.counters[1] = nIsl;
+    }
+    ctx.sync();
+}
+
+// Phase D: ContactSolver velocity phase per island (warm start, velIters sweeps, store impulses)
+template <class Ctx>
+PS_HD void physSolveVelocity(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaState& st) {
+    int nIsl = wk.counters[1];
+    PS_FOR(k, nIsl) {
+        int lo = wk.islandStart[k], hi = wk.islandStart[k + 1];
+        for (int i = lo; i < hi; ++i) warmStartOne(e, wk, wk.tc[wk.order[i]]);
+        for (int it = 0; it < e.cfg.velIters; ++it)
+            for (int i = lo; i < hi; ++i) solveVelocityOne(e, wk, wk.tc[wk.order[i]]);
+        // ContactSolver.storeImpulses
+        for (int i = lo; i < hi; ++i) {
+            const TC& c = wk.tc[wk.order[i]];
+            for (int j = 0; j < c.solverPoints; ++j) {
+                st.cimp[4 * c.ci + 2 * j] = c.nImp[j];
+                st.cimp[4 * c.ci + 2 * j + 1] = c.tImp[j];
+            }
+        }
+    }
+    ctx.sync();
+}
+
+// Phase E: integrate positions (Island.solve step 6), remember the start-of-step transform for synchronizeFixtures
+template <class Ctx>
+PS_HD void physIntegrate(Ctx& ctx, const PhysEnv& e, const PhysWork& wk) {
+    const Dims& d = e.cfg.d;
+    float dt = e.cfg.dt;
+    PS_FOR(b, d.NB) {
+        float vx = wk.vx[b], vy = wk.vy[b], w = wk.w[b];
+        V2 tr = mk(dt * vx, dt * vy);
+        if (dot(tr, tr) > kMaxTranslationSquared) {
+            float ratio = kMaxTranslation / len(tr);
+            vx *= ratio;
+            vy *= ratio;
+        }
+        float rot = dt * w;
+        if (rot * rot > kMaxRotationSquared) {
+            float ratio = kMaxRotation / fabsf(rot);
+            w *= ratio;
+        }
+        wk.vx[b] = vx;
+        wk.vy[b] = vy;
+        wk.w[b] = w;
+        wk.c0x[b] = wk.cx[b];
+        wk.c0y[b] = wk.cy[b];
+        wk.a0[b] = wk.a[b];
+        if (b >= d.P) {
+            int r = b - d.P;
+            wk.r0px[r] = wk.rpx[r];
+            wk.r0py[r] = wk.rpy[r];
+            wk.r0c[r] = wk.rc[r];
+            wk.r0s[r] = wk.rs[r];
+        }
+        wk.cx[b] += dt * vx;
+        wk.cy[b] += dt * vy;
+        wk.a[b] += dt * w;
+        syncBodyXf(e, wk, b);
+    }
+    ctx.sync();
+}
+
+// Phase F: ContactSolver.solvePositionConstraints per island until minSeparation >= -1.5 linearSlop
+template <class Ctx>
+PS_HD void physSolvePosition(Ctx& ctx, const PhysEnv& e, const PhysWork& wk) {
+    int nIsl = wk.counters[1];
+    const BodyConst &kp = e.scene->puck, &kr = e.scene->robot;
+    // mass-scaled inverse masses: invMass = mass * invMass, invI = mass * invI
+    float pmP = kp.mass * kp.invMass, piP = kp.mass * kp.invI, pmR = kr.mass * kr.invMass, piR = kr.mass * kr.invI;
+    int P = e.cfg.d.P;
+    PS_FOR(k, nIsl) {
+        int lo = wk.islandStart[k], hi = wk.islandStart[k + 1];
+        int iters = 0;
+        for (int it = 0; it < e.cfg.posIters; ++it) {
+            ++iters;
+            float minSeparation = 0.0f;
+            for (int i = lo; i < hi; ++i) {
+                const TC& c = wk.tc[wk.order[i]];
+                int bA = c.bodyA, bB = c.bodyB;
+                float imA = bA < 0 ? 0.0f : (bA < P ? pmP : pmR), iiA = bA < 0 ? 0.0f : (bA < P ? piP : piR);
+                float imB = bB < 0 ? 0.0f : (bB < P ? pmP : pmR), iiB = bB < 0 ? 0.0f : (bB < P ? piP : piR);
+                for (int j = 0; j < c.solverPoints; ++j) {
+                    float sep = correctPoint(e, wk, bA, bB, c.type, c.localNormal, c.localPoint, c.lp[j], c.radius, kContactBaumgarte, imA, iiA, imB, iiB);
+                    minSeparation = fminf_(minSeparation, sep);
+                }
+            }
+            if (minSeparation >= -1.5f * kLinearSlop) break;
+        }
+        ctx.atomicMaxI(&wk.stats[0], iters);
+    }
+    if (ctx.tid() == 0) wk.stats[2] = nIsl;
+    ctx.sync();
+}
+
+// Phase G: Body.synchronizeFixtures for every dynamic body: swept AABBs, DynamicTree.moveProxy
+template <class Ctx>
+PS_HD void physSyncFixtures(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaState& st) {
+    const Dims& d = e.cfg.d;
+    int NP = d.NP, NB = d.NB;
+    int nMoved = 0;
+    int nRound = roundUpThreads(ctx, NP);
+    for (int base = 0; base < nRound; base += ctx.nthreads()) {
+        int i = base + ctx.tid();
+        bool mv = false;
+        if (i < NP) {
+            int proxy = kWallFixtures + i;
+            int b = proxyBody(d, proxy);
+            const Shape& s = e.scene->shapes[proxyShape(d, proxy)];
+            Xf xf1 = bodyXf0(e, wk, b), xf2 = bodyXf(e, wk, b);
+            Aabb a1 = shapeAabb(s, xf1), a2 = shapeAabb(s, xf2);
+            Aabb u;
+            u.lx = fminf_(a1.lx, a2.lx);
+            u.ly = fminf_(a1.ly, a2.ly);
+            u.ux = fmaxf_(a1.ux, a2.ux);
+            u.uy = fmaxf_(a1.uy, a2.uy);
+            // Fixture.m_aabb of the fixture PointSensor can see: robot hull (fixture 0), puck inner disc (fixture 1)
+            bool sensed = b < d.P ? (proxy - bodyFirstProxy(d, b)) == 1 : (proxy - bodyFirstProxy(d, b)) == 0;
+            if (sensed) storeAabb(st.senseAabb, NB, b, u);
+            Aabb fat = loadAabb(st.fat, NP, i);
+            if (!aabbContains(fat, u)) {
+                storeAabb(wk.fatOld, NP, i, fat);
+                float dx = xf2.px - xf1.px, dy = xf2.py - xf1.py;
+                Aabb nb;
+                nb.lx = u.lx - kAabbExtension;
+                nb.ly = u.ly - kAabbExtension;
+                nb.ux = u.ux + kAabbExtension;
+                nb.uy = u.uy + kAabbExtension;
+                float ddx = kAabbMultiplier * dx, ddy = kAabbMultiplier * dy;
+                if (ddx < 0.0f) nb.lx += ddx; else nb.ux += ddx;
+                if (ddy < 0.0f) nb.ly += ddy; else nb.uy += ddy;
+                storeAabb(st.fat, NP, i, nb);
+                mv = true;
+            }
+            wk.moved[i] = mv ? 1 : 0;
+        }
+        int total;
+        int pos = nMoved + ctx.exscanFlag(mv, total);
+        if (mv) wk.movedList[pos] = i;
+        nMoved += total;
+    }
+    if (ctx.tid() == 0) wk.counters[2] = nMoved;
+    ctx.sync();
+}
+
+// Union of each body's fat AABBs (pair-search culling)
+template <class Ctx>
+PS_HD void physBodyFat(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaState& st) {
+    const Dims& d = e.cfg.d;
+    PS_FOR(b, d.NB) {
+        int first = bodyFirstProxy(d, b) - kWallFixtures, cnt = bodyProxyCount(d, b);
+        Aabb u = loadAabb(st.fat, d.NP, first);
+        for (int k = 1; k < cnt; ++k) {
+            Aabb f = loadAabb(st.fat, d.NP, first + k);
+            u.lx = fminf_(u.lx, f.lx);
+            u.ly = fminf_(u.ly, f.ly);
+            u.ux = fmaxf_(u.ux, f.ux);
+            u.uy = fmaxf_(u.uy, f.uy);
+        }
+        storeAabb(wk.bodyFat, d.NB, b, u);
+    }
+    ctx.sync();
+}
+
+// Candidate test of BroadPhase.updatePairs + ContactManager.addPair for (moved proxy q, other proxy p).
+// A pair is new iff the fat AABBs overlap now and did not overlap before this step's moveProxy calls: the contact cache
+// always equals the set of filtered pairs with overlapping fat AABBs (contacts die in collide() exactly when they stop
+// overlapping, and are born here exactly when they start), so "already has a contact" == "overlapped before".
+template <class Ctx>
+PS_HD void tryPair(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaState& st, int q, const Aabb& fatQ, int p, bool allNew) {
+    const Dims& d = e.cfg.d;
+    if (p == q) return;
+    int bq = proxyBody(d, q), bp = proxyBody(d, p);
+    if (bq == bp) return;
+    const Shape& sq = e.scene->shapes[proxyShape(d, q)];
+    const Shape& sp = e.scene->shapes[proxyShape(d, p)];
+    if (!shouldCollide(sq, sp)) return;
+    Aabb fatP = proxyFat(e, st, p);
+    if (!aabbOverlap(fatP, fatQ)) return;
+    if (!allNew) {
+        Aabb oq = loadAabb(wk.fatOld, d.NP, q - kWallFixtures);   // q moved: its old box was saved
+        Aabb op = (p >= kWallFixtures && wk.moved[p - kWallFixtures]) ? loadAabb(wk.fatOld, d.NP, p - kWallFixtures) : fatP;
+        if (aabbOverlap(op, oq)) return;
+    }
+    int lo = p < q ? p : q, hi = p < q ? q : p;
+    int slot = ctx.atomicAddI(&wk.counters[3], 1);
+    if (slot < e.cfg.MPAIR) wk.pairs[slot] = ((uint32_t)lo << 16) | (uint32_t)hi;
+}
+
+// Phase H: ContactManager.findNewContacts. allNew = every proxy counts as moved and there is no previous cache (reset).
+template <class Ctx>
+PS_HD void physFindNewContacts(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaState& st, bool allNew) {
+    const Dims& d = e.cfg.d;
+    int NB = d.NB;
+    int nMoved = allNew ? d.NP : wk.counters[2];
+    // (moved proxy) x (dynamic bodies + the wall)
+    int nItems = nMoved * (NB + 1);
+    PS_FOR(it, nItems) {
+        int mi = it / (NB + 1), b = it - mi * (NB + 1);
+        int q = kWallFixtures + (allNew ? mi : wk.movedList[mi]);
+        Aabb fatQ = proxyFat(e, st, q);
+        if (b < NB) {
+            if (!aabbOverlap(loadAabb(wk.bodyFat, NB, b), fatQ)) continue;
+            int first = bodyFirstProxy(d, b), cnt = bodyProxyCount(d, b);
+            for (int k = 0; k < cnt; ++k) tryPair(ctx, e, wk, st, q, fatQ, first + k, allNew);
+        } else {
+            // wall: only proxies reaching the band where wall boxes live need the 84 tests
+            float inner = e.scene->cornerX - 1.0f;
+            if (fatQ.lx > -inner && fatQ.ux < inner && fatQ.ly > -inner && fatQ.uy < inner) continue;
+            for (int k = 0; k < kWallFixtures; ++k) tryPair(ctx, e, wk, st, q, fatQ, k, allNew);
+        }
+    }
+    ctx.sync();
+    int nPairs = wk.counters[3];
+    if (nPairs > e.cfg.MPAIR) {
+        if (ctx.tid() == 0) *st.errorFlags |= ERR_PAIR_CAP;
+        nPairs = e.cfg.MPAIR;
+    }
+    // bitonic sort of the pair keys (padded with 0xFFFFFFFF), then unique -> append in sorted order
+    int n2 = 1;
+    while (n2 < nPairs) n2 <<= 1;
+    PS_FOR(i, n2) if (i >= nPairs) wk.pairs[i] = 0xFFFFFFFFu;
+    ctx.sync();
+    for (int k = 2; k <= n2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            PS_FOR(i, n2) {
+                int l = i ^ j;
+                if (l > i) {
+                    uint32_t a = wk.pairs[i], b = wk.pairs[l];
+                    bool up = (i & k) == 0;
+                    if ((a > b) == up) {
+                        wk.pairs[i] = b;
+                        wk.pairs[l] = a;
+                    }
+                }
+            }
+            ctx.sync();
+        }
+    int nOld = *st.nContacts;
+    int nNew = 0;
+    int nRound = roundUpThreads(ctx, nPairs);
+    for (int base = 0; base < nRound; base += ctx.nthreads()) {
+        int i = base + ctx.tid();
+        bool uniq = false;
+        uint32_t key = 0;
+        if (i < nPairs) {
+            key = wk.pairs[i];
+            uniq = i == 0 || wk.pairs[i - 1] != key;
+        }
+        int total;
+        int pos = nOld + nNew + ctx.exscanFlag(uniq, total);
+        if (uniq) {
+            if (pos < e.cfg.MC) {
+                int pa = (int)(key >> 16), pb = (int)(key & 0xFFFFu);
+                // Contact.create: the polygon is fixture A of a polygon-circle contact
+                const Shape& sA = e.scene->shapes[proxyShape(d, pa)];
+                const Shape& sB = e.scene->shapes[proxyShape(d, pb)];
+                if (sA.type == SHAPE_CIRCLE && sB.type == SHAPE_POLYGON) key = ((uint32_t)pb << 16) | (uint32_t)pa;
+                st.ckey[pos] = key;
+                st.cinfo[pos] = 0;
+                st.cimp[4 * pos + 0] = 0.0f;
+                st.cimp[4 * pos + 1] = 0.0f;
+                st.cimp[4 * pos + 2] = 0.0f;
+                st.cimp[4 * pos + 3] = 0.0f;
+            } else {
+                *st.errorFlags |= ERR_CONTACT_CAP;
+            }
+        }
+        nNew += total;
+    }
+    ctx.sync();
+    if (ctx.tid() == 0) {
+        int nc = nOld + nNew;
+        *st.nContacts = nc > e.cfg.MC ? e.cfg.MC : nc;
+    }
+    ctx.sync();
+}
+
+// World.solveTOI(Body) for one dynamic body against the wall. wallList holds the cache indices of all wall contacts
+// (ascending); the body's contact-edge order is newest first, i.e. descending index.
+PS_HDN void toiBody(const PhysEnv& e, const PhysWork& wk, const ArenaState& st, int body, int nWall) {
+    const Dims& d = e.cfg.d;
+    const BodyConst& k = bodyConst(e, body);
+    Sweep sw;
+    sw.lcx = k.lcx;
+    sw.lcy = k.lcy;
+    if (body < d.P) {
+        sw.lcx = 0.0f;
+        sw.lcy = 0.0f;
+    }
+    Sweep wall;
+    wall.lcx = wall.lcy = wall.c0x = wall.c0y = wall.cx = wall.cy = wall.a0 = wall.a = 0.0f;
+    int toiContact = -1;
+    float toi = 1.0f;
+    bool found;
+    int count, iter = 0;
+    do {
+        count = 0;
+        found = false;
+        sw.c0x = wk.c0x[body];
+        sw.c0y = wk.c0y[body];
+        sw.cx = wk.cx[body];
+        sw.cy = wk.cy[body];
+        sw.a0 = wk.a0[body];
+        sw.a = wk.a[body];
+        for (int wi = nWall - 1; wi >= 0; --wi) {
+            int ci = wk.wallList[wi];
+            uint32_t key = st.ckey[ci];
+            int pa = (int)(key >> 16), pb = (int)(key & 0xFFFFu);
+            int bA = proxyBody(d, pa), bB = proxyBody(d, pb);
+            if (bA != body && bB != body) continue;
+            if (ci == toiContact) continue;
+            DProxy prA, prB;
+            proxyFromShape(prA, e.scene->shapes[proxyShape(d, pa)]);
+            proxyFromShape(prB, e.scene->shapes[proxyShape(d, pb)]);
+            int state;
+            float t;
+            timeOfImpact(state, t, e.trig, prA, bA == body ? sw : wall, prB, bB == body ? sw : wall, toi);
+            if (state == TOI_TOUCHING && t < toi) {
+                toiContact = ci;
+                toi = t;
+                found = true;
+            }
+            ++count;
+        }
+        ++iter;
+    } while (found && count > 1 && iter < 50);
+    if (toiContact < 0) return;   // Body.advance(1): c0 = c, a0 = a -- nothing later reads them
+    wk.stats[1] += 1;             // diagnostic only (racy increments are acceptable)
+    // Body.advance(toi)
+    sweepAdvance(sw, toi);
+    wk.c0x[body] = sw.c0x;
+    wk.c0y[body] = sw.c0y;
+    wk.a0[body] = sw.a0;
+    wk.cx[body] = sw.c0x;
+    wk.cy[body] = sw.c0y;
+    wk.a[body] = sw.a0;
+    syncBodyXf(e, wk, body);
+    // update the TOI contact, then every other wall contact of the body (edge order), gather the touching ones
+    int cIdx[kMaxTOIContacts];
+    Manifold mans[kMaxTOIContacts];
+    int n = 0;
+    {
+        Manifold m;
+        float imp[4];
+        updateContact(e, wk, st, toiContact, m, imp);
+    }
+    for (int wi = nWall - 1; wi >= 0 && n < kMaxTOIContacts; --wi) {
+        int ci = wk.wallList[wi];
+        uint32_t key = st.ckey[ci];
+        int pa = (int)(key >> 16), pb = (int)(key & 0xFFFFu);
+        int bA = proxyBody(d, pa), bB = proxyBody(d, pb);
+        if (bA != body && bB != body) continue;
+        Manifold m;
+        float imp[4];
+        if (ci != toiContact) {
+            updateContact(e, wk, st, ci, m, imp);
+        } else {
+            // already updated above; re-evaluating at the same transforms gives the same manifold
+            const Shape& sA = e.scene->shapes[proxyShape(d, pa)];
+            const Shape& sB = e.scene->shapes[proxyShape(d, pb)];
+            evaluateManifold(m, sA, bodyXf(e, wk, bA), sB, bodyXf(e, wk, bB));
+        }
+        if (m.pointCount == 0) continue;
+        cIdx[n] = ci;
+        mans[n] = m;
+        ++n;
+    }
+    // TOISolver: only the TOI body moves
+    float pm = k.mass * k.invMass, pi = k.mass * k.invI;
+    for (int it = 0; it < 20; ++it) {
+        float minSeparation = 0.0f;
+        for (int c = 0; c < n; ++c) {
+            uint32_t key = st.ckey[cIdx[c]];
+            int pa = (int)(key >> 16), pb = (int)(key & 0xFFFFu);
+            int bA = proxyBody(d, pa), bB = proxyBody(d, pb);
+            float radius = e.scene->shapes[proxyShape(d, pa)].radius + e.scene->shapes[proxyShape(d, pb)].radius;
+            float imA = bA == body ? pm : 0.0f, iiA = bA == body ? pi : 0.0f;
+            float imB = bB == body ? pm : 0.0f, iiB = bB == body ? pi : 0.0f;
+            const Manifold& m = mans[c];
+            for (int j = 0; j < m.pointCount; ++j) {
+                float sep = correctPoint(e, wk, bA, bB, m.type, m.localNormal, m.localPoint, m.p[j], radius, kToiBaumgarte, imA, iiA, imB, iiB);
+                minSeparation = fminf_(minSeparation, sep);
+            }
+        }
+        if (minSeparation >= -1.5f * kLinearSlop) break;
+    }
+}
+
+// Phase I: World.solveTOI -- every dynamic body that has cached contacts with the wall
+template <class Ctx>
+PS_HD void physSolveTOI(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaState& st) {
+    const Dims& d = e.cfg.d;
+    int n = *st.nContacts;
+    PS_FOR(b, d.NB) wk.bodyFlag[b] = 0;
+    ctx.sync();
+    int nWall = 0;
+    int nRound = roundUpThreads(ctx, n);
+    for (int base = 0; base < nRound; base += ctx.nthreads()) {
+        int i = base + ctx.tid();
+        bool isWall = false;
+        if (i < n) {
+            uint32_t key = st.ckey[i];
+            int pa = (int)(key >> 16), pb = (int)(key & 0xFFFFu);
+            isWall = pa < kWallFixtures || pb < kWallFixtures;
+            if (isWall) wk.bodyFlag[proxyBody(d, pa < kWallFixtures ? pb : pa)] = 1;
+        }
+        int total;
+        int pos = nWall + ctx.exscanFlag(isWall, total);
+        if (isWall) {
+            if (pos < e.cfg.MW) wk.wallList[pos] = i;
+            else *st.errorFlags |= ERR_CONTACT_CAP;
+        }
+        nWall += total;
+    }
+    if (nWall > e.cfg.MW) nWall = e.cfg.MW;
+    ctx.sync();
+    PS_FOR(b, d.NB) {
+        if (wk.bodyFlag[b]) toiBody(e, wk, st, b, nWall);
+    }
+    ctx.sync();
+}
+
+// Phase J: write the bodies back
+template <class Ctx>
+PS_HD void physStore(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaState& st) {
+    int NB = e.cfg.d.NB;
+    PS_FOR(b, NB) {
+        st.body[0 * NB + b] = wk.cx[b];
+        st.body[1 * NB + b] = wk.cy[b];
+        st.body[2 * NB + b] = wk.a[b];
+        st.body[3 * NB + b] = wk.vx[b];
+        st.body[4 * NB + b] = wk.vy[b];
+        st.body[5 * NB + b] = wk.w[b];
+    }
+    if (ctx.tid() == 0) *st.invDt0 = 1.0f / e.cfg.dt;
+    ctx.sync();
+}
+
+// World.step
+template <class Ctx>
+PS_HD void worldStep(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaState& st, const float* cmdFwd, const float* cmdTorque) {
+    float dtRatio = *st.invDt0 * e.cfg.dt;
+    ctx.sync();
+    physLoad(ctx, e, wk, st, cmdFwd, cmdTorque);
+    physCollide(ctx, e, wk, st, dtRatio);
+    physIslands(ctx, e, wk);
+    physSolveVelocity(ctx, e, wk, st);
+    physIntegrate(ctx, e, wk);
+    physSolvePosition(ctx, e, wk);
+    physSyncFixtures(ctx, e, wk, st);
+    physBodyFat(ctx, e, wk, st);
+    physFindNewContacts(ctx, e, wk, st, false);
+    if (e.cfg.toiEnabled) physSolveTOI(ctx, e, wk, st);
+    physStore(ctx, e, wk, st);
+}
+
+}  // namespace ps

@@ -1,0 +1,198 @@
+// puckswarm_b200 -- seeded arena construction on the device.
+//
+// Replaces `new Experiment(seed)` + `new Arena(world, null, false)` for one arena
+// (src/experiment/Experiment.java:21-24, src/arena/Arena.java:45-120,143-181,
+// src/arena/RoundedRectangleEnclosure.java:55-93): java.util.Random(seed), rejection-sampled puck and robot
+// poses, fixture proxies (tight AABB + 0.1) and the first BroadPhase.updatePairs over all proxies.
+#pragma once
+#include "ps_physics.cuh"
+#include "../../include/puckswarm_b200.h"
+
+namespace ps {
+
+// java.util.Random
+struct JRandom {
+    uint64_t seed;
+    int haveNextNextGaussian;
+    double nextNextGaussian;
+};
+PS_HD void jrSetSeed(JRandom& r, int64_t s) {
+    r.seed = ((uint64_t)s ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1);
+    r.haveNextNextGaussian = 0;
+    r.nextNextGaussian = 0.0;
+}
+PS_HD int32_t jrNext(JRandom& r, int bits) {
+    r.seed = (r.seed * 0x5DEECE66DULL + 0xBULL) & ((1ULL << 48) - 1);
+    return (int32_t)(r.seed >> (48 - bits));
+}
+PS_HD float jrNextFloat(JRandom& r) { return jrNext(r, 24) / (float)(1 << 24); }
+PS_HD int32_t jrNextInt(JRandom& r, int32_t n) {
+    if ((n & -n) == n) return (int32_t)(((int64_t)n * (int64_t)jrNext(r, 31)) >> 31);
+    int32_t bits, val;
+    do {
+        bits = jrNext(r, 31);
+        val = bits % n;
+    } while ((int32_t)((uint32_t)bits - (uint32_t)val + (uint32_t)(n - 1)) < 0);
+    return val;
+}
+PS_HD double jrNextDouble(JRandom& r) {
+    int64_t hi = (int64_t)jrNext(r, 26) << 27;
+    return (double)(hi + jrNext(r, 27)) * (1.0 / (double)(1LL << 53));
+}
+PS_HD double jrNextGaussian(JRandom& r) {
+    if (r.haveNextNextGaussian) {
+        r.haveNextNextGaussian = 0;
+        return r.nextNextGaussian;
+    }
+    double v1, v2, s;
+    do {
+        v1 = 2 * jrNextDouble(r) - 1;
+        v2 = 2 * jrNextDouble(r) - 1;
+        s = v1 * v1 + v2 * v2;
+    } while (s >= 1 || s == 0);
+    double multiplier = sqrt(-2 * log(s) / s);
+    r.nextNextGaussian = v2 * multiplier;
+    r.haveNextNextGaussian = 1;
+    return v1 * multiplier;
+}
+
+// RoundedRectangleEnclosure.inFreeSpace (src/arena/RoundedRectangleEnclosure.java:73-93)
+PS_HD bool inFreeSpace(const Scene& sc, V2 v, float minDistance) {
+    float ax = fabsf(v.x), ay = fabsf(v.y);
+    float W = sc.W, H = sc.H, R = sc.R;
+    if (ax < W / 2 - R - minDistance && ay < H / 2 - minDistance) return true;
+    else if (ax > W / 2 - R && ax < W / 2 - minDistance && ay < H / 2 - R - minDistance) return true;
+    else if (dist(v, mk(-sc.cornerX, sc.cornerY)) < R - minDistance) return true;
+    else if (dist(v, mk(sc.cornerX, sc.cornerY)) < R - minDistance) return true;
+    else if (dist(v, mk(-sc.cornerX, -sc.cornerY)) < R - minDistance) return true;
+    else if (dist(v, mk(sc.cornerX, -sc.cornerY)) < R - minDistance) return true;
+    return false;
+}
+PS_HD bool randomInside(const Scene& sc, JRandom& rng, float minDistance, V2& out) {
+    for (int i = 0; i < 100000; i++) {
+        float fx = jrNextFloat(rng);
+        float fy = jrNextFloat(rng);
+        V2 v = mk(fx * sc.W - sc.W / 2.0f, fy * sc.H - sc.H / 2.0f);
+        if (inFreeSpace(sc, v, minDistance)) {
+            out = v;
+            return true;
+        }
+    }
+    return false;
+}
+
+struct ResetOut {
+    ps_robot_state* robot;   // [R]
+    ps_arena_state* arena;
+};
+
+template <class Ctx>
+PS_HD void arenaReset(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaState& st, const ResetOut& out, int64_t seed,
+                      const ps_robot_state* robotInit /* [2]: plain, informed */, int nInformed) {
+    const Dims& d = e.cfg.d;
+    const Scene& sc = *e.scene;
+    int NB = d.NB, NP = d.NP;
+    if (ctx.tid() == 0) {
+        JRandom rng;
+        jrSetSeed(rng, seed);
+        const float PUCK_WIDTH = 6.3f, SRV_LENGTH = 22.0f;
+        // pucks: Arena.createPuck (the minX/maxX band is the whole arena for modifiedPuckPlacement = false)
+        for (int p = 0; p < d.P; ++p) {
+            V2 pos = mk(0, 0);
+            float closest = 0.0f;
+            do {
+                if (!randomInside(sc, rng, PUCK_WIDTH / 2, pos)) break;
+                closest = INFINITY;
+                for (int o = 0; o < p; ++o) {
+                    float dd = dist(mk(wk.cx[o], wk.cy[o]), pos);
+                    if (dd < closest) closest = dd;
+                }
+            } while (closest < PUCK_WIDTH);
+            float ang = (float)(2.0 * 3.14159265358979323846 * (double)jrNextFloat(rng));
+            wk.cx[p] = pos.x;
+            wk.cy[p] = pos.y;
+            wk.a[p] = ang;
+        }
+        // robots: Arena.createRobot (distance to other robots only, at most 1000 attempts)
+        for (int r = 0; r < d.R; ++r) {
+            V2 pos = mk(0, 0);
+            float closest = 0.0f;
+            int attempts = 0;
+            do {
+                if (!randomInside(sc, rng, SRV_LENGTH / 2, pos)) break;
+                closest = INFINITY;
+                for (int o = 0; o < r; ++o) {
+                    float dd = dist(mk(wk.rpx[o], wk.rpy[o]), pos);
+                    if (dd < closest) closest = dd;
+                }
+                attempts++;
+            } while (attempts < 1000 && closest < 2 * SRV_LENGTH);
+            float ang = (float)(2.0 * 3.14159265358979323846 * (double)jrNextFloat(rng));
+            int b = d.P + r;
+            // BodyDef -> Body: xf.position = pos, R.set(angle); resetMassData: sweep.c = xf * localCenter
+            Xf T;
+            T.px = pos.x;
+            T.py = pos.y;
+            T.c = psCos(e.trig, ang);
+            T.s = psSin(e.trig, ang);
+            wk.rpx[r] = T.px;
+            wk.rpy[r] = T.py;
+            wk.rc[r] = T.c;
+            wk.rs[r] = T.s;
+            V2 c = mulX(T, mk(sc.robot.lcx, sc.robot.lcy));
+            wk.cx[b] = c.x;
+            wk.cy[b] = c.y;
+            wk.a[b] = ang;
+        }
+        ps_arena_state as;
+        as.rng_next_gaussian = rng.nextNextGaussian;
+        as.rng_seed = rng.seed;
+        as.rng_have_gaussian = rng.haveNextNextGaussian;
+        as.update_count = 0;
+        as.step_count = 0;
+        as.n_contacts = 0;
+        as.inv_dt0 = 0.0f;
+        as.error_flags = 0;
+        *out.arena = as;
+        for (int i = 0; i < 8; i++) wk.counters[i] = 0;
+    }
+    ctx.sync();
+    PS_FOR(r, d.R) {
+        ps_robot_state rs = robotInit[r < nInformed ? 1 : 0];
+        // PS_RNG_PER_ROBOT streams: java.util.Random(seed * 1000003 + 7919 * (r + 1))
+        JRandom rr;
+        jrSetSeed(rr, seed * 1000003LL + 7919LL * (int64_t)(r + 1));
+        rs.rng_seed = rr.seed;
+        rs.rng_have_gaussian = 0;
+        rs.rng_next_gaussian = 0.0;
+        out.robot[r] = rs;
+    }
+    PS_FOR(b, NB) {
+        st.body[0 * NB + b] = wk.cx[b];
+        st.body[1 * NB + b] = wk.cy[b];
+        st.body[2 * NB + b] = wk.a[b];
+        st.body[3 * NB + b] = 0.0f;
+        st.body[4 * NB + b] = 0.0f;
+        st.body[5 * NB + b] = 0.0f;
+    }
+    // Fixture.createProxy: tight AABB at the creation transform, fattened by aabbExtension
+    PS_FOR(i, NP) {
+        int proxy = kWallFixtures + i;
+        int b = proxyBody(d, proxy);
+        const Shape& s = sc.shapes[proxyShape(d, proxy)];
+        Aabb a = shapeAabb(s, bodyXf(e, wk, b));
+        bool sensed = b < d.P ? (proxy - bodyFirstProxy(d, b)) == 1 : (proxy - bodyFirstProxy(d, b)) == 0;
+        if (sensed) storeAabb(st.senseAabb, NB, b, a);
+        a.lx -= kAabbExtension;
+        a.ly -= kAabbExtension;
+        a.ux += kAabbExtension;
+        a.uy += kAabbExtension;
+        storeAabb(st.fat, NP, i, a);
+        wk.moved[i] = 1;
+    }
+    ctx.sync();
+    physBodyFat(ctx, e, wk, st);
+    physFindNewContacts(ctx, e, wk, st, true);
+}
+
+}  // namespace ps

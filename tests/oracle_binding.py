@@ -42,6 +42,7 @@ def lib():
         L.orc_get_observations.argtypes = [C.c_void_p, C.POINTER(abi.ps_obs_view)]
         L.orc_compute_stats.argtypes = [C.c_void_p, C.c_float, C.POINTER(abi.ps_stats)]
         L.orc_step_info.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_solve_order.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.orc_manifold.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float,
                                    C.c_float, C.c_void_p]
         L.orc_random_ints.argtypes = [C.c_int64, C.c_int, C.c_void_p]
@@ -133,6 +134,11 @@ class Oracle:
         self.L.orc_step_info(self.h, arena, out.ctypes.data)
         return dict(pos_iters=int(out[0]), toi_events=int(out[1]), islands=int(out[2]), contacts=int(out[3]),
                     touching=int(out[4]), points=int(out[5]))
+
+    def solve_order(self, arena=0):
+        out = np.zeros(65536, np.uint32)
+        n = self.L.orc_solve_order(self.h, arena, out.ctypes.data, len(out))
+        return out[:n].copy()
 
     def manifold(self, pa, xa, pb, xb):
         out = np.zeros(12, np.float32)

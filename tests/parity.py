@@ -1,0 +1,67 @@
+"""Shared comparison helpers for the parity tests (engine or host emulation vs the oracle)."""
+import numpy as np
+
+
+def bits(a):
+    a = np.ascontiguousarray(a)
+    if a.dtype == np.float32:
+        return a.view(np.uint32)
+    if a.dtype == np.float64:
+        return a.view(np.uint64)
+    return a
+
+
+def compare_states(sa, sb, n_arenas, tol=0.0, what=("body", "sense_aabb", "fat_aabb", "contacts", "arena", "robot")):
+    """Return a list of human-readable mismatches between two abi.State (empty = identical)."""
+    out = []
+    for a in range(n_arenas):
+        na, nb = int(sa.arena[a]["n_contacts"]), int(sb.arena[a]["n_contacts"])
+        if "contacts" in what:
+            if na != nb:
+                out.append("arena %d: n_contacts %d vs %d" % (a, na, nb))
+            n = min(na, nb)
+            if not np.array_equal(sa.contact_key[a, :n], sb.contact_key[a, :n]):
+                i = int(np.nonzero(sa.contact_key[a, :n] != sb.contact_key[a, :n])[0][0])
+                out.append("arena %d: contact_key differs first at %d: %08x vs %08x" % (a, i, sa.contact_key[a, i], sb.contact_key[a, i]))
+            elif not np.array_equal(sa.contact_info[a, :n], sb.contact_info[a, :n]):
+                i = int(np.nonzero(sa.contact_info[a, :n] != sb.contact_info[a, :n])[0][0])
+                out.append("arena %d: contact_info differs first at %d (key %08x): %06x vs %06x" % (a, i, sa.contact_key[a, i], sa.contact_info[a, i], sb.contact_info[a, i]))
+            else:
+                x, y = sa.contact_impulse[a, :n], sb.contact_impulse[a, :n]
+                bad = ~close(x, y, tol)
+                if bad.any():
+                    i = int(np.nonzero(bad.any(axis=1))[0][0])
+                    out.append("arena %d: contact_impulse differs at %d (key %08x): %s vs %s" % (a, i, sa.contact_key[a, i], x[i], y[i]))
+        for name in ("body", "sense_aabb", "fat_aabb"):
+            if name in what:
+                x, y = getattr(sa, name)[a], getattr(sb, name)[a]
+                bad = ~close(x, y, tol)
+                if bad.any():
+                    idx = np.argwhere(bad)[0]
+                    out.append("arena %d: %s differs at %s (%d entries): %r vs %r" % (a, name, tuple(idx), int(bad.sum()), x[tuple(idx)], y[tuple(idx)]))
+        if "arena" in what:
+            for f in ("rng_seed", "rng_have_gaussian", "update_count", "step_count", "inv_dt0", "rng_next_gaussian"):
+                if sa.arena[a][f] != sb.arena[a][f]:
+                    out.append("arena %d: arena.%s %r vs %r" % (a, f, sa.arena[a][f], sb.arena[a][f]))
+        if "robot" in what:
+            for r in range(sa.robot.shape[1]):
+                ra, rb = sa.robot[a, r], sb.robot[a, r]
+                for f in ra.dtype.names:
+                    if f in ("pad_", "rng_seed", "rng_have_gaussian", "rng_next_gaussian"):
+                        continue
+                    x, y = np.asarray(ra[f]), np.asarray(rb[f])
+                    if x.dtype.kind == "f":
+                        ok = close(x, y, tol).all()
+                    else:
+                        ok = np.array_equal(x, y)
+                    if not ok:
+                        out.append("arena %d robot %d: %s %r vs %r" % (a, r, f, x, y))
+    return out
+
+
+def close(x, y, tol):
+    x = np.asarray(x)
+    y = np.asarray(y)
+    if tol == 0.0:
+        return (bits(x) == bits(y)) | ((x == 0) & (y == 0))
+    return np.abs(x.astype(np.float64) - y.astype(np.float64)) <= tol * np.maximum(1.0, np.maximum(np.abs(x), np.abs(y)))
