@@ -72,6 +72,8 @@ struct CtaCtx {
     __device__ __forceinline__ void atomicOrU(unsigned* p, unsigned v) const { atomicOr(p, v); }
     __device__ __forceinline__ void atomicMaxU(unsigned* p, unsigned v) const { atomicMax(p, v); }
     __device__ __forceinline__ void atomicMinI(int* p, int v) const { atomicMin(p, v); }
+    __device__ __forceinline__ int atomicMinRet(int* p, int v) const { return atomicMin(p, v); }
+    __device__ __forceinline__ void atomicMinU(unsigned* p, unsigned v) const { atomicMin(p, v); }
     __device__ __forceinline__ void atomicMaxI(int* p, int v) const { atomicMax(p, v); }
 };
 #endif
@@ -99,6 +101,14 @@ struct HostCtx {
         if (v > *p) *p = v;
     }
     void atomicMinI(int* p, int v) const {
+        if (v < *p) *p = v;
+    }
+    int atomicMinRet(int* p, int v) const {
+        int o = *p;
+        if (v < o) *p = v;
+        return o;
+    }
+    void atomicMinU(unsigned* p, unsigned v) const {
         if (v < *p) *p = v;
     }
     void atomicMaxI(int* p, int v) const {

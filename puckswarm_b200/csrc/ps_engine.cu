@@ -1,0 +1,451 @@
+// puckswarm_b200 -- the engine: CUDA kernels (sm_100a) and the C-ABI of include/puckswarm_b200.h.
+//
+// One CTA steps one arena at a time (persistent grid: CTA i takes arenas i, i + grid, ...). Per-arena state
+// lives in HBM in the ps_state_view layout; a CTA stages the bodies into shared memory, runs World.step there
+// (ps_physics.cuh) and writes them back. Sensing runs one CTA per robot (ps_sense.cuh). There is no CPU path:
+// without a CUDA device every entry point fails with PS_E_NODEVICE / PS_E_CUDA.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+#include "ps_host.hpp"
+#include "ps_sense.cuh"
+
+using namespace ps;
+
+static thread_local std::string g_lastError;
+static int setError(int code, const std::string& msg) {
+    g_lastError = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                             \
+    do {                                                                                                           \
+        cudaError_t err__ = (expr);                                                                                \
+        if (err__ != cudaSuccess) return setError(PS_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(err__)); \
+    } while (0)
+
+struct KParams {
+    PhysEnv env;
+    StatePtrs sp;
+    char* slow;              // per-slot working memory in HBM
+    size_t slowStride;
+    size_t fastCap;          // dynamic shared memory handed to the carver
+    int nArenas;
+    int stepInterval;
+    const int64_t* seeds;
+    const ps_robot_state* robotInit;
+    int nInformed;
+    int* stepStats;          // [nArenas][8] diagnostics of the last World.step
+};
+
+extern __shared__ __align__(16) char g_smem[];
+
+__device__ __forceinline__ PhysWork ctaWork(const KParams& p) {
+    Carver cv;
+    cv.fast = g_smem;
+    cv.fastCap = p.fastCap;
+    cv.fastUsed = 0;
+    cv.slow = p.slow + (size_t)blockIdx.x * p.slowStride;
+    cv.slowUsed = 0;
+    return carveWork(p.env.cfg, cv);
+}
+
+// Seeded construction of every arena (ps_spawn.cuh)
+__global__ void __launch_bounds__(256) k_reset(KParams p) {
+    __shared__ int scan[40];
+    CtaCtx ctx;
+    ctx.scanScratch = scan;
+    PhysWork wk = ctaWork(p);
+    for (int a = blockIdx.x; a < p.nArenas; a += gridDim.x) {
+        ArenaState st = arenaState(p.sp, p.env.cfg, a);
+        ResetOut out;
+        out.robot = p.sp.robot + (size_t)a * p.env.cfg.d.R;
+        out.arena = p.sp.arena + a;
+        arenaReset(ctx, p.env, wk, st, out, p.seeds[a], p.robotInit, p.nInformed);
+        __syncthreads();
+    }
+}
+
+// RunOffline.step minus sensing: Robot.move with the current commands + World.step, nTicks times per launch
+__global__ void __launch_bounds__(256) k_physics(KParams p, int nTicks) {
+    __shared__ int scan[40];
+    CtaCtx ctx;
+    ctx.scanScratch = scan;
+    PhysWork wk = ctaWork(p);
+    int R = p.env.cfg.d.R;
+    for (int a = blockIdx.x; a < p.nArenas; a += gridDim.x) {
+        ArenaState st = arenaState(p.sp, p.env.cfg, a);
+        const ps_robot_state* rs = p.sp.robot + (size_t)a * R;
+        // the commands live in fx/fy scratch of the force arrays until physLoad consumes them
+        for (int t = 0; t < nTicks; ++t) {
+            __syncthreads();
+            for (int r = threadIdx.x; r < R; r += blockDim.x) {
+                wk.fx[r] = rs[r].cmd_forwards;
+                wk.fy[r] = rs[r].cmd_torque;
+            }
+            __syncthreads();
+            worldStep(ctx, p.env, wk, st, wk.fx, wk.fy);
+            if (threadIdx.x == 0) p.sp.arena[a].update_count += 1;
+        }
+        if (threadIdx.x < 8) p.stepStats[a * 8 + threadIdx.x] = wk.stats[threadIdx.x];
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+struct ps_engine {
+    HostSetup hs;
+    SenseSetup sense;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    KParams kp;
+    Scene* dScene = nullptr;
+    float* dLut = nullptr;
+    ps_robot_state* dRobotInit = nullptr;
+    int64_t* dSeeds = nullptr;
+    int* dStepStats = nullptr;
+    int nSlots = 0, threads = 128;
+    size_t smemBytes = 0;
+    int64_t launches = 0;
+    int updateCount = 0;     // all arenas advance in lock step
+    SenseDevice sd;
+    bool isReset = false;
+};
+
+static size_t envSize(const char* name, size_t dflt) {
+    const char* v = getenv(name);
+    return v && *v ? (size_t)strtoull(v, nullptr, 10) : dflt;
+}
+
+extern "C" {
+
+const char* ps_last_error(void) { return g_lastError.c_str(); }
+int ps_abi_version(void) { return PS_ABI_VERSION; }
+
+void ps_config_defaults(ps_config* c) {
+    std::memset(c, 0, sizeof(*c));
+    c->abi_version = PS_ABI_VERSION;
+    c->n_arenas = 1;
+    c->n_robots = 4;
+    c->n_pucks = 10;
+    c->n_puck_types = 2;
+    c->n_informed_robots = 0;
+    c->controller = PS_CTRL_CACHECONS;
+    c->rng_mode = PS_RNG_JAVA_SHARED;
+    c->step_interval = 3;
+    c->vel_iters = 3;
+    c->pos_iters = 100;
+    c->dt = 1.0f / 14.0f;
+    c->enclosure_scale = 1.0f;
+    c->sincos_lut = 1;
+    c->toi_enabled = 1;
+    c->max_contacts = 0;
+    c->cluster_distance_threshold = 1.5f;
+    c->carry_threshold_lo = 0.1f;
+    c->carry_threshold_hi = 0.4f;
+    c->vfh_safety_gamma = 2.0f;
+    c->vfh_safety_mask = 5.0f;
+    c->vfh_tau_lo = 0.7f;
+    c->vfh_tau_hi = 0.85f;
+    c->cc_k1 = 1.0f;
+    c->cc_k2 = 8.0f;
+    c->cc_pick_up_time = 20;
+    c->cc_push_in_time = 1;
+    c->cc_backup_time = 5;
+    c->cc_prediction_distance_sqd = 100.0f;
+    c->cc_st_dev = 0.5f;
+    c->cc_exile_time = 20;
+    c->cc_spit_out_time = 10;
+    c->cc_cache_selection = PS_SEL_RELATIVE;
+    c->cc_k_absolute = 40.0f;
+    c->cc_k_relative = 8.0f;
+    c->cc_forget_prob = 0.001f;
+    c->cc_cache_separation = PS_SEP_ACCEPT_LARGER;
+    c->cc_home_separation_distance = 50.0f;
+    c->cc_ignore_pucks = 0;
+    c->bhd_push_in_time = 1;
+    c->bhd_backup_time = 5;
+}
+
+int ps_destroy(ps_handle h) {
+    if (!h) return PS_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->kp.sp.body);
+    cudaFree(h->kp.sp.senseAabb);
+    cudaFree(h->kp.sp.fat);
+    cudaFree(h->kp.sp.ckey);
+    cudaFree(h->kp.sp.cinfo);
+    cudaFree(h->kp.sp.cimp);
+    cudaFree(h->kp.sp.robot);
+    cudaFree(h->kp.sp.arena);
+    cudaFree(h->kp.slow);
+    cudaFree(h->dScene);
+    cudaFree(h->dLut);
+    cudaFree(h->dRobotInit);
+    cudaFree(h->dSeeds);
+    cudaFree(h->dStepStats);
+    h->sd.release();
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return PS_OK;
+}
+
+int ps_create(const ps_config* cfg, int device, ps_handle* out) {
+    if (!cfg || !out) return setError(PS_E_INVALID, "null argument");
+    *out = nullptr;
+    int nDev = 0;
+    if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0)
+        return setError(PS_E_NODEVICE, "no CUDA device: puckswarm_b200 has no CPU fallback");
+    if (device < 0 || device >= nDev) return setError(PS_E_INVALID, "bad device index");
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return setError(PS_E_NODEVICE, "device is not sm_100: the kernels are built for sm_100a only");
+    ps_engine* e = new ps_engine();
+    std::memset(&e->kp, 0, sizeof(e->kp));
+    if (!e->hs.init(*cfg)) {
+        std::string m = e->hs.error;
+        delete e;
+        return setError(PS_E_INVALID, m);
+    }
+    e->device = device;
+#define TRY_OR_FREE(expr)                 \
+    do {                                  \
+        int rc__ = [&]() -> int {         \
+            CUDA_TRY(expr);               \
+            return PS_OK;                 \
+        }();                              \
+        if (rc__ != PS_OK) {              \
+            ps_destroy(e);                \
+            return rc__;                  \
+        }                                 \
+    } while (0)
+    TRY_OR_FREE(cudaSetDevice(device));
+    TRY_OR_FREE(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    const PhysCfg& pc = e->hs.phys;
+    size_t A = cfg->n_arenas;
+    TRY_OR_FREE(cudaMalloc(&e->kp.sp.body, A * 6 * pc.d.NB * sizeof(float)));
+    TRY_OR_FREE(cudaMalloc(&e->kp.sp.senseAabb, A * 4 * pc.d.NB * sizeof(float)));
+    TRY_OR_FREE(cudaMalloc(&e->kp.sp.fat, A * 4 * pc.d.NP * sizeof(float)));
+    TRY_OR_FREE(cudaMalloc(&e->kp.sp.ckey, A * pc.MC * sizeof(uint32_t)));
+    TRY_OR_FREE(cudaMalloc(&e->kp.sp.cinfo, A * pc.MC * sizeof(uint32_t)));
+    TRY_OR_FREE(cudaMalloc(&e->kp.sp.cimp, A * pc.MC * 4 * sizeof(float)));
+    TRY_OR_FREE(cudaMalloc(&e->kp.sp.robot, A * pc.d.R * sizeof(ps_robot_state)));
+    TRY_OR_FREE(cudaMalloc(&e->kp.sp.arena, A * sizeof(ps_arena_state)));
+    TRY_OR_FREE(cudaMemset(e->kp.sp.body, 0, A * 6 * pc.d.NB * sizeof(float)));
+    TRY_OR_FREE(cudaMemset(e->kp.sp.senseAabb, 0, A * 4 * pc.d.NB * sizeof(float)));
+    TRY_OR_FREE(cudaMemset(e->kp.sp.fat, 0, A * 4 * pc.d.NP * sizeof(float)));
+    TRY_OR_FREE(cudaMemset(e->kp.sp.ckey, 0, A * pc.MC * sizeof(uint32_t)));
+    TRY_OR_FREE(cudaMemset(e->kp.sp.cinfo, 0, A * pc.MC * sizeof(uint32_t)));
+    TRY_OR_FREE(cudaMemset(e->kp.sp.cimp, 0, A * pc.MC * 4 * sizeof(float)));
+    TRY_OR_FREE(cudaMemset(e->kp.sp.robot, 0, A * pc.d.R * sizeof(ps_robot_state)));
+    TRY_OR_FREE(cudaMemset(e->kp.sp.arena, 0, A * sizeof(ps_arena_state)));
+    TRY_OR_FREE(cudaMalloc(&e->dScene, sizeof(Scene)));
+    TRY_OR_FREE(cudaMemcpy(e->dScene, &e->hs.scene, sizeof(Scene), cudaMemcpyHostToDevice));
+    TRY_OR_FREE(cudaMalloc(&e->dLut, kLutLength * sizeof(float)));
+    TRY_OR_FREE(cudaMemcpy(e->dLut, e->hs.sinLut.data(), kLutLength * sizeof(float), cudaMemcpyHostToDevice));
+    TRY_OR_FREE(cudaMalloc(&e->dRobotInit, 2 * sizeof(ps_robot_state)));
+    TRY_OR_FREE(cudaMemcpy(e->dRobotInit, e->hs.robotInit, 2 * sizeof(ps_robot_state), cudaMemcpyHostToDevice));
+    TRY_OR_FREE(cudaMalloc(&e->dSeeds, A * sizeof(int64_t)));
+    TRY_OR_FREE(cudaMalloc(&e->dStepStats, A * 8 * sizeof(int)));
+    TRY_OR_FREE(cudaMemset(e->dStepStats, 0, A * 8 * sizeof(int)));
+    // working memory: shared memory up to the budget, the rest per slot in HBM
+    e->threads = (int)envSize("PS_THREADS", 128);
+    if (e->threads < 32 || e->threads > 256 || (e->threads & 31)) e->threads = 128;
+    size_t budget = envSize("PS_SMEM_BUDGET", 40 * 1024);
+    if (budget > 200 * 1024) budget = 200 * 1024;
+    Carver m = {nullptr, budget, 0, nullptr, 0};
+    carveWork(pc, m);
+    e->smemBytes = m.fastUsed;
+    size_t slowStride = (m.slowUsed + 255) & ~(size_t)255;
+    int slotsPerSm = (int)envSize("PS_SLOTS_PER_SM", 8);
+    e->nSlots = prop.multiProcessorCount * slotsPerSm;
+    if ((size_t)e->nSlots > A) e->nSlots = (int)A;
+    TRY_OR_FREE(cudaMalloc(&e->kp.slow, (size_t)e->nSlots * slowStride + 256));
+    TRY_OR_FREE(cudaMemset(e->kp.slow, 0, (size_t)e->nSlots * slowStride + 256));
+    TRY_OR_FREE(cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smemBytes));
+    TRY_OR_FREE(cudaFuncSetAttribute(k_physics, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smemBytes));
+    e->kp.env.scene = e->dScene;
+    e->kp.env.trig.lut = e->dLut;
+    e->kp.env.trig.useLut = cfg->sincos_lut;
+    e->kp.env.cfg = pc;
+    e->kp.slowStride = slowStride;
+    e->kp.fastCap = e->smemBytes;
+    e->kp.nArenas = cfg->n_arenas;
+    e->kp.stepInterval = cfg->step_interval;
+    e->kp.seeds = e->dSeeds;
+    e->kp.robotInit = e->dRobotInit;
+    e->kp.nInformed = cfg->n_informed_robots;
+    e->kp.stepStats = e->dStepStats;
+    *out = e;
+    return PS_OK;
+}
+
+int ps_load_calibration(ps_handle h, const float* XrYr, const uint16_t* xy, const uint8_t* flags, int n, int img_w, int img_h) {
+    if (!h || !XrYr || !xy || !flags || n <= 0) return setError(PS_E_INVALID, "bad calibration arguments");
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (!h->sense.build(h->hs.cfg, XrYr, xy, flags, n, img_w, img_h)) return setError(PS_E_INVALID, "calibration rejected: " + h->sense.error);
+    int rc = h->sd.upload(h->sense, h->hs, h->stream);
+    if (rc != PS_OK) return setError(rc, "calibration upload failed: " + h->sd.error);
+    return PS_OK;
+}
+
+int ps_sync(ps_handle h) {
+    if (!h) return setError(PS_E_INVALID, "null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return PS_OK;
+}
+
+int ps_reset(ps_handle h, const int64_t* seeds) {
+    if (!h || !seeds) return setError(PS_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemcpyAsync(h->dSeeds, seeds, (size_t)h->kp.nArenas * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    k_reset<<<h->nSlots, h->threads, h->smemBytes, h->stream>>>(h->kp);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->updateCount = 0;
+    h->isReset = true;
+    return PS_OK;
+}
+
+static int launchPhysics(ps_handle h, int nTicks) {
+    k_physics<<<h->nSlots, h->threads, h->smemBytes, h->stream>>>(h->kp, nTicks);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    h->updateCount += nTicks;
+    return PS_OK;
+}
+
+int ps_step(ps_handle h, int n_ticks) {
+    if (!h || n_ticks < 0) return setError(PS_E_INVALID, "bad argument");
+    if (!h->isReset) return setError(PS_E_INVALID, "ps_reset or ps_set_state first");
+    CUDA_TRY(cudaSetDevice(h->device));
+    int interval = h->hs.cfg.step_interval;
+    int t = 0;
+    while (t < n_ticks) {
+        if (h->updateCount % interval == 0) {
+            if (h->hs.cfg.controller != PS_CTRL_EXTERNAL) {
+                if (!h->sd.ready) return setError(PS_E_NOCALIB, "ps_load_calibration has not been called");
+                int rc = h->sd.launchSenseThink(h->kp.env, h->kp.sp, h->kp.nArenas, h->stream, &h->launches);
+                if (rc != PS_OK) return setError(rc, h->sd.error);
+            } else {
+                int rc = h->sd.launchCountStep(h->kp.sp, h->kp.nArenas, h->stream, &h->launches);
+                if (rc != PS_OK) return setError(rc, h->sd.error);
+            }
+        }
+        // run up to the next think tick in one launch
+        int run = interval - h->updateCount % interval;
+        if (run > n_ticks - t) run = n_ticks - t;
+        int rc = launchPhysics(h, run);
+        if (rc != PS_OK) return rc;
+        t += run;
+    }
+    return PS_OK;
+}
+
+int ps_sense(ps_handle h) {
+    if (!h) return setError(PS_E_INVALID, "null handle");
+    if (!h->sd.ready) return setError(PS_E_NOCALIB, "ps_load_calibration has not been called");
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = h->sd.launchSenseOnly(h->kp.env, h->kp.sp, h->kp.nArenas, h->stream, &h->launches);
+    if (rc != PS_OK) return setError(rc, h->sd.error);
+    return PS_OK;
+}
+
+int ps_step_external(ps_handle h, const float* forwards, const float* torque) {
+    if (!h || !forwards || !torque) return setError(PS_E_INVALID, "null argument");
+    if (!h->isReset) return setError(PS_E_INVALID, "ps_reset or ps_set_state first");
+    CUDA_TRY(cudaSetDevice(h->device));
+    size_t n = (size_t)h->kp.nArenas * h->hs.phys.d.R;
+    int rc = h->sd.setCommands(h->kp.sp, forwards, torque, n, h->kp.nArenas, h->stream, &h->launches);
+    if (rc != PS_OK) return setError(rc, h->sd.error);
+    return launchPhysics(h, h->hs.cfg.step_interval);
+}
+
+static int copyState(ps_handle h, const ps_state_view* v, bool toHost) {
+    const PhysCfg& pc = h->hs.phys;
+    size_t A = h->kp.nArenas;
+    cudaMemcpyKind kind = toHost ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice;
+#define CP(field, dptr, bytes)                                                                          \
+    if (v->field) {                                                                                     \
+        if (toHost) CUDA_TRY(cudaMemcpyAsync((void*)v->field, dptr, bytes, kind, h->stream));           \
+        else CUDA_TRY(cudaMemcpyAsync(dptr, (const void*)v->field, bytes, kind, h->stream));            \
+    }
+    CP(body, h->kp.sp.body, A * 6 * pc.d.NB * sizeof(float))
+    CP(sense_aabb, h->kp.sp.senseAabb, A * 4 * pc.d.NB * sizeof(float))
+    CP(fat_aabb, h->kp.sp.fat, A * 4 * pc.d.NP * sizeof(float))
+    CP(contact_key, h->kp.sp.ckey, A * pc.MC * sizeof(uint32_t))
+    CP(contact_info, h->kp.sp.cinfo, A * pc.MC * sizeof(uint32_t))
+    CP(contact_impulse, h->kp.sp.cimp, A * pc.MC * 4 * sizeof(float))
+    CP(robot, h->kp.sp.robot, A * pc.d.R * sizeof(ps_robot_state))
+    CP(arena, h->kp.sp.arena, A * sizeof(ps_arena_state))
+#undef CP
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return PS_OK;
+}
+
+int ps_get_state(ps_handle h, ps_state_view* v) {
+    if (!h || !v) return setError(PS_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    return copyState(h, v, true);
+}
+
+int ps_set_state(ps_handle h, const ps_state_view* v) {
+    if (!h || !v) return setError(PS_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = copyState(h, v, false);
+    if (rc != PS_OK) return rc;
+    if (v->arena) h->updateCount = v->arena[0].update_count;
+    h->isReset = true;
+    return PS_OK;
+}
+
+int ps_get_observations(ps_handle h, ps_obs_view* v) {
+    if (!h || !v) return setError(PS_E_INVALID, "null argument");
+    if (!h->sd.ready) return setError(PS_E_NOCALIB, "ps_load_calibration has not been called");
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = h->sd.readObservations(v, h->kp.nArenas, h->hs.phys.d.R, h->stream);
+    if (rc != PS_OK) return setError(rc, h->sd.error);
+    return PS_OK;
+}
+
+int ps_compute_stats(ps_handle h, float cluster_threshold, ps_stats* out) {
+    if (!h || !out) return setError(PS_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = h->sd.computeStats(h->kp.env, h->kp.sp, h->kp.nArenas, h->hs.cfg, cluster_threshold, out, h->stream, &h->launches);
+    if (rc != PS_OK) return setError(rc, h->sd.error);
+    return PS_OK;
+}
+
+int ps_stats_device_ptr(ps_handle h, void** dptr, int64_t* n_bytes) {
+    if (!h || !dptr || !n_bytes) return setError(PS_E_INVALID, "null argument");
+    *dptr = h->sd.dStats;
+    *n_bytes = (int64_t)sizeof(ps_stats);
+    return PS_OK;
+}
+
+int ps_get_dims(ps_handle h, int32_t* n_bodies, int32_t* n_proxies, int32_t* max_contacts, int32_t* occ_w, int32_t* occ_h) {
+    if (!h) return setError(PS_E_INVALID, "null handle");
+    if (n_bodies) *n_bodies = h->hs.phys.d.NB;
+    if (n_proxies) *n_proxies = h->hs.phys.d.NP;
+    if (max_contacts) *max_contacts = h->hs.phys.MC;
+    if (occ_w) *occ_w = h->sense.occW;
+    if (occ_h) *occ_h = h->sense.occH;
+    return PS_OK;
+}
+
+int ps_get_step_stats(ps_handle h, int32_t* out /* [n_arenas][8] */) {
+    if (!h || !out) return setError(PS_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemcpyAsync(out, h->dStepStats, (size_t)h->kp.nArenas * 8 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return PS_OK;
+}
+
+int64_t ps_kernel_launches(ps_handle h) { return h ? h->launches : 0; }
+void* ps_stream(ps_handle h) { return h ? (void*)h->stream : nullptr; }
+
+}  // extern "C"

@@ -100,9 +100,10 @@ int emu_step(Emu* e, int nTicks) {
             if (as->update_count % e->hs.cfg.step_interval == 0) {
                 if (e->hs.cfg.controller != PS_CTRL_EXTERNAL) {
                     if (!e->sense.ready) return PS_E_NOCALIB;
-                    senseAndThinkArena(ctx, e->env, e->sense, e->senseBuf, st, rs, as, nullptr);
+                    senseAndThinkArena(ctx, e->env, e->sense, e->senseBuf, st, rs, as, nullptr);   // counts the think step
+                } else {
+                    as->step_count++;
                 }
-                as->step_count++;
             }
             for (int r = 0; r < R; r++) {
                 fwd[r] = rs[r].cmd_forwards;

@@ -65,3 +65,44 @@ def close(x, y, tol):
     if tol == 0.0:
         return (bits(x) == bits(y)) | ((x == 0) & (y == 0))
     return np.abs(x.astype(np.float64) - y.astype(np.float64)) <= tol * np.maximum(1.0, np.maximum(np.abs(x), np.abs(y)))
+
+
+def compare_observations(oa, ob, tol=0.0):
+    """Mismatches between two abi.Observations (camera, occupancy, local map, pose)."""
+    out = []
+    if oa.camera is not None and ob.camera is not None and not np.array_equal(oa.camera, ob.camera):
+        idx = np.argwhere(oa.camera != ob.camera)
+        out.append("camera differs at %d pixels, first (arena, robot, y, x) = %s: %d vs %d" % (
+            len(idx), tuple(idx[0]), oa.camera[tuple(idx[0])], ob.camera[tuple(idx[0])]))
+    if not np.array_equal(oa.occupancy, ob.occupancy):
+        idx = np.argwhere(oa.occupancy != ob.occupancy)
+        out.append("occupancy differs at %d cells, first %s: %d vs %d" % (len(idx), tuple(idx[0]), oa.occupancy[tuple(idx[0])], ob.occupancy[tuple(idx[0])]))
+    if not close(oa.pose, ob.pose, tol).all():
+        out.append("pose differs")
+    A, R = oa.localmap.shape
+    for a in range(A):
+        for r in range(R):
+            la, lb = oa.localmap[a, r], ob.localmap[a, r]
+            for f in ("carrying", "carried_type", "carried_cluster", "n_pucks", "n_clusters", "left_sum", "right_sum", "overflow"):
+                if la[f] != lb[f]:
+                    out.append("arena %d robot %d: localmap.%s %r vs %r" % (a, r, f, la[f], lb[f]))
+            for f in ("carried_x", "carried_y"):
+                if not close(la[f], lb[f], tol):
+                    out.append("arena %d robot %d: localmap.%s %r vs %r" % (a, r, f, la[f], lb[f]))
+            if la["n_pucks"] == lb["n_pucks"]:
+                n = int(la["n_pucks"])
+                for f in ("puck_x", "puck_y"):
+                    if not close(la[f][:n], lb[f][:n], tol).all():
+                        out.append("arena %d robot %d: localmap.%s differs" % (a, r, f))
+                for f in ("puck_type", "puck_cluster", "puck_degree"):
+                    if not np.array_equal(la[f][:n], lb[f][:n]):
+                        out.append("arena %d robot %d: localmap.%s %s vs %s" % (a, r, f, la[f][:n], lb[f][:n]))
+            if la["n_clusters"] == lb["n_clusters"]:
+                n = int(la["n_clusters"])
+                for f in ("cluster_x", "cluster_y"):
+                    if not close(la[f][:n], lb[f][:n], tol).all():
+                        out.append("arena %d robot %d: localmap.%s differs" % (a, r, f))
+                for f in ("cluster_type", "cluster_size", "cluster_kept"):
+                    if not np.array_equal(la[f][:n], lb[f][:n]):
+                        out.append("arena %d robot %d: localmap.%s %s vs %s" % (a, r, f, la[f][:n], lb[f][:n]))
+    return out
