@@ -224,6 +224,9 @@ typedef struct ps_engine* ps_handle;
 
 const char* ps_last_error(void);
 int  ps_abi_version(void);
+/* sizeof() of the ABI structs as the library was compiled: 0 ps_config, 1 ps_robot_state, 2 ps_arena_state,
+ * 3 ps_localmap, 4 ps_stats, 5 ps_state_view, 6 ps_obs_view (lets a foreign-language binding verify its layout) */
+int  ps_struct_size(int which);
 void ps_config_defaults(ps_config* cfg);
 
 int ps_create(const ps_config* cfg, int device, ps_handle* out);
@@ -260,6 +263,9 @@ int ps_stats_device_ptr(ps_handle h, void** dptr, int64_t* n_bytes);
 /* Engine introspection */
 int ps_get_dims(ps_handle h, int32_t* n_bodies, int32_t* n_proxies, int32_t* max_contacts,
                 int32_t* occ_w, int32_t* occ_h);
+/* Diagnostics of the last World.step of every arena, [n_arenas][8] int32: 0 = max position iterations of an island,
+ * 1 = TOI events, 2 = islands with contacts. */
+int ps_get_step_stats(ps_handle h, int32_t* out);
 int64_t ps_kernel_launches(ps_handle h);   /* kernels launched by this handle so far */
 void*   ps_stream(ps_handle h);            /* the cudaStream_t the engine launches on */
 

@@ -10,7 +10,7 @@
 #include <string>
 #include <vector>
 #include "ps_host.hpp"
-#include "ps_sense.cuh"
+#include "ps_sense_dev.cuh"
 
 using namespace ps;
 
@@ -110,6 +110,9 @@ struct ps_engine {
     int64_t launches = 0;
     int updateCount = 0;     // all arenas advance in lock step
     SenseDevice sd;
+    StatsDev* dStatsDev = nullptr;
+    ps_stats* dStats = nullptr;
+    float* dCmd = nullptr;
     bool isReset = false;
 };
 
@@ -122,6 +125,18 @@ extern "C" {
 
 const char* ps_last_error(void) { return g_lastError.c_str(); }
 int ps_abi_version(void) { return PS_ABI_VERSION; }
+int ps_struct_size(int which) {
+    switch (which) {
+        case 0: return (int)sizeof(ps_config);
+        case 1: return (int)sizeof(ps_robot_state);
+        case 2: return (int)sizeof(ps_arena_state);
+        case 3: return (int)sizeof(ps_localmap);
+        case 4: return (int)sizeof(ps_stats);
+        case 5: return (int)sizeof(ps_state_view);
+        case 6: return (int)sizeof(ps_obs_view);
+        default: return -1;
+    }
+}
 
 void ps_config_defaults(ps_config* c) {
     std::memset(c, 0, sizeof(*c));
@@ -186,6 +201,9 @@ int ps_destroy(ps_handle h) {
     cudaFree(h->dRobotInit);
     cudaFree(h->dSeeds);
     cudaFree(h->dStepStats);
+    cudaFree(h->dStatsDev);
+    cudaFree(h->dStats);
+    cudaFree(h->dCmd);
     h->sd.release();
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -250,6 +268,10 @@ int ps_create(const ps_config* cfg, int device, ps_handle* out) {
     TRY_OR_FREE(cudaMalloc(&e->dSeeds, A * sizeof(int64_t)));
     TRY_OR_FREE(cudaMalloc(&e->dStepStats, A * 8 * sizeof(int)));
     TRY_OR_FREE(cudaMemset(e->dStepStats, 0, A * 8 * sizeof(int)));
+    TRY_OR_FREE(cudaMalloc(&e->dStatsDev, sizeof(StatsDev)));
+    TRY_OR_FREE(cudaMalloc(&e->dStats, sizeof(ps_stats)));
+    TRY_OR_FREE(cudaMemset(e->dStats, 0, sizeof(ps_stats)));
+    TRY_OR_FREE(cudaMalloc(&e->dCmd, 2 * A * pc.d.R * sizeof(float) + 16));
     // working memory: shared memory up to the budget, the rest per slot in HBM
     e->threads = (int)envSize("PS_THREADS", 128);
     if (e->threads < 32 || e->threads > 256 || (e->threads & 31)) e->threads = 128;
@@ -332,8 +354,9 @@ int ps_step(ps_handle h, int n_ticks) {
                 int rc = h->sd.launchSenseThink(h->kp.env, h->kp.sp, h->kp.nArenas, h->stream, &h->launches);
                 if (rc != PS_OK) return setError(rc, h->sd.error);
             } else {
-                int rc = h->sd.launchCountStep(h->kp.sp, h->kp.nArenas, h->stream, &h->launches);
-                if (rc != PS_OK) return setError(rc, h->sd.error);
+                k_count_step<<<(h->kp.nArenas + 127) / 128, 128, 0, h->stream>>>(h->kp.sp.arena, h->kp.nArenas);
+                h->launches++;
+                CUDA_TRY(cudaGetLastError());
             }
         }
         // run up to the next think tick in one launch
@@ -360,8 +383,14 @@ int ps_step_external(ps_handle h, const float* forwards, const float* torque) {
     if (!h->isReset) return setError(PS_E_INVALID, "ps_reset or ps_set_state first");
     CUDA_TRY(cudaSetDevice(h->device));
     size_t n = (size_t)h->kp.nArenas * h->hs.phys.d.R;
-    int rc = h->sd.setCommands(h->kp.sp, forwards, torque, n, h->kp.nArenas, h->stream, &h->launches);
-    if (rc != PS_OK) return setError(rc, h->sd.error);
+    CUDA_TRY(cudaMemcpyAsync(h->dCmd, forwards, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->dCmd + n, torque, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    k_set_commands<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->kp.sp.robot, h->dCmd, h->dCmd + n, n);
+    k_count_step<<<(h->kp.nArenas + 127) / 128, 128, 0, h->stream>>>(h->kp.sp.arena, h->kp.nArenas);
+    h->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    // the caller may reuse its arrays as soon as we return
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
     return launchPhysics(h, h->hs.cfg.step_interval);
 }
 
@@ -415,14 +444,34 @@ int ps_get_observations(ps_handle h, ps_obs_view* v) {
 int ps_compute_stats(ps_handle h, float cluster_threshold, ps_stats* out) {
     if (!h || !out) return setError(PS_E_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(h->device));
-    int rc = h->sd.computeStats(h->kp.env, h->kp.sp, h->kp.nArenas, h->hs.cfg, cluster_threshold, out, h->stream, &h->launches);
-    if (rc != PS_OK) return setError(rc, h->sd.error);
+    CUDA_TRY(cudaMemsetAsync(h->dStatsDev, 0, sizeof(StatsDev), h->stream));
+    int P = h->hs.phys.d.P;
+    size_t sh = (size_t)2 * (P > 0 ? P : 1) * sizeof(int);
+    if (sh > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+    k_stats<<<h->kp.nArenas, 128, sh, h->stream>>>(h->kp.env, h->kp.sp, h->hs.cfg.n_puck_types, h->hs.cfg.controller, cluster_threshold, h->dStatsDev);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    StatsDev sd;
+    CUDA_TRY(cudaMemcpyAsync(&sd, h->dStatsDev, sizeof(sd), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    std::memset(out, 0, sizeof(*out));
+    out->n_arenas = h->kp.nArenas;
+    for (int k = 0; k < PS_MAX_COLOURS; k++)
+        for (int i = 0; i < 64; i++) out->cluster_size_hist[k][i] = (int64_t)sd.clusterHist[k][i];
+    for (int i = 0; i < 8; i++) out->ctrl_state_hist[i] = (int64_t)sd.ctrlState[i];
+    out->n_carrying = (int64_t)sd.nCarrying;
+    out->n_caches = (int64_t)sd.nCaches;
+    out->sum_completion = P > 0 ? 100.0 * (double)sd.sumMax / (double)P : 0.0;
+    out->n_touching_points = (int64_t)sd.nTouching;
+    out->n_contacts = (int64_t)sd.nContacts;
+    CUDA_TRY(cudaMemcpyAsync(h->dStats, out, sizeof(*out), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
     return PS_OK;
 }
 
 int ps_stats_device_ptr(ps_handle h, void** dptr, int64_t* n_bytes) {
     if (!h || !dptr || !n_bytes) return setError(PS_E_INVALID, "null argument");
-    *dptr = h->sd.dStats;
+    *dptr = h->dStats;
     *n_bytes = (int64_t)sizeof(ps_stats);
     return PS_OK;
 }

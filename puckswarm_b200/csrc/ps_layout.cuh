@@ -41,14 +41,15 @@ struct Carver {
     size_t fastCap, fastUsed;
     char* slow;
     size_t slowUsed;
+    // With null base pointers (host-side measuring pass) the returned addresses are meaningless and never used.
     PS_HD void* take(size_t bytes) {
         bytes = (bytes + 15) & ~(size_t)15;
         if (fastUsed + bytes <= fastCap) {
-            void* p = fast ? (void*)(fast + fastUsed) : nullptr;
+            void* p = (void*)(fast + fastUsed);
             fastUsed += bytes;
             return p;
         }
-        void* p = slow ? (void*)(slow + slowUsed) : nullptr;
+        void* p = (void*)(slow + slowUsed);
         slowUsed += bytes;
         return p;
     }
@@ -62,26 +63,26 @@ PS_HD PhysWork carveWork(const PhysCfg& c, Carver& cv) {
     w.stats = (int*)cv.take(8 * sizeof(int));
     float* bodyArr = (float*)cv.take((size_t)9 * NB * sizeof(float));
     w.cx = bodyArr;
-    w.cy = bodyArr ? bodyArr + NB : nullptr;
-    w.a = bodyArr ? bodyArr + 2 * NB : nullptr;
-    w.vx = bodyArr ? bodyArr + 3 * NB : nullptr;
-    w.vy = bodyArr ? bodyArr + 4 * NB : nullptr;
-    w.w = bodyArr ? bodyArr + 5 * NB : nullptr;
-    w.c0x = bodyArr ? bodyArr + 6 * NB : nullptr;
-    w.c0y = bodyArr ? bodyArr + 7 * NB : nullptr;
-    w.a0 = bodyArr ? bodyArr + 8 * NB : nullptr;
+    w.cy = bodyArr + NB;
+    w.a = bodyArr + 2 * NB;
+    w.vx = bodyArr + 3 * NB;
+    w.vy = bodyArr + 4 * NB;
+    w.w = bodyArr + 5 * NB;
+    w.c0x = bodyArr + 6 * NB;
+    w.c0y = bodyArr + 7 * NB;
+    w.a0 = bodyArr + 8 * NB;
     float* rob = (float*)cv.take((size_t)11 * R * sizeof(float));
     w.rpx = rob;
-    w.rpy = rob ? rob + R : nullptr;
-    w.rc = rob ? rob + 2 * R : nullptr;
-    w.rs = rob ? rob + 3 * R : nullptr;
-    w.r0px = rob ? rob + 4 * R : nullptr;
-    w.r0py = rob ? rob + 5 * R : nullptr;
-    w.r0c = rob ? rob + 6 * R : nullptr;
-    w.r0s = rob ? rob + 7 * R : nullptr;
-    w.fx = rob ? rob + 8 * R : nullptr;
-    w.fy = rob ? rob + 9 * R : nullptr;
-    w.tq = rob ? rob + 10 * R : nullptr;
+    w.rpy = rob + R;
+    w.rc = rob + 2 * R;
+    w.rs = rob + 3 * R;
+    w.r0px = rob + 4 * R;
+    w.r0py = rob + 5 * R;
+    w.r0c = rob + 6 * R;
+    w.r0s = rob + 7 * R;
+    w.fx = rob + 8 * R;
+    w.fy = rob + 9 * R;
+    w.tq = rob + 10 * R;
     w.adjOff = (int*)cv.take((size_t)(NB + 1) * sizeof(int));
     w.adjFill = (int*)cv.take((size_t)NB * sizeof(int));
     w.islandStart = (int*)cv.take((size_t)(NB + 1) * sizeof(int));

@@ -730,7 +730,12 @@ PS_HD void physSolvePosition(Ctx& ctx, const PhysEnv& e, const PhysWork& wk) {
         }
         ctx.atomicMaxI(&wk.stats[0], iters);
     }
-    if (ctx.tid() == 0) wk.stats[2] = nIsl;
+    ctx.sync();
+    if (ctx.tid() == 0) {
+        wk.stats[2] = nIsl;
+        // islands without contacts also run the position loop once (it breaks immediately)
+        if (wk.stats[0] < 1 && e.cfg.posIters > 0) wk.stats[0] = 1;
+    }
     ctx.sync();
 }
 

@@ -1188,7 +1188,6 @@ PS_HD void thinkArena(Ctx& ctx, const SenseTables& T, const SenseCfg& sc, const 
     ctx.sync();
 }
 
-#if !defined(__CUDA_ARCH__)
 // ------------------------------------------------------------------ host-side table construction
 struct SenseSetup {
     bool ready = false;
@@ -1373,7 +1372,6 @@ struct SenseSetup {
         return true;
     }
 };
-#endif
 
 #if defined(PS_HOST_EMU)
 // ------------------------------------------------------------------ host emulation entry points (tests only)

@@ -1,0 +1,275 @@
+// puckswarm_b200 -- device side of sensing / thinking / statistics: table upload, kernels, launch helpers.
+// (CUDA only; the per-robot and per-arena programs themselves are in ps_sense.cuh.)
+#pragma once
+#include <cuda_runtime.h>
+#include "ps_host.hpp"
+#include "ps_sense.cuh"
+
+namespace ps {
+
+struct SenseKParams {
+    PhysEnv env;
+    StatePtrs sp;
+    SenseTables T;
+    SenseCfg sc;
+    ObsPtrs obs;
+    int nArenas;
+    size_t fastCap;
+};
+
+extern __shared__ __align__(16) char g_senseSmem[];
+
+// one CTA per (arena, robot): camera + local map
+__global__ void __launch_bounds__(256) k_sense(SenseKParams p) {
+    __shared__ int scan[40];
+    CtaCtx ctx;
+    ctx.scanScratch = scan;
+    Carver cv;
+    cv.fast = g_senseSmem;
+    cv.fastCap = p.fastCap;
+    cv.fastUsed = 0;
+    cv.slow = (char*)p.obs.pose;   // never used: the host checked that everything fits in shared memory
+    cv.slowUsed = 0;
+    SenseWork wk = carveSense(p.T, cv);
+    int R = p.env.cfg.d.R;
+    int a = blockIdx.x / R, r = blockIdx.x - a * R;
+    ArenaState st = arenaState(p.sp, p.env.cfg, a);
+    size_t ri = (size_t)a * R + r;
+    int nCells = p.T.occW * p.T.occH;
+    uint8_t* cam = p.obs.camera ? p.obs.camera + ri * (size_t)(p.T.imgW * p.T.imgH) : nullptr;
+    if (threadIdx.x == 0) p.obs.lm[ri].overflow = 0;
+    __syncthreads();
+    senseRobot(ctx, p.env, p.T, p.sc, wk, st, r, p.sp.robot + ri, cam, p.obs.occupancy + ri * nCells, p.obs.lm + ri, p.obs.pose + ri * 3);
+}
+
+// one CTA per arena: controllers in robot order (shared java.util.Random)
+__global__ void __launch_bounds__(128) k_think(SenseKParams p) {
+    __shared__ int scan[40];
+    __shared__ unsigned primary[kSectors];
+    __shared__ unsigned limits[2];
+    __shared__ int flag[4];
+    __shared__ JRandom rng;
+    CtaCtx ctx;
+    ctx.scanScratch = scan;
+    ThinkWork tw;
+    tw.primary = primary;
+    tw.limits = limits;
+    tw.flag = flag;
+    int R = p.env.cfg.d.R;
+    int a = blockIdx.x;
+    size_t r0 = (size_t)a * R;
+    int nCells = p.T.occW * p.T.occH;
+    thinkArena(ctx, p.T, p.sc, tw, R, p.obs.occupancy + r0 * nCells, p.obs.lm + r0, p.obs.pose + r0 * 3, p.sp.robot + r0, p.sp.arena + a, &rng);
+}
+
+__global__ void k_count_step(ps_arena_state* arena, int nArenas) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a < nArenas) arena[a].step_count += 1;
+}
+
+__global__ void k_set_commands(ps_robot_state* robot, const float* fwd, const float* tq, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        robot[i].cmd_forwards = fwd[i];
+        robot[i].cmd_torque = tq[i];
+    }
+}
+
+// Per-arena experiment statistics (PositionList.getClusterStats, src/arena/PositionList.java:85-96, over the true puck
+// positions of each colour; Analyze.java:187-218 percent completion = 100 * sum_k max cluster size_k / nPucks),
+// controller-state occupancy, carry and cache counts, contact counts. One CTA per arena, integer atomics into one ps_stats.
+struct StatsDev {
+    unsigned long long clusterHist[PS_MAX_COLOURS][64];
+    unsigned long long ctrlState[8];
+    unsigned long long nCarrying, nCaches, sumMax, nTouching, nContacts;
+};
+__global__ void __launch_bounds__(128) k_stats(PhysEnv env, StatePtrs sp, int nTypes, int controller, float threshold, StatsDev* out) {
+    extern __shared__ int sh[];   // parent[P], size[P]
+    const Dims& d = env.cfg.d;
+    int a = blockIdx.x;
+    ArenaState st = arenaState(sp, env.cfg, a);
+    int P = d.P, NB = d.NB;
+    int* parent = sh;
+    int* size = sh + P;
+    int perType = P / nTypes;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        parent[i] = i;
+        size[i] = 0;
+    }
+    __syncthreads();
+    CtaCtx ctx;
+    ctx.scanScratch = nullptr;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        V2 pi = mk(st.body[i], st.body[NB + i]);
+        int k = i / perType;
+        for (int j = k * perType; j < i; ++j) {
+            V2 pj = mk(st.body[j], st.body[NB + j]);
+            bool same = pi.x == pj.x && pi.y == pj.y;
+            if (!same && dist(pi, pj) < threshold) ufUnion(ctx, parent, i, j);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < P; i += blockDim.x) atomicAdd(&size[ufFind(parent, i)], 1);
+    __syncthreads();
+    __shared__ int maxOfType[PS_MAX_COLOURS];
+    if (threadIdx.x < PS_MAX_COLOURS) maxOfType[threadIdx.x] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        int s = size[i];
+        if (s > 0) {
+            int k = i / perType;
+            atomicAdd(&out->clusterHist[k][s < 63 ? s : 63], 1ULL);
+            atomicMax(&maxOfType[k], s);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int sum = 0;
+        for (int k = 0; k < nTypes; ++k) sum += maxOfType[k];
+        atomicAdd(&out->sumMax, (unsigned long long)sum);
+    }
+    const ps_robot_state* rs = sp.robot + (size_t)a * d.R;
+    for (int r = threadIdx.x; r < d.R; r += blockDim.x) {
+        atomicAdd(&out->ctrlState[rs[r].ctrl_state & 7], 1ULL);
+        if (rs[r].lm_carrying) atomicAdd(&out->nCarrying, 1ULL);
+        if (controller == PS_CTRL_CACHECONS) {
+            int c = 0;
+            for (int k = 0; k < PS_MAX_COLOURS; ++k) c += rs[r].cache_valid[k] ? 1 : 0;
+            if (c) atomicAdd(&out->nCaches, (unsigned long long)c);
+        }
+    }
+    int nc = *st.nContacts;
+    int touching = 0;
+    for (int i = threadIdx.x; i < nc; i += blockDim.x) touching += (int)(st.cinfo[i] & 3u);
+    if (touching) atomicAdd(&out->nTouching, (unsigned long long)touching);
+    if (threadIdx.x == 0) atomicAdd(&out->nContacts, (unsigned long long)nc);
+}
+
+struct SenseDevice {
+    bool ready = false;
+    std::string error;
+    SenseKParams kp;
+    std::vector<void*> allocs;
+    size_t senseSmem = 0;
+    int threads = 256;
+    bool haveCamera = false;
+    size_t nRobotsTotal = 0;
+
+    int fail(int code, const std::string& m) {
+        error = m;
+        return code;
+    }
+    template <class Tp>
+    int up(const std::vector<Tp>& v, const Tp** dst) {
+        void* p = nullptr;
+        size_t bytes = v.size() * sizeof(Tp);
+        if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) return fail(PS_E_NOMEM, "cudaMalloc (calibration tables)");
+        allocs.push_back(p);
+        if (bytes && cudaMemcpy(p, v.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess) return fail(PS_E_CUDA, "cudaMemcpy (calibration tables)");
+        *dst = (const Tp*)p;
+        return PS_OK;
+    }
+    template <class Tp>
+    int alloc(Tp** dst, size_t count) {
+        void* p = nullptr;
+        if (cudaMalloc(&p, count * sizeof(Tp) + 16) != cudaSuccess) return fail(PS_E_NOMEM, "cudaMalloc (observation buffers)");
+        if (cudaMemset(p, 0, count * sizeof(Tp) + 16) != cudaSuccess) return fail(PS_E_CUDA, "cudaMemset");
+        allocs.push_back(p);
+        *dst = (Tp*)p;
+        return PS_OK;
+    }
+    void release() {
+        for (void* p : allocs) cudaFree(p);
+        allocs.clear();
+        ready = false;
+    }
+    int upload(const SenseSetup& ss, const HostSetup& hs, cudaStream_t stream) {
+        release();
+        std::memset(&kp, 0, sizeof(kp));
+        kp.T = ss.T;
+        kp.sc = ss.sc;
+        int rc;
+#define UP(vec, field) \
+    if ((rc = up(ss.vec, &kp.T.field)) != PS_OK) return rc;
+        UP(aXr, aXr)
+        UP(aYr, aYr)
+        UP(aRect, aRect)
+        UP(aImg, aImg)
+        UP(calibIdx, calibIdx)
+        UP(cXr, cXr)
+        UP(cYr, cYr)
+        UP(cFlags, cFlags)
+        UP(cellSrc, cellSrc)
+        UP(vfhBeta, vfhBeta)
+        UP(vfhMag, vfhMag)
+        UP(vfhStartK, vfhStartK)
+        UP(vfhStopK, vfhStopK)
+        UP(vfhSide, vfhSide)
+#undef UP
+        size_t A = hs.cfg.n_arenas, R = hs.phys.d.R;
+        nRobotsTotal = A * R;
+        size_t nCells = (size_t)ss.occW * ss.occH, nImg = (size_t)ss.T.imgW * ss.T.imgH;
+        if ((rc = alloc(&kp.obs.occupancy, nRobotsTotal * nCells)) != PS_OK) return rc;
+        if ((rc = alloc(&kp.obs.lm, nRobotsTotal)) != PS_OK) return rc;
+        if ((rc = alloc(&kp.obs.pose, nRobotsTotal * 3)) != PS_OK) return rc;
+        // the camera image is an optional observation: kept only when the whole batch fits in 256 MiB
+        haveCamera = nRobotsTotal * nImg <= ((size_t)256 << 20);
+        kp.obs.camera = nullptr;
+        if (haveCamera && (rc = alloc(&kp.obs.camera, nRobotsTotal * nImg)) != PS_OK) return rc;
+        Carver m = {nullptr, (size_t)200 * 1024, 0, nullptr, 0};
+        carveSense(kp.T, m);
+        if (m.slowUsed) return fail(PS_E_INVALID, "camera image too large for shared memory");
+        senseSmem = m.fastUsed;
+        kp.fastCap = senseSmem;
+        if (cudaFuncSetAttribute(k_sense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)senseSmem) != cudaSuccess)
+            return fail(PS_E_CUDA, "cudaFuncSetAttribute(k_sense)");
+        const char* tv = getenv("PS_SENSE_THREADS");
+        threads = tv && *tv ? atoi(tv) : 256;
+        if (threads < 32 || threads > 256 || (threads & 31)) threads = 256;
+        kp.nArenas = hs.cfg.n_arenas;
+        ready = true;
+        return PS_OK;
+    }
+    void bind(const PhysEnv& env, const StatePtrs& sp) {
+        kp.env = env;
+        kp.sp = sp;
+    }
+    int launchSense(const PhysEnv& env, const StatePtrs& sp, cudaStream_t stream, int64_t* launches, bool camera) {
+        bind(env, sp);
+        SenseKParams p = kp;
+        if (!camera) p.obs.camera = nullptr;
+        k_sense<<<(unsigned)nRobotsTotal, threads, senseSmem, stream>>>(p);
+        (*launches)++;
+        if (cudaGetLastError() != cudaSuccess) return fail(PS_E_CUDA, "k_sense launch failed");
+        return PS_OK;
+    }
+    int launchSenseThink(const PhysEnv& env, const StatePtrs& sp, int nArenas, cudaStream_t stream, int64_t* launches) {
+        int rc = launchSense(env, sp, stream, launches, false);
+        if (rc != PS_OK) return rc;
+        k_think<<<nArenas, 128, 0, stream>>>(kp);
+        (*launches)++;
+        if (cudaGetLastError() != cudaSuccess) return fail(PS_E_CUDA, "k_think launch failed");
+        return PS_OK;
+    }
+    int launchSenseOnly(const PhysEnv& env, const StatePtrs& sp, int nArenas, cudaStream_t stream, int64_t* launches) {
+        return launchSense(env, sp, stream, launches, haveCamera);
+    }
+    int readObservations(ps_obs_view* v, int nArenas, int R, cudaStream_t stream) {
+        size_t n = (size_t)nArenas * R;
+        size_t nCells = (size_t)kp.T.occW * kp.T.occH, nImg = (size_t)kp.T.imgW * kp.T.imgH;
+        if (v->camera) {
+            if (!haveCamera) return fail(PS_E_CAPACITY, "camera images are not kept for a batch this large");
+            if (cudaMemcpyAsync(v->camera, kp.obs.camera, n * nImg, cudaMemcpyDeviceToHost, stream) != cudaSuccess) return fail(PS_E_CUDA, "copy camera");
+        }
+        if (v->occupancy && cudaMemcpyAsync(v->occupancy, kp.obs.occupancy, n * nCells, cudaMemcpyDeviceToHost, stream) != cudaSuccess)
+            return fail(PS_E_CUDA, "copy occupancy");
+        if (v->localmap && cudaMemcpyAsync(v->localmap, kp.obs.lm, n * sizeof(ps_localmap), cudaMemcpyDeviceToHost, stream) != cudaSuccess)
+            return fail(PS_E_CUDA, "copy localmap");
+        if (v->pose && cudaMemcpyAsync(v->pose, kp.obs.pose, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, stream) != cudaSuccess)
+            return fail(PS_E_CUDA, "copy pose");
+        if (cudaStreamSynchronize(stream) != cudaSuccess) return fail(PS_E_CUDA, "sync after observation copy");
+        return PS_OK;
+    }
+};
+
+}  // namespace ps

@@ -107,7 +107,6 @@ PS_HD bool shapeTestPoint(const Shape& s, const Xf& xf, V2 p) {
     return true;
 }
 
-#if !defined(__CUDA_ARCH__)
 // ------------------------------------------------------------------ host-side construction
 namespace build {
 
@@ -313,6 +312,5 @@ inline void scene(Scene* sc, float scale, const Trig& trig) {
 }
 
 }  // namespace build
-#endif
 
 }  // namespace ps

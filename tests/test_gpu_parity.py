@@ -1,0 +1,224 @@
+"""GPU parity tests: the CUDA engine (through the C-ABI) against the CPU oracle on identical seeded inputs.
+
+Bar (BASELINE.json north_star): contact pair lists and discrete sensor outputs bit-exact, poses and velocities
+within 1e-5 relative. The physics path and the sensing path use IEEE float arithmetic in JBox2D's operation
+order on both sides, so they are asserted bit-exact here; only the controllers' double-precision libm calls
+(atan2 / sin / cos / log on the device vs glibc) may differ in the last ulp, hence TOL for full steps.
+"""
+import numpy as np
+import pytest
+
+from puckswarm_b200 import abi
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def _engine(cfg, **kw):
+    from puckswarm_b200 import engine
+    return engine.Engine(cfg, device=0, **kw)
+
+
+def _oracle(cfg, threads=8):
+    import oracle_binding
+    return oracle_binding.Oracle(cfg, threads=threads)
+
+
+@pytest.mark.parametrize("shape", [(1, 2, 10, 2), (3, 4, 40, 2), (2, 16, 200, 2), (2, 5, 21, 3)])
+def test_reset_matches_oracle(shape):
+    import parity
+    A, R, P, K = shape
+    cfg = abi.config_defaults(n_arenas=A, n_robots=R, n_pucks=P, n_puck_types=K)
+    e, o = _engine(cfg), _oracle(cfg)
+    seeds = np.arange(100, 100 + A)
+    e.reset(seeds)
+    o.reset(seeds)
+    assert parity.compare_states(e.get_state(), o.get_state(), A) == []
+
+
+@pytest.mark.parametrize("shape,steps", [((2, 4, 40), 200), ((2, 16, 200), 60)])
+def test_world_step_bit_exact_with_external_commands(shape, steps):
+    """Free-running World.step parity: random force/torque commands, no re-synchronisation, compared every think step."""
+    import parity
+    A, R, P = shape
+    cfg = abi.config_defaults(n_arenas=A, n_robots=R, n_pucks=P, controller=abi.PS_CTRL_EXTERNAL)
+    e, o = _engine(cfg), _oracle(cfg)
+    seeds = np.arange(A)
+    e.reset(seeds)
+    o.reset(seeds)
+    rng = np.random.RandomState(1)
+    toi = 0
+    for k in range(steps):
+        fwd = ((rng.rand(A, R) * 2 - 0.5) * 750000).astype(np.float32)
+        tq = ((rng.rand(A, R) * 2 - 1) * 2375000).astype(np.float32)
+        e.step_external(fwd, tq)
+        o.step_external(fwd, tq)
+        bad = parity.compare_states(e.get_state(), o.get_state(), A, what=("body", "sense_aabb", "fat_aabb", "contacts", "arena"))
+        assert bad == [], "think step %d: %s" % (k, bad[:5])
+        toi += o.step_info(0)["toi_events"]
+        assert e.step_info(0)["pos_iters"] == o.step_info(0)["pos_iters"]
+    assert toi > 0 or steps < 100   # the long case exercises the TOI path
+
+
+def test_camera_and_localmap_bit_exact():
+    """Sense-only parity from identical states taken along an oracle trajectory: camera image, occupancy grid,
+    perceived pucks, clusters, carry flag."""
+    import parity
+    A, R, P = 3, 6, 60
+    cfg = abi.config_defaults(n_arenas=A, n_robots=R, n_pucks=P, n_puck_types=3)
+    e, o = _engine(cfg), _oracle(cfg)
+    o.reset(np.arange(7, 7 + A))
+    seen_puck = seen_robot = seen_carry = 0
+    for k in range(40):
+        o.step(9)
+        st = o.get_state()
+        e.set_state(st)
+        o.sense()
+        e.sense()
+        oo, eo = o.get_observations(), e.get_observations()
+        bad = parity.compare_observations(eo, oo)
+        assert bad == [], "sample %d: %s" % (k, bad[:5])
+        o.set_state(st)
+        seen_puck += int((oo.camera < 8).sum())
+        seen_robot += int((oo.camera == abi.PS_T_ROBOT).sum())
+        seen_carry += int(oo.localmap["carrying"].sum())
+    assert seen_puck > 0 and seen_robot > 0 and seen_carry > 0
+
+
+@pytest.mark.parametrize("controller", [abi.PS_CTRL_CACHECONS, abi.PS_CTRL_BHD])
+def test_full_tick_lockstep(controller):
+    """Stepping the reference restatement and the engine one think interval from identical states."""
+    import parity
+    A, R, P = 4, 4, 40
+    cfg = abi.config_defaults(n_arenas=A, n_robots=R, n_pucks=P, controller=controller)
+    e, o = _engine(cfg), _oracle(cfg)
+    o.reset(np.arange(A))
+    exact = 0
+    for k in range(150):
+        e.set_state(o.get_state())
+        e.step(3)
+        o.step(3)
+        se, so = e.get_state(), o.get_state()
+        bad = parity.compare_states(se, so, A, tol=TOL)
+        assert bad == [], "think step %d: %s" % (k, bad[:5])
+        exact += parity.compare_states(se, so, A) == []
+    print("bit-exact think steps: %d / 150" % exact)
+
+
+@pytest.mark.parametrize("controller", [abi.PS_CTRL_CACHECONS, abi.PS_CTRL_BHD])
+def test_full_tick_free_running(controller):
+    """No re-synchronisation: both sides run 100 think steps (300 ticks) from the same seeds."""
+    import parity
+    A, R, P = 2, 4, 40
+    cfg = abi.config_defaults(n_arenas=A, n_robots=R, n_pucks=P, controller=controller)
+    e, o = _engine(cfg), _oracle(cfg)
+    e.reset(np.arange(A))
+    o.reset(np.arange(A))
+    e.step(300)
+    o.step(300)
+    bad = parity.compare_states(e.get_state(), o.get_state(), A, tol=TOL)
+    assert bad == [], bad[:5]
+
+
+def test_c3_shape_against_oracle():
+    """16 robots / 200 pucks (the shape of the headline config), CacheCons on device, 20 think steps free-running."""
+    import parity
+    A = 4
+    cfg = abi.config_defaults(n_arenas=A, n_robots=16, n_pucks=200, controller=abi.PS_CTRL_CACHECONS)
+    e, o = _engine(cfg), _oracle(cfg)
+    seeds = np.arange(40, 40 + A)
+    e.reset(seeds)
+    o.reset(seeds)
+    e.step(60)
+    o.step(60)
+    bad = parity.compare_states(e.get_state(), o.get_state(), A, tol=TOL)
+    assert bad == [], bad[:5]
+
+
+def test_batch_position_independence_and_determinism():
+    """Size-independent properties at a large batch: an arena's trajectory depends only on its seed, not on where it
+    sits in the batch or how large the batch is; two runs give identical bits."""
+    A = 512
+    cfg = abi.config_defaults(n_arenas=A, n_robots=16, n_pucks=200, rng_mode=abi.PS_RNG_JAVA_SHARED)
+    seeds = np.arange(A)
+    e = _engine(cfg)
+    e.reset(seeds)
+    e.step(12)
+    s1 = e.get_state()
+    e2 = _engine(cfg)
+    e2.reset(seeds[::-1].copy())
+    e2.step(12)
+    s2 = e2.get_state()
+    assert np.array_equal(s1.body.view(np.uint32), s2.body[::-1].view(np.uint32))
+    assert np.array_equal(s1.arena["n_contacts"], s2.arena["n_contacts"][::-1])
+    assert np.array_equal(s1.contact_key, s2.contact_key[::-1])
+    assert (s1.arena["error_flags"] == 0).all()
+    small = abi.config_defaults(n_arenas=2, n_robots=16, n_pucks=200)
+    e3 = _engine(small)
+    e3.reset(seeds[5:7])
+    e3.step(12)
+    s3 = e3.get_state()
+    assert np.array_equal(s3.body.view(np.uint32), s1.body[5:7].view(np.uint32))
+    # physical sanity at scale: finite, inside the enclosure, contact cache == overlapping fat boxes invariant
+    assert np.isfinite(s1.body).all()
+    assert (np.abs(s1.body[:, 0:2, :]) < 187.0 / 2 + 1).all()
+
+
+def test_contact_cache_invariant():
+    """The cache must equal the set of filtered proxy pairs whose fat AABBs overlap (what findNewContacts / collide keep)."""
+    cfg = abi.config_defaults(n_arenas=2, n_robots=8, n_pucks=100)
+    e = _engine(cfg)
+    e.reset([3, 4])
+    e.step(30)
+    st = e.get_state()
+    P, R = 100, 8
+    for a in range(2):
+        fat = st.fat_aabb[a]   # [4][NP]
+        n = int(st.arena[a]["n_contacts"])
+        keys = st.contact_key[a, :n]
+        dyn = set()
+        for k in keys:
+            pa, pb = int(k >> 16), int(k & 0xFFFF)
+            if pa >= 84 and pb >= 84:
+                dyn.add((min(pa, pb), max(pa, pb)))
+        assert len(set(keys.tolist())) == n, "duplicate contacts"
+        # brute force over dynamic proxies
+        NP = fat.shape[1]
+        body = np.array([(i // 2) if i < 2 * P else P + (i - 2 * P) // 14 for i in range(NP)])
+        kind = np.array([0 if i < 2 * P else (2 if (i - 2 * P) % 14 == 13 else 1) for i in range(NP)])  # 0 puck, 1 robot poly, 2 bow
+        lx, ly, ux, uy = fat
+        ov = (lx[:, None] <= ux[None, :]) & (lx[None, :] <= ux[:, None]) & (ly[:, None] <= uy[None, :]) & (ly[None, :] <= uy[:, None])
+        ok = body[:, None] != body[None, :]
+        ok &= ~(((kind[:, None] == 2) & (kind[None, :] == 0)) | ((kind[:, None] == 0) & (kind[None, :] == 2)))
+        ii, jj = np.nonzero(np.triu(ov & ok, 1))
+        want = set((int(i) + 84, int(j) + 84) for i, j in zip(ii, jj))
+        assert dyn == want
+
+
+def test_stats_match_oracle():
+    cfg = abi.config_defaults(n_arenas=6, n_robots=4, n_pucks=40)
+    e, o = _engine(cfg), _oracle(cfg)
+    e.reset(np.arange(6))
+    o.reset(np.arange(6))
+    e.step(90)
+    o.step(90)
+    for thr in (1.5, 9.45):
+        se, so = e.compute_stats(thr), o.compute_stats(thr)
+        assert np.array_equal(np.ctypeslib.as_array(se.cluster_size_hist), np.ctypeslib.as_array(so.cluster_size_hist))
+        assert list(se.ctrl_state_hist) == list(so.ctrl_state_hist)
+        assert (se.n_carrying, se.n_caches, se.n_contacts, se.n_touching_points) == (so.n_carrying, so.n_caches, so.n_contacts, so.n_touching_points)
+        assert abs(se.sum_completion - so.sum_completion) < 1e-9 * max(1.0, so.sum_completion)
+
+
+def test_errors_are_loud():
+    from puckswarm_b200 import engine
+    cfg = abi.config_defaults(n_arenas=1)
+    e = engine.Engine(cfg, device=0, load_calibration=False)
+    e.reset([0])
+    with pytest.raises(engine.EngineError) as ei:
+        e.step(3)          # CacheCons on device needs the calibration
+    assert ei.value.code == abi.PS_E_NOCALIB
+    bad = abi.config_defaults(n_arenas=0)
+    with pytest.raises(engine.EngineError):
+        engine.Engine(bad, device=0)

@@ -1,0 +1,94 @@
+"""CPU-only check of the engine's device programs: the same templates the kernels instantiate with a CUDA block
+context are instantiated with a one-thread host context (tests/hostemu) and compared with the oracle.
+This validates the device logic (not the GPU execution -- that is tests/test_gpu_parity.py)."""
+import numpy as np
+import pytest
+
+from puckswarm_b200 import abi
+import emu_binding as emu
+import oracle_binding as oracle
+import parity
+
+
+@pytest.mark.parametrize("shape", [(2, 2, 10, 2), (2, 16, 200, 2), (1, 5, 21, 3)])
+def test_reset(shape):
+    A, R, P, K = shape
+    cfg = abi.config_defaults(n_arenas=A, n_robots=R, n_pucks=P, n_puck_types=K)
+    e, o = emu.Emu(cfg), oracle.Oracle(cfg)
+    seeds = np.arange(11, 11 + A)
+    e.reset(seeds)
+    o.reset(seeds)
+    assert parity.compare_states(e.get_state(), o.get_state(), A) == []
+
+
+@pytest.mark.parametrize("shape,steps", [((2, 4, 40), 150), ((1, 16, 200), 40)])
+def test_world_step_external(shape, steps):
+    A, R, P = shape
+    cfg = abi.config_defaults(n_arenas=A, n_robots=R, n_pucks=P, controller=abi.PS_CTRL_EXTERNAL)
+    e, o = emu.Emu(cfg), oracle.Oracle(cfg)
+    e.reset(np.arange(A))
+    o.reset(np.arange(A))
+    rng = np.random.RandomState(0)
+    se = e.get_state()
+    for k in range(steps):
+        fwd = ((rng.rand(A, R) * 2 - 0.5) * 750000).astype(np.float32)
+        tq = ((rng.rand(A, R) * 2 - 1) * 2375000).astype(np.float32)
+        o.step_external(fwd, tq)
+        se.robot["cmd_forwards"], se.robot["cmd_torque"] = fwd, tq
+        e.set_state(se)
+        e.step(3)
+        se = e.get_state()
+        bad = parity.compare_states(se, o.get_state(), A, what=("body", "sense_aabb", "fat_aabb", "contacts"))
+        assert bad == [], "think step %d: %s" % (k, bad[:4])
+        assert np.array_equal(e.solve_order(0), o.solve_order(0))
+
+
+@pytest.mark.parametrize("controller", [abi.PS_CTRL_CACHECONS, abi.PS_CTRL_BHD])
+def test_sense_think_step(controller):
+    A, R, P = 2, 4, 40
+    cfg = abi.config_defaults(n_arenas=A, n_robots=R, n_pucks=P, controller=controller)
+    e, o = emu.Emu(cfg), oracle.Oracle(cfg)
+    e.reset([0, 1])
+    o.reset([0, 1])
+    for k in range(120):
+        if k % 15 == 0:
+            st = o.get_state()
+            e.set_state(st)
+            o.sense()
+            bad = parity.compare_observations(e.sense(), o.get_observations())
+            assert bad == [], "sense %d: %s" % (k, bad[:4])
+            o.set_state(st)
+            e.set_state(st)
+        o.step(3)
+        e.step(3)
+        bad = parity.compare_states(e.get_state(), o.get_state(), A)
+        assert bad == [], "think step %d: %s" % (k, bad[:4])
+
+
+def test_narrow_phase_samples():
+    """Manifolds of every shape-pair kind at random relative poses: type, points, ids bit-exact."""
+    cfg = abi.config_defaults(n_arenas=1, n_robots=2, n_pucks=2)
+    e, o = emu.Emu(cfg), oracle.Oracle(cfg)
+    e.reset([0])
+    o.reset([0])
+    rng = np.random.RandomState(3)
+    r0, r1 = 84 + 4, 84 + 4 + 14
+    pairs = [(84, 86), (r0, 84), (r0 + 5, 85), (0, 84), (83, 84), (r0, r1), (r0 + 1, r1 + 7), (r0 + 13, r1 + 13), (40, r0), (81, r0 + 13), (r0 + 3, r1 + 4)]
+    hits = 0
+    for pa, pb in pairs:
+        for _ in range(300):
+            if pa < 84:
+                xa = (0.0, 0.0, 0.0)
+                xb = (rng.uniform(-95, 95), rng.uniform(-95, 95), rng.uniform(-7, 7))
+            else:
+                xa = (rng.uniform(-5, 5), rng.uniform(-5, 5), rng.uniform(-7, 7))
+                xb = (xa[0] + rng.uniform(-14, 14), xa[1] + rng.uniform(-14, 14), rng.uniform(-7, 7))
+            me, mo = e.manifold(pa, xa, pb, xb), o.manifold(pa, xa, pb, xb)
+            n = int(mo[0])
+            assert me[0] == mo[0]
+            if n:
+                hits += 1
+                assert np.array_equal(me[1:8].view(np.uint32), mo[1:8].view(np.uint32)) and me[10] == mo[10]
+                if n == 2:
+                    assert np.array_equal(me[8:10].view(np.uint32), mo[8:10].view(np.uint32)) and me[11] == mo[11]
+    assert hits > 100
