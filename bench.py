@@ -1,0 +1,332 @@
+#!/usr/bin/env python3
+"""Benchmark of the PuckSwarm per-tick hot path (BASELINE.json): robot-steps/sec, 16 robots / 200 pucks x N arenas.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one think interval of RunOffline.step (src/arena/RunOffline.java:72-95) over the whole batch:
+Arena.step (sense + think + move, CacheCons on device) followed by stepInterval = 3 World.step(1/14, 3, 100)
+ticks. One robot-step = one robot advanced through one physics tick. At N = 1 the workload is BASELINE config
+[2]: 4096 arenas x 16 robots x 200 pucks, seeds = arena index, spawned by the reference's rejection sampling;
+for N > 1 every rank owns 4096 arenas (weak scaling, arenas shard by index, no data-path collective; the
+statistics all-reduce over NCCL runs once at the end of the timed region).
+
+value : device-resident state, CUDA events on the engine's stream around K steps, max over ranks.
+e2e   : the same K steps through the C-ABI with HOST buffers: every step uploads the bodies' poses/velocities
+        from pinned host memory (ps_set_state), steps, and reads them back (ps_get_state) plus the step counters.
+--impl reference: the CPU restatement of the reference (oracle/, "port": the Java reference cannot be built in this
+        image) on all host cores, one arena per thread, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+N_ROBOTS, N_PUCKS, ARENAS_PER_GPU, STEP_INTERVAL = 16, 200, 4096, 3
+METRIC = "robot-steps/sec, 16 robots/200 pucks x N arenas"
+UNIT = "robot-steps/s"
+
+
+def workload_config(n_arenas, parallelism):
+    return {
+        "workload": "BASELINE config[2]: %d arenas x 16 robots x 200 pucks (2 colours), CacheCons on device, camera + local map "
+                    "every 3rd tick, World.step(1/14,3,100), enclosure scale 1, seeds = arena index" % n_arenas,
+        "arenas": n_arenas, "robots_per_arena": N_ROBOTS, "pucks_per_arena": N_PUCKS, "step_interval": STEP_INTERVAL,
+        "ticks_per_step": STEP_INTERVAL, "rng": "java.util.Random shared per arena (parity mode)",
+        "parallelism": parallelism,
+        "cache": "inputs larger than L2: per-arena state x arenas = ~1 GB per GPU vs 126 MB L2, no flush needed",
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_port_run(n_threads, budget_s, warm_ticks=30):
+    """The oracle (CPU restatement) on n_threads arenas of the benchmark shape, one arena per thread. Returns robot-steps/s."""
+    from puckswarm_b200 import abi
+    import oracle_binding
+    cfg = abi.config_defaults(n_arenas=n_threads, n_robots=N_ROBOTS, n_pucks=N_PUCKS, controller=abi.PS_CTRL_CACHECONS)
+    o = oracle_binding.Oracle(cfg, threads=n_threads)
+    o.reset(np.arange(n_threads))
+    o.step(warm_ticks)
+    t0 = time.perf_counter()
+    o.step(9)
+    per_tick = (time.perf_counter() - t0) / 9
+    ticks = int(max(9, min(3000, budget_s / max(per_tick, 1e-6)))) // 3 * 3
+    t0 = time.perf_counter()
+    o.step(ticks)
+    dt = time.perf_counter() - t0
+    return n_threads * N_ROBOTS * ticks / dt, ticks, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    import __graft_entry__ as g
+    g.build_oracle()
+    cores = os.cpu_count() or 1
+    per_step_budget = 8.0
+    vals = []
+    total_ticks = 0
+    for i in range(args.warmup + args.steps):
+        v, ticks, dt = cpu_port_run(cores, per_step_budget, warm_ticks=30)
+        if i >= args.warmup:
+            vals.append(v)
+            total_ticks += ticks
+    value = float(np.mean(vals))
+    sample = "%d arenas (one per host thread) x 16 robots x 200 pucks, %d timed ticks per step after 30 warm-up ticks" % (cores, total_ticks // max(1, len(vals)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * cores * N_ROBOTS * STEP_INTERVAL / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(ARENAS_PER_GPU * args.gpus, "host threads, one arena per core"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU restatement of JBox2D 2.1.2.2 + PuckSwarm sensing/controllers (oracle/), not the JVM reference: no JDK / JBox2D jar in this image",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--arenas", type=int, default=ARENAS_PER_GPU, help="arenas per GPU (default: BASELINE config[2])")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from puckswarm_b200 import abi, engine, dist as psd
+    import __graft_entry__ as g
+
+    if not os.path.exists(engine.LIB_PATH):
+        g.build_engine()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    A = args.arenas
+    lo = rank * A   # arenas shard by index: rank r owns [r * A, (r + 1) * A)
+    cfg = abi.config_defaults(n_arenas=A, n_robots=N_ROBOTS, n_pucks=N_PUCKS, controller=abi.PS_CTRL_CACHECONS,
+                              rng_mode=abi.PS_RNG_JAVA_SHARED)
+    eng = engine.Engine(cfg, device=local_rank)
+    eng.reset(np.arange(lo, lo + A))
+    stream = torch.cuda.ExternalStream(eng.stream, device=local_rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value") ----
+    for _ in range(args.warmup):
+        eng.step(STEP_INTERVAL, sync=False)
+    eng.sync()
+    eng.profile(True)
+    eng.kernel_ms()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = eng.kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        eng.step(STEP_INTERVAL, sync=False)
+    ev1.record(stream)
+    eng.sync()
+    local_stats = eng.compute_stats()
+    total_stats = psd.allreduce_stats(local_stats, device=torch.device("cuda", local_rank)) if world > 1 else local_stats
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.kernel_launches - launches0
+    kms, kcnt = eng.kernel_ms()
+    eng.profile(False)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    robot_steps = world * A * N_ROBOTS * STEP_INTERVAL * args.steps
+    value = robot_steps / (ms_max / 1000.0)
+
+    # ---- end to end through the C-ABI with host buffers ("e2e") ----
+    st = eng.new_state()
+    pinned_body = torch.empty(st.body.shape, dtype=torch.float32).pin_memory()
+    st.body = pinned_body.numpy()
+    pinned_arena = torch.empty(st.arena.nbytes, dtype=torch.uint8).pin_memory()
+    st.arena = pinned_arena.numpy().view(abi.ARENA_DTYPE)
+    st.sense_aabb = st.fat_aabb = st.contact_key = st.contact_info = st.contact_impulse = st.robot = None
+
+    import ctypes as C
+
+    def body_view(with_arena):
+        v = abi.ps_state_view()
+        v.body = st.body.ctypes.data_as(C.POINTER(C.c_float))
+        if with_arena:
+            v.arena = st.arena.ctypes.data_as(C.POINTER(abi.ps_arena_state))
+        return v
+
+    vin, vout = body_view(False), body_view(True)
+    eng._check(eng.L.ps_get_state(eng.h, C.byref(vout)))
+    h2d = st.body.nbytes
+    d2h = st.body.nbytes + st.arena.nbytes
+
+    def e2e_step():
+        eng._check(eng.L.ps_set_state(eng.h, C.byref(vin)))     # H2D: poses + velocities of every body
+        eng._check(eng.L.ps_step(eng.h, STEP_INTERVAL))
+        eng._check(eng.L.ps_get_state(eng.h, C.byref(vout)))    # D2H: poses + velocities + step counters (synchronous)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        e2e_step()
+    ev1.record(stream)
+    eng.sync()
+    wall = time.perf_counter() - t0
+    e2e_ms = max(ev0.elapsed_time(ev1), wall * 1000.0)
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = robot_steps / (float(t.item()) / 1000.0)
+
+    # ---- roofline of the dominant kernel (k_physics: World.step) ----
+    peak, peak_src = measured_peaks()
+    c_hat = total_stats.n_touching_points / max(1, total_stats.n_arenas)   # live touching manifold points per arena
+    bytes_per_arena_tick = 2.0 * (24.0 * (N_ROBOTS + N_PUCKS) + 24.0 * c_hat + 96.0 * N_ROBOTS)
+    n_phys = max(1, kcnt["physics"])
+    phys_ms = kms["physics"] / n_phys
+    ticks_per_launch = STEP_INTERVAL
+    alg_bytes_per_launch = bytes_per_arena_tick * A * ticks_per_launch
+    achieved = alg_bytes_per_launch / (phys_ms / 1000.0) / 1e9 if phys_ms > 0 else 0.0
+    top = ("sense", "think", "physics", "other")
+    total_k = sum(kms[k] for k in top)
+    roofline = {
+        "kernel": "World.step pipeline (k_phys_pre + k_island_worker + k_phys_post) x %d ticks" % ticks_per_launch,
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+        "traffic": None,
+        "algorithmic_bytes_per_arena_tick": bytes_per_arena_tick, "touching_points_per_arena": c_hat,
+        "kernel_ms_per_launch": phys_ms,
+        "kernel_share_of_step": {k: (kms[k] / total_k if total_k > 0 else 0.0) for k in top},
+        "world_step_stage_ms_per_tick": {k: kms[k] / max(1, kcnt[k]) for k in ("phys_pre", "phys_islands", "phys_post")},
+        "kernel_ms_total": kms, "kernel_launch_counts": kcnt,
+    }
+    ncu_traffic = os.path.join(ROOT, "profiles", "k_physics_traffic.json")
+    if os.path.exists(ncu_traffic):
+        try:
+            roofline["traffic"] = json.load(open(ncu_traffic)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            g.build_oracle()
+            cores = os.cpu_count() or 1
+            v, ticks, dt = cpu_port_run(cores, 15.0)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "%d arenas (one per host thread) x 16 robots x 200 pucks, CacheCons, %d ticks after 30 warm-up ticks (%.1f s)" % (cores, ticks, dt)}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": workload_config(A * world, "arenas sharded by index, %d per GPU, one process per GPU" % A),
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "call": "ps_set_state(body) + ps_step(3) + ps_get_state(body, arena) per step, pinned host buffers"},
+            "roofline": roofline, "cpu_baseline": cpu,
+            "stats": {"mean_percent_completion": psd.mean_completion(total_stats), "arenas": int(total_stats.n_arenas),
+                      "robots_carrying": int(total_stats.n_carrying), "cache_points": int(total_stats.n_caches),
+                      "cached_contacts_per_arena": total_stats.n_contacts / max(1, total_stats.n_arenas)},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -266,6 +266,12 @@ int ps_get_dims(ps_handle h, int32_t* n_bodies, int32_t* n_proxies, int32_t* max
 /* Diagnostics of the last World.step of every arena, [n_arenas][8] int32: 0 = max position iterations of an island,
  * 1 = TOI events, 2 = islands with contacts. */
 int ps_get_step_stats(ps_handle h, int32_t* out);
+/* Per-kernel device time, measured with CUDA events on the engine's stream while enabled. ps_get_kernel_ms waits for the
+ * stream, returns the accumulated milliseconds and launch counts of 0 = sense, 1 = think, 2 = physics (World.step, all stages),
+ * 3 = other, 4 / 5 / 6 = the three stages of World.step (collide + islands, island workers, broad phase + TOI), 7 unused,
+ * and clears the accumulators. */
+int ps_profile(ps_handle h, int enable);
+int ps_get_kernel_ms(ps_handle h, double* ms /*[8]*/, int64_t* counts /*[8]*/);
 int64_t ps_kernel_launches(ps_handle h);   /* kernels launched by this handle so far */
 void*   ps_stream(ps_handle h);            /* the cudaStream_t the engine launches on */
 

@@ -11,6 +11,7 @@
 #include <vector>
 #include "ps_host.hpp"
 #include "ps_sense_dev.cuh"
+#include "ps_pipeline.cuh"
 
 using namespace ps;
 
@@ -37,6 +38,11 @@ struct KParams {
     const ps_robot_state* robotInit;
     int nInformed;
     int* stepStats;          // [nArenas][8] diagnostics of the last World.step
+    // three-stage pipeline (ps_pipeline.cuh): per-arena scratch blocks in HBM + the batch-wide island queue
+    PhysWork workOff;        // byte offsets of the working arrays inside one arena's scratch block
+    char* arenaScratch;
+    size_t arenaScratchStride;
+    IslandQueue queue;
 };
 
 extern __shared__ __align__(16) char g_smem[];
@@ -93,6 +99,94 @@ __global__ void __launch_bounds__(256) k_physics(KParams p, int nTicks) {
     }
 }
 
+__device__ __forceinline__ PhysWork arenaWork(const KParams& p, int a) { return rebaseWork(p.workOff, p.arenaScratch + (size_t)a * p.arenaScratchStride); }
+
+// stage A: one CTA per arena
+__global__ void __launch_bounds__(128) k_phys_pre(KParams p) {
+    __shared__ int scan[40];
+    CtaCtx ctx;
+    ctx.scanScratch = scan;
+    int a = blockIdx.x;
+    int R = p.env.cfg.d.R;
+    PhysWork wk = arenaWork(p, a);
+    ArenaState st = arenaState(p.sp, p.env.cfg, a);
+    const ps_robot_state* rs = p.sp.robot + (size_t)a * R;
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        wk.fx[r] = rs[r].cmd_forwards;
+        wk.fy[r] = rs[r].cmd_torque;
+    }
+    __syncthreads();
+    physPre(ctx, p.env, wk, st, wk.fx, wk.fy, p.queue, a);
+}
+
+// stage B1: islands with >= 3 contacts (queue buckets 0 and 1): one warp per island, staged in shared memory
+__global__ void __launch_bounds__(128) k_island_warp(KParams p) {
+    extern __shared__ __align__(16) char smem[];
+    WarpSlot* slot = reinterpret_cast<WarpSlot*>(smem) + (threadIdx.x >> 5);
+    int cap = p.queue.cap;
+    int n0 = min(p.queue.counts[0], cap), n1 = min(p.queue.counts[1], cap);
+    int total = n0 + n1;
+    unsigned NB = (unsigned)p.env.cfg.d.NB;
+    int lane = threadIdx.x & 31;
+    for (;;) {
+        int idx = 0;
+        if (lane == 0) idx = atomicAdd(&p.queue.counts[3], 1);
+        idx = __shfl_sync(0xFFFFFFFFu, idx, 0);
+        if (idx >= total) break;
+        unsigned entry = idx < n0 ? p.queue.entries[idx] : p.queue.entries[(size_t)cap + (idx - n0)];
+        int a = (int)(entry / NB), k = (int)(entry % NB);
+        PhysWork wk = arenaWork(p, a);
+        ArenaState st = arenaState(p.sp, p.env.cfg, a);
+        int iters = 0;
+        bool ok = islandSolveWarp(p.env, wk, st, k, *slot, &iters);
+        if (!ok && lane == 0) {
+            // too large for a slot: lane 0 runs the island straight from HBM / L2
+            IslandCursor cur;
+            islandBegin(cur, wk, k);
+            while (islandStep(p.env, wk, st, cur, &iters)) {
+            }
+        }
+        if (lane == 0) atomicMax(&wk.stats[0], iters);
+        __syncwarp();
+    }
+}
+
+// stage B2: islands with 1-2 contacts (queue bucket 2): one lane per island
+__global__ void __launch_bounds__(128) k_island_lane(KParams p) {
+    int cap = p.queue.cap;
+    int total = min(p.queue.counts[2], cap);
+    unsigned NB = (unsigned)p.env.cfg.d.NB;
+    int stride = gridDim.x * blockDim.x;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        unsigned entry = p.queue.entries[(size_t)2 * cap + idx];
+        int a = (int)(entry / NB), k = (int)(entry % NB);
+        PhysWork wk = arenaWork(p, a);
+        ArenaState st = arenaState(p.sp, p.env.cfg, a);
+        IslandCursor cur;
+        islandBegin(cur, wk, k);
+        int iters = 0;
+        while (islandStep(p.env, wk, st, cur, &iters)) {
+        }
+        atomicMax(&wk.stats[0], iters);
+    }
+}
+
+// stage C: one CTA per arena
+__global__ void __launch_bounds__(128) k_phys_post(KParams p) {
+    __shared__ int scan[40];
+    CtaCtx ctx;
+    ctx.scanScratch = scan;
+    int a = blockIdx.x;
+    PhysWork wk = arenaWork(p, a);
+    ArenaState st = arenaState(p.sp, p.env.cfg, a);
+    // the pair search reads every body's box union once per moved proxy: keep that table in shared memory when it fits
+    __shared__ float sBodyFat[4 * 512];
+    if (p.env.cfg.d.NB <= 512) wk.bodyFat = sBodyFat;
+    physPost(ctx, p.env, wk, st);
+    if (threadIdx.x == 0) p.sp.arena[a].update_count += 1;
+    if (threadIdx.x < 8) p.stepStats[a * 8 + threadIdx.x] = wk.stats[threadIdx.x];
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 struct ps_engine {
     HostSetup hs;
@@ -106,6 +200,8 @@ struct ps_engine {
     int64_t* dSeeds = nullptr;
     int* dStepStats = nullptr;
     int nSlots = 0, threads = 128;
+    bool fused = false;      // PS_FUSED=1: the single-kernel World.step (kept for comparison)
+    int workerBlocks = 0;
     size_t smemBytes = 0;
     int64_t launches = 0;
     int updateCount = 0;     // all arenas advance in lock step
@@ -114,6 +210,35 @@ struct ps_engine {
     ps_stats* dStats = nullptr;
     float* dCmd = nullptr;
     bool isReset = false;
+    // optional per-kernel timing (CUDA events on the engine's stream): classes 0 sense, 1 think, 2 physics, 3 other
+    bool profiling = false;
+    struct Timed {
+        cudaEvent_t a, b;
+        int cls;
+    };
+    std::vector<Timed> timed;
+    double kernelMs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int64_t kernelCount[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+struct ScopedTimer {   // records an event pair around the launches issued during its lifetime
+    ps_engine* e;
+    ps_engine::Timed t;
+    bool on;
+    ScopedTimer(ps_engine* e_, int cls) : e(e_), on(e_->profiling) {
+        if (!on) return;
+        t.cls = cls;
+        if (cudaEventCreate(&t.a) != cudaSuccess || cudaEventCreate(&t.b) != cudaSuccess) {
+            on = false;
+            return;
+        }
+        cudaEventRecord(t.a, e->stream);
+    }
+    ~ScopedTimer() {
+        if (!on) return;
+        cudaEventRecord(t.b, e->stream);
+        e->timed.push_back(t);
+    }
 };
 
 static size_t envSize(const char* name, size_t dflt) {
@@ -196,6 +321,9 @@ int ps_destroy(ps_handle h) {
     cudaFree(h->kp.sp.robot);
     cudaFree(h->kp.sp.arena);
     cudaFree(h->kp.slow);
+    cudaFree(h->kp.arenaScratch);
+    cudaFree(h->kp.queue.entries);
+    cudaFree(h->kp.queue.counts);
     cudaFree(h->dScene);
     cudaFree(h->dLut);
     cudaFree(h->dRobotInit);
@@ -288,6 +416,21 @@ int ps_create(const ps_config* cfg, int device, ps_handle* out) {
     TRY_OR_FREE(cudaMemset(e->kp.slow, 0, (size_t)e->nSlots * slowStride + 256));
     TRY_OR_FREE(cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smemBytes));
     TRY_OR_FREE(cudaFuncSetAttribute(k_physics, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smemBytes));
+    // pipeline: one scratch block per arena (all working arrays in HBM / L2), island queue
+    {
+        Carver mo = {nullptr, 0, 0, nullptr, 0};
+        e->kp.workOff = carveWork(pc, mo);
+        e->kp.arenaScratchStride = (mo.slowUsed + 255) & ~(size_t)255;
+        e->fused = envSize("PS_FUSED", 0) != 0;
+        size_t nBlocks = e->fused ? 1 : A;
+        TRY_OR_FREE(cudaMalloc(&e->kp.arenaScratch, nBlocks * e->kp.arenaScratchStride + 256));
+        TRY_OR_FREE(cudaMemset(e->kp.arenaScratch, 0, nBlocks * e->kp.arenaScratchStride + 256));
+        e->kp.queue.cap = (int)std::min<size_t>(A * (size_t)pc.d.NB, (size_t)1 << 28);
+        TRY_OR_FREE(cudaMalloc(&e->kp.queue.entries, (size_t)3 * e->kp.queue.cap * sizeof(unsigned)));
+        TRY_OR_FREE(cudaMalloc(&e->kp.queue.counts, 4 * sizeof(int)));
+        e->workerBlocks = prop.multiProcessorCount * (int)envSize("PS_WORKER_BLOCKS_PER_SM", 4);
+        TRY_OR_FREE(cudaFuncSetAttribute(k_island_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(WarpSlot))));
+    }
     e->kp.env.scene = e->dScene;
     e->kp.env.trig.lut = e->dLut;
     e->kp.env.trig.useLut = cfg->sincos_lut;
@@ -334,9 +477,31 @@ int ps_reset(ps_handle h, const int64_t* seeds) {
 }
 
 static int launchPhysics(ps_handle h, int nTicks) {
-    k_physics<<<h->nSlots, h->threads, h->smemBytes, h->stream>>>(h->kp, nTicks);
-    h->launches++;
-    CUDA_TRY(cudaGetLastError());
+    ScopedTimer timer(h, 2);
+    if (h->fused) {
+        k_physics<<<h->nSlots, h->threads, h->smemBytes, h->stream>>>(h->kp, nTicks);
+        h->launches++;
+        CUDA_TRY(cudaGetLastError());
+    } else {
+        for (int t = 0; t < nTicks; ++t) {
+            CUDA_TRY(cudaMemsetAsync(h->kp.queue.counts, 0, 4 * sizeof(int), h->stream));
+            {
+                ScopedTimer t4(h, 4);
+                k_phys_pre<<<h->kp.nArenas, 128, 0, h->stream>>>(h->kp);
+            }
+            {
+                ScopedTimer t5(h, 5);
+                k_island_warp<<<h->workerBlocks, 128, 4 * sizeof(WarpSlot), h->stream>>>(h->kp);
+                k_island_lane<<<h->workerBlocks, 128, 0, h->stream>>>(h->kp);
+            }
+            {
+                ScopedTimer t6(h, 6);
+                k_phys_post<<<h->kp.nArenas, 128, 0, h->stream>>>(h->kp);
+            }
+            h->launches += 4;
+            CUDA_TRY(cudaGetLastError());
+        }
+    }
     h->updateCount += nTicks;
     return PS_OK;
 }
@@ -351,7 +516,16 @@ int ps_step(ps_handle h, int n_ticks) {
         if (h->updateCount % interval == 0) {
             if (h->hs.cfg.controller != PS_CTRL_EXTERNAL) {
                 if (!h->sd.ready) return setError(PS_E_NOCALIB, "ps_load_calibration has not been called");
-                int rc = h->sd.launchSenseThink(h->kp.env, h->kp.sp, h->kp.nArenas, h->stream, &h->launches);
+                int rc;
+                {
+                    ScopedTimer timer(h, 0);
+                    rc = h->sd.launchSense(h->kp.env, h->kp.sp, h->stream, &h->launches, false);
+                }
+                if (rc != PS_OK) return setError(rc, h->sd.error);
+                {
+                    ScopedTimer timer(h, 1);
+                    rc = h->sd.launchThink(h->kp.nArenas, h->stream, &h->launches);
+                }
                 if (rc != PS_OK) return setError(rc, h->sd.error);
             } else {
                 k_count_step<<<(h->kp.nArenas + 127) / 128, 128, 0, h->stream>>>(h->kp.sp.arena, h->kp.nArenas);
@@ -491,6 +665,35 @@ int ps_get_step_stats(ps_handle h, int32_t* out /* [n_arenas][8] */) {
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaMemcpyAsync(out, h->dStepStats, (size_t)h->kp.nArenas * 8 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return PS_OK;
+}
+
+int ps_profile(ps_handle h, int enable) {
+    if (!h) return setError(PS_E_INVALID, "null handle");
+    h->profiling = enable != 0;
+    return PS_OK;
+}
+
+int ps_get_kernel_ms(ps_handle h, double* ms, int64_t* counts) {
+    if (!h || !ms || !counts) return setError(PS_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    for (auto& t : h->timed) {
+        float f = 0;
+        if (cudaEventElapsedTime(&f, t.a, t.b) == cudaSuccess) {
+            h->kernelMs[t.cls] += f;
+            h->kernelCount[t.cls] += 1;
+        }
+        cudaEventDestroy(t.a);
+        cudaEventDestroy(t.b);
+    }
+    h->timed.clear();
+    for (int i = 0; i < 8; i++) {
+        ms[i] = h->kernelMs[i];
+        counts[i] = h->kernelCount[i];
+        h->kernelMs[i] = 0;
+        h->kernelCount[i] = 0;
+    }
     return PS_OK;
 }
 

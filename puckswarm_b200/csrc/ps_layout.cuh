@@ -86,6 +86,8 @@ PS_HD PhysWork carveWork(const PhysCfg& c, Carver& cv) {
     w.adjOff = (int*)cv.take((size_t)(NB + 1) * sizeof(int));
     w.adjFill = (int*)cv.take((size_t)NB * sizeof(int));
     w.islandStart = (int*)cv.take((size_t)(NB + 1) * sizeof(int));
+    w.islandBodyStart = (int*)cv.take((size_t)(NB + 1) * sizeof(int));
+    w.ibody = (uint16_t*)cv.take((size_t)NB * sizeof(uint16_t));
     w.stack = (uint16_t*)cv.take((size_t)NB * sizeof(uint16_t));
     w.bodyFlag = (uint8_t*)cv.take((size_t)NB);
     w.adj = (uint16_t*)cv.take((size_t)2 * c.MT * sizeof(uint16_t));
@@ -97,7 +99,33 @@ PS_HD PhysWork carveWork(const PhysCfg& c, Carver& cv) {
     w.pairs = (uint32_t*)cv.take((size_t)c.MPAIR * sizeof(uint32_t));
     w.fatOld = (float*)cv.take((size_t)4 * NP * sizeof(float));
     w.wallList = (int*)cv.take((size_t)c.MW * sizeof(int));
+    w.wallBody = (int*)cv.take((size_t)c.MW * sizeof(int));
+    w.wallT = (float*)cv.take((size_t)c.MW * sizeof(float));
+    w.wallState = (uint8_t*)cv.take((size_t)c.MW);
+    w.wallNeed = (uint8_t*)cv.take((size_t)c.MW);
+    w.toiT = (float*)cv.take((size_t)NB * sizeof(float));
+    w.toiContact = (int*)cv.take((size_t)NB * sizeof(int));
+    w.toiCur = (int*)cv.take((size_t)NB * sizeof(int));
+    w.toiCount = (int*)cv.take((size_t)NB * sizeof(int));
+    w.toiFound = (uint8_t*)cv.take((size_t)NB);
+    w.toiIter = (uint8_t*)cv.take((size_t)NB);
+    w.toiActive = (uint8_t*)cv.take((size_t)NB);
     w.tc = (TC*)cv.take((size_t)c.MT * sizeof(TC));
+    return w;
+}
+
+// PhysWork whose pointers are byte offsets (carved from a null base) -> real pointers for one arena's scratch block.
+// The offsets live in kernel parameters, so a kernel only materialises the few pointers it uses (one add each).
+PS_HD PhysWork rebaseWork(const PhysWork& o, char* base) {
+    PhysWork w;
+    size_t b = (size_t)base;
+#define RB(f) w.f = (decltype(w.f))((size_t)o.f + b);
+    RB(cx) RB(cy) RB(a) RB(vx) RB(vy) RB(w) RB(c0x) RB(c0y) RB(a0)
+    RB(rpx) RB(rpy) RB(rc) RB(rs) RB(r0px) RB(r0py) RB(r0c) RB(r0s) RB(fx) RB(fy) RB(tq)
+    RB(adjOff) RB(adjFill) RB(adj) RB(order) RB(islandStart) RB(islandBodyStart) RB(ibody) RB(stack) RB(bodyFlag) RB(tcFlag)
+    RB(moved) RB(bodyFat) RB(movedList) RB(fatOld) RB(pairs) RB(wallList) RB(wallBody) RB(wallT) RB(wallState) RB(wallNeed)
+    RB(toiT) RB(toiContact) RB(toiCur) RB(toiCount) RB(toiFound) RB(toiIter) RB(toiActive) RB(tc) RB(counters) RB(stats)
+#undef RB
     return w;
 }
 

@@ -66,6 +66,8 @@ struct PhysWork {
     uint16_t* adj;                                       // [2 * MT] touching contacts per body, newest first
     uint16_t* order;                                     // [MT] Gauss-Seidel order, island after island
     int* islandStart;                                    // [NB + 1]
+    int* islandBodyStart;                                // [NB + 1] ranges into ibody, one per recorded island
+    uint16_t* ibody;                                     // [NB] bodies of the recorded islands (DFS pop order)
     uint16_t* stack;                                     // [NB]
     uint8_t* bodyFlag;                                   // [NB]
     uint8_t* tcFlag;                                     // [MT]
@@ -75,6 +77,17 @@ struct PhysWork {
     float* fatOld;                                       // [4][NP] fat AABB before this step's moveProxy
     uint32_t* pairs;                                     // [MPAIR]
     int* wallList;                                       // [MW] cached contacts with the wall
+    int* wallBody;                                       // [MW] the dynamic body of each wall contact
+    float* wallT;                                        // [MW] speculative TimeOfImpact result of the current round
+    uint8_t* wallState;                                  // [MW] TOI state of the current round
+    uint8_t* wallNeed;                                   // [MW] needs (re-)evaluation with the body's current tMax
+    float* toiT;                                         // [NB] World.solveTOI(Body): current minimum toi
+    int* toiContact;                                     // [NB] cache index of the current toiContact, -1 = none
+    int* toiCur;                                         // [NB] scan position in the wall list (descending)
+    int* toiCount;                                       // [NB] count / found / iter of the current do-while pass
+    uint8_t* toiFound;
+    uint8_t* toiIter;
+    uint8_t* toiActive;
     TC* tc;                                              // [MT]
     int* counters;                                       // [8]: 0 nTouching, 1 nIslands, 2 nMoved, 3 nPairs, 4 nWall, 5 scratch
     int* stats;                                          // [8] per-step diagnostics: 0 max position iterations, 1 TOI events, 2 islands
@@ -393,9 +406,9 @@ PS_HD void solveVelocityOne(const PhysEnv& e, const PhysWork& wk, TC& c) {
 }
 
 // One position-correction of one manifold point; massA/massB let the TOI solver freeze one side.
-// Returns the separation it saw.
+// Returns the separation it saw; *changed is set when a body's (c, a) actually moved (bitwise).
 PS_HD float correctPoint(const PhysEnv& e, const PhysWork& wk, int bA, int bB, int type, V2 localNormal, V2 localPoint, V2 pointLocal,
-                         float radius, float baumgarte, float invMassA, float invIA, float invMassB, float invIB) {
+                         float radius, float baumgarte, float invMassA, float invIA, float invMassB, float invIB, bool* changed = nullptr) {
     Xf xfA = bodyXf(e, wk, bA), xfB = bodyXf(e, wk, bB);
     V2 normal, point;
     float separation;
@@ -408,20 +421,33 @@ PS_HD float correctPoint(const PhysEnv& e, const PhysWork& wk, int bA, int bB, i
     float K = invMassA + invMassB + invIA * rnA * rnA + invIB * rnB * rnB;
     float impulse = K > 0.0f ? -C / K : 0.0f;
     V2 P = impulse * normal;
+    bool moved = false;
     if (bA >= 0) {
         V2 nc = cA - invMassA * P;
-        wk.cx[bA] = nc.x;
-        wk.cy[bA] = nc.y;
-        wk.a[bA] -= invIA * cross(rA, P);
-        syncBodyXf(e, wk, bA);
+        float oa = wk.a[bA];
+        float na = oa - invIA * cross(rA, P);
+        if (nc.x != cA.x || nc.y != cA.y || na != oa) {
+            // (an unchanged body keeps its transform: synchronizeTransform is a pure function of (c, a))
+            wk.cx[bA] = nc.x;
+            wk.cy[bA] = nc.y;
+            wk.a[bA] = na;
+            syncBodyXf(e, wk, bA);
+            moved = true;
+        }
     }
     if (bB >= 0) {
         V2 nc = cB + invMassB * P;
-        wk.cx[bB] = nc.x;
-        wk.cy[bB] = nc.y;
-        wk.a[bB] += invIB * cross(rB, P);
-        syncBodyXf(e, wk, bB);
+        float oa = wk.a[bB];
+        float na = oa + invIB * cross(rB, P);
+        if (nc.x != cB.x || nc.y != cB.y || na != oa) {
+            wk.cx[bB] = nc.x;
+            wk.cy[bB] = nc.y;
+            wk.a[bB] = na;
+            syncBodyXf(e, wk, bB);
+            moved = true;
+        }
     }
+    if (changed && moved) *changed = true;
     return separation;
 }
 
@@ -457,7 +483,7 @@ PS_HD void physLoad(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaS
     }
     if (ctx.tid() == 0) {
         for (int i = 0; i < 8; i++) wk.counters[i] = 0;
-        wk.stats[0] = wk.stats[1] = wk.stats[2] = 0;
+        for (int i = 0; i < 8; i++) wk.stats[i] = 0;
     }
     ctx.sync();
 }
@@ -598,17 +624,19 @@ PS_HD void physIslands(Ctx& ctx, const PhysEnv& e, const PhysWork& wk) {
     ctx.sync();
     // stack DFS: seeds in body-list order (newest body first), edges newest first; only islands with contacts are recorded
     if (ctx.tid() == 0) {
-        int nIsl = 0, ordN = 0;
+        int nIsl = 0, ordN = 0, nIb = 0;
         for (int seed = NB - 1; seed >= 0; --seed) {
             if (wk.bodyFlag[seed]) continue;
             wk.bodyFlag[seed] = 1;
             if (wk.adjOff[seed] == wk.adjOff[seed + 1]) continue;
             int start = ordN;
             wk.islandStart[nIsl] = start;
+            wk.islandBodyStart[nIsl] = nIb;
             int sp = 0;
             wk.stack[sp++] = (uint16_t)seed;
             while (sp > 0) {
                 int b = wk.stack[--sp];
+                wk.ibody[nIb++] = (uint16_t)b;
                 for (int i = wk.adjOff[b]; i < wk.adjOff[b + 1]; ++i) {
                     int t = wk.adj[i];
                     if (wk.tcFlag[t]) continue;
@@ -637,6 +665,7 @@ PS_HD void physIslands(Ctx& ctx, const PhysEnv& e, const PhysWork& wk) {
             ++nIsl;
         }
         wk.islandStart[nIsl] = ordN;
+        wk.islandBodyStart[nIsl] = nIb;
         wk.counters[1] = nIsl;
     }
     ctx.sync();
@@ -663,42 +692,45 @@ PS_HD void physSolveVelocity(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, con
     ctx.sync();
 }
 
-// Phase E: integrate positions (Island.solve step 6), remember the start-of-step transform for synchronizeFixtures
-template <class Ctx>
-PS_HD void physIntegrate(Ctx& ctx, const PhysEnv& e, const PhysWork& wk) {
+// Island.solve step 6 for one body: clamp the step, remember the start-of-step transform, advance, synchronizeTransform
+PS_HD void integrateBody(const PhysEnv& e, const PhysWork& wk, int b) {
     const Dims& d = e.cfg.d;
     float dt = e.cfg.dt;
-    PS_FOR(b, d.NB) {
-        float vx = wk.vx[b], vy = wk.vy[b], w = wk.w[b];
-        V2 tr = mk(dt * vx, dt * vy);
-        if (dot(tr, tr) > kMaxTranslationSquared) {
-            float ratio = kMaxTranslation / len(tr);
-            vx *= ratio;
-            vy *= ratio;
-        }
-        float rot = dt * w;
-        if (rot * rot > kMaxRotationSquared) {
-            float ratio = kMaxRotation / fabsf(rot);
-            w *= ratio;
-        }
-        wk.vx[b] = vx;
-        wk.vy[b] = vy;
-        wk.w[b] = w;
-        wk.c0x[b] = wk.cx[b];
-        wk.c0y[b] = wk.cy[b];
-        wk.a0[b] = wk.a[b];
-        if (b >= d.P) {
-            int r = b - d.P;
-            wk.r0px[r] = wk.rpx[r];
-            wk.r0py[r] = wk.rpy[r];
-            wk.r0c[r] = wk.rc[r];
-            wk.r0s[r] = wk.rs[r];
-        }
-        wk.cx[b] += dt * vx;
-        wk.cy[b] += dt * vy;
-        wk.a[b] += dt * w;
-        syncBodyXf(e, wk, b);
+    float vx = wk.vx[b], vy = wk.vy[b], w = wk.w[b];
+    V2 tr = mk(dt * vx, dt * vy);
+    if (dot(tr, tr) > kMaxTranslationSquared) {
+        float ratio = kMaxTranslation / len(tr);
+        vx *= ratio;
+        vy *= ratio;
     }
+    float rot = dt * w;
+    if (rot * rot > kMaxRotationSquared) {
+        float ratio = kMaxRotation / fabsf(rot);
+        w *= ratio;
+    }
+    wk.vx[b] = vx;
+    wk.vy[b] = vy;
+    wk.w[b] = w;
+    wk.c0x[b] = wk.cx[b];
+    wk.c0y[b] = wk.cy[b];
+    wk.a0[b] = wk.a[b];
+    if (b >= d.P) {
+        int r = b - d.P;
+        wk.r0px[r] = wk.rpx[r];
+        wk.r0py[r] = wk.rpy[r];
+        wk.r0c[r] = wk.rc[r];
+        wk.r0s[r] = wk.rs[r];
+    }
+    wk.cx[b] += dt * vx;
+    wk.cy[b] += dt * vy;
+    wk.a[b] += dt * w;
+    syncBodyXf(e, wk, b);
+}
+
+// Phase E: integrate positions (Island.solve step 6) of every body (fused pipeline)
+template <class Ctx>
+PS_HD void physIntegrate(Ctx& ctx, const PhysEnv& e, const PhysWork& wk) {
+    PS_FOR(b, e.cfg.d.NB) integrateBody(e, wk, b);
     ctx.sync();
 }
 
@@ -839,22 +871,19 @@ PS_HD void physFindNewContacts(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, c
     const Dims& d = e.cfg.d;
     int NB = d.NB;
     int nMoved = allNew ? d.NP : wk.counters[2];
-    // (moved proxy) x (dynamic bodies + the wall)
-    int nItems = nMoved * (NB + 1);
-    PS_FOR(it, nItems) {
-        int mi = it / (NB + 1), b = it - mi * (NB + 1);
+    // one thread per moved proxy: its new fat box against every body's box union (then that body's proxies), then the wall
+    PS_FOR(mi, nMoved) {
         int q = kWallFixtures + (allNew ? mi : wk.movedList[mi]);
         Aabb fatQ = proxyFat(e, st, q);
-        if (b < NB) {
+        for (int b = 0; b < NB; ++b) {
             if (!aabbOverlap(loadAabb(wk.bodyFat, NB, b), fatQ)) continue;
             int first = bodyFirstProxy(d, b), cnt = bodyProxyCount(d, b);
             for (int k = 0; k < cnt; ++k) tryPair(ctx, e, wk, st, q, fatQ, first + k, allNew);
-        } else {
-            // wall: only proxies reaching the band where wall boxes live need the 84 tests
-            float inner = e.scene->cornerX - 1.0f;
-            if (fatQ.lx > -inner && fatQ.ux < inner && fatQ.ly > -inner && fatQ.uy < inner) continue;
-            for (int k = 0; k < kWallFixtures; ++k) tryPair(ctx, e, wk, st, q, fatQ, k, allNew);
         }
+        // wall: only proxies reaching the band where wall boxes live need the 84 tests
+        float inner = e.scene->cornerX - 1.0f;
+        if (fatQ.lx > -inner && fatQ.ux < inner && fatQ.ly > -inner && fatQ.uy < inner) continue;
+        for (int k = 0; k < kWallFixtures; ++k) tryPair(ctx, e, wk, st, q, fatQ, k, allNew);
     }
     ctx.sync();
     int nPairs = wk.counters[3];
@@ -922,58 +951,49 @@ PS_HD void physFindNewContacts(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, c
     ctx.sync();
 }
 
-// World.solveTOI(Body) for one dynamic body against the wall. wallList holds the cache indices of all wall contacts
-// (ascending); the body's contact-edge order is newest first, i.e. descending index.
-PS_HDN void toiBody(const PhysEnv& e, const PhysWork& wk, const ArenaState& st, int body, int nWall) {
-    const Dims& d = e.cfg.d;
-    const BodyConst& k = bodyConst(e, body);
+// Sweep of a body over the current step. Pucks carry no rotation that anything reads (circle fixtures centred on the
+// origin, localCenter = 0), so their transform is a pure translation.
+PS_HD Sweep bodySweep(const PhysEnv& e, const PhysWork& wk, int body) {
     Sweep sw;
-    sw.lcx = k.lcx;
-    sw.lcy = k.lcy;
-    if (body < d.P) {
+    if (body < e.cfg.d.P) {
         sw.lcx = 0.0f;
         sw.lcy = 0.0f;
+    } else {
+        sw.lcx = e.scene->robot.lcx;
+        sw.lcy = e.scene->robot.lcy;
     }
+    sw.c0x = wk.c0x[body];
+    sw.c0y = wk.c0y[body];
+    sw.cx = wk.cx[body];
+    sw.cy = wk.cy[body];
+    sw.a0 = wk.a0[body];
+    sw.a = wk.a[body];
+    return sw;
+}
+
+// TimeOfImpact of one cached wall contact of `body` on [0, tMax]
+PS_HDN void toiEval(const PhysEnv& e, const PhysWork& wk, const ArenaState& st, int body, int ci, float tMax, int& state, float& t) {
+    const Dims& d = e.cfg.d;
+    uint32_t key = st.ckey[ci];
+    int pa = (int)(key >> 16), pb = (int)(key & 0xFFFFu);
+    int bA = proxyBody(d, pa);
+    DProxy prA, prB;
+    proxyFromShape(prA, e.scene->shapes[proxyShape(d, pa)]);
+    proxyFromShape(prB, e.scene->shapes[proxyShape(d, pb)]);
+    Sweep sw = bodySweep(e, wk, body);
     Sweep wall;
     wall.lcx = wall.lcy = wall.c0x = wall.c0y = wall.cx = wall.cy = wall.a0 = wall.a = 0.0f;
-    int toiContact = -1;
-    float toi = 1.0f;
-    bool found;
-    int count, iter = 0;
-    do {
-        count = 0;
-        found = false;
-        sw.c0x = wk.c0x[body];
-        sw.c0y = wk.c0y[body];
-        sw.cx = wk.cx[body];
-        sw.cy = wk.cy[body];
-        sw.a0 = wk.a0[body];
-        sw.a = wk.a[body];
-        for (int wi = nWall - 1; wi >= 0; --wi) {
-            int ci = wk.wallList[wi];
-            uint32_t key = st.ckey[ci];
-            int pa = (int)(key >> 16), pb = (int)(key & 0xFFFFu);
-            int bA = proxyBody(d, pa), bB = proxyBody(d, pb);
-            if (bA != body && bB != body) continue;
-            if (ci == toiContact) continue;
-            DProxy prA, prB;
-            proxyFromShape(prA, e.scene->shapes[proxyShape(d, pa)]);
-            proxyFromShape(prB, e.scene->shapes[proxyShape(d, pb)]);
-            int state;
-            float t;
-            timeOfImpact(state, t, e.trig, prA, bA == body ? sw : wall, prB, bB == body ? sw : wall, toi);
-            if (state == TOI_TOUCHING && t < toi) {
-                toiContact = ci;
-                toi = t;
-                found = true;
-            }
-            ++count;
-        }
-        ++iter;
-    } while (found && count > 1 && iter < 50);
-    if (toiContact < 0) return;   // Body.advance(1): c0 = c, a0 = a -- nothing later reads them
-    wk.stats[1] += 1;             // diagnostic only (racy increments are acceptable)
-    // Body.advance(toi)
+    int kindBody = body < d.P ? SWEEP_TRANSLATE : SWEEP_FULL;
+    if (bA == body) timeOfImpact(state, t, e.trig, prA, sw, kindBody, prB, wall, SWEEP_STATIC, e.scene->wallXf, tMax);
+    else timeOfImpact(state, t, e.trig, prA, wall, SWEEP_STATIC, prB, sw, kindBody, e.scene->wallXf, tMax);
+}
+
+// Second half of World.solveTOI(Body) once the minimum-TOI contact is known: Body.advance(toi), refresh the body's wall
+// contacts (contact-edge order = newest first = descending cache index), then the TOISolver (only this body moves).
+PS_HDN void toiResolve(const PhysEnv& e, const PhysWork& wk, const ArenaState& st, int body, int toiContact, float toi, int nWall) {
+    const Dims& d = e.cfg.d;
+    const BodyConst& k = bodyConst(e, body);
+    Sweep sw = bodySweep(e, wk, body);
     sweepAdvance(sw, toi);
     wk.c0x[body] = sw.c0x;
     wk.c0y[body] = sw.c0y;
@@ -982,7 +1002,6 @@ PS_HDN void toiBody(const PhysEnv& e, const PhysWork& wk, const ArenaState& st, 
     wk.cy[body] = sw.c0y;
     wk.a[body] = sw.a0;
     syncBodyXf(e, wk, body);
-    // update the TOI contact, then every other wall contact of the body (edge order), gather the touching ones
     int cIdx[kMaxTOIContacts];
     Manifold mans[kMaxTOIContacts];
     int n = 0;
@@ -992,11 +1011,11 @@ PS_HDN void toiBody(const PhysEnv& e, const PhysWork& wk, const ArenaState& st, 
         updateContact(e, wk, st, toiContact, m, imp);
     }
     for (int wi = nWall - 1; wi >= 0 && n < kMaxTOIContacts; --wi) {
+        if (wk.wallBody[wi] != body) continue;
         int ci = wk.wallList[wi];
         uint32_t key = st.ckey[ci];
         int pa = (int)(key >> 16), pb = (int)(key & 0xFFFFu);
         int bA = proxyBody(d, pa), bB = proxyBody(d, pb);
-        if (bA != body && bB != body) continue;
         Manifold m;
         float imp[4];
         if (ci != toiContact) {
@@ -1012,7 +1031,6 @@ PS_HDN void toiBody(const PhysEnv& e, const PhysWork& wk, const ArenaState& st, 
         mans[n] = m;
         ++n;
     }
-    // TOISolver: only the TOI body moves
     float pm = k.mass * k.invMass, pi = k.mass * k.invI;
     for (int it = 0; it < 20; ++it) {
         float minSeparation = 0.0f;
@@ -1033,36 +1051,146 @@ PS_HDN void toiBody(const PhysEnv& e, const PhysWork& wk, const ArenaState& st, 
     }
 }
 
-// Phase I: World.solveTOI -- every dynamic body that has cached contacts with the wall
+// Phase I: World.solveTOI. Every dynamic body with cached wall contacts runs, independently of the others,
+//     do { for each wall contact != toiContact (edge order): TOI on [0, toi]; TOUCHING && t < toi -> toiContact, toi = t }
+//     while (found && count > 1 && iter < 50)
+// The evaluations of one pass are independent except through tMax = toi, which only changes when a hit is found. So
+// all wall contacts of the arena are evaluated speculatively in parallel with their body's current toi; each body then
+// walks its list in edge order, accepts the first hit, and only the contacts after it are re-evaluated with the new
+// toi in the next round. Every evaluation that is consumed used exactly the tMax the sequential loop would have used.
 template <class Ctx>
 PS_HD void physSolveTOI(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaState& st) {
     const Dims& d = e.cfg.d;
     int n = *st.nContacts;
-    PS_FOR(b, d.NB) wk.bodyFlag[b] = 0;
+    PS_FOR(b, d.NB) {
+        wk.bodyFlag[b] = 0;
+        wk.toiActive[b] = 0;
+    }
     ctx.sync();
     int nWall = 0;
     int nRound = roundUpThreads(ctx, n);
     for (int base = 0; base < nRound; base += ctx.nthreads()) {
         int i = base + ctx.tid();
         bool isWall = false;
+        int body = -1;
         if (i < n) {
             uint32_t key = st.ckey[i];
             int pa = (int)(key >> 16), pb = (int)(key & 0xFFFFu);
             isWall = pa < kWallFixtures || pb < kWallFixtures;
-            if (isWall) wk.bodyFlag[proxyBody(d, pa < kWallFixtures ? pb : pa)] = 1;
+            if (isWall) body = proxyBody(d, pa < kWallFixtures ? pb : pa);
         }
         int total;
         int pos = nWall + ctx.exscanFlag(isWall, total);
         if (isWall) {
-            if (pos < e.cfg.MW) wk.wallList[pos] = i;
-            else *st.errorFlags |= ERR_CONTACT_CAP;
+            if (pos < e.cfg.MW) {
+                wk.wallList[pos] = i;
+                wk.wallBody[pos] = body;
+                wk.wallNeed[pos] = 1;
+                wk.bodyFlag[body] = 1;
+            } else {
+                *st.errorFlags |= ERR_CONTACT_CAP;
+            }
         }
         nWall += total;
     }
     if (nWall > e.cfg.MW) nWall = e.cfg.MW;
     ctx.sync();
     PS_FOR(b, d.NB) {
-        if (wk.bodyFlag[b]) toiBody(e, wk, st, b, nWall);
+        if (wk.bodyFlag[b]) {
+            wk.toiActive[b] = 1;
+            wk.toiT[b] = 1.0f;
+            wk.toiContact[b] = -1;
+            wk.toiCur[b] = nWall - 1;
+            wk.toiCount[b] = 0;
+            wk.toiFound[b] = 0;
+            wk.toiIter[b] = 0;
+        }
+    }
+    if (ctx.tid() == 0) wk.counters[4] = nWall > 0 ? 1 : 0;
+    ctx.sync();
+    while (wk.counters[4]) {
+        ctx.sync();
+        if (ctx.tid() == 0) {
+            wk.counters[4] = 0;
+            wk.stats[3] += 1;   // diagnostic: speculative rounds
+        }
+        PS_FOR(w, nWall) {
+            if (!wk.wallNeed[w]) continue;
+            int body = wk.wallBody[w];
+            int state;
+            float t;
+            toiEval(e, wk, st, body, wk.wallList[w], wk.toiT[body], state, t);
+            ctx.atomicAddI(&wk.stats[4], 1);   // diagnostic: TimeOfImpact evaluations
+            wk.wallState[w] = (uint8_t)state;
+            wk.wallT[w] = t;
+            wk.wallNeed[w] = 0;
+        }
+        ctx.sync();
+        PS_FOR(b, d.NB) {
+            if (!wk.toiActive[b]) continue;
+            bool again = false;
+            for (;;) {
+                // continue the current pass from toiCur
+                bool hit = false;
+                int wi = wk.toiCur[b];
+                for (; wi >= 0; --wi) {
+                    if (wk.wallBody[wi] != b) continue;
+                    if (wk.wallList[wi] == wk.toiContact[b]) continue;
+                    wk.toiCount[b] += 1;
+                    if (wk.wallState[wi] == TOI_TOUCHING && wk.wallT[wi] < wk.toiT[b]) {
+                        wk.toiContact[b] = wk.wallList[wi];
+                        wk.toiT[b] = wk.wallT[wi];
+                        wk.toiFound[b] = 1;
+                        hit = true;
+                        break;
+                    }
+                }
+                if (hit) {
+                    // the rest of the pass runs against the smaller toi
+                    wk.toiCur[b] = wi - 1;
+                    bool any = false;
+                    for (int w2 = wi - 1; w2 >= 0; --w2)
+                        if (wk.wallBody[w2] == b && wk.wallList[w2] != wk.toiContact[b]) {
+                            wk.wallNeed[w2] = 1;
+                            any = true;
+                        }
+                    if (any) {
+                        again = true;
+                        break;
+                    }
+                    // nothing left in this pass: fall through to the end-of-pass test
+                }
+                // end of pass
+                wk.toiIter[b] += 1;
+                if (wk.toiFound[b] && wk.toiCount[b] > 1 && wk.toiIter[b] < 50) {
+                    wk.toiCount[b] = 0;
+                    wk.toiFound[b] = 0;
+                    wk.toiCur[b] = nWall - 1;
+                    bool any = false;
+                    for (int w2 = nWall - 1; w2 >= 0; --w2)
+                        if (wk.wallBody[w2] == b && wk.wallList[w2] != wk.toiContact[b]) {
+                            wk.wallNeed[w2] = 1;
+                            any = true;
+                        }
+                    if (any) {
+                        again = true;
+                        break;
+                    }
+                    continue;   // a pass over zero contacts: count stays 0, the loop condition ends it next time round
+                }
+                wk.toiActive[b] = 0;
+                break;
+            }
+            if (again) wk.counters[4] = 1;
+        }
+        ctx.sync();
+    }
+    // bodies that found a TOI contact: advance + TOISolver (rare)
+    PS_FOR(b, d.NB) {
+        if (wk.bodyFlag[b] && wk.toiContact[b] >= 0) {
+            toiResolve(e, wk, st, b, wk.toiContact[b], wk.toiT[b], nWall);
+            wk.stats[1] += 1;   // diagnostic only
+        }
     }
     ctx.sync();
 }
@@ -1083,22 +1211,45 @@ PS_HD void physStore(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const Arena
     ctx.sync();
 }
 
+// Phase clock for the per-step diagnostics (stats[3..7]: cycles of collide, islands, velocity, position, broadphase + TOI)
+PS_HD long long phaseClock() {
+#if defined(__CUDA_ARCH__)
+    return clock64();
+#else
+    return 0;
+#endif
+}
+
 // World.step
 template <class Ctx>
 PS_HD void worldStep(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaState& st, const float* cmdFwd, const float* cmdTorque) {
     float dtRatio = *st.invDt0 * e.cfg.dt;
     ctx.sync();
     physLoad(ctx, e, wk, st, cmdFwd, cmdTorque);
+    long long t0 = phaseClock();
     physCollide(ctx, e, wk, st, dtRatio);
+    long long t1 = phaseClock();
     physIslands(ctx, e, wk);
+    long long t2 = phaseClock();
     physSolveVelocity(ctx, e, wk, st);
     physIntegrate(ctx, e, wk);
+    long long t3 = phaseClock();
     physSolvePosition(ctx, e, wk);
+    long long t4 = phaseClock();
     physSyncFixtures(ctx, e, wk, st);
     physBodyFat(ctx, e, wk, st);
     physFindNewContacts(ctx, e, wk, st, false);
     if (e.cfg.toiEnabled) physSolveTOI(ctx, e, wk, st);
+    long long t5 = phaseClock();
     physStore(ctx, e, wk, st);
+    if (ctx.tid() == 0) {
+        wk.stats[3] = (int)((t1 - t0) >> 4);
+        wk.stats[4] = (int)((t2 - t1) >> 4);
+        wk.stats[5] = (int)((t3 - t2) >> 4);
+        wk.stats[6] = (int)((t4 - t3) >> 4);
+        wk.stats[7] = (int)((t5 - t4) >> 4);
+    }
+    ctx.sync();
 }
 
 }  // namespace ps

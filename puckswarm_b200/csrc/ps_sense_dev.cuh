@@ -243,9 +243,7 @@ struct SenseDevice {
         if (cudaGetLastError() != cudaSuccess) return fail(PS_E_CUDA, "k_sense launch failed");
         return PS_OK;
     }
-    int launchSenseThink(const PhysEnv& env, const StatePtrs& sp, int nArenas, cudaStream_t stream, int64_t* launches) {
-        int rc = launchSense(env, sp, stream, launches, false);
-        if (rc != PS_OK) return rc;
+    int launchThink(int nArenas, cudaStream_t stream, int64_t* launches) {
         k_think<<<nArenas, 128, 0, stream>>>(kp);
         (*launches)++;
         if (cudaGetLastError() != cudaSuccess) return fail(PS_E_CUDA, "k_think launch failed");

@@ -23,6 +23,22 @@ PS_HD Xf sweepXf(const Trig& tr, const Sweep& s, float alpha) {
     T.py = py - (T.s * s.lcx + T.c * s.lcy);
     return T;
 }
+// How a body's transform depends on the sweep parameter: a static body never moves (the wall), a puck only translates
+// (its rotation is never read: circle fixtures centred on the body origin, localCenter = 0), a robot needs the full
+// Sweep.getTransform with MathUtils sin / cos. The shortcuts return exactly what the full formula would.
+enum { SWEEP_STATIC = 0, SWEEP_TRANSLATE = 1, SWEEP_FULL = 2 };
+PS_HD Xf sweepXfKind(const Trig& tr, const Sweep& s, int kind, const Xf& staticXf, float alpha) {
+    if (kind == SWEEP_STATIC) return staticXf;
+    if (kind == SWEEP_TRANSLATE) {
+        Xf T;
+        T.px = (1.0f - alpha) * s.c0x + alpha * s.cx;
+        T.py = (1.0f - alpha) * s.c0y + alpha * s.cy;
+        T.c = 1.0f;
+        T.s = 0.0f;
+        return T;
+    }
+    return sweepXf(tr, s, alpha);
+}
 PS_HD void sweepNormalize(Sweep& s) {
     float d = kTwoPi * floorf(s.a0 / kTwoPi);
     s.a0 -= d;
@@ -334,9 +350,9 @@ PS_HD float sepEvaluate(const SepFn& f, int indexA, int indexB, const DProxy& pA
     }
 }
 
-// TimeOfImpact.timeOfImpact. One side may be static: pass staticB != 0 with its (fixed) transform in xfStatic to
-// skip the sweep interpolation of that side (a static body's sweep is constant, so the result is identical).
-PS_HDN void timeOfImpact(int& outState, float& outT, const Trig& tr, const DProxy& pA, Sweep sweepA, const DProxy& pB, Sweep sweepB, float tMax) {
+// TimeOfImpact.timeOfImpact; kindA / kindB select the exact transform shortcut of each side (see sweepXfKind).
+PS_HDN void timeOfImpact(int& outState, float& outT, const Trig& tr, const DProxy& pA, Sweep sweepA, int kindA, const DProxy& pB, Sweep sweepB, int kindB,
+                         const Xf& staticXf, float tMax) {
     outState = TOI_UNKNOWN;
     outT = tMax;
     sweepNormalize(sweepA);
@@ -350,7 +366,12 @@ PS_HDN void timeOfImpact(int& outState, float& outT, const Trig& tr, const DProx
     cache.count = 0;
     cache.metric = 0.0f;
     for (;;) {
-        Xf xfA = sweepXf(tr, sweepA, t1), xfB = sweepXf(tr, sweepB, t1);
+        // One outer iteration is a pure function of (t1, simplex cache). If it ends without a verdict and leaves both
+        // unchanged (the push-back loop ran out of its 8 rounds), every later iteration repeats it bit for bit until the
+        // iteration cap turns the result into FAILED at t1 -- so that verdict can be returned right away.
+        float t1In = t1;
+        SimplexCache cacheIn = cache;
+        Xf xfA = sweepXfKind(tr, sweepA, kindA, staticXf, t1), xfB = sweepXfKind(tr, sweepB, kindB, staticXf, t1);
         float d = gjkDistance(cache, pA, xfA, pB, xfB);
         if (d <= 0.0f) {
             outState = TOI_OVERLAPPED;
@@ -369,7 +390,7 @@ PS_HDN void timeOfImpact(int& outState, float& outT, const Trig& tr, const DProx
         int pushBackIter = 0;
         for (;;) {
             int indexA, indexB;
-            Xf xfA2 = sweepXf(tr, sweepA, t2), xfB2 = sweepXf(tr, sweepB, t2);
+            Xf xfA2 = sweepXfKind(tr, sweepA, kindA, staticXf, t2), xfB2 = sweepXfKind(tr, sweepB, kindB, staticXf, t2);
             float s2 = sepFindMin(fcn, indexA, indexB, pA, xfA2, pB, xfB2);
             if (s2 > target + tolerance) {
                 outState = TOI_SEPARATED;
@@ -381,7 +402,7 @@ PS_HDN void timeOfImpact(int& outState, float& outT, const Trig& tr, const DProx
                 t1 = t2;
                 break;
             }
-            Xf xfA1 = sweepXf(tr, sweepA, t1), xfB1 = sweepXf(tr, sweepB, t1);
+            Xf xfA1 = sweepXfKind(tr, sweepA, kindA, staticXf, t1), xfB1 = sweepXfKind(tr, sweepB, kindB, staticXf, t1);
             float s1 = sepEvaluate(fcn, indexA, indexB, pA, xfA1, pB, xfB1);
             if (s1 < target - tolerance) {
                 outState = TOI_FAILED;
@@ -401,7 +422,7 @@ PS_HDN void timeOfImpact(int& outState, float& outT, const Trig& tr, const DProx
                 float t;
                 if (rootIterCount & 1) t = a1 + (target - s1) * (a2 - a1) / (s2 - s1);
                 else t = 0.5f * (a1 + a2);
-                Xf xfAt = sweepXf(tr, sweepA, t), xfBt = sweepXf(tr, sweepB, t);
+                Xf xfAt = sweepXfKind(tr, sweepA, kindA, staticXf, t), xfBt = sweepXfKind(tr, sweepB, kindB, staticXf, t);
                 float s = sepEvaluate(fcn, indexA, indexB, pA, xfAt, pB, xfBt);
                 if (fabsf(s - target) < tolerance) {
                     t2 = t;
@@ -426,6 +447,15 @@ PS_HDN void timeOfImpact(int& outState, float& outT, const Trig& tr, const DProx
             outState = TOI_FAILED;
             outT = t1;
             break;
+        }
+        if (iter > 1 && t1 == t1In && cache.count == cacheIn.count && cache.metric == cacheIn.metric) {
+            bool same = true;
+            for (int i = 0; i < cache.count; ++i) same = same && cache.indexA[i] == cacheIn.indexA[i] && cache.indexB[i] == cacheIn.indexB[i];
+            if (same) {
+                outState = TOI_FAILED;
+                outT = t1;
+                break;
+            }
         }
     }
 }

@@ -16,7 +16,7 @@ EXPORTS = [
     "ps_last_error", "ps_abi_version", "ps_struct_size", "ps_config_defaults", "ps_create", "ps_destroy", "ps_load_calibration",
     "ps_reset", "ps_set_state", "ps_get_state", "ps_step", "ps_sync", "ps_sense", "ps_step_external",
     "ps_get_observations", "ps_compute_stats", "ps_stats_device_ptr", "ps_get_dims", "ps_get_step_stats",
-    "ps_kernel_launches", "ps_stream",
+    "ps_profile", "ps_get_kernel_ms", "ps_kernel_launches", "ps_stream",
 ]
 
 
@@ -66,6 +66,8 @@ def load_library(path=None):
     L.ps_stats_device_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     L.ps_get_dims.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 5
     L.ps_get_step_stats.argtypes = [C.c_void_p, C.c_void_p]
+    L.ps_profile.argtypes = [C.c_void_p, C.c_int]
+    L.ps_get_kernel_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.ps_kernel_launches.restype = C.c_int64
     L.ps_kernel_launches.argtypes = [C.c_void_p]
     L.ps_stream.restype = C.c_void_p
@@ -178,6 +180,17 @@ class Engine:
         out = np.zeros((self.cfg.n_arenas, 8), np.int32)
         self._check(self.L.ps_get_step_stats(self.h, out.ctypes.data))
         return out
+
+    def profile(self, enable=True):
+        self._check(self.L.ps_profile(self.h, 1 if enable else 0))
+
+    def kernel_ms(self):
+        """({'sense': ms, 'think': ms, 'physics': ms, 'other': ms}, counts) accumulated since the last call."""
+        ms = np.zeros(8, np.float64)
+        cnt = np.zeros(8, np.int64)
+        self._check(self.L.ps_get_kernel_ms(self.h, ms.ctypes.data, cnt.ctypes.data))
+        names = ("sense", "think", "physics", "other", "phys_pre", "phys_islands", "phys_post", "unused")
+        return dict(zip(names, ms.tolist())), dict(zip(names, cnt.tolist()))
 
     @property
     def kernel_launches(self):

@@ -5,6 +5,8 @@
 #define PS_HOST_EMU 1
 #include "../../puckswarm_b200/csrc/ps_host.hpp"
 #include "../../puckswarm_b200/csrc/ps_sense.cuh"
+#include "../../puckswarm_b200/csrc/ps_pipeline.cuh"
+#include <cstdlib>
 #include <memory>
 
 using namespace ps;
@@ -110,7 +112,26 @@ int emu_step(Emu* e, int nTicks) {
                 tq[r] = rs[r].cmd_torque;
             }
             as->update_count++;
-            worldStep(ctx, e->env, e->wk, st, fwd.data(), tq.data());
+            if (getenv("PS_EMU_FUSED")) {
+                worldStep(ctx, e->env, e->wk, st, fwd.data(), tq.data());
+            } else {
+                // the three-stage pipeline of the engine, run for one arena: pre, every queued island, post
+                std::vector<unsigned> qe((size_t)3 * e->hs.phys.d.NB);
+                int qc[4] = {0, 0, 0, 0};
+                IslandQueue q = {qe.data(), qc, e->hs.phys.d.NB};
+                physPre(ctx, e->env, e->wk, st, fwd.data(), tq.data(), q, 0);
+                for (int bucket = 0; bucket < 3; bucket++)
+                    for (int i = 0; i < qc[bucket]; i++) {
+                        int k = (int)(qe[(size_t)bucket * q.cap + i] % (unsigned)e->hs.phys.d.NB);
+                        IslandCursor cur;
+                        islandBegin(cur, e->wk, k);
+                        int iters = 0;
+                        while (islandStep(e->env, e->wk, st, cur, &iters)) {
+                        }
+                        if (iters > e->wk.stats[0]) e->wk.stats[0] = iters;
+                    }
+                physPost(ctx, e->env, e->wk, st);
+            }
             for (int i = 0; i < 8; i++) e->lastStats[a * 8 + i] = e->wk.stats[i];
             e->lastOrder[a].clear();
             for (int i = 0; i < e->wk.islandStart[e->wk.counters[1]]; i++) {

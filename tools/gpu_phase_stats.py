@@ -1,0 +1,26 @@
+"""Phase breakdown of k_physics from its in-kernel cycle counters (diagnostic; run on the GPU box)."""
+import sys, time
+sys.path.insert(0, '.')
+import numpy as np
+from puckswarm_b200 import abi, engine
+A = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+cfg = abi.config_defaults(n_arenas=A, n_robots=16, n_pucks=200)
+e = engine.Engine(cfg)
+e.reset(np.arange(A))
+e.step(45)
+e.profile(True); e.kernel_ms()
+t = time.time(); e.step(30); dt = time.time() - t
+kms, kc = e.kernel_ms()
+print('robot-steps/s', A * 16 * 30 / dt, 'kernel ms', kms, kc)
+st = e.step_stats().astype(np.float64)
+names = ['pos_iters', 'toi', 'islands', 'toi_rounds', 'toi_evals', 'syncfix', 'findnew', 'toi_cycles']
+for i, n in enumerate(names):
+    scale = 16 if i >= 5 else 1
+    print('%-12s mean %12.1f  max %12.1f' % (n, st[:, i].mean() * scale, st[:, i].max() * scale))
+tot = st[:, 3:8].sum(axis=1) * 16
+print('cycles per arena-tick mean', tot.mean(), 'max', tot.max())
+
+w = np.argsort(-st[:, 7])[:8]
+print('worst TOI arenas: idx, rounds, evals, toi_events, Mcycles')
+for a in w:
+    print(int(a), int(st[a, 3]), int(st[a, 4]), int(st[a, 1]), st[a, 7] * 16 / 1e6)
