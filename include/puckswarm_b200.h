@@ -266,6 +266,9 @@ int ps_get_dims(ps_handle h, int32_t* n_bodies, int32_t* n_proxies, int32_t* max
 /* Diagnostics of the last World.step of every arena, [n_arenas][8] int32: 0 = max position iterations of an island,
  * 1 = TOI events, 2 = islands with contacts. */
 int ps_get_step_stats(ps_handle h, int32_t* out);
+/* Diagnostics of the last sense of every robot, [n_arenas][n_robots][8] int32: cycles / 16 of 0 = candidate cull, 1 = camera,
+ * 2 = occupancy + blob labelling, 3 = pucks + clusters, 4 = cluster filter; 5 = perceived pucks, 6 = candidate bodies, 7 = blobs. */
+int ps_get_sense_stats(ps_handle h, int32_t* out);
 /* Per-kernel device time, measured with CUDA events on the engine's stream while enabled. ps_get_kernel_ms waits for the
  * stream, returns the accumulated milliseconds and launch counts of 0 = sense, 1 = think, 2 = physics (World.step, all stages),
  * 3 = other, 4 / 5 / 6 = the three stages of World.step (collide + islands, island workers, broad phase + TOI), 7 unused,

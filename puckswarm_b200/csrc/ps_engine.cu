@@ -668,6 +668,15 @@ int ps_get_step_stats(ps_handle h, int32_t* out /* [n_arenas][8] */) {
     return PS_OK;
 }
 
+int ps_get_sense_stats(ps_handle h, int32_t* out /* [n_arenas][n_robots][8] */) {
+    if (!h || !out) return setError(PS_E_INVALID, "null argument");
+    if (!h->sd.ready) return setError(PS_E_NOCALIB, "ps_load_calibration has not been called");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemcpyAsync(out, h->sd.kp.senseDbg, h->sd.nRobotsTotal * 8 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return PS_OK;
+}
+
 int ps_profile(ps_handle h, int enable) {
     if (!h) return setError(PS_E_INVALID, "null handle");
     h->profiling = enable != 0;

@@ -1213,7 +1213,7 @@ PS_HD void physStore(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const Arena
 
 // Phase clock for the per-step diagnostics (stats[3..7]: cycles of collide, islands, velocity, position, broadphase + TOI)
 PS_HD long long phaseClock() {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(PS_PHASE_CLOCKS)
     return clock64();
 #else
     return 0;

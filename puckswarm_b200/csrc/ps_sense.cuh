@@ -19,8 +19,11 @@
 
 namespace ps {
 
-static constexpr int kMaxBlobs = 192;
+static constexpr int kMaxBlobs = 128;
 static constexpr int kMaxCand = 256;
+static constexpr int kMaxColPix = 4096;   // puck-coloured pixels listed per robot; beyond that the blob passes scan the whole rectangle
+static constexpr int kMaxBins = 64;       // robot-frame grid over the pixel footprint
+static constexpr int kBinCap = 30;        // candidates per bin; an overfull bin falls back to the full candidate list
 static constexpr int kSectors = PS_N_SECTORS;
 
 // Static tables derived from the camera calibration (built on the host by SenseSetup)
@@ -31,6 +34,9 @@ struct SenseTables {
     const float* aYr;
     const uint16_t* aRect;       // [nActive] index in the bounding rectangle, x-major: (x - x0) * RH + (y - y0)
     const uint16_t* aImg;        // [nActive] index in the camera image, y * imgW + x
+    const uint8_t* aBin;         // [nActive] bin of the pixel's ground point in the robot-frame grid below
+    float binSize;               // bins of binSize x binSize cm over [bbXmin, bbXmax] x [bbYmin, bbYmax]
+    int binsX, binsY;
     int x0, y0, RW, RH;          // bounding rectangle of the active pixels
     const int16_t* calibIdx;     // [imgW * imgH] at x * imgH + y: row in cXr / cYr / cFlags, -1 = uncalibrated
     const float* cXr;
@@ -70,6 +76,21 @@ struct ObsPtrs {
     float* pose;          // [A][R][3]
 };
 
+// What the camera stage hands to the local-map stage, per robot
+struct BlobRec {
+    uint8_t x0, x1, y0, y1;   // bounding box in image pixels
+    uint16_t area;
+    uint16_t seed;            // x * imgH + y of BlobFinder's seed pixel, 0xFFFF = the blob never seeds (only row imgH-1)
+    uint8_t colour, pad0, pad1, pad2;
+};
+struct SenseHead {
+    int nBlobs, leftSum, rightSum, overflow;
+};
+struct SenseOut {
+    SenseHead* head;
+    BlobRec* blobs;           // [kMaxBlobs]
+};
+
 // Per-CTA scratch of senseRobot
 struct SenseWork {
     uint8_t* img;         // [RW * RH] SensedType per rectangle pixel
@@ -77,6 +98,16 @@ struct SenseWork {
     float* candX;         // [kMaxCand]
     float* candY;
     int* candBody;        // body index
+    float* candLx;        // Fixture.m_aabb of the sensed fixture
+    float* candLy;
+    float* candUx;
+    float* candUy;
+    float* candC;         // robots: cos / sin of the body transform
+    float* candS;
+    float* candRx;        // candidate origin in the sensing robot's frame (binning only, never decides a pixel)
+    float* candRy;
+    uint8_t* binCount;    // [kMaxBins]
+    uint8_t* binList;     // [kMaxBins][kBinCap] candidate indices in body-list order
     int* blobArea;        // [kMaxBlobs]
     int* blobX0;
     int* blobX1;
@@ -85,17 +116,30 @@ struct SenseWork {
     int* blobSeed;
     int* blobRoot;
     int* blobOrder;
+    uint16_t* colList;    // [kMaxColPix] (x - x0) << 8 | (y - y0) of the pixels that show a puck colour
     int* counters;        // [8]
+    int* phase;           // [8] diagnostics: cycles / 16 of the phases of senseRobot (thread 0)
 };
 PS_HD SenseWork carveSense(const SenseTables& t, Carver& cv) {
     SenseWork w;
     int n = t.RW * t.RH;
     w.counters = (int*)cv.take(8 * sizeof(int));
+    w.phase = (int*)cv.take(8 * sizeof(int));
     w.img = (uint8_t*)cv.take((size_t)n);
     w.parent = (int*)cv.take((size_t)n * sizeof(int));
     w.candX = (float*)cv.take(kMaxCand * sizeof(float));
     w.candY = (float*)cv.take(kMaxCand * sizeof(float));
     w.candBody = (int*)cv.take(kMaxCand * sizeof(int));
+    w.candLx = (float*)cv.take(kMaxCand * sizeof(float));
+    w.candLy = (float*)cv.take(kMaxCand * sizeof(float));
+    w.candUx = (float*)cv.take(kMaxCand * sizeof(float));
+    w.candUy = (float*)cv.take(kMaxCand * sizeof(float));
+    w.candC = (float*)cv.take(kMaxCand * sizeof(float));
+    w.candS = (float*)cv.take(kMaxCand * sizeof(float));
+    w.candRx = (float*)cv.take(kMaxCand * sizeof(float));
+    w.candRy = (float*)cv.take(kMaxCand * sizeof(float));
+    w.binCount = (uint8_t*)cv.take(kMaxBins);
+    w.binList = (uint8_t*)cv.take(kMaxBins * kBinCap);
     w.blobArea = (int*)cv.take(kMaxBlobs * sizeof(int));
     w.blobX0 = (int*)cv.take(kMaxBlobs * sizeof(int));
     w.blobX1 = (int*)cv.take(kMaxBlobs * sizeof(int));
@@ -104,6 +148,7 @@ PS_HD SenseWork carveSense(const SenseTables& t, Carver& cv) {
     w.blobSeed = (int*)cv.take(kMaxBlobs * sizeof(int));
     w.blobRoot = (int*)cv.take(kMaxBlobs * sizeof(int));
     w.blobOrder = (int*)cv.take(kMaxBlobs * sizeof(int));
+    w.colList = (uint16_t*)cv.take(kMaxColPix * sizeof(uint16_t));
     return w;
 }
 
@@ -115,11 +160,23 @@ PS_HD int ufFind(const int* parent, int i) {
     }
     return i;
 }
+// find with path halving; parents only ever decrease, so atomicMin keeps concurrent updates consistent
+template <class Ctx>
+PS_HD int ufFindHalve(Ctx& ctx, int* parent, int i) {
+    int p = parent[i];
+    while (p != i) {
+        int gp = parent[p];
+        if (gp != p) ctx.atomicMinI(&parent[i], gp);
+        i = p;
+        p = gp;
+    }
+    return i;
+}
 template <class Ctx>
 PS_HD void ufUnion(Ctx& ctx, int* parent, int a, int b) {
     for (;;) {
-        a = ufFind(parent, a);
-        b = ufFind(parent, b);
+        a = ufFindHalve(ctx, parent, a);
+        b = ufFindHalve(ctx, parent, b);
         if (a == b) return;
         if (a < b) {
             int t = a;
@@ -146,7 +203,7 @@ PS_HD bool lmReachable(float vx, float vy) {
 // senseRobot: camera image -> occupancy grid -> blobs -> perceived pucks -> clusters -> filtered clusters
 template <class Ctx>
 PS_HD void senseRobot(Ctx& ctx, const PhysEnv& e, const SenseTables& T, const SenseCfg& sc, const SenseWork& wk, const ArenaState& st,
-                      int robot, ps_robot_state* rstate, uint8_t* camOut, uint8_t* occOut, ps_localmap* lmOut, float* poseOut) {
+                      int robot, uint8_t* camOut, uint8_t* occOut, float* poseOut, const SenseOut& out) {
     const Dims& d = e.cfg.d;
     const Scene& scene = *e.scene;
     int NB = d.NB;
@@ -160,14 +217,12 @@ PS_HD void senseRobot(Ctx& ctx, const PhysEnv& e, const SenseTables& T, const Se
         poseOut[2] = st.body[2 * NB + self];
     }
     int nRect = T.RW * T.RH;
-    PS_FOR(i, nRect) {
-        wk.img[i] = PS_T_HIDDEN;
-        wk.parent[i] = i;
-    }
+    PS_FOR(i, nRect) wk.img[i] = PS_T_HIDDEN;
     if (camOut) {
         PS_FOR(i, T.imgW * T.imgH) camOut[i] = PS_T_HIDDEN;
     }
     ctx.sync();
+    long long tc0 = phaseClock();
     // ---- candidate bodies in world body-list order (newest first): robots R-1..0, pucks P-1..0
     // conservative cull: a body can only be sensed by a pixel within 22 cm (+ a margin) of its origin
     int nCand = 0;
@@ -179,7 +234,7 @@ PS_HD void senseRobot(Ctx& ctx, const PhysEnv& e, const SenseTables& T, const Se
             int li = base + ctx.tid();          // position in the body list
             bool take = false;
             int b = -1;
-            float bx = 0, by = 0;
+            float bx = 0, by = 0, bc = 1.0f, bs = 0.0f, rlx = 0, rly = 0;
             if (li < NB) {
                 b = NB - 1 - li;
                 if (b != self) {
@@ -187,6 +242,8 @@ PS_HD void senseRobot(Ctx& ctx, const PhysEnv& e, const SenseTables& T, const Se
                         Xf o = makeXf(e.trig, st.body[0 * NB + b], st.body[1 * NB + b], st.body[2 * NB + b], scene.robot.lcx, scene.robot.lcy);
                         bx = o.px;
                         by = o.py;
+                        bc = o.c;
+                        bs = o.s;
                     } else {
                         bx = st.body[0 * NB + b];
                         by = st.body[1 * NB + b];
@@ -195,6 +252,8 @@ PS_HD void senseRobot(Ctx& ctx, const PhysEnv& e, const SenseTables& T, const Se
                     if (dx * dx + dy * dy <= reachSq) {
                         // robot-frame bounding box of the pixel footprint
                         float lx = dx * xf.c + dy * xf.s, ly = -dx * xf.s + dy * xf.c;
+                        rlx = lx;
+                        rly = ly;
                         take = lx >= T.bbXmin - 22.5f && lx <= T.bbXmax + 22.5f && ly >= T.bbYmin - 22.5f && ly <= T.bbYmax + 22.5f;
                     }
                 }
@@ -206,8 +265,17 @@ PS_HD void senseRobot(Ctx& ctx, const PhysEnv& e, const SenseTables& T, const Se
                     wk.candX[pos] = bx;
                     wk.candY[pos] = by;
                     wk.candBody[pos] = b;
+                    Aabb bb = loadAabb(st.senseAabb, NB, b);
+                    wk.candLx[pos] = bb.lx;
+                    wk.candLy[pos] = bb.ly;
+                    wk.candUx[pos] = bb.ux;
+                    wk.candUy[pos] = bb.uy;
+                    wk.candC[pos] = bc;
+                    wk.candS[pos] = bs;
+                    wk.candRx[pos] = rlx;
+                    wk.candRy[pos] = rly;
                 } else {
-                    lmOut->overflow = 1;
+                    wk.counters[5] = 1;
                 }
             }
             nCand += total;
@@ -215,6 +283,26 @@ PS_HD void senseRobot(Ctx& ctx, const PhysEnv& e, const SenseTables& T, const Se
         if (nCand > kMaxCand) nCand = kMaxCand;
     }
     ctx.sync();
+    // ---- bin the candidates over the pixel footprint (robot frame). A bin lists, in body-list order, every candidate
+    // whose sensed fixture could contain a point of the bin: pucks reach 2.1 cm from their origin, robot hulls < 13 cm.
+    // The lists only prune the search; every listed candidate still goes through the reference's exact tests.
+    int nBins = T.binsX * T.binsY;
+    PS_FOR(bin, nBins) {
+        int bxi = bin / T.binsY, byi = bin - bxi * T.binsY;
+        float x0 = T.bbXmin + bxi * T.binSize, y0 = T.bbYmin + byi * T.binSize;
+        float x1 = x0 + T.binSize, y1 = y0 + T.binSize;
+        int n = 0;
+        for (int c = 0; c < nCand; ++c) {
+            float rad = wk.candBody[c] < d.P ? 2.25f : 13.0f;
+            float cx = wk.candRx[c], cy = wk.candRy[c];
+            if (cx + rad < x0 || cx - rad > x1 || cy + rad < y0 || cy - rad > y1) continue;
+            if (n < kBinCap) wk.binList[bin * kBinCap + n] = (uint8_t)c;
+            ++n;
+        }
+        wk.binCount[bin] = (uint8_t)(n > kBinCap ? 255 : n);
+    }
+    ctx.sync();
+    long long tc1 = phaseClock();
     // ---- PointSensor.pointSense for every active pixel
     const Shape& hull = scene.shapes[kShapeRobot0];
     float innerR = scene.shapes[kShapePuck0 + 1].radius;
@@ -226,13 +314,17 @@ PS_HD void senseRobot(Ctx& ctx, const PhysEnv& e, const SenseTables& T, const Se
             type = PS_T_WALL;
         } else {
             bool hit = false;
-            for (int c = 0; c < nCand && !hit; ++c) {
+            int bin = T.aBin[k];
+            int nList = wk.binCount[bin];
+            bool full = nList == 255;   // overfull bin: walk the whole candidate list
+            if (full) nList = nCand;
+            for (int li = 0; li < nList && !hit; ++li) {
+                int c = full ? li : (int)wk.binList[bin * kBinCap + li];
                 V2 bp = mk(wk.candX[c], wk.candY[c]);
                 float d2 = distSq(bp, g);
                 if (d2 > 484.0f) continue;
                 int b = wk.candBody[c];
-                Aabb bb = loadAabb(st.senseAabb, NB, b);
-                if (!(g.x <= bb.ux && g.x >= bb.lx && g.y <= bb.uy && g.y >= bb.ly)) continue;
+                if (!(g.x <= wk.candUx[c] && g.x >= wk.candLx[c] && g.y <= wk.candUy[c] && g.y >= wk.candLy[c])) continue;
                 if (b < d.P) {
                     // inner disc, centre = body origin: (g - c).(g - c) <= r * r, same magnitude as d2
                     if (d2 <= innerRSq) {
@@ -240,7 +332,11 @@ PS_HD void senseRobot(Ctx& ctx, const PhysEnv& e, const SenseTables& T, const Se
                         hit = true;
                     }
                 } else {
-                    Xf o = makeXf(e.trig, st.body[0 * NB + b], st.body[1 * NB + b], st.body[2 * NB + b], scene.robot.lcx, scene.robot.lcy);
+                    Xf o;
+                    o.px = bp.x;
+                    o.py = bp.y;
+                    o.c = wk.candC[c];
+                    o.s = wk.candS[c];
                     if (shapeTestPoint(hull, o, g)) {
                         type = PS_T_ROBOT;
                         hit = true;
@@ -265,6 +361,7 @@ PS_HD void senseRobot(Ctx& ctx, const PhysEnv& e, const SenseTables& T, const Se
         if (camOut) camOut[T.aImg[k]] = (uint8_t)type;
     }
     ctx.sync();
+    long long tc2 = phaseClock();
     // ---- LocalMap.extractOccupancy: every cell takes the type of its last writer in (x, y) scan order
     int nCells = T.occW * T.occH;
     int leftSum = 0, rightSum = 0;
@@ -274,298 +371,359 @@ PS_HD void senseRobot(Ctx& ctx, const PhysEnv& e, const SenseTables& T, const Se
         occOut[c] = t;
         if (t == PS_T_ROBOT || t == PS_T_WALL) {
             // LocalMap.getFreeerSide tallies (src/localmap/LocalMap.java:565-587)
-            if (c / T.occH < T.occW / 2) leftSum++;
+            if (c < (T.occW / 2) * T.occH) leftSum++;
             else rightSum++;
         }
     }
     if (leftSum) ctx.atomicAddI(&wk.counters[1], leftSum);
     if (rightSum) ctx.atomicAddI(&wk.counters[2], rightSum);
-    // ---- BlobFinder: 8-connected components of equal puck colour; union with the 4 already-scanned neighbours
-    PS_FOR(i, nRect) {
-        uint8_t t = wk.img[i];
-        if (t >= PS_MAX_COLOURS) continue;
-        int x = i / T.RH, y = i - x * T.RH;
-        if (y > 0 && wk.img[i - 1] == t) ufUnion(ctx, wk.parent, i, i - 1);
-        if (x > 0) {
-            int j = i - T.RH;
-            if (wk.img[j] == t) ufUnion(ctx, wk.parent, i, j);
-            if (y > 0 && wk.img[j - 1] == t) ufUnion(ctx, wk.parent, i, j - 1);
-            if (y + 1 < T.RH && wk.img[j + 1] == t) ufUnion(ctx, wk.parent, i, j + 1);
-        }
-    }
     ctx.sync();
-    // roots -> blob slots (in root order), then flatten every pixel to "-(slot + 1)" via its root
-    int nBlobs = 0;
-    {
-        int nRound = roundUpThreads(ctx, nRect);
-        for (int base = 0; base < nRound; base += ctx.nthreads()) {
-            int i = base + ctx.tid();
-            bool root = i < nRect && wk.img[i] < PS_MAX_COLOURS && wk.parent[i] == i;
-            int total;
-            int pos = nBlobs + ctx.exscanFlag(root, total);
-            if (root) {
-                if (pos < kMaxBlobs) {
-                    wk.blobRoot[pos] = i;
-                    wk.blobArea[pos] = 0;
-                    wk.blobX0[pos] = 1 << 30;
-                    wk.blobX1[pos] = -(1 << 30);
-                    wk.blobY0[pos] = 1 << 30;
-                    wk.blobY1[pos] = -(1 << 30);
-                    wk.blobSeed[pos] = 1 << 30;
-                } else {
-                    lmOut->overflow = 1;
-                }
+    long long tq0 = phaseClock();
+    // ---- BlobFinder: 8-connected components of equal puck colour.
+    // (1) vertical runs: the rectangle is stored column-major, so a run of equal colour inside a column is a contiguous
+    //     index range; one thread per column labels every pixel with the index of its run's first pixel and appends the
+    //     coloured pixels to a list, so that the passes below touch those pixels only.
+    PS_FOR(cx, T.RW) {
+        int base = cx * T.RH;
+        int start = base;
+        uint8_t prev = 255;
+        for (int y = 0; y < T.RH; ++y) {
+            uint8_t t = wk.img[base + y];
+            if (t < PS_MAX_COLOURS) {
+                if (t != prev) start = base + y;
+                wk.parent[base + y] = start;
+                int pos = ctx.atomicAddI(&wk.counters[6], 1);
+                if (pos < kMaxColPix) wk.colList[pos] = (uint16_t)((cx << 8) | y);
             }
-            nBlobs += total;
+            prev = t < PS_MAX_COLOURS ? t : (uint8_t)255;
         }
-        if (nBlobs > kMaxBlobs) nBlobs = kMaxBlobs;
     }
     ctx.sync();
-    PS_FOR(i, nRect) {
-        if (wk.img[i] < PS_MAX_COLOURS && wk.parent[i] != i) wk.parent[i] = ufFind(wk.parent, i);
+    int nCol = wk.counters[6];
+    bool listed = nCol <= kMaxColPix;        // otherwise fall back to scanning the rectangle
+    int nScan = listed ? nCol : nRect;
+    // decode entry n of the scan into (i, x, y); returns false for pixels without a puck colour
+#define PS_COLPIX(n, i, x, y)                                   \
+    int i, x, y;                                                \
+    if (listed) {                                               \
+        int xy_ = wk.colList[n];                                \
+        x = xy_ >> 8;                                           \
+        y = xy_ & 255;                                          \
+        i = x * T.RH + y;                                       \
+    } else {                                                    \
+        i = n;                                                  \
+        x = i / T.RH;                                           \
+        y = i - x * T.RH;                                       \
+        if (wk.img[i] >= PS_MAX_COLOURS) continue;              \
+    }
+    // (2) merge runs of neighbouring columns (8-connectivity: rows y-1, y, y+1 of column x-1). A pair of runs is united
+    //     once, by the first pixel at which the two runs face each other.
+    PS_FOR(n, nScan) {
+        PS_COLPIX(n, i, x, y)
+        uint8_t t = wk.img[i];
+        if (x == 0) continue;
+        bool upSame = y > 0 && wk.img[i - 1] == t;
+        int j0 = i - T.RH;
+        for (int dy = -1; dy <= 1; ++dy) {
+            int yy = y + dy;
+            if (yy < 0 || yy >= T.RH) continue;
+            if (wk.img[j0 + dy] != t) continue;
+            // the pixel above already joined these two runs if it saw the neighbour run one row up
+            if (upSame && yy - 1 >= 0 && wk.img[j0 + dy - 1] == t) continue;
+            ufUnion(ctx, wk.parent, wk.parent[i], wk.parent[j0 + dy]);
+        }
+    }
+    ctx.sync();
+    // roots -> blob slots (any order: the local-map stage sorts the blobs by colour and seed)
+    PS_FOR(n, nScan) {
+        PS_COLPIX(n, i, x, y)
+        if (wk.parent[i] == i) {
+            int pos = ctx.atomicAddI(&wk.counters[0], 1);
+            if (pos < kMaxBlobs) {
+                wk.blobRoot[pos] = i;
+                wk.blobArea[pos] = 0;
+                wk.blobX0[pos] = 1 << 30;
+                wk.blobX1[pos] = -(1 << 30);
+                wk.blobY0[pos] = 1 << 30;
+                wk.blobY1[pos] = -(1 << 30);
+                wk.blobSeed[pos] = 1 << 30;
+            } else {
+                wk.counters[5] = 1;
+            }
+        }
+    }
+    ctx.sync();
+    int nBlobs = wk.counters[0];
+    if (nBlobs > kMaxBlobs) nBlobs = kMaxBlobs;
+    // flatten every pixel to its root, then to "-(slot + 1)" via the root
+    PS_FOR(n, nScan) {
+        PS_COLPIX(n, i, x, y)
+        if (wk.parent[i] != i) wk.parent[i] = ufFind(wk.parent, wk.parent[i]);
     }
     ctx.sync();
     PS_FOR(s, nBlobs) wk.parent[wk.blobRoot[s]] = -(s + 1);
     ctx.sync();
-    PS_FOR(i, nRect) {
-        if (wk.img[i] >= PS_MAX_COLOURS) continue;
+    PS_FOR(n, nScan) {
+        PS_COLPIX(n, i, x, y)
         int p = wk.parent[i];
         if (p >= 0) p = wk.parent[p];
         int s = -p - 1;
         if (s < 0 || s >= kMaxBlobs) continue;   // blob table overflow
-        int x = T.x0 + i / T.RH, y = T.y0 + i % T.RH;
+        int px = T.x0 + x, py = T.y0 + y;
         ctx.atomicAddI(&wk.blobArea[s], 1);
-        ctx.atomicMinI(&wk.blobX0[s], x);
-        ctx.atomicMaxI(&wk.blobX1[s], x);
-        ctx.atomicMinI(&wk.blobY0[s], y);
-        ctx.atomicMaxI(&wk.blobY1[s], y);
+        ctx.atomicMinI(&wk.blobX0[s], px);
+        ctx.atomicMaxI(&wk.blobX1[s], px);
+        ctx.atomicMinI(&wk.blobY0[s], py);
+        ctx.atomicMaxI(&wk.blobY1[s], py);
         // BlobFinder seeds only at y < yMax (= imgH - 1); the seed fixes the blob's position in the list
-        if (y < T.imgH - 1) ctx.atomicMinI(&wk.blobSeed[s], (x * T.imgH + y));
+        if (py < T.imgH - 1) ctx.atomicMinI(&wk.blobSeed[s], (px * T.imgH + py));
+    }
+#undef PS_COLPIX
+    ctx.sync();
+    long long tc3 = phaseClock();
+    // ---- blob table for the local-map stage (one record per blob, in root order; sorted by (colour, seed) there)
+    PS_FOR(b, nBlobs) {
+        BlobRec r;
+        r.x0 = (uint8_t)wk.blobX0[b];
+        r.x1 = (uint8_t)wk.blobX1[b];
+        r.y0 = (uint8_t)wk.blobY0[b];
+        r.y1 = (uint8_t)wk.blobY1[b];
+        r.area = (uint16_t)wk.blobArea[b];
+        r.seed = wk.blobSeed[b] == (1 << 30) ? (uint16_t)0xFFFF : (uint16_t)wk.blobSeed[b];
+        r.colour = wk.img[wk.blobRoot[b]];
+        r.pad0 = r.pad1 = r.pad2 = 0;
+        out.blobs[b] = r;
     }
     ctx.sync();
-    // ---- the rest is short and sequential: one thread walks the blob list like LocalMap does
     if (ctx.tid() == 0) {
-        ps_localmap& lm = *lmOut;
-        // blob list order: by colour, then by seed (scan order); blobs that never seed are not found at all
-        int nb = 0;
-        for (int s = 0; s < nBlobs; ++s)
-            if (wk.blobSeed[s] != (1 << 30)) wk.blobOrder[nb++] = s;
-        for (int i = 1; i < nb; ++i) {
-            int v = wk.blobOrder[i];
-            int kv = wk.img[wk.blobRoot[v]], sv = wk.blobSeed[v];
-            int j = i - 1;
-            while (j >= 0) {
-                int u = wk.blobOrder[j];
-                int ku = wk.img[wk.blobRoot[u]], su = wk.blobSeed[u];
-                if (ku < kv || (ku == kv && su < sv)) break;
-                wk.blobOrder[j + 1] = u;
-                --j;
-            }
-            wk.blobOrder[j + 1] = v;
+        out.head->nBlobs = nBlobs;
+        out.head->leftSum = wk.counters[1];
+        out.head->rightSum = wk.counters[2];
+        out.head->overflow = wk.counters[5];
+        long long tc4 = phaseClock();
+        wk.phase[0] = (int)((tc1 - tc0) >> 4);   // candidates
+        wk.phase[1] = (int)((tc2 - tc1) >> 4);   // camera
+        wk.phase[2] = (int)((tc3 - tc2) >> 4);   // occupancy + blob labelling
+        wk.phase[3] = (int)((tc4 - tc3) >> 4);   // blob table
+        wk.phase[3] = (int)((tq0 - tc2) >> 4);   // occupancy
+        wk.phase[4] = 0;
+        wk.phase[5] = wk.counters[6];            // puck-coloured pixels
+        wk.phase[6] = nCand;
+        wk.phase[7] = nBlobs;
+    }
+    ctx.sync();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// LocalMap.update after the blobs are known: extractPucks (:236-317), extractClusters (:326-370), carriedCluster,
+// filterClusters (:375-437). Short, branchy and sequential -- executed by ONE thread per robot, all robots of the
+// batch in parallel (the working arrays are thread-local).
+PS_HD void localMapFromBlobs(const SenseTables& T, const SenseCfg& sc, const SenseHead& head, const BlobRec* blobs, const uint8_t* occ,
+                             ps_robot_state* rstate, ps_localmap& lm) {
+    int nBlobs = head.nBlobs;
+    if (nBlobs > kMaxBlobs) nBlobs = kMaxBlobs;
+    // blob list order: by colour, then by seed (scan order); blobs that never seed are not found at all
+    uint8_t order[kMaxBlobs];
+    int16_t calib[kMaxBlobs];     // calibration row of the blob centre, -1 = uncalibrated
+    uint8_t alive[kMaxBlobs];
+    int nb = 0;
+    for (int s = 0; s < nBlobs; ++s)
+        if (blobs[s].seed != 0xFFFF) order[nb++] = (uint8_t)s;
+    for (int i = 1; i < nb; ++i) {
+        int v = order[i];
+        int kv = blobs[v].colour, sv = blobs[v].seed;
+        int j = i - 1;
+        while (j >= 0) {
+            int u = order[j];
+            int ku = blobs[u].colour, su = blobs[u].seed;
+            if (ku < kv || (ku == kv && su < sv)) break;
+            order[j + 1] = (uint8_t)u;
+            --j;
         }
-        bool lastCarrying = rstate->lm_carrying != 0;
-        bool carrying = false;
-        int carriedType = PS_T_NOTHING;
-        float carriedX = 0, carriedY = 0;
-        int nP = 0;
-        int overflow = 0;
-        int bi = 0;
-        for (int k = 0; k < PS_MAX_COLOURS; ++k) {
-            int lo = bi;
-            while (bi < nb && wk.img[wk.blobRoot[wk.blobOrder[bi]]] == k) ++bi;
-            int hi = bi;
-            if (lo == hi) continue;
-            // blobArea doubles as the "alive" flag: area <= 0 means removed. blobX0 is reused for the calibration row.
-            int holeBlob = -1;
+        order[j + 1] = (uint8_t)v;
+    }
+    bool lastCarrying = rstate->lm_carrying != 0;
+    bool carrying = false;
+    int carriedType = PS_T_NOTHING;
+    float carriedX = 0, carriedY = 0;
+    int nP = 0;
+    int overflow = head.overflow;
+    int bi = 0;
+    for (int k = 0; k < PS_MAX_COLOURS; ++k) {
+        int lo = bi;
+        while (bi < nb && blobs[order[bi]].colour == k) ++bi;
+        int hi = bi;
+        if (lo == hi) continue;
+        int holeBlob = -1;
+        for (int q = lo; q < hi; ++q) {
+            int s = order[q];
+            int cx = ((int)blobs[s].x0 + (int)blobs[s].x1) / 2, cy = ((int)blobs[s].y0 + (int)blobs[s].y1) / 2;
+            int ci = T.calibIdx[cx * T.imgH + cy];
+            calib[s] = (int16_t)ci;
+            alive[s] = ci >= 0 ? 1 : 0;   // blobs centred outside the calibrated area are dropped
+            if (ci < 0) continue;
+            if (T.cFlags[ci] & 2)
+                if (holeBlob < 0 || blobs[s].area > blobs[holeBlob].area) holeBlob = s;
+        }
+        for (int q = lo; q < hi; ++q) {
+            int s = order[q];
+            if (!alive[s] || s == holeBlob) continue;
+            if (T.cFlags[calib[s]] & 2) alive[s] = 0;
+        }
+        if (holeBlob >= 0) {
+            int hc = calib[holeBlob];
+            float hx = T.cXr[hc], hy = T.cYr[hc];
+            const float INNER_WIDTH = 2 / 3.0f * 6.3f;
             for (int q = lo; q < hi; ++q) {
-                int s = wk.blobOrder[q];
-                int cx = (wk.blobX0[s] + wk.blobX1[s]) / 2, cy = (wk.blobY0[s] + wk.blobY1[s]) / 2;
-                int ci = T.calibIdx[cx * T.imgH + cy];
-                wk.blobX0[s] = ci;
-                if (ci < 0) {
-                    wk.blobArea[s] = -wk.blobArea[s];   // outside the calibrated area
+                int s = order[q];
+                if (!alive[s] || s == holeBlob) continue;
+                float dx = T.cXr[calib[s]] - hx, dy = T.cYr[calib[s]] - hy;
+                if (sqrt((double)(dx * dx + dy * dy)) < (double)INNER_WIDTH) alive[s] = 0;
+            }
+            float holeFraction = blobs[holeBlob].area / (float)T.nHolePixels;
+            if ((lastCarrying && holeFraction > sc.carryLo) || (!carrying && holeFraction > sc.carryHi)) {
+                carrying = true;
+                carriedType = k;
+                carriedX = hx;
+                carriedY = hy;
+            }
+        }
+        for (int q = lo; q < hi; ++q) {
+            int s = order[q];
+            if (!alive[s]) continue;
+            if (nP >= PS_MAX_LM_PUCKS) {
+                overflow = 1;
+                break;
+            }
+            lm.puck_x[nP] = T.cXr[calib[s]];
+            lm.puck_y[nP] = T.cYr[calib[s]];
+            lm.puck_type[nP] = (uint8_t)k;
+            ++nP;
+        }
+    }
+    lm.n_pucks = nP;
+    lm.carrying = carrying ? 1 : 0;
+    lm.carried_type = carriedType;
+    lm.carried_x = carrying ? carriedX : 0.0f;
+    lm.carried_y = carrying ? carriedY : 0.0f;
+    rstate->lm_carrying = carrying ? 1 : 0;
+    // ---- LocalMap.extractClusters per colour: graph over distinct positions, edge if distance < threshold,
+    // connected components in first-vertex order, members in insertion order
+    // rep[p] = first puck of the same colour at the bitwise-same position (the graph vertex p stands for)
+    uint8_t rep[PS_MAX_LM_PUCKS];
+    for (int p = 0; p < nP; ++p) {
+        rep[p] = (uint8_t)p;
+        for (int q = 0; q < p; ++q)
+            if (lm.puck_type[q] == lm.puck_type[p] && lm.puck_x[q] == lm.puck_x[p] && lm.puck_y[q] == lm.puck_y[p]) {
+                rep[p] = (uint8_t)q;
+                break;
+            }
+        lm.puck_cluster[p] = 255;
+        lm.puck_degree[p] = 0;
+    }
+    for (int p = 0; p < nP; ++p) {
+        if (rep[p] != p) continue;
+        int deg = 0;
+        for (int q = 0; q < nP; ++q) {
+            if (q == p || rep[q] != q || lm.puck_type[q] != lm.puck_type[p]) continue;
+            if (dist(mk(lm.puck_x[p], lm.puck_y[p]), mk(lm.puck_x[q], lm.puck_y[q])) < sc.clusterThreshold) ++deg;
+        }
+        lm.puck_degree[p] = (uint8_t)(deg > 250 ? 250 : deg);
+    }
+    int nC = 0;
+    for (int p = 0; p < nP; ++p) {
+        if (rep[p] != p || lm.puck_cluster[p] != 255) continue;
+        int cid = nC++;
+        lm.puck_cluster[p] = (uint8_t)cid;
+        // grow the component until no vertex is added (discovery order is irrelevant: members are listed in insertion order)
+        bool grew = true;
+        while (grew) {
+            grew = false;
+            for (int a = 0; a < nP; ++a) {
+                if (lm.puck_cluster[a] != cid || rep[a] != a) continue;
+                for (int q = 0; q < nP; ++q) {
+                    if (lm.puck_cluster[q] != 255 || rep[q] != q || lm.puck_type[q] != lm.puck_type[a]) continue;
+                    if (dist(mk(lm.puck_x[a], lm.puck_y[a]), mk(lm.puck_x[q], lm.puck_y[q])) < sc.clusterThreshold) {
+                        lm.puck_cluster[q] = (uint8_t)cid;
+                        grew = true;
+                    }
+                }
+            }
+        }
+        float sx = 0.0f, sy = 0.0f;
+        int size = 0;
+        for (int a = 0; a < nP; ++a)
+            if (lm.puck_cluster[a] == cid && rep[a] == a) {
+                sx += lm.puck_x[a];
+                sy += lm.puck_y[a];
+                ++size;
+            }
+        float inv = 1.0f / size;
+        lm.cluster_x[cid] = sx * inv;
+        lm.cluster_y[cid] = sy * inv;
+        lm.cluster_type[cid] = lm.puck_type[p];
+        lm.cluster_size[cid] = (uint8_t)size;
+        lm.cluster_kept[cid] = 1;
+    }
+    // duplicates share the cluster and degree of their first occurrence
+    for (int p = 0; p < nP; ++p)
+        if (rep[p] != p) {
+            lm.puck_cluster[p] = lm.puck_cluster[rep[p]];
+            lm.puck_degree[p] = lm.puck_degree[rep[p]];
+        }
+    lm.n_clusters = nC;
+    // carriedCluster: the last cluster (any colour) holding a vertex equal to carriedV
+    int carriedCluster = -1;
+    if (carrying)
+        for (int p = 0; p < nP; ++p)
+            if (lm.puck_x[p] == carriedX && lm.puck_y[p] == carriedY && (int)lm.puck_cluster[p] > carriedCluster) carriedCluster = lm.puck_cluster[p];
+    lm.carried_cluster = carriedCluster;
+    lm.overflow = overflow;
+    // ---- LocalMap.filterClusters, part 1: clusters with a puck closer than 10 cm to a ROBOT cell
+    int nCells = T.occW * T.occH;
+    if (nP > 0) {
+        for (int c = 0; c < nCells; ++c) {
+            // four cells per load while the pointer is word-aligned; most words hold no ROBOT cell at all
+            if ((c & 3) == 0 && c + 4 <= nCells && (((size_t)(occ + c)) & 3) == 0) {
+                uint32_t wv = *(const uint32_t*)(occ + c);
+                uint32_t xr = wv ^ (0x01010101u * (uint32_t)PS_T_ROBOT);
+                if (((xr - 0x01010101u) & ~xr & 0x80808080u) == 0) {   // no byte equals ROBOT
+                    c += 3;
                     continue;
                 }
-                if (T.cFlags[ci] & 2)
-                    if (holeBlob < 0 || wk.blobArea[s] > wk.blobArea[holeBlob]) holeBlob = s;
             }
-            for (int q = lo; q < hi; ++q) {
-                int s = wk.blobOrder[q];
-                if (wk.blobArea[s] <= 0 || s == holeBlob) continue;
-                if (T.cFlags[wk.blobX0[s]] & 2) wk.blobArea[s] = -wk.blobArea[s];
-            }
-            if (holeBlob >= 0) {
-                int hc = wk.blobX0[holeBlob];
-                float hx = T.cXr[hc], hy = T.cYr[hc];
-                const float INNER_WIDTH = 2 / 3.0f * 6.3f;
-                for (int q = lo; q < hi; ++q) {
-                    int s = wk.blobOrder[q];
-                    if (wk.blobArea[s] <= 0 || s == holeBlob) continue;
-                    float dx = T.cXr[wk.blobX0[s]] - hx, dy = T.cYr[wk.blobX0[s]] - hy;
-                    if (sqrt((double)(dx * dx + dy * dy)) < (double)INNER_WIDTH) wk.blobArea[s] = -wk.blobArea[s];
-                }
-                float holeFraction = wk.blobArea[holeBlob] / (float)T.nHolePixels;
-                if ((lastCarrying && holeFraction > sc.carryLo) || (!carrying && holeFraction > sc.carryHi)) {
-                    carrying = true;
-                    carriedType = k;
-                    carriedX = hx;
-                    carriedY = hy;
-                }
-            }
-            for (int q = lo; q < hi; ++q) {
-                int s = wk.blobOrder[q];
-                if (wk.blobArea[s] <= 0) continue;
-                if (nP >= PS_MAX_LM_PUCKS) {
-                    overflow = 1;
-                    break;
-                }
-                lm.puck_x[nP] = T.cXr[wk.blobX0[s]];
-                lm.puck_y[nP] = T.cYr[wk.blobX0[s]];
-                lm.puck_type[nP] = (uint8_t)k;
-                ++nP;
-            }
-        }
-        lm.n_pucks = nP;
-        lm.carrying = carrying ? 1 : 0;
-        lm.carried_type = carriedType;
-        lm.carried_x = carrying ? carriedX : 0.0f;
-        lm.carried_y = carrying ? carriedY : 0.0f;
-        rstate->lm_carrying = carrying ? 1 : 0;
-        // ---- LocalMap.extractClusters per colour: graph over distinct positions, edge if distance < threshold,
-        // connected components in first-vertex order, members in insertion order
-        int nC = 0;
-        for (int p = 0; p < nP; ++p) {
-            lm.puck_cluster[p] = 255;
-            lm.puck_degree[p] = 0;
-        }
-        for (int p = 0; p < nP; ++p) {
-            // a puck whose position repeats an earlier one of its colour is the same graph vertex
-            int rep = p;
-            for (int q = 0; q < p; ++q)
-                if (lm.puck_type[q] == lm.puck_type[p] && lm.puck_x[q] == lm.puck_x[p] && lm.puck_y[q] == lm.puck_y[p] &&
-                    !(lm.puck_x[q] != lm.puck_x[q])) {
-                    rep = q;
-                    break;
-                }
-            if (rep != p) {
-                lm.puck_degree[p] = 254;   // marker: duplicate of an earlier vertex (fixed up below)
-                continue;
-            }
-            int deg = 0;
-            for (int q = 0; q < nP; ++q) {
-                if (q == p || lm.puck_type[q] != lm.puck_type[p]) continue;
-                if (lm.puck_x[q] == lm.puck_x[p] && lm.puck_y[q] == lm.puck_y[p]) continue;   // same vertex
-                // count distinct neighbours only once: skip duplicates of an earlier q
-                bool dup = false;
-                for (int r2 = 0; r2 < q; ++r2)
-                    if (lm.puck_type[r2] == lm.puck_type[q] && lm.puck_x[r2] == lm.puck_x[q] && lm.puck_y[r2] == lm.puck_y[q]) {
-                        dup = true;
-                        break;
-                    }
-                if (dup) continue;
-                if (dist(mk(lm.puck_x[p], lm.puck_y[p]), mk(lm.puck_x[q], lm.puck_y[q])) < sc.clusterThreshold) ++deg;
-            }
-            lm.puck_degree[p] = (uint8_t)(deg > 250 ? 250 : deg);
-        }
-        // components: BFS from every unassigned vertex in insertion order (queue kept in cluster_kept scratch)
-        for (int p = 0; p < nP; ++p) {
-            if (lm.puck_degree[p] == 254 || lm.puck_cluster[p] != 255) continue;
-            int cid = nC++;
-            lm.puck_cluster[p] = (uint8_t)cid;
-            // frontier expansion until no vertex is added (order of discovery does not matter: members are listed in insertion order)
-            bool grew = true;
-            while (grew) {
-                grew = false;
-                for (int a = 0; a < nP; ++a) {
-                    if (lm.puck_cluster[a] != cid) continue;
-                    for (int q = 0; q < nP; ++q) {
-                        if (lm.puck_cluster[q] != 255 || lm.puck_degree[q] == 254 || lm.puck_type[q] != lm.puck_type[a]) continue;
-                        if (dist(mk(lm.puck_x[a], lm.puck_y[a]), mk(lm.puck_x[q], lm.puck_y[q])) < sc.clusterThreshold) {
-                            lm.puck_cluster[q] = (uint8_t)cid;
-                            grew = true;
-                        }
-                    }
-                }
-            }
-            float sx = 0.0f, sy = 0.0f;
-            int size = 0;
-            for (int a = 0; a < nP; ++a)
-                if (lm.puck_cluster[a] == cid) {
-                    sx += lm.puck_x[a];
-                    sy += lm.puck_y[a];
-                    ++size;
-                }
-            float inv = 1.0f / size;
-            lm.cluster_x[cid] = sx * inv;
-            lm.cluster_y[cid] = sy * inv;
-            lm.cluster_type[cid] = lm.puck_type[p];
-            lm.cluster_size[cid] = (uint8_t)size;
-            lm.cluster_kept[cid] = 1;
-        }
-        // duplicates share the cluster and degree of their first occurrence
-        for (int p = 0; p < nP; ++p)
-            if (lm.puck_degree[p] == 254)
-                for (int q = 0; q < p; ++q)
-                    if (lm.puck_type[q] == lm.puck_type[p] && lm.puck_x[q] == lm.puck_x[p] && lm.puck_y[q] == lm.puck_y[p]) {
-                        lm.puck_cluster[p] = lm.puck_cluster[q];
-                        lm.puck_degree[p] = lm.puck_degree[q];
-                        break;
-                    }
-        lm.n_clusters = nC;
-        // carriedCluster: the last cluster (any colour) holding a vertex equal to carriedV
-        int carriedCluster = -1;
-        if (carrying)
-            for (int p = 0; p < nP; ++p)
-                if (lm.puck_x[p] == carriedX && lm.puck_y[p] == carriedY && (int)lm.puck_cluster[p] > carriedCluster) carriedCluster = lm.puck_cluster[p];
-        lm.carried_cluster = carriedCluster;
-        lm.overflow = overflow;
-        wk.counters[3] = nP;
-        wk.counters[4] = nC;
-    }
-    ctx.sync();
-    // ---- LocalMap.filterClusters, part 1: clusters with a puck closer than 10 cm to a ROBOT cell
-    {
-        int nP = wk.counters[3];
-        PS_FOR(c, nCells) {
-            if (occOut[c] != PS_T_ROBOT) continue;
+            if (occ[c] != PS_T_ROBOT) continue;
             int i = c / T.occH, j = c - i * T.occH;
             V2 robotV = mk(1.0f * j, T.maxYr - 1.0f * i);
             for (int p = 0; p < nP; ++p)
-                if (distSq(robotV, mk(lmOut->puck_x[p], lmOut->puck_y[p])) < 100.0f) lmOut->cluster_kept[lmOut->puck_cluster[p]] = 0;
+                if (distSq(robotV, mk(lm.puck_x[p], lm.puck_y[p])) < 100.0f) lm.cluster_kept[lm.puck_cluster[p]] = 0;
         }
     }
-    ctx.sync();
     // part 2: sequential pass over the surviving clusters
-    if (ctx.tid() == 0) {
-        ps_localmap& lm = *lmOut;
-        int nP = lm.n_pucks, nC = lm.n_clusters;
-        bool carrying = lm.carrying != 0;
-        for (int c = 0; c < nC; ++c) {
-            if (!lm.cluster_kept[c]) continue;
-            bool remove = false;
-            if (carrying && c == lm.carried_cluster) remove = true;
-            else if (!lmReachable(lm.cluster_x[c], lm.cluster_y[c])) remove = true;
-            else if (carrying && lm.carried_type != lm.cluster_type[c]) remove = true;
-            else if (carrying) {
-                for (int o = 0; o < nC && !remove; ++o) {
-                    if (o == c || !lm.cluster_kept[o] || lm.cluster_type[o] == lm.cluster_type[c]) continue;
-                    for (int p = 0; p < nP && !remove; ++p) {
-                        if (lm.puck_cluster[p] != c) continue;
-                        for (int q = 0; q < nP; ++q)
-                            if (lm.puck_cluster[q] == o &&
-                                dist(mk(lm.puck_x[p], lm.puck_y[p]), mk(lm.puck_x[q], lm.puck_y[q])) < sc.clusterThreshold) {
-                                remove = true;
-                                break;
-                            }
-                    }
+    for (int c = 0; c < nC; ++c) {
+        if (!lm.cluster_kept[c]) continue;
+        bool remove = false;
+        if (carrying && c == lm.carried_cluster) remove = true;
+        else if (!lmReachable(lm.cluster_x[c], lm.cluster_y[c])) remove = true;
+        else if (carrying && lm.carried_type != lm.cluster_type[c]) remove = true;
+        else if (carrying) {
+            for (int o = 0; o < nC && !remove; ++o) {
+                if (o == c || !lm.cluster_kept[o] || lm.cluster_type[o] == lm.cluster_type[c]) continue;
+                for (int p = 0; p < nP && !remove; ++p) {
+                    if (lm.puck_cluster[p] != c) continue;
+                    for (int q = 0; q < nP; ++q)
+                        if (lm.puck_cluster[q] == o &&
+                            dist(mk(lm.puck_x[p], lm.puck_y[p]), mk(lm.puck_x[q], lm.puck_y[q])) < sc.clusterThreshold) {
+                            remove = true;
+                            break;
+                        }
                 }
             }
-            if (remove) lm.cluster_kept[c] = 0;
         }
-        lm.left_sum = wk.counters[1];
-        lm.right_sum = wk.counters[2];
+        if (remove) lm.cluster_kept[c] = 0;
     }
-    ctx.sync();
+    lm.left_sum = head.leftSum;
+    lm.right_sum = head.rightSum;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1198,7 +1356,7 @@ struct SenseSetup {
     std::vector<float> aXr, aYr, cXr, cYr, vfhBeta, vfhMag;
     std::vector<uint16_t> aRect, aImg;
     std::vector<int16_t> calibIdx, cellSrc, vfhStartK, vfhStopK;
-    std::vector<uint8_t> cFlags, vfhSide;
+    std::vector<uint8_t> cFlags, vfhSide, aBin;
 
     bool build(const ps_config& cfg, const float* XrYr, const uint16_t* xy, const uint8_t* flags, int n, int w, int h) {
         ready = false;
@@ -1284,6 +1442,20 @@ struct SenseSetup {
             }
         T.nActive = (int)aXr.size();
         T.maxRange = std::sqrt(maxRangeSq);
+        // robot-frame grid over the footprint of the active pixels (candidate binning of the camera stage)
+        T.binSize = 8.0f;
+        for (;;) {
+            T.binsX = (int)std::floor((T.bbXmax - T.bbXmin) / T.binSize) + 1;
+            T.binsY = (int)std::floor((T.bbYmax - T.bbYmin) / T.binSize) + 1;
+            if (T.binsX * T.binsY <= kMaxBins) break;
+            T.binSize *= 1.25f;
+        }
+        aBin.resize(aXr.size());
+        for (size_t k = 0; k < aXr.size(); k++) {
+            int bxi = std::min(T.binsX - 1, std::max(0, (int)std::floor((aXr[k] - T.bbXmin) / T.binSize)));
+            int byi = std::min(T.binsY - 1, std::max(0, (int)std::floor((aYr[k] - T.bbYmin) / T.binSize)));
+            aBin[k] = (uint8_t)(bxi * T.binsY + byi);
+        }
         // LocalMap.extractOccupancy (:210-229): writers are the calibrated, non-hole pixels whose type is not HIDDEN,
         // i.e. statically the non-gripperBody ones; the last writer in (x outer, y inner) order wins.
         cellSrc.assign((size_t)occW * occH, -1);
@@ -1332,6 +1504,7 @@ struct SenseSetup {
         T.aYr = aYr.data();
         T.aRect = aRect.data();
         T.aImg = aImg.data();
+        T.aBin = aBin.data();
         T.calibIdx = calibIdx.data();
         T.cXr = cXr.data();
         T.cYr = cYr.data();
@@ -1394,10 +1567,15 @@ inline void emuSenseArena(HostCtx& ctx, const PhysEnv& e, const SenseSetup& ss, 
     o.lm.assign(R, ps_localmap());
     o.pose.assign((size_t)R * 3, 0);
     if (camera) o.camera.assign((size_t)R * ss.T.imgW * ss.T.imgH, 0);
+    std::vector<BlobRec> blobs(kMaxBlobs);
     for (int r = 0; r < R; r++) {
         std::memset(&o.lm[r], 0, sizeof(ps_localmap));
-        senseRobot(ctx, e, ss.T, ss.sc, sw, st, r, rs + r, camera ? o.camera.data() + (size_t)r * ss.T.imgW * ss.T.imgH : nullptr,
-                   o.occ.data() + (size_t)r * nCells, &o.lm[r], o.pose.data() + 3 * r);
+        SenseHead head;
+        SenseOut so = {&head, blobs.data()};
+        // camera stage (one CTA per robot on the GPU), then the local-map stage (one thread per robot)
+        senseRobot(ctx, e, ss.T, ss.sc, sw, st, r, camera ? o.camera.data() + (size_t)r * ss.T.imgW * ss.T.imgH : nullptr,
+                   o.occ.data() + (size_t)r * nCells, o.pose.data() + 3 * r, so);
+        localMapFromBlobs(ss.T, ss.sc, head, blobs.data(), o.occ.data() + (size_t)r * nCells, rs + r, o.lm[r]);
     }
 }
 template <class Ctx>

@@ -15,6 +15,9 @@ struct SenseKParams {
     ObsPtrs obs;
     int nArenas;
     size_t fastCap;
+    int* senseDbg;     // [nRobots][8] phase diagnostics of the last sense
+    SenseHead* senseHead;   // [nRobots] camera stage -> local-map stage
+    BlobRec* blobs;         // [nRobots][kMaxBlobs]
 };
 
 extern __shared__ __align__(16) char g_senseSmem[];
@@ -37,9 +40,29 @@ __global__ void __launch_bounds__(256) k_sense(SenseKParams p) {
     size_t ri = (size_t)a * R + r;
     int nCells = p.T.occW * p.T.occH;
     uint8_t* cam = p.obs.camera ? p.obs.camera + ri * (size_t)(p.T.imgW * p.T.imgH) : nullptr;
-    if (threadIdx.x == 0) p.obs.lm[ri].overflow = 0;
+    __shared__ float poseS[4];
+    SenseOut so;
+    so.head = p.senseHead + ri;
+    so.blobs = p.blobs + ri * kMaxBlobs;
+    senseRobot(ctx, p.env, p.T, p.sc, wk, st, r, cam, p.obs.occupancy + ri * nCells, poseS, so);
     __syncthreads();
-    senseRobot(ctx, p.env, p.T, p.sc, wk, st, r, p.sp.robot + ri, cam, p.obs.occupancy + ri * nCells, p.obs.lm + ri, p.obs.pose + ri * 3);
+    if (threadIdx.x < 3) p.obs.pose[ri * 3 + threadIdx.x] = poseS[threadIdx.x];
+    if (threadIdx.x < 8) p.senseDbg[ri * 8 + threadIdx.x] = wk.phase[threadIdx.x];
+}
+
+// LocalMap stage: one thread per robot over the whole batch
+__global__ void __launch_bounds__(128) k_localmap(SenseKParams p, int nRobots) {
+    int ri = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ri >= nRobots) return;
+    int nCells = p.T.occW * p.T.occH;
+    ps_localmap lm;
+    uint32_t* w = (uint32_t*)&lm;
+    for (int i = 0; i < (int)(sizeof(ps_localmap) / 4); ++i) w[i] = 0u;
+    long long t0 = clock64();
+    localMapFromBlobs(p.T, p.sc, p.senseHead[ri], p.blobs + (size_t)ri * kMaxBlobs, p.obs.occupancy + (size_t)ri * nCells, p.sp.robot + ri, lm);
+    long long t1 = clock64();
+    uint32_t* g = (uint32_t*)(p.obs.lm + ri);
+    for (int i = 0; i < (int)(sizeof(ps_localmap) / 4); ++i) g[i] = w[i];
 }
 
 // one CTA per arena: controllers in robot order (shared java.util.Random)
@@ -195,6 +218,7 @@ struct SenseDevice {
         UP(aYr, aYr)
         UP(aRect, aRect)
         UP(aImg, aImg)
+        UP(aBin, aBin)
         UP(calibIdx, calibIdx)
         UP(cXr, cXr)
         UP(cYr, cYr)
@@ -212,6 +236,9 @@ struct SenseDevice {
         if ((rc = alloc(&kp.obs.occupancy, nRobotsTotal * nCells)) != PS_OK) return rc;
         if ((rc = alloc(&kp.obs.lm, nRobotsTotal)) != PS_OK) return rc;
         if ((rc = alloc(&kp.obs.pose, nRobotsTotal * 3)) != PS_OK) return rc;
+        if ((rc = alloc(&kp.senseDbg, nRobotsTotal * 8)) != PS_OK) return rc;
+        if ((rc = alloc(&kp.senseHead, nRobotsTotal)) != PS_OK) return rc;
+        if ((rc = alloc(&kp.blobs, nRobotsTotal * kMaxBlobs)) != PS_OK) return rc;
         // the camera image is an optional observation: kept only when the whole batch fits in 256 MiB
         haveCamera = nRobotsTotal * nImg <= ((size_t)256 << 20);
         kp.obs.camera = nullptr;
@@ -239,8 +266,9 @@ struct SenseDevice {
         SenseKParams p = kp;
         if (!camera) p.obs.camera = nullptr;
         k_sense<<<(unsigned)nRobotsTotal, threads, senseSmem, stream>>>(p);
-        (*launches)++;
-        if (cudaGetLastError() != cudaSuccess) return fail(PS_E_CUDA, "k_sense launch failed");
+        k_localmap<<<(unsigned)((nRobotsTotal + 127) / 128), 128, 0, stream>>>(p, (int)nRobotsTotal);
+        (*launches) += 2;
+        if (cudaGetLastError() != cudaSuccess) return fail(PS_E_CUDA, "k_sense / k_localmap launch failed");
         return PS_OK;
     }
     int launchThink(int nArenas, cudaStream_t stream, int64_t* launches) {

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libpuckswarm_b200.so")
 EXPORTS = [
     "ps_last_error", "ps_abi_version", "ps_struct_size", "ps_config_defaults", "ps_create", "ps_destroy", "ps_load_calibration",
     "ps_reset", "ps_set_state", "ps_get_state", "ps_step", "ps_sync", "ps_sense", "ps_step_external",
-    "ps_get_observations", "ps_compute_stats", "ps_stats_device_ptr", "ps_get_dims", "ps_get_step_stats",
+    "ps_get_observations", "ps_compute_stats", "ps_stats_device_ptr", "ps_get_dims", "ps_get_step_stats", "ps_get_sense_stats",
     "ps_profile", "ps_get_kernel_ms", "ps_kernel_launches", "ps_stream",
 ]
 
@@ -66,6 +66,7 @@ def load_library(path=None):
     L.ps_stats_device_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     L.ps_get_dims.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 5
     L.ps_get_step_stats.argtypes = [C.c_void_p, C.c_void_p]
+    L.ps_get_sense_stats.argtypes = [C.c_void_p, C.c_void_p]
     L.ps_profile.argtypes = [C.c_void_p, C.c_int]
     L.ps_get_kernel_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.ps_kernel_launches.restype = C.c_int64
@@ -179,6 +180,11 @@ class Engine:
     def step_stats(self):
         out = np.zeros((self.cfg.n_arenas, 8), np.int32)
         self._check(self.L.ps_get_step_stats(self.h, out.ctypes.data))
+        return out
+
+    def sense_stats(self):
+        out = np.zeros((self.cfg.n_arenas, self.cfg.n_robots, 8), np.int32)
+        self._check(self.L.ps_get_sense_stats(self.h, out.ctypes.data))
         return out
 
     def profile(self, enable=True):

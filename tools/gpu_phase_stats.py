@@ -24,3 +24,8 @@ w = np.argsort(-st[:, 7])[:8]
 print('worst TOI arenas: idx, rounds, evals, toi_events, Mcycles')
 for a in w:
     print(int(a), int(st[a, 3]), int(st[a, 4]), int(st[a, 1]), st[a, 7] * 16 / 1e6)
+
+ss = e.sense_stats().reshape(-1, 8).astype(np.float64)
+for i, n in enumerate(['candidates', 'camera', 'occ+ccl', 'occupancy', 'union', 'runs', 'n_unions', 'n_blobs']):
+    sc = 16 if i < 6 else 1
+    print('sense %-15s mean %10.1f max %10.1f' % (n, ss[:, i].mean() * sc, ss[:, i].max() * sc))
