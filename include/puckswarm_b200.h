@@ -247,6 +247,9 @@ int ps_get_state(ps_handle h, ps_state_view* v);
  * handle's stream; ps_sync waits and reports device-side capacity errors. */
 int ps_step(ps_handle h, int n_ticks);
 int ps_sync(ps_handle h);
+/* Order the handle's main stream (ps_stream) after everything ps_step has queued so far, without waiting on the host:
+ * an event recorded on that stream afterwards completes when the steps have. */
+int ps_join(ps_handle h);
 
 /* Host-controller path: run sense (camera + local map) for every robot now. */
 int ps_sense(ps_handle h);
@@ -269,12 +272,16 @@ int ps_get_step_stats(ps_handle h, int32_t* out);
 /* Diagnostics of the last sense of every robot, [n_arenas][n_robots][8] int32: cycles / 16 of 0 = candidate cull, 1 = camera,
  * 2 = occupancy + blob labelling, 3 = pucks + clusters, 4 = cluster filter; 5 = perceived pucks, 6 = candidate bodies, 7 = blobs. */
 int ps_get_sense_stats(ps_handle h, int32_t* out);
+/* Diagnostics: islands with >= 3 contacts solved since the last reset, as an 8 x 8 histogram [position-iteration bucket][contact
+ * bucket]; iterations <=1, <=3, <=6, <=12, <=25, <=50, <100, 100; contacts <=3, <=5, <=8, <=12, <=16, <=32, <=64, >64. */
+int ps_get_island_hist(ps_handle h, int64_t* out /*[64]*/, int reset);
 /* Per-kernel device time, measured with CUDA events on the engine's stream while enabled. ps_get_kernel_ms waits for the
  * stream, returns the accumulated milliseconds and launch counts of 0 = sense, 1 = think, 2 = physics (World.step, all stages),
  * 3 = other, 4 / 5 / 6 = the three stages of World.step (collide + islands, island workers, broad phase + TOI), 7 unused,
  * and clears the accumulators. */
 int ps_profile(ps_handle h, int enable);
 int ps_get_kernel_ms(ps_handle h, double* ms /*[8]*/, int64_t* counts /*[8]*/);
+int     ps_num_groups(ps_handle h);        /* arena groups (each runs its kernel sequence on its own stream) */
 int64_t ps_kernel_launches(ps_handle h);   /* kernels launched by this handle so far */
 void*   ps_stream(ps_handle h);            /* the cudaStream_t the engine launches on */
 

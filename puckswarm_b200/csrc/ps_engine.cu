@@ -33,6 +33,7 @@ struct KParams {
     size_t slowStride;
     size_t fastCap;          // dynamic shared memory handed to the carver
     int nArenas;
+    int a0;                  // first arena of the launch (arena groups run on their own streams)
     int stepInterval;
     const int64_t* seeds;
     const ps_robot_state* robotInit;
@@ -43,6 +44,7 @@ struct KParams {
     char* arenaScratch;
     size_t arenaScratchStride;
     IslandQueue queue;
+    unsigned long long* islandHist;   // [8][8] diagnostics: islands by (position iterations bucket, contact count bucket)
 };
 
 extern __shared__ __align__(16) char g_smem[];
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(128) k_phys_pre(KParams p) {
     __shared__ int scan[40];
     CtaCtx ctx;
     ctx.scanScratch = scan;
-    int a = blockIdx.x;
+    int a = p.a0 + blockIdx.x;
     int R = p.env.cfg.d.R;
     PhysWork wk = arenaWork(p, a);
     ArenaState st = arenaState(p.sp, p.env.cfg, a);
@@ -119,13 +121,11 @@ __global__ void __launch_bounds__(128) k_phys_pre(KParams p) {
     physPre(ctx, p.env, wk, st, wk.fx, wk.fy, p.queue, a);
 }
 
-// stage B1: islands with >= 3 contacts (queue buckets 0 and 1): one warp per island, staged in shared memory
+// stage B1: islands too large for a lane slot (queue bucket 0): one warp per island, staged in shared memory
 __global__ void __launch_bounds__(128) k_island_warp(KParams p) {
     extern __shared__ __align__(16) char smem[];
     WarpSlot* slot = reinterpret_cast<WarpSlot*>(smem) + (threadIdx.x >> 5);
-    int cap = p.queue.cap;
-    int n0 = min(p.queue.counts[0], cap), n1 = min(p.queue.counts[1], cap);
-    int total = n0 + n1;
+    int total = min(p.queue.counts[0], p.queue.cap);
     unsigned NB = (unsigned)p.env.cfg.d.NB;
     int lane = threadIdx.x & 31;
     for (;;) {
@@ -133,11 +133,12 @@ __global__ void __launch_bounds__(128) k_island_warp(KParams p) {
         if (lane == 0) idx = atomicAdd(&p.queue.counts[3], 1);
         idx = __shfl_sync(0xFFFFFFFFu, idx, 0);
         if (idx >= total) break;
-        unsigned entry = idx < n0 ? p.queue.entries[idx] : p.queue.entries[(size_t)cap + (idx - n0)];
+        unsigned entry = p.queue.entries[idx];
         int a = (int)(entry / NB), k = (int)(entry % NB);
         PhysWork wk = arenaWork(p, a);
         ArenaState st = arenaState(p.sp, p.env.cfg, a);
         int iters = 0;
+        long long tw0 = clock64();
         bool ok = islandSolveWarp(p.env, wk, st, k, *slot, &iters);
         if (!ok && lane == 0) {
             // too large for a slot: lane 0 runs the island straight from HBM / L2
@@ -146,28 +147,62 @@ __global__ void __launch_bounds__(128) k_island_warp(KParams p) {
             while (islandStep(p.env, wk, st, cur, &iters)) {
             }
         }
-        if (lane == 0) atomicMax(&wk.stats[0], iters);
+        if (lane == 0) {
+            atomicMax(&wk.stats[0], iters);
+            // diagnostic: the slowest oversized island of the run: kilo-cycles << 32 | contacts << 20 | bodies << 10 | sweeps
+            unsigned long long kc = (unsigned long long)((clock64() - tw0) >> 10);
+            unsigned long long nc = (unsigned long long)(wk.islandStart[k + 1] - wk.islandStart[k]);
+            unsigned long long nb = (unsigned long long)(wk.islandBodyStart[k + 1] - wk.islandBodyStart[k]);
+            atomicMax(&p.islandHist[63], (kc << 32) | ((nc & 0xFFF) << 20) | ((nb & 0x3FF) << 10) | (unsigned long long)(iters & 0x3FF) | (ok ? 0ULL : (1ULL << 31)));
+        }
         __syncwarp();
     }
 }
 
-// stage B2: islands with 1-2 contacts (queue bucket 2): one lane per island
-__global__ void __launch_bounds__(128) k_island_lane(KParams p) {
+// stage B2: all other islands (queue bucket 1): one lane per island, 32 islands per warp, bodies in shared memory
+__global__ void __launch_bounds__(128) k_island_batch(KParams p, int bucket) {
+    extern __shared__ __align__(16) char smem[];
+    LaneSlots* slots = reinterpret_cast<LaneSlots*>(smem) + (threadIdx.x >> 5);
     int cap = p.queue.cap;
-    int total = min(p.queue.counts[2], cap);
+    int total = min(p.queue.counts[bucket], cap);
     unsigned NB = (unsigned)p.env.cfg.d.NB;
+    int lane = threadIdx.x & 31;
     int stride = gridDim.x * blockDim.x;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-        unsigned entry = p.queue.entries[(size_t)2 * cap + idx];
-        int a = (int)(entry / NB), k = (int)(entry % NB);
-        PhysWork wk = arenaWork(p, a);
-        ArenaState st = arenaState(p.sp, p.env.cfg, a);
-        IslandCursor cur;
-        islandBegin(cur, wk, k);
-        int iters = 0;
-        while (islandStep(p.env, wk, st, cur, &iters)) {
+    int rounds = (total + stride - 1) / stride;
+    for (int rnd = 0; rnd < rounds; ++rnd) {
+        int idx = rnd * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        bool active = idx < total;
+        PhysWork wk;
+        ArenaState st;
+        LaneIsland L;
+        int k = 0;
+        if (active) {
+            unsigned entry = p.queue.entries[(size_t)bucket * cap + idx];
+            int a = (int)(entry / NB);
+            k = (int)(entry % NB);
+            wk = arenaWork(p, a);
+            st = arenaState(p.sp, p.env.cfg, a);
+            islandStageLane(p.env, wk, k, *slots, lane, L);
+            L.integ.g = &wk;
         }
-        atomicMax(&wk.stats[0], iters);
+        int iters = 0;
+        // one state-machine step per trip for every lane that still has work; the warp re-converges at every trip
+        bool running = active;
+        while (__any_sync(0xFFFFFFFFu, running)) {
+            if (running) running = islandStepT(L.le, L.lw, st, L.c, &iters, L.integ);
+            __syncwarp();
+        }
+        if (active) {
+            islandFinishLane(p.env, wk, *slots, lane, L);
+            atomicMax(&wk.stats[0], iters);
+            int nc = wk.islandStart[k + 1] - wk.islandStart[k];
+            if (nc >= 3) {
+                int ib = iters <= 1 ? 0 : iters <= 3 ? 1 : iters <= 6 ? 2 : iters <= 12 ? 3 : iters <= 25 ? 4 : iters <= 50 ? 5 : iters < 100 ? 6 : 7;
+                int cb = nc <= 3 ? 0 : nc <= 5 ? 1 : nc <= 8 ? 2 : nc <= 12 ? 3 : nc <= 16 ? 4 : nc <= 32 ? 5 : nc <= 64 ? 6 : 7;
+                atomicAdd(&p.islandHist[ib * 8 + cb], 1ULL);
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -176,7 +211,7 @@ __global__ void __launch_bounds__(128) k_phys_post(KParams p) {
     __shared__ int scan[40];
     CtaCtx ctx;
     ctx.scanScratch = scan;
-    int a = blockIdx.x;
+    int a = p.a0 + blockIdx.x;
     PhysWork wk = arenaWork(p, a);
     ArenaState st = arenaState(p.sp, p.env.cfg, a);
     // the pair search reads every body's box union once per moved proxy: keep that table in shared memory when it fits
@@ -193,6 +228,18 @@ struct ps_engine {
     SenseSetup sense;
     int device = 0;
     cudaStream_t stream = nullptr;
+    // Arena groups: arenas are independent, so the batch is cut into groups that run their kernel sequences on separate
+    // streams; the latency tail of one group's slowest island overlaps with the other groups' work.
+    struct Group {
+        cudaStream_t s = nullptr, s2 = nullptr;   // s2: the few oversized islands, next to the lane batches
+        cudaEvent_t evPre = nullptr, evBig = nullptr, done = nullptr;
+        int a0 = 0, n = 0;
+        IslandQueue q;
+    };
+    std::vector<Group> groups;
+    cudaEvent_t evStart = nullptr;
+    bool mainDirty = true;     // the main stream has work the group streams have not been ordered after yet
+    bool groupsDirty = false;  // the group streams have work the main stream has not been ordered after yet
     KParams kp;
     Scene* dScene = nullptr;
     float* dLut = nullptr;
@@ -201,7 +248,7 @@ struct ps_engine {
     int* dStepStats = nullptr;
     int nSlots = 0, threads = 128;
     bool fused = false;      // PS_FUSED=1: the single-kernel World.step (kept for comparison)
-    int workerBlocks = 0;
+    int workerBlocks = 0, batchBlocks = 0;
     size_t smemBytes = 0;
     int64_t launches = 0;
     int updateCount = 0;     // all arenas advance in lock step
@@ -225,21 +272,27 @@ struct ScopedTimer {   // records an event pair around the launches issued durin
     ps_engine* e;
     ps_engine::Timed t;
     bool on;
-    ScopedTimer(ps_engine* e_, int cls) : e(e_), on(e_->profiling) {
+    cudaStream_t s;
+    ScopedTimer(ps_engine* e_, int cls, cudaStream_t s_ = nullptr) : e(e_), on(e_->profiling), s(s_ ? s_ : e_->stream) {
         if (!on) return;
         t.cls = cls;
         if (cudaEventCreate(&t.a) != cudaSuccess || cudaEventCreate(&t.b) != cudaSuccess) {
             on = false;
             return;
         }
-        cudaEventRecord(t.a, e->stream);
+        cudaEventRecord(t.a, s);
     }
     ~ScopedTimer() {
         if (!on) return;
-        cudaEventRecord(t.b, e->stream);
+        cudaEventRecord(t.b, s);
         e->timed.push_back(t);
     }
 };
+
+extern "C" {
+static int forkGroups(ps_handle h);
+static int joinGroups(ps_handle h);
+}
 
 static size_t envSize(const char* name, size_t dflt) {
     const char* v = getenv(name);
@@ -311,6 +364,10 @@ void ps_config_defaults(ps_config* c) {
 int ps_destroy(ps_handle h) {
     if (!h) return PS_OK;
     cudaSetDevice(h->device);
+    for (auto& g : h->groups) {
+        if (g.s) cudaStreamSynchronize(g.s);
+        if (g.s2) cudaStreamSynchronize(g.s2);
+    }
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->kp.sp.body);
     cudaFree(h->kp.sp.senseAabb);
@@ -324,6 +381,7 @@ int ps_destroy(ps_handle h) {
     cudaFree(h->kp.arenaScratch);
     cudaFree(h->kp.queue.entries);
     cudaFree(h->kp.queue.counts);
+    cudaFree(h->kp.islandHist);
     cudaFree(h->dScene);
     cudaFree(h->dLut);
     cudaFree(h->dRobotInit);
@@ -333,6 +391,14 @@ int ps_destroy(ps_handle h) {
     cudaFree(h->dStats);
     cudaFree(h->dCmd);
     h->sd.release();
+    for (auto& g : h->groups) {
+        if (g.evPre) cudaEventDestroy(g.evPre);
+        if (g.evBig) cudaEventDestroy(g.evBig);
+        if (g.done) cudaEventDestroy(g.done);
+        if (g.s2) cudaStreamDestroy(g.s2);
+        if (g.s) cudaStreamDestroy(g.s);
+    }
+    if (h->evStart) cudaEventDestroy(h->evStart);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return PS_OK;
@@ -369,6 +435,7 @@ int ps_create(const ps_config* cfg, int device, ps_handle* out) {
     } while (0)
     TRY_OR_FREE(cudaSetDevice(device));
     TRY_OR_FREE(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    TRY_OR_FREE(cudaEventCreateWithFlags(&e->evStart, cudaEventDisableTiming));
     const PhysCfg& pc = e->hs.phys;
     size_t A = cfg->n_arenas;
     TRY_OR_FREE(cudaMalloc(&e->kp.sp.body, A * 6 * pc.d.NB * sizeof(float)));
@@ -425,16 +492,41 @@ int ps_create(const ps_config* cfg, int device, ps_handle* out) {
         size_t nBlocks = e->fused ? 1 : A;
         TRY_OR_FREE(cudaMalloc(&e->kp.arenaScratch, nBlocks * e->kp.arenaScratchStride + 256));
         TRY_OR_FREE(cudaMemset(e->kp.arenaScratch, 0, nBlocks * e->kp.arenaScratchStride + 256));
-        e->kp.queue.cap = (int)std::min<size_t>(A * (size_t)pc.d.NB, (size_t)1 << 28);
-        TRY_OR_FREE(cudaMalloc(&e->kp.queue.entries, (size_t)3 * e->kp.queue.cap * sizeof(unsigned)));
-        TRY_OR_FREE(cudaMalloc(&e->kp.queue.counts, 4 * sizeof(int)));
+        // arena groups, each with its own streams, events and island queue
+        int nGroups = (int)envSize("PS_GROUPS", 4);
+        if (e->fused || nGroups < 1) nGroups = 1;
+        if ((size_t)nGroups > A) nGroups = (int)A;
+        size_t perGroup = (A + nGroups - 1) / nGroups;
+        int qcap = (int)std::min<size_t>(perGroup * (size_t)pc.d.NB, (size_t)1 << 27);
+        TRY_OR_FREE(cudaMalloc(&e->kp.queue.entries, (size_t)nGroups * 3 * qcap * sizeof(unsigned)));
+        TRY_OR_FREE(cudaMalloc(&e->kp.queue.counts, (size_t)nGroups * 4 * sizeof(int)));
+        e->kp.queue.cap = qcap;
+        e->groups.resize(nGroups);
+        for (int g = 0; g < nGroups; g++) {
+            ps_engine::Group& G = e->groups[g];
+            G.a0 = (int)std::min<size_t>(A, g * perGroup);
+            G.n = (int)(std::min<size_t>(A, (g + 1) * perGroup) - G.a0);
+            G.q.entries = e->kp.queue.entries + (size_t)g * 3 * qcap;
+            G.q.counts = e->kp.queue.counts + (size_t)g * 4;
+            G.q.cap = qcap;
+            TRY_OR_FREE(cudaStreamCreateWithFlags(&G.s, cudaStreamNonBlocking));
+            TRY_OR_FREE(cudaStreamCreateWithFlags(&G.s2, cudaStreamNonBlocking));
+            TRY_OR_FREE(cudaEventCreateWithFlags(&G.evPre, cudaEventDisableTiming));
+            TRY_OR_FREE(cudaEventCreateWithFlags(&G.evBig, cudaEventDisableTiming));
+            TRY_OR_FREE(cudaEventCreateWithFlags(&G.done, cudaEventDisableTiming));
+        }
+        TRY_OR_FREE(cudaMalloc(&e->kp.islandHist, 64 * sizeof(unsigned long long)));
+        TRY_OR_FREE(cudaMemset(e->kp.islandHist, 0, 64 * sizeof(unsigned long long)));
         e->workerBlocks = prop.multiProcessorCount * (int)envSize("PS_WORKER_BLOCKS_PER_SM", 4);
         TRY_OR_FREE(cudaFuncSetAttribute(k_island_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(WarpSlot))));
+        TRY_OR_FREE(cudaFuncSetAttribute(k_island_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(LaneSlots))));
+        e->batchBlocks = prop.multiProcessorCount * (int)envSize("PS_BATCH_BLOCKS_PER_SM", 4);
     }
     e->kp.env.scene = e->dScene;
     e->kp.env.trig.lut = e->dLut;
     e->kp.env.trig.useLut = cfg->sincos_lut;
     e->kp.env.cfg = pc;
+    e->kp.env.hot = e->hs.hot;
     e->kp.slowStride = slowStride;
     e->kp.fastCap = e->smemBytes;
     e->kp.nArenas = cfg->n_arenas;
@@ -459,6 +551,7 @@ int ps_load_calibration(ps_handle h, const float* XrYr, const uint16_t* xy, cons
 int ps_sync(ps_handle h) {
     if (!h) return setError(PS_E_INVALID, "null handle");
     CUDA_TRY(cudaSetDevice(h->device));
+    { int jr = joinGroups(h); if (jr != PS_OK) return jr; }
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return PS_OK;
 }
@@ -466,6 +559,7 @@ int ps_sync(ps_handle h) {
 int ps_reset(ps_handle h, const int64_t* seeds) {
     if (!h || !seeds) return setError(PS_E_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(h->device));
+    { int jr = joinGroups(h); if (jr != PS_OK) return jr; }
     CUDA_TRY(cudaMemcpyAsync(h->dSeeds, seeds, (size_t)h->kp.nArenas * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
     k_reset<<<h->nSlots, h->threads, h->smemBytes, h->stream>>>(h->kp);
     h->launches++;
@@ -476,33 +570,64 @@ int ps_reset(ps_handle h, const int64_t* seeds) {
     return PS_OK;
 }
 
-static int launchPhysics(ps_handle h, int nTicks) {
-    ScopedTimer timer(h, 2);
+// World.step x nTicks for one arena group on its stream
+static int launchPhysics(ps_handle h, ps_engine::Group& G, int nTicks) {
+    ScopedTimer timer(h, 2, G.s);
     if (h->fused) {
-        k_physics<<<h->nSlots, h->threads, h->smemBytes, h->stream>>>(h->kp, nTicks);
+        k_physics<<<h->nSlots, h->threads, h->smemBytes, G.s>>>(h->kp, nTicks);
         h->launches++;
         CUDA_TRY(cudaGetLastError());
-    } else {
-        for (int t = 0; t < nTicks; ++t) {
-            CUDA_TRY(cudaMemsetAsync(h->kp.queue.counts, 0, 4 * sizeof(int), h->stream));
-            {
-                ScopedTimer t4(h, 4);
-                k_phys_pre<<<h->kp.nArenas, 128, 0, h->stream>>>(h->kp);
-            }
-            {
-                ScopedTimer t5(h, 5);
-                k_island_warp<<<h->workerBlocks, 128, 4 * sizeof(WarpSlot), h->stream>>>(h->kp);
-                k_island_lane<<<h->workerBlocks, 128, 0, h->stream>>>(h->kp);
-            }
-            {
-                ScopedTimer t6(h, 6);
-                k_phys_post<<<h->kp.nArenas, 128, 0, h->stream>>>(h->kp);
-            }
-            h->launches += 4;
-            CUDA_TRY(cudaGetLastError());
-        }
+        return PS_OK;
     }
-    h->updateCount += nTicks;
+    KParams kp = h->kp;
+    kp.a0 = G.a0;
+    kp.queue = G.q;
+    for (int t = 0; t < nTicks; ++t) {
+        CUDA_TRY(cudaMemsetAsync(G.q.counts, 0, 4 * sizeof(int), G.s));
+        {
+            ScopedTimer t4(h, 4, G.s);
+            k_phys_pre<<<G.n, 128, 0, G.s>>>(kp);
+        }
+        {
+            ScopedTimer t5(h, 5, G.s);
+            // islands are independent: the oversized ones (one warp each) run beside the lane batches
+            CUDA_TRY(cudaEventRecord(G.evPre, G.s));
+            CUDA_TRY(cudaStreamWaitEvent(G.s2, G.evPre, 0));
+            int wb = std::max(1, std::min(h->workerBlocks, G.n * 3));
+            k_island_warp<<<wb, 128, 4 * sizeof(WarpSlot), G.s2>>>(kp);
+            CUDA_TRY(cudaEventRecord(G.evBig, G.s2));
+            int bb = std::max(1, std::min(h->batchBlocks, (G.n * 12 + 127) / 128));
+            k_island_batch<<<bb, 128, 4 * sizeof(LaneSlots), G.s>>>(kp, 2);
+            CUDA_TRY(cudaStreamWaitEvent(G.s, G.evBig, 0));
+        }
+        {
+            ScopedTimer t6(h, 6, G.s);
+            k_phys_post<<<G.n, 128, 0, G.s>>>(kp);
+        }
+        h->launches += 4;
+        CUDA_TRY(cudaGetLastError());
+    }
+    return PS_OK;
+}
+
+// The group streams run free: consecutive ps_step calls just keep appending to them, so a group whose slowest island
+// takes long this tick does not hold the others back. They are ordered after the main stream only when that stream got
+// new work (fork), and the main stream waits for them only when somebody needs the result (join).
+static int forkGroups(ps_handle h) {
+    if (!h->mainDirty) return PS_OK;
+    CUDA_TRY(cudaEventRecord(h->evStart, h->stream));
+    for (auto& G : h->groups) CUDA_TRY(cudaStreamWaitEvent(G.s, h->evStart, 0));
+    h->mainDirty = false;
+    return PS_OK;
+}
+static int joinGroups(ps_handle h) {
+    h->mainDirty = true;   // whoever joins is about to use the main stream
+    if (!h->groupsDirty) return PS_OK;
+    for (auto& G : h->groups) {
+        CUDA_TRY(cudaEventRecord(G.done, G.s));
+        CUDA_TRY(cudaStreamWaitEvent(h->stream, G.done, 0));
+    }
+    h->groupsDirty = false;
     return PS_OK;
 }
 
@@ -511,35 +636,45 @@ int ps_step(ps_handle h, int n_ticks) {
     if (!h->isReset) return setError(PS_E_INVALID, "ps_reset or ps_set_state first");
     CUDA_TRY(cudaSetDevice(h->device));
     int interval = h->hs.cfg.step_interval;
-    int t = 0;
-    while (t < n_ticks) {
-        if (h->updateCount % interval == 0) {
-            if (h->hs.cfg.controller != PS_CTRL_EXTERNAL) {
-                if (!h->sd.ready) return setError(PS_E_NOCALIB, "ps_load_calibration has not been called");
-                int rc;
-                {
-                    ScopedTimer timer(h, 0);
-                    rc = h->sd.launchSense(h->kp.env, h->kp.sp, h->stream, &h->launches, false);
+    bool onDevice = h->hs.cfg.controller != PS_CTRL_EXTERNAL;
+    if (onDevice && !h->sd.ready) return setError(PS_E_NOCALIB, "ps_load_calibration has not been called");
+    int rc = forkGroups(h);
+    if (rc != PS_OK) return rc;
+    int R = h->hs.phys.d.R;
+    for (auto& G : h->groups) {
+        if (G.n == 0) continue;
+        int uc = h->updateCount;
+        int t = 0;
+        while (t < n_ticks) {
+            if (uc % interval == 0) {
+                if (onDevice) {
+                    {
+                        ScopedTimer timer(h, 0, G.s);
+                        rc = h->sd.launchSense(h->kp.env, h->kp.sp, G.s, &h->launches, false, G.a0 * R, G.n * R);
+                    }
+                    if (rc != PS_OK) return setError(rc, h->sd.error);
+                    {
+                        ScopedTimer timer(h, 1, G.s);
+                        rc = h->sd.launchThink(G.a0, G.n, G.s, &h->launches);
+                    }
+                    if (rc != PS_OK) return setError(rc, h->sd.error);
+                } else {
+                    k_count_step<<<(G.n + 127) / 128, 128, 0, G.s>>>(h->kp.sp.arena + G.a0, G.n);
+                    h->launches++;
+                    CUDA_TRY(cudaGetLastError());
                 }
-                if (rc != PS_OK) return setError(rc, h->sd.error);
-                {
-                    ScopedTimer timer(h, 1);
-                    rc = h->sd.launchThink(h->kp.nArenas, h->stream, &h->launches);
-                }
-                if (rc != PS_OK) return setError(rc, h->sd.error);
-            } else {
-                k_count_step<<<(h->kp.nArenas + 127) / 128, 128, 0, h->stream>>>(h->kp.sp.arena, h->kp.nArenas);
-                h->launches++;
-                CUDA_TRY(cudaGetLastError());
             }
+            // run up to the next think tick
+            int run = interval - uc % interval;
+            if (run > n_ticks - t) run = n_ticks - t;
+            rc = launchPhysics(h, G, run);
+            if (rc != PS_OK) return rc;
+            t += run;
+            uc += run;
         }
-        // run up to the next think tick in one launch
-        int run = interval - h->updateCount % interval;
-        if (run > n_ticks - t) run = n_ticks - t;
-        int rc = launchPhysics(h, run);
-        if (rc != PS_OK) return rc;
-        t += run;
     }
+    h->updateCount += n_ticks;
+    h->groupsDirty = true;
     return PS_OK;
 }
 
@@ -547,7 +682,8 @@ int ps_sense(ps_handle h) {
     if (!h) return setError(PS_E_INVALID, "null handle");
     if (!h->sd.ready) return setError(PS_E_NOCALIB, "ps_load_calibration has not been called");
     CUDA_TRY(cudaSetDevice(h->device));
-    int rc = h->sd.launchSenseOnly(h->kp.env, h->kp.sp, h->kp.nArenas, h->stream, &h->launches);
+    { int jr = joinGroups(h); if (jr != PS_OK) return jr; }
+    int rc = h->sd.launchSense(h->kp.env, h->kp.sp, h->stream, &h->launches, h->sd.haveCamera, 0, (int)h->sd.nRobotsTotal);
     if (rc != PS_OK) return setError(rc, h->sd.error);
     return PS_OK;
 }
@@ -556,6 +692,7 @@ int ps_step_external(ps_handle h, const float* forwards, const float* torque) {
     if (!h || !forwards || !torque) return setError(PS_E_INVALID, "null argument");
     if (!h->isReset) return setError(PS_E_INVALID, "ps_reset or ps_set_state first");
     CUDA_TRY(cudaSetDevice(h->device));
+    { int jr = joinGroups(h); if (jr != PS_OK) return jr; }
     size_t n = (size_t)h->kp.nArenas * h->hs.phys.d.R;
     CUDA_TRY(cudaMemcpyAsync(h->dCmd, forwards, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->dCmd + n, torque, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
@@ -565,7 +702,16 @@ int ps_step_external(ps_handle h, const float* forwards, const float* torque) {
     CUDA_TRY(cudaGetLastError());
     // the caller may reuse its arrays as soon as we return
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    return launchPhysics(h, h->hs.cfg.step_interval);
+    int rc = forkGroups(h);
+    if (rc != PS_OK) return rc;
+    for (auto& G : h->groups) {
+        if (G.n == 0) continue;
+        rc = launchPhysics(h, G, h->hs.cfg.step_interval);
+        if (rc != PS_OK) return rc;
+    }
+    h->updateCount += h->hs.cfg.step_interval;
+    h->groupsDirty = true;
+    return PS_OK;
 }
 
 static int copyState(ps_handle h, const ps_state_view* v, bool toHost) {
@@ -593,12 +739,14 @@ static int copyState(ps_handle h, const ps_state_view* v, bool toHost) {
 int ps_get_state(ps_handle h, ps_state_view* v) {
     if (!h || !v) return setError(PS_E_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(h->device));
+    { int jr = joinGroups(h); if (jr != PS_OK) return jr; }
     return copyState(h, v, true);
 }
 
 int ps_set_state(ps_handle h, const ps_state_view* v) {
     if (!h || !v) return setError(PS_E_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(h->device));
+    { int jr = joinGroups(h); if (jr != PS_OK) return jr; }
     int rc = copyState(h, v, false);
     if (rc != PS_OK) return rc;
     if (v->arena) h->updateCount = v->arena[0].update_count;
@@ -610,6 +758,7 @@ int ps_get_observations(ps_handle h, ps_obs_view* v) {
     if (!h || !v) return setError(PS_E_INVALID, "null argument");
     if (!h->sd.ready) return setError(PS_E_NOCALIB, "ps_load_calibration has not been called");
     CUDA_TRY(cudaSetDevice(h->device));
+    { int jr = joinGroups(h); if (jr != PS_OK) return jr; }
     int rc = h->sd.readObservations(v, h->kp.nArenas, h->hs.phys.d.R, h->stream);
     if (rc != PS_OK) return setError(rc, h->sd.error);
     return PS_OK;
@@ -618,6 +767,7 @@ int ps_get_observations(ps_handle h, ps_obs_view* v) {
 int ps_compute_stats(ps_handle h, float cluster_threshold, ps_stats* out) {
     if (!h || !out) return setError(PS_E_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(h->device));
+    { int jr = joinGroups(h); if (jr != PS_OK) return jr; }
     CUDA_TRY(cudaMemsetAsync(h->dStatsDev, 0, sizeof(StatsDev), h->stream));
     int P = h->hs.phys.d.P;
     size_t sh = (size_t)2 * (P > 0 ? P : 1) * sizeof(int);
@@ -663,6 +813,7 @@ int ps_get_dims(ps_handle h, int32_t* n_bodies, int32_t* n_proxies, int32_t* max
 int ps_get_step_stats(ps_handle h, int32_t* out /* [n_arenas][8] */) {
     if (!h || !out) return setError(PS_E_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(h->device));
+    { int jr = joinGroups(h); if (jr != PS_OK) return jr; }
     CUDA_TRY(cudaMemcpyAsync(out, h->dStepStats, (size_t)h->kp.nArenas * 8 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return PS_OK;
@@ -672,7 +823,18 @@ int ps_get_sense_stats(ps_handle h, int32_t* out /* [n_arenas][n_robots][8] */) 
     if (!h || !out) return setError(PS_E_INVALID, "null argument");
     if (!h->sd.ready) return setError(PS_E_NOCALIB, "ps_load_calibration has not been called");
     CUDA_TRY(cudaSetDevice(h->device));
+    { int jr = joinGroups(h); if (jr != PS_OK) return jr; }
     CUDA_TRY(cudaMemcpyAsync(out, h->sd.kp.senseDbg, h->sd.nRobotsTotal * 8 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return PS_OK;
+}
+
+int ps_get_island_hist(ps_handle h, int64_t* out /*[64]*/, int reset) {
+    if (!h || !out) return setError(PS_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    { int jr = joinGroups(h); if (jr != PS_OK) return jr; }
+    CUDA_TRY(cudaMemcpyAsync(out, h->kp.islandHist, 64 * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    if (reset) CUDA_TRY(cudaMemsetAsync(h->kp.islandHist, 0, 64 * sizeof(int64_t), h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return PS_OK;
 }
@@ -686,6 +848,7 @@ int ps_profile(ps_handle h, int enable) {
 int ps_get_kernel_ms(ps_handle h, double* ms, int64_t* counts) {
     if (!h || !ms || !counts) return setError(PS_E_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(h->device));
+    { int jr = joinGroups(h); if (jr != PS_OK) return jr; }
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     for (auto& t : h->timed) {
         float f = 0;
@@ -706,6 +869,12 @@ int ps_get_kernel_ms(ps_handle h, double* ms, int64_t* counts) {
     return PS_OK;
 }
 
+int ps_join(ps_handle h) {
+    if (!h) return setError(PS_E_INVALID, "null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    return joinGroups(h);
+}
+int ps_num_groups(ps_handle h) { return h ? (int)h->groups.size() : 0; }
 int64_t ps_kernel_launches(ps_handle h) { return h ? h->launches : 0; }
 void* ps_stream(ps_handle h) { return h ? (void*)h->stream : nullptr; }
 

@@ -15,6 +15,7 @@ struct HostSetup {
     Scene scene;
     std::vector<float> sinLut;     // (float)Math.sin(i * 0.00011f), i < 57120 (MathUtils static initialiser)
     ps_robot_state robotInit[2];   // initial controller state: plain, informed (preset caches)
+    HotConsts hot;
     std::string error;
 
     bool init(const ps_config& c) {
@@ -51,6 +52,14 @@ struct HostSetup {
         tr.lut = sinLut.data();
         tr.useLut = c.sincos_lut;
         build::scene(&scene, c.enclosure_scale, tr);
+        hot.puck = scene.puck;
+        hot.robot = scene.robot;
+        hot.wallXf = scene.wallXf;
+        hot.friction = scene.friction;
+        hot.pmPuck = scene.puck.mass * scene.puck.invMass;
+        hot.piPuck = scene.puck.mass * scene.puck.invI;
+        hot.pmRobot = scene.robot.mass * scene.robot.invMass;
+        hot.piRobot = scene.robot.mass * scene.robot.invI;
         // initial controller state (CacheConsController.java:205-243, BHDController.java:56-80)
         std::memset(robotInit, 0, sizeof(robotInit));
         for (int k = 0; k < 2; k++) robotInit[k].last_carried_type = -1;

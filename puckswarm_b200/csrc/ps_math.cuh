@@ -95,7 +95,8 @@ struct Trig {
 };
 PS_HD float psSin(const Trig& t, float x) {
     if (t.useLut) {
-        x = fmodf(x, kTwoPi);
+        // x %= TWOPI; fmod is exact, and the identity below 2 pi (the common case) -- skip the slow path there
+        if (!(fabsf(x) < kTwoPi)) x = fmodf(x, kTwoPi);
         if (x < 0) x += kTwoPi;
         int idx = (int)(x / kLutPrecision + 0.5f);
         return t.lut[idx % kLutLength];

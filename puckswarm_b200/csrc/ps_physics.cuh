@@ -95,10 +95,19 @@ struct PhysWork {
 
 enum { ERR_CONTACT_CAP = 1, ERR_LM_CAP = 2, ERR_TOUCH_CAP = 4, ERR_PAIR_CAP = 8 };
 
+// The handful of scene constants the solver loops read on every step, carried by value (kernel parameter /
+// constant bank) so that the Gauss-Seidel dependency chain does not wait on loads through the scene pointer.
+struct HotConsts {
+    BodyConst puck, robot;
+    Xf wallXf;
+    float friction;
+    float pmPuck, piPuck, pmRobot, piRobot;   // mass-scaled inverse masses of the position solver: mass * invMass, mass * invI
+};
 struct PhysEnv {
     const Scene* scene;
     Trig trig;
     PhysCfg cfg;
+    HotConsts hot;
 };
 
 PS_HD bool isRobot(const Dims& d, int b) { return b >= d.P; }
@@ -106,7 +115,7 @@ PS_HD bool isRobot(const Dims& d, int b) { return b >= d.P; }
 PS_HD Xf bodyXf(const PhysEnv& e, const PhysWork& wk, int b) {
     Xf T;
     if (b < 0) {
-        T = e.scene->wallXf;
+        T = e.hot.wallXf;
     } else if (b < e.cfg.d.P) {
         T.px = wk.cx[b];
         T.py = wk.cy[b];
@@ -141,14 +150,14 @@ PS_HD Xf bodyXf0(const PhysEnv& e, const PhysWork& wk, int b) {
 PS_HD void syncBodyXf(const PhysEnv& e, const PhysWork& wk, int b) {
     if (b >= e.cfg.d.P) {
         int r = b - e.cfg.d.P;
-        Xf T = makeXf(e.trig, wk.cx[b], wk.cy[b], wk.a[b], e.scene->robot.lcx, e.scene->robot.lcy);
+        Xf T = makeXf(e.trig, wk.cx[b], wk.cy[b], wk.a[b], e.hot.robot.lcx, e.hot.robot.lcy);
         wk.rpx[r] = T.px;
         wk.rpy[r] = T.py;
         wk.rc[r] = T.c;
         wk.rs[r] = T.s;
     }
 }
-PS_HD const BodyConst& bodyConst(const PhysEnv& e, int b) { return b < e.cfg.d.P ? e.scene->puck : e.scene->robot; }
+PS_HD const BodyConst& bodyConst(const PhysEnv& e, int b) { return b < e.cfg.d.P ? e.hot.puck : e.hot.robot; }
 
 PS_HD Aabb loadAabb(const float* base, int n, int i) {
     Aabb a;
@@ -328,7 +337,7 @@ PS_HD void solveVelocityOne(const PhysEnv& e, const PhysWork& wk, TC& c) {
     float wA = A.w, wB = B.w;
     float invMassA = A.invMass, invIA = A.invI, invMassB = B.invMass, invIB = B.invI;
     V2 normal = c.normal, tangent = crossVS(normal, 1.0f);
-    float friction = e.scene->friction;
+    float friction = e.hot.friction;
     for (int j = 0; j < c.solverPoints; ++j) {
         V2 dv = vB + crossSV(wB, c.rB[j]) - vA - crossSV(wA, c.rA[j]);
         float vt = dot(dv, tangent);
@@ -417,6 +426,8 @@ PS_HD float correctPoint(const PhysEnv& e, const PhysWork& wk, int bA, int bB, i
     V2 cB = bB >= 0 ? mk(wk.cx[bB], wk.cy[bB]) : mk(0, 0);
     V2 rA = point - cA, rB = point - cB;
     float C = clampf(baumgarte * (separation + kLinearSlop), -kMaxLinearCorrection, 0.0f);
+    // C == 0 (no penetration beyond the slop): the impulse is -0 / K = (-)0, P = 0 and neither body moves
+    if (C == 0.0f) return separation;
     float rnA = cross(rA, normal), rnB = cross(rB, normal);
     float K = invMassA + invMassB + invIA * rnA * rnA + invIB * rnB * rnB;
     float impulse = K > 0.0f ? -C / K : 0.0f;

@@ -18,11 +18,12 @@
 namespace ps {
 
 struct IslandQueue {
-    unsigned* entries;     // [3][cap]: arena * NB + island, bucketed by contact count (>= 8, 3..7, 1..2)
+    unsigned* entries;     // [3][cap]: arena * NB + island; bucket 0 = islands with >= 3 contacts (one warp each),
+                           // bucket 1 unused, bucket 2 = lane batches of islands with 1-2 contacts
     int* counts;           // [4]: entries per bucket, [3] = consumer head
     int cap;
 };
-PS_HD int islandBucket(int nContacts) { return nContacts >= 8 ? 0 : (nContacts >= 3 ? 1 : 2); }
+static constexpr int kLaneBodies = 12, kLaneRobots = 4;   // capacity of one lane's shared-memory slot (k_island_batch)
 
 template <class Ctx>
 PS_HD void physPre(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaState& st, const float* cmdFwd, const float* cmdTorque,
@@ -39,7 +40,12 @@ PS_HD void physPre(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaSt
     }
     int nIsl = wk.counters[1];
     PS_FOR(k, nIsl) {
-        int bucket = islandBucket(wk.islandStart[k + 1] - wk.islandStart[k]);
+        int nb = wk.islandBodyStart[k + 1] - wk.islandBodyStart[k], nr = 0;
+        for (int i = wk.islandBodyStart[k]; i < wk.islandBodyStart[k + 1]; ++i) nr += wk.ibody[i] >= d.P ? 1 : 0;
+        int nc = wk.islandStart[k + 1] - wk.islandStart[k];
+        // islands with one or two contacts nearly always converge at once: 32 of them share a warp (one lane each).
+        // Larger islands mostly run tens of sweeps: each gets a warp that works through the sweep level by level.
+        int bucket = (nc >= 3 || nb > kLaneBodies || nr > kLaneRobots) ? 0 : 2;
         int pos = ctx.atomicAddI(&q.counts[bucket], 1);
         if (pos < q.cap) q.entries[(size_t)bucket * q.cap + pos] = (unsigned)arena * (unsigned)d.NB + (unsigned)k;
     }
@@ -67,8 +73,12 @@ PS_HD void islandBegin(IslandCursor& c, const PhysWork& wk, int k) {
     c.minSep = 0.0f;
     c.changed = false;
 }
+struct DefaultIntegrator {   // integrates the i-th entry of the island's body list
+    PS_HD void operator()(const PhysEnv& e, const PhysWork& wk, int i) const { integrateBody(e, wk, wk.ibody[i]); }
+};
 // Returns false when the island is finished; *itersOut then holds its position iterations.
-PS_HD bool islandStep(const PhysEnv& e, const PhysWork& wk, const ArenaState& st, IslandCursor& c, int* itersOut) {
+template <class Integrator>
+PS_HD bool islandStepT(const PhysEnv& e, const PhysWork& wk, const ArenaState& st, IslandCursor& c, int* itersOut, const Integrator& integrate) {
     if (c.phase == 0) {
         warmStartOne(e, wk, wk.tc[wk.order[c.i]]);
         if (++c.i < c.hi) return true;
@@ -90,7 +100,7 @@ PS_HD bool islandStep(const PhysEnv& e, const PhysWork& wk, const ArenaState& st
                 st.cimp[4 * t.ci + 2 * j + 1] = t.tImp[j];
             }
         }
-        for (int i = c.blo; i < c.bhi; ++i) integrateBody(e, wk, wk.ibody[i]);
+        for (int i = c.blo; i < c.bhi; ++i) integrate(e, wk, i);
         c.phase = 2;
         c.it = 0;
         c.i = c.lo;
@@ -102,14 +112,13 @@ PS_HD bool islandStep(const PhysEnv& e, const PhysWork& wk, const ArenaState& st
     }
     // position sweep: one contact
     {
-        const BodyConst &kp = e.scene->puck, &kr = e.scene->robot;
         int P = e.cfg.d.P;
         const TC& t = wk.tc[wk.order[c.i]];
         int bA = t.bodyA, bB = t.bodyB;
-        float imA = bA < 0 ? 0.0f : (bA < P ? kp.mass * kp.invMass : kr.mass * kr.invMass);
-        float iiA = bA < 0 ? 0.0f : (bA < P ? kp.mass * kp.invI : kr.mass * kr.invI);
-        float imB = bB < 0 ? 0.0f : (bB < P ? kp.mass * kp.invMass : kr.mass * kr.invMass);
-        float iiB = bB < 0 ? 0.0f : (bB < P ? kp.mass * kp.invI : kr.mass * kr.invI);
+        float imA = bA < 0 ? 0.0f : (bA < P ? e.hot.pmPuck : e.hot.pmRobot);
+        float iiA = bA < 0 ? 0.0f : (bA < P ? e.hot.piPuck : e.hot.piRobot);
+        float imB = bB < 0 ? 0.0f : (bB < P ? e.hot.pmPuck : e.hot.pmRobot);
+        float iiB = bB < 0 ? 0.0f : (bB < P ? e.hot.piPuck : e.hot.piRobot);
         for (int j = 0; j < t.solverPoints; ++j) {
             float sep = correctPoint(e, wk, bA, bB, t.type, t.localNormal, t.localPoint, t.lp[j], t.radius, kContactBaumgarte, imA, iiA, imB, iiB, &c.changed);
             c.minSep = fminf_(c.minSep, sep);
@@ -133,7 +142,157 @@ PS_HD bool islandStep(const PhysEnv& e, const PhysWork& wk, const ArenaState& st
     }
 }
 
+PS_HD bool islandStep(const PhysEnv& e, const PhysWork& wk, const ArenaState& st, IslandCursor& c, int* itersOut) {
+    return islandStepT(e, wk, st, c, itersOut, DefaultIntegrator());
+}
+
 #if defined(__CUDACC__)
+// Lane-per-island solver: every lane of a warp runs a different island. The island's bodies live in a lane-interleaved
+// shared-memory slot (element e of lane l at [e][l], conflict-free); the constraints stay in HBM / L2 (they are read,
+// not chased: no dependent latency). Body indices inside the staged island are pre-multiplied by 32 so that the
+// ordinary solver routines address the interleaved arrays unchanged: wk.cx[b * 32] with wk.cx offset by the lane.
+struct LaneSlots {
+    float body[6][kLaneBodies][32];    // cx cy a vx vy w
+    float rob[4][kLaneRobots][32];     // rpx rpy rc rs
+    uint16_t gidx[kLaneBodies][32];    // local -> arena body index
+};
+struct StagedIntegrator {
+    const PhysWork* g;                 // the arena's arrays in HBM (c0 / xf0 are only needed by the later stages)
+    const uint16_t* gidx;              // lane's column of LaneSlots::gidx (stride 32)
+    int nPuckLocal, P;
+    __device__ __forceinline__ void operator()(const PhysEnv& e, const PhysWork& wk, int local) const {
+        // staged index = local * 32; same arithmetic as integrateBody
+        int bl = local * 32;
+        int gb = gidx[local * 32];
+        float dt = e.cfg.dt;
+        float vx = wk.vx[bl], vy = wk.vy[bl], w = wk.w[bl];
+        V2 tr = mk(dt * vx, dt * vy);
+        if (dot(tr, tr) > kMaxTranslationSquared) {
+            float ratio = kMaxTranslation / len(tr);
+            vx *= ratio;
+            vy *= ratio;
+        }
+        float rot = dt * w;
+        if (rot * rot > kMaxRotationSquared) {
+            float ratio = kMaxRotation / fabsf(rot);
+            w *= ratio;
+        }
+        wk.vx[bl] = vx;
+        wk.vy[bl] = vy;
+        wk.w[bl] = w;
+        g->c0x[gb] = wk.cx[bl];
+        g->c0y[gb] = wk.cy[bl];
+        g->a0[gb] = wk.a[bl];
+        if (gb >= P) {
+            int r = gb - P, lr = (local - nPuckLocal) * 32;
+            g->r0px[r] = wk.rpx[lr];
+            g->r0py[r] = wk.rpy[lr];
+            g->r0c[r] = wk.rc[lr];
+            g->r0s[r] = wk.rs[lr];
+        }
+        wk.cx[bl] += dt * vx;
+        wk.cy[bl] += dt * vy;
+        wk.a[bl] += dt * w;
+        syncBodyXf(e, wk, bl);
+    }
+};
+// One lane's staged island: the cursor plus the rebased working set
+struct LaneIsland {
+    IslandCursor c;
+    PhysEnv le;
+    PhysWork lw;
+    StagedIntegrator integ;
+    int nb, nPuck;
+};
+// Stage island k of the arena behind wk into this lane's slot. The caller guarantees the island fits.
+__device__ __forceinline__ void islandStageLane(const PhysEnv& e, const PhysWork& wk, int k, LaneSlots& s, int lane, LaneIsland& L) {
+    int lo = wk.islandStart[k], hi = wk.islandStart[k + 1];
+    int blo = wk.islandBodyStart[k], bhi = wk.islandBodyStart[k + 1];
+    int nb = bhi - blo;
+    int P = e.cfg.d.P;
+    int nPuck = 0;
+    for (int i = 0; i < nb; ++i) nPuck += wk.ibody[blo + i] < P ? 1 : 0;
+    // local numbering: pucks first (ibody order), then robots
+    int ip = 0, ir = nPuck;
+    for (int i = 0; i < nb; ++i) {
+        int g = wk.ibody[blo + i];
+        int l = g < P ? ip++ : ir++;
+        s.gidx[l][lane] = (uint16_t)g;
+        s.body[0][l][lane] = wk.cx[g];
+        s.body[1][l][lane] = wk.cy[g];
+        s.body[2][l][lane] = wk.a[g];
+        s.body[3][l][lane] = wk.vx[g];
+        s.body[4][l][lane] = wk.vy[g];
+        s.body[5][l][lane] = wk.w[g];
+        if (g >= P) {
+            int r = g - P, lr = l - nPuck;
+            s.rob[0][lr][lane] = wk.rpx[r];
+            s.rob[1][lr][lane] = wk.rpy[r];
+            s.rob[2][lr][lane] = wk.rc[r];
+            s.rob[3][lr][lane] = wk.rs[r];
+        }
+    }
+    // constraints: body references -> staged indices (the arena-level indices are not needed again this step)
+    for (int i = lo; i < hi; ++i) {
+        TC& t = wk.tc[wk.order[i]];
+        int a = t.bodyA, b = t.bodyB;
+        int la = -1, lb = -1;
+        for (int j = 0; j < nb; ++j) {
+            int g = s.gidx[j][lane];
+            if (g == a) la = j * 32;
+            if (g == b) lb = j * 32;
+        }
+        t.bodyA = a < 0 ? -1 : la;
+        t.bodyB = b < 0 ? -1 : lb;
+    }
+    L.le = e;
+    L.le.cfg.d.P = nPuck * 32;
+    L.lw = wk;
+    L.lw.cx = &s.body[0][0][lane];
+    L.lw.cy = &s.body[1][0][lane];
+    L.lw.a = &s.body[2][0][lane];
+    L.lw.vx = &s.body[3][0][lane];
+    L.lw.vy = &s.body[4][0][lane];
+    L.lw.w = &s.body[5][0][lane];
+    L.lw.rpx = &s.rob[0][0][lane];
+    L.lw.rpy = &s.rob[1][0][lane];
+    L.lw.rc = &s.rob[2][0][lane];
+    L.lw.rs = &s.rob[3][0][lane];
+    L.integ.gidx = &s.gidx[0][lane];
+    L.integ.nPuckLocal = nPuck;
+    L.integ.P = P;
+    L.c.lo = lo;
+    L.c.hi = hi;
+    L.c.blo = 0;       // the integrator is handed the local body numbers 0 .. nb-1
+    L.c.bhi = nb;
+    L.c.phase = 0;
+    L.c.it = 0;
+    L.c.i = lo;
+    L.c.minSep = 0.0f;
+    L.c.changed = false;
+    L.nb = nb;
+    L.nPuck = nPuck;
+}
+__device__ __forceinline__ void islandFinishLane(const PhysEnv& e, const PhysWork& wk, LaneSlots& s, int lane, const LaneIsland& L) {
+    int P = e.cfg.d.P;
+    for (int l = 0; l < L.nb; ++l) {
+        int g = s.gidx[l][lane];
+        wk.cx[g] = s.body[0][l][lane];
+        wk.cy[g] = s.body[1][l][lane];
+        wk.a[g] = s.body[2][l][lane];
+        wk.vx[g] = s.body[3][l][lane];
+        wk.vy[g] = s.body[4][l][lane];
+        wk.w[g] = s.body[5][l][lane];
+        if (g >= P) {
+            int r = g - P, lr = l - L.nPuck;
+            wk.rpx[r] = s.rob[0][lr][lane];
+            wk.rpy[r] = s.rob[1][lr][lane];
+            wk.rc[r] = s.rob[2][lr][lane];
+            wk.rs[r] = s.rob[3][lr][lane];
+        }
+    }
+}
+
 // Warp-per-island solver for islands of up to kWarpBodies bodies / kWarpContacts contacts: the warp stages the island's
 // bodies and constraints into its shared-memory slot (local body indices: pucks first, then robots), lane 0 runs the
 // same state machine on the staged copy (shared-memory latency instead of L2 on the Gauss-Seidel dependency chain),
@@ -146,6 +305,9 @@ struct WarpSlot {
     uint16_t order[kWarpContacts];
     uint16_t ibody[kWarpBodies];
     uint16_t lmap[kWarpBodies];          // local -> arena body index
+    uint8_t level[kWarpContacts], sched[kWarpContacts], bodyLevel[kWarpBodies];
+    int levelStart[kWarpContacts + 3];
+    int nLevels;
 };
 // Returns false if the island does not fit the slot (the caller falls back to the lane path).
 __device__ __forceinline__ bool islandSolveWarp(const PhysEnv& e, const PhysWork& wk, const ArenaState& st, int k, WarpSlot& s, int* itersOut) {
@@ -213,7 +375,36 @@ __device__ __forceinline__ bool islandSolveWarp(const PhysEnv& e, const PhysWork
         s.order[i] = (uint16_t)i;
     }
     __syncwarp();
+    // ---- level schedule of one Gauss-Seidel sweep: contact i (in solve order) goes to level 1 + the highest level of an
+    // earlier contact that shares a dynamic body with it. Contacts of one level touch disjoint bodies, so the lanes
+    // process them together; levels run in order, so every body still sees its contacts in the reference's order and
+    // the sweep is bit-identical to the sequential one.
     if (lane == 0) {
+        int nLevels = 0;
+        for (int b = 0; b < nb; ++b) s.bodyLevel[b] = 0;
+        for (int i = 0; i < nc; ++i) {
+            int a = s.tc[i].bodyA, b = s.tc[i].bodyB;
+            int lv = 0;
+            if (a >= 0) lv = s.bodyLevel[a];
+            if (b >= 0 && s.bodyLevel[b] > lv) lv = s.bodyLevel[b];
+            lv += 1;
+            if (a >= 0) s.bodyLevel[a] = (uint8_t)lv;
+            if (b >= 0) s.bodyLevel[b] = (uint8_t)lv;
+            s.level[i] = (uint8_t)lv;
+            if (lv > nLevels) nLevels = lv;
+        }
+        // counting sort by level (stable)
+        for (int l = 0; l <= nLevels + 1; ++l) s.levelStart[l] = 0;
+        for (int i = 0; i < nc; ++i) s.levelStart[s.level[i] + 1]++;
+        for (int l = 1; l <= nLevels + 1; ++l) s.levelStart[l] += s.levelStart[l - 1];
+        for (int i = 0; i < nc; ++i) s.sched[s.levelStart[s.level[i]]++] = (uint8_t)i;
+        // levelStart[l] now holds the end of level l == start of level l + 1; shift back
+        for (int l = nLevels + 1; l >= 1; --l) s.levelStart[l] = s.levelStart[l - 1];
+        s.levelStart[0] = 0;
+        s.nLevels = nLevels;
+    }
+    __syncwarp();
+    {
         PhysEnv le = e;
         le.cfg.d.P = nPuck;
         PhysWork lw = wk;
@@ -235,22 +426,64 @@ __device__ __forceinline__ bool islandSolveWarp(const PhysEnv& e, const PhysWork
         lw.r0c = s.rob[6];
         lw.r0s = s.rob[7];
         lw.tc = s.tc;
-        lw.order = s.order;
-        lw.ibody = s.ibody;
-        IslandCursor c;
-        c.lo = 0;
-        c.hi = nc;
-        c.blo = 0;
-        c.bhi = nb;
-        c.phase = 0;
-        c.it = 0;
-        c.i = 0;
-        c.minSep = 0.0f;
-        c.changed = false;
-        int iters = 0;
-        while (islandStep(le, lw, st, c, &iters)) {
+        int nLevels = s.nLevels;
+        // levels are 1-based: level l holds sched[levelStart[l] .. levelStart[l + 1])
+        // ContactSolver.warmStart
+        for (int l = 1; l <= nLevels; ++l) {
+            for (int q = s.levelStart[l] + lane; q < s.levelStart[l + 1]; q += 32) warmStartOne(le, lw, s.tc[s.sched[q]]);
+            __syncwarp();
         }
-        *itersOut = iters;
+        // velocity sweeps
+        for (int it = 0; it < e.cfg.velIters; ++it)
+            for (int l = 1; l <= nLevels; ++l) {
+                for (int q = s.levelStart[l] + lane; q < s.levelStart[l + 1]; q += 32) solveVelocityOne(le, lw, s.tc[s.sched[q]]);
+                __syncwarp();
+            }
+        // ContactSolver.storeImpulses
+        for (int i = lane; i < nc; i += 32) {
+            const TC& t = s.tc[i];
+            for (int j2 = 0; j2 < t.solverPoints; ++j2) {
+                st.cimp[4 * t.ci + 2 * j2] = t.nImp[j2];
+                st.cimp[4 * t.ci + 2 * j2 + 1] = t.tImp[j2];
+            }
+        }
+        // integrate the island's bodies
+        for (int b = lane; b < nb; b += 32) integrateBody(le, lw, b);
+        __syncwarp();
+        // position sweeps
+        int iters = 0;
+        int P = le.cfg.d.P;
+        for (int it = 0; it < e.cfg.posIters; ++it) {
+            float minSep = 0.0f;
+            bool changed = false;
+            for (int l = 1; l <= nLevels; ++l) {
+                for (int q = s.levelStart[l] + lane; q < s.levelStart[l + 1]; q += 32) {
+                    const TC& t = s.tc[s.sched[q]];
+                    int bA = t.bodyA, bB = t.bodyB;
+                    float imA = bA < 0 ? 0.0f : (bA < P ? e.hot.pmPuck : e.hot.pmRobot);
+                    float iiA = bA < 0 ? 0.0f : (bA < P ? e.hot.piPuck : e.hot.piRobot);
+                    float imB = bB < 0 ? 0.0f : (bB < P ? e.hot.pmPuck : e.hot.pmRobot);
+                    float iiB = bB < 0 ? 0.0f : (bB < P ? e.hot.piPuck : e.hot.piRobot);
+                    for (int j2 = 0; j2 < t.solverPoints; ++j2) {
+                        float sep = correctPoint(le, lw, bA, bB, t.type, t.localNormal, t.localPoint, t.lp[j2], t.radius, kContactBaumgarte, imA, iiA, imB, iiB, &changed);
+                        minSep = fminf_(minSep, sep);
+                    }
+                }
+                __syncwarp();
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                float other = __shfl_xor_sync(FULL, minSep, o);
+                minSep = fminf_(minSep, other);
+            }
+            bool anyChanged = __any_sync(FULL, changed);
+            ++iters;
+            if (minSep >= -1.5f * kLinearSlop) break;
+            if (!anyChanged) {   // fixed point: every later sweep repeats this one
+                iters = e.cfg.posIters;
+                break;
+            }
+        }
+        if (lane == 0) *itersOut = iters;
     }
     __syncwarp();
     for (int i = lane; i < nb; i += 32) {

@@ -15,6 +15,7 @@ struct SenseKParams {
     ObsPtrs obs;
     int nArenas;
     size_t fastCap;
+    int r0;            // first robot (k_sense, k_localmap) / first arena (k_think) of the launch
     int* senseDbg;     // [nRobots][8] phase diagnostics of the last sense
     SenseHead* senseHead;   // [nRobots] camera stage -> local-map stage
     BlobRec* blobs;         // [nRobots][kMaxBlobs]
@@ -35,9 +36,10 @@ __global__ void __launch_bounds__(256) k_sense(SenseKParams p) {
     cv.slowUsed = 0;
     SenseWork wk = carveSense(p.T, cv);
     int R = p.env.cfg.d.R;
-    int a = blockIdx.x / R, r = blockIdx.x - a * R;
+    int rg = p.r0 + (int)blockIdx.x;
+    int a = rg / R, r = rg - a * R;
     ArenaState st = arenaState(p.sp, p.env.cfg, a);
-    size_t ri = (size_t)a * R + r;
+    size_t ri = (size_t)rg;
     int nCells = p.T.occW * p.T.occH;
     uint8_t* cam = p.obs.camera ? p.obs.camera + ri * (size_t)(p.T.imgW * p.T.imgH) : nullptr;
     __shared__ float poseS[4];
@@ -54,6 +56,7 @@ __global__ void __launch_bounds__(256) k_sense(SenseKParams p) {
 __global__ void __launch_bounds__(128) k_localmap(SenseKParams p, int nRobots) {
     int ri = blockIdx.x * blockDim.x + threadIdx.x;
     if (ri >= nRobots) return;
+    ri += p.r0;
     int nCells = p.T.occW * p.T.occH;
     ps_localmap lm;
     uint32_t* w = (uint32_t*)&lm;
@@ -79,7 +82,7 @@ __global__ void __launch_bounds__(128) k_think(SenseKParams p) {
     tw.limits = limits;
     tw.flag = flag;
     int R = p.env.cfg.d.R;
-    int a = blockIdx.x;
+    int a = p.r0 + (int)blockIdx.x;
     size_t r0 = (size_t)a * R;
     int nCells = p.T.occW * p.T.occH;
     thinkArena(ctx, p.T, p.sc, tw, R, p.obs.occupancy + r0 * nCells, p.obs.lm + r0, p.obs.pose + r0 * 3, p.sp.robot + r0, p.sp.arena + a, &rng);
@@ -261,24 +264,24 @@ struct SenseDevice {
         kp.env = env;
         kp.sp = sp;
     }
-    int launchSense(const PhysEnv& env, const StatePtrs& sp, cudaStream_t stream, int64_t* launches, bool camera) {
+    int launchSense(const PhysEnv& env, const StatePtrs& sp, cudaStream_t stream, int64_t* launches, bool camera, int firstRobot, int nRobots) {
         bind(env, sp);
         SenseKParams p = kp;
         if (!camera) p.obs.camera = nullptr;
-        k_sense<<<(unsigned)nRobotsTotal, threads, senseSmem, stream>>>(p);
-        k_localmap<<<(unsigned)((nRobotsTotal + 127) / 128), 128, 0, stream>>>(p, (int)nRobotsTotal);
+        p.r0 = firstRobot;
+        k_sense<<<(unsigned)nRobots, threads, senseSmem, stream>>>(p);
+        k_localmap<<<(unsigned)((nRobots + 127) / 128), 128, 0, stream>>>(p, nRobots);
         (*launches) += 2;
         if (cudaGetLastError() != cudaSuccess) return fail(PS_E_CUDA, "k_sense / k_localmap launch failed");
         return PS_OK;
     }
-    int launchThink(int nArenas, cudaStream_t stream, int64_t* launches) {
-        k_think<<<nArenas, 128, 0, stream>>>(kp);
+    int launchThink(int firstArena, int nArenas, cudaStream_t stream, int64_t* launches) {
+        SenseKParams p = kp;
+        p.r0 = firstArena;
+        k_think<<<nArenas, 128, 0, stream>>>(p);
         (*launches)++;
         if (cudaGetLastError() != cudaSuccess) return fail(PS_E_CUDA, "k_think launch failed");
         return PS_OK;
-    }
-    int launchSenseOnly(const PhysEnv& env, const StatePtrs& sp, int nArenas, cudaStream_t stream, int64_t* launches) {
-        return launchSense(env, sp, stream, launches, haveCamera);
     }
     int readObservations(ps_obs_view* v, int nArenas, int R, cudaStream_t stream) {
         size_t n = (size_t)nArenas * R;

@@ -14,9 +14,9 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libpuckswarm_b200.so")
 
 EXPORTS = [
     "ps_last_error", "ps_abi_version", "ps_struct_size", "ps_config_defaults", "ps_create", "ps_destroy", "ps_load_calibration",
-    "ps_reset", "ps_set_state", "ps_get_state", "ps_step", "ps_sync", "ps_sense", "ps_step_external",
-    "ps_get_observations", "ps_compute_stats", "ps_stats_device_ptr", "ps_get_dims", "ps_get_step_stats", "ps_get_sense_stats",
-    "ps_profile", "ps_get_kernel_ms", "ps_kernel_launches", "ps_stream",
+    "ps_reset", "ps_set_state", "ps_get_state", "ps_step", "ps_sync", "ps_join", "ps_sense", "ps_step_external",
+    "ps_get_observations", "ps_compute_stats", "ps_stats_device_ptr", "ps_get_dims", "ps_get_step_stats", "ps_get_sense_stats", "ps_get_island_hist",
+    "ps_profile", "ps_get_kernel_ms", "ps_num_groups", "ps_kernel_launches", "ps_stream",
 ]
 
 
@@ -59,6 +59,7 @@ def load_library(path=None):
     L.ps_get_state.argtypes = [C.c_void_p, C.POINTER(abi.ps_state_view)]
     L.ps_step.argtypes = [C.c_void_p, C.c_int]
     L.ps_sync.argtypes = [C.c_void_p]
+    L.ps_join.argtypes = [C.c_void_p]
     L.ps_sense.argtypes = [C.c_void_p]
     L.ps_step_external.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.ps_get_observations.argtypes = [C.c_void_p, C.POINTER(abi.ps_obs_view)]
@@ -67,8 +68,10 @@ def load_library(path=None):
     L.ps_get_dims.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 5
     L.ps_get_step_stats.argtypes = [C.c_void_p, C.c_void_p]
     L.ps_get_sense_stats.argtypes = [C.c_void_p, C.c_void_p]
+    L.ps_get_island_hist.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.ps_profile.argtypes = [C.c_void_p, C.c_int]
     L.ps_get_kernel_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ps_num_groups.argtypes = [C.c_void_p]
     L.ps_kernel_launches.restype = C.c_int64
     L.ps_kernel_launches.argtypes = [C.c_void_p]
     L.ps_stream.restype = C.c_void_p
@@ -129,6 +132,10 @@ class Engine:
     def sync(self):
         self._check(self.L.ps_sync(self.h))
 
+    def join(self):
+        """Order the main stream after all queued steps (no host wait): events recorded on `stream` then cover them."""
+        self._check(self.L.ps_join(self.h))
+
     def sense(self):
         self._check(self.L.ps_sense(self.h))
         self.sync()
@@ -187,6 +194,11 @@ class Engine:
         self._check(self.L.ps_get_sense_stats(self.h, out.ctypes.data))
         return out
 
+    def island_hist(self, reset=True):
+        out = np.zeros((8, 8), np.int64)
+        self._check(self.L.ps_get_island_hist(self.h, out.ctypes.data, 1 if reset else 0))
+        return out
+
     def profile(self, enable=True):
         self._check(self.L.ps_profile(self.h, 1 if enable else 0))
 
@@ -197,6 +209,10 @@ class Engine:
         self._check(self.L.ps_get_kernel_ms(self.h, ms.ctypes.data, cnt.ctypes.data))
         names = ("sense", "think", "physics", "other", "phys_pre", "phys_islands", "phys_post", "unused")
         return dict(zip(names, ms.tolist())), dict(zip(names, cnt.tolist()))
+
+    @property
+    def num_groups(self):
+        return int(self.L.ps_num_groups(self.h))
 
     @property
     def kernel_launches(self):

@@ -51,6 +51,7 @@ Emu* emu_create(const ps_config* cfg) {
     e->env.trig.lut = e->hs.sinLut.data();
     e->env.trig.useLut = cfg->sincos_lut;
     e->env.cfg = pc;
+    e->env.hot = e->hs.hot;
     e->sp.body = e->body.data();
     e->sp.senseAabb = e->senseAabb.data();
     e->sp.fat = e->fat.data();
