@@ -1,0 +1,53 @@
+package puckswarm.b200;
+
+import java.nio.ByteBuffer;
+
+/**
+ * JNI face of libpuckswarm_b200.so (include/puckswarm_b200.h). One instance = one ps_handle = one batch of arenas on
+ * one GPU, confined to one Java thread. Every native method returns the C error code (0 = PS_OK); on failure
+ * {@link #lastError()} holds the message. Direct ByteBuffers are used for the caller-allocated arrays of the C-ABI so
+ * that no copy happens on the Java side.
+ *
+ * NOT COMPILED in the build image of this repository (no JDK there); see INTEGRATION.md for the build line.
+ */
+public final class NativeEngine implements AutoCloseable {
+    static { System.loadLibrary("puckswarm_b200_jni"); }
+
+    private long handle;   // ps_handle
+
+    /** cfg: a ps_config image laid out as in the header (use {@link Config#toBuffer()}). */
+    public NativeEngine(ByteBuffer cfg, int device) {
+        long[] out = new long[1];
+        check(psCreate(cfg, device, out));
+        handle = out[0];
+    }
+
+    public void loadCalibration(ByteBuffer xrYr, ByteBuffer xy, ByteBuffer flags, int n, int w, int h) { check(psLoadCalibration(handle, xrYr, xy, flags, n, w, h)); }
+    public void reset(long[] seeds) { check(psReset(handle, seeds)); }
+    /** n ticks of RunOffline.step(): {Arena.step | Arena.coast} + World.step(1/14f, 3, 100). Asynchronous. */
+    public void step(int nTicks) { check(psStep(handle, nTicks)); }
+    public void sync() { check(psSync(handle)); }
+    /** Host-controller path: sense now, then one think interval with the given commands [nArenas][nRobots]. */
+    public void sense() { check(psSense(handle)); }
+    public void stepExternal(float[] forwards, float[] torque) { check(psStepExternal(handle, forwards, torque)); }
+    /** poses [nArenas][nRobots][3], local maps and occupancy grids into direct buffers (null = skip). */
+    public void getObservations(ByteBuffer camera, ByteBuffer occupancy, ByteBuffer localmap, ByteBuffer pose) { check(psGetObservations(handle, camera, occupancy, localmap, pose)); }
+    public void getBodies(ByteBuffer body, ByteBuffer arena) { check(psGetBodies(handle, body, arena)); }
+    public void computeStats(float clusterThreshold, ByteBuffer stats) { check(psComputeStats(handle, clusterThreshold, stats)); }
+    @Override public void close() { if (handle != 0) { psDestroy(handle); handle = 0; } }
+
+    public static native String lastError();
+    private static void check(int rc) { if (rc != 0) throw new IllegalStateException("puckswarm_b200 error " + rc + ": " + lastError()); }
+
+    private static native int psCreate(ByteBuffer cfg, int device, long[] outHandle);
+    private static native int psDestroy(long h);
+    private static native int psLoadCalibration(long h, ByteBuffer xrYr, ByteBuffer xy, ByteBuffer flags, int n, int w, int hgt);
+    private static native int psReset(long h, long[] seeds);
+    private static native int psStep(long h, int nTicks);
+    private static native int psSync(long h);
+    private static native int psSense(long h);
+    private static native int psStepExternal(long h, float[] forwards, float[] torque);
+    private static native int psGetObservations(long h, ByteBuffer camera, ByteBuffer occupancy, ByteBuffer localmap, ByteBuffer pose);
+    private static native int psGetBodies(long h, ByteBuffer body, ByteBuffer arena);
+    private static native int psComputeStats(long h, float clusterThreshold, ByteBuffer stats);
+}

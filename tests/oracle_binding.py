@@ -117,8 +117,8 @@ class Oracle:
     def new_observations(self, camera=True):
         return abi.Observations(self.cfg.n_arenas, self.cfg.n_robots, self.img_w, self.img_h, self.occ_w, self.occ_h, camera)
 
-    def get_observations(self, obs=None):
-        obs = obs or self.new_observations()
+    def get_observations(self, obs=None, camera=True):
+        obs = obs or self.new_observations(camera)
         v = obs.view()
         assert self.L.orc_get_observations(self.h, C.byref(v)) == 0
         return obs

@@ -225,3 +225,85 @@ def test_errors_are_loud():
     bad = abi.config_defaults(n_arenas=0)
     with pytest.raises(engine.EngineError):
         engine.Engine(bad, device=0)
+
+
+def test_baseline_config_1_and_2():
+    """BASELINE configs[0] (1 arena, 2 robots, CacheCons, default pucks) and configs[1] (1 arena, 4 robots, BHD, 2 puck
+    colours; seeds 0..19 as ExperimentManager.java:274-281,368): free-running against the oracle."""
+    import parity
+    c1 = abi.config_defaults(n_arenas=1, n_robots=2, n_pucks=10, n_puck_types=2, controller=abi.PS_CTRL_CACHECONS)
+    e, o = _engine(c1), _oracle(c1)
+    e.reset([0])
+    o.reset([0])
+    e.step(600)
+    o.step(600)
+    assert parity.compare_states(e.get_state(), o.get_state(), 1, tol=TOL) == []
+    c2 = abi.config_defaults(n_arenas=20, n_robots=4, n_pucks=40, n_puck_types=2, controller=abi.PS_CTRL_BHD)
+    e, o = _engine(c2), _oracle(c2)
+    e.reset(np.arange(20))
+    o.reset(np.arange(20))
+    for _ in range(4):
+        e.step(75)
+        o.step(75)
+        assert parity.compare_states(e.get_state(), o.get_state(), 20, tol=TOL) == []
+
+
+def test_single_tick_parity_from_identical_states():
+    """The north_star's correctness statement, literally: one tick from identical states, many states."""
+    import parity
+    A, R, P = 6, 4, 40
+    cfg = abi.config_defaults(n_arenas=A, n_robots=R, n_pucks=P, controller=abi.PS_CTRL_BHD, step_interval=1)
+    e, o = _engine(cfg), _oracle(cfg)
+    o.reset(np.arange(A))
+    for k in range(120):
+        e.set_state(o.get_state())
+        e.step(1)
+        o.step(1)
+        se, so = e.get_state(), o.get_state()
+        assert parity.compare_states(se, so, A, tol=TOL) == [], k
+        # touching pair lists (contacts with manifold points) identical, in order
+        for a in range(A):
+            ke, ie, _ = se.contacts(a)
+            ko, io, _ = so.contacts(a)
+            assert np.array_equal(ke[(ie & 3) > 0], ko[(io & 3) > 0])
+
+
+def test_large_arena_shape_c5():
+    """BASELINE configs[4] shape: 256 robots / 4000 pucks, enclosure scale 6 (one arena; the oracle needs ~0.2 s per tick
+    and ~25 s per sense at this size): World.step under commands bit-exact, one sense bit-exact."""
+    import parity
+    cfg = abi.config_defaults(n_arenas=1, n_robots=256, n_pucks=4000, enclosure_scale=6.0, controller=abi.PS_CTRL_EXTERNAL)
+    e, o = _engine(cfg), _oracle(cfg, threads=1)
+    e.reset([0])
+    o.reset([0])
+    assert parity.compare_states(e.get_state(), o.get_state(), 1) == []
+    rng = np.random.RandomState(5)
+    for k in range(6):
+        fwd = ((rng.rand(1, 256) * 1.5) * 750000).astype(np.float32)
+        tq = ((rng.rand(1, 256) * 2 - 1) * 2375000).astype(np.float32)
+        e.step_external(fwd, tq)
+        o.step_external(fwd, tq)
+        bad = parity.compare_states(e.get_state(), o.get_state(), 1, what=("body", "sense_aabb", "fat_aabb", "contacts", "arena"))
+        assert bad == [], "think step %d: %s" % (k, bad[:5])
+    o.sense()
+    e.sense()
+    bad = parity.compare_observations(e.get_observations(camera=False), o.get_observations(camera=False))
+    assert bad == [], bad[:5]
+    assert (e.get_state().arena["error_flags"] == 0).all()
+
+
+def test_ensemble_statistics_match():
+    """Ensemble statistics over seeded episodes (the north_star asks for matching distributions; here they are compared
+    exactly): 64 episodes x 150 think steps, cluster-size histograms at the paper threshold and controller-state occupancy."""
+    cfg = abi.config_defaults(n_arenas=64, n_robots=4, n_pucks=40, controller=abi.PS_CTRL_CACHECONS)
+    e, o = _engine(cfg), _oracle(cfg)
+    e.reset(np.arange(64))
+    o.reset(np.arange(64))
+    for _ in range(3):
+        e.step(150)
+        o.step(150)
+        se, so = e.compute_stats(9.45), o.compute_stats(9.45)
+        assert np.array_equal(np.ctypeslib.as_array(se.cluster_size_hist), np.ctypeslib.as_array(so.cluster_size_hist))
+        assert list(se.ctrl_state_hist) == list(so.ctrl_state_hist)
+        assert se.n_carrying == so.n_carrying and se.n_caches == so.n_caches
+        assert abs(se.sum_completion - so.sum_completion) < 1e-9 * max(1.0, so.sum_completion)

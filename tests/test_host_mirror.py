@@ -1,0 +1,85 @@
+"""Host-side mirror of the reference interfaces (puckswarm_b200/host.py): the parts that need no GPU."""
+import numpy as np
+import pytest
+
+from puckswarm_b200 import abi, host
+
+
+def test_java_number_formatting():
+    # Float.toString / Double.toString as PositionList.save / PoseList.save write them
+    assert host.java_float_str(np.float32(1.5)) == "1.5"
+    assert host.java_float_str(np.float32(-38.847805)) == "-38.847805"
+    assert host.java_float_str(np.float32(100.0)) == "100.0"
+    assert host.java_float_str(np.float32(1e-4)) == "1.0E-4"
+    assert host.java_float_str(np.float32(1.25e7)) == "1.25E7"
+    assert host.java_float_str(np.float32(0.0)) == "0.0"
+    assert host.java_double_str(np.float32(1.1)) == "1.100000023841858"
+    assert host.java_double_str(2.0) == "2.0"
+    assert host.java_double_str(np.float32(-0.5)) == "-0.5"
+
+
+def test_properties_to_config(tmp_path):
+    (tmp_path / "common.properties").write_text("#comment\nrepetitions=20\nArena.nRobots=4\nArena.nPucks=40\nArena.nPuckTypes=2\n")
+    (tmp_path / "X.properties").write_text("code=X\ncontrollerType=BHD\nCacheConsController.CACHE_SEPARATION_OPTION=NULLIFY_OLD\n"
+                                            "VFHPlus.TAU_LO=0.6\nCacheConsController.IGNORE_PUCKS=true\nArena.nRobots=6\n")
+    e = host.Experiment.from_files(str(tmp_path), "X", seed=3)
+    assert e.getIndex() == 3 and e.code == "X"
+    assert e.getProperty("Arena.nRobots", 4) == 6 and e.getProperty("Arena.maxStepCount", 10000) == 10000
+    assert e.getProperty("CacheConsController.IGNORE_PUCKS", False) is True
+    cfg = e.to_config(n_arenas=5)
+    assert (cfg.n_arenas, cfg.n_robots, cfg.n_pucks, cfg.n_puck_types) == (5, 6, 40, 2)
+    assert cfg.controller == abi.PS_CTRL_BHD and cfg.cc_cache_separation == abi.PS_SEP_NULLIFY_OLD and cfg.cc_ignore_pucks == 1
+    assert abs(cfg.vfh_tau_lo - 0.6) < 1e-7 and abs(cfg.vfh_tau_hi - 0.85) < 1e-7
+    with pytest.raises(ValueError):
+        host.Experiment(0, {"Arena.nRobots": "four"}).getProperty("Arena.nRobots", 4)
+    with pytest.raises(ValueError):
+        host.Experiment(0, {"controllerType": "Nope"}).to_config()
+
+
+@pytest.mark.gpu
+def test_arena_runoffline_snapshot_and_host_controllers(tmp_path):
+    """The mirror drives the engine like RunOffline drives Arena; snapshots come out in the reference's text format;
+    a Java-style host controller runs through the batched external path."""
+    import oracle_binding as oracle
+    import parity
+    exp = host.Experiment(0, {"Arena.nRobots": "3", "Arena.nPucks": "20", "code": "T"})
+    seeds = [0, 1]
+    arena = host.Arena(exp, seeds)
+    run = host.RunOffline(arena, str(tmp_path))
+    for _ in range(30):
+        run.step()
+    assert arena.getStepCount() == 10
+    files = sorted(p.name for p in (tmp_path / "T" / "0").iterdir())
+    assert files == ["step0000000_GREEN_pucks.txt", "step0000000_RED_pucks.txt", "step0000000_robots.txt"]
+    rows = (tmp_path / "T" / "1" / "step0000000_robots.txt").read_text().strip().split("\n")
+    assert len(rows) == 3 and all(len(r.split(", ")) == 3 for r in rows)
+    # same trajectory as the oracle stepping the same experiment
+    o = oracle.Oracle(arena.cfg)
+    o.reset(seeds)
+    o.step(30)
+    assert parity.compare_states(arena.engine.get_state(), o.get_state(), 2, tol=1e-5) == []
+    suite = arena.getSuite(1, 2)
+    assert suite.getCameraImage().shape == (120, 160) and suite.getRobotName() == "R2"
+    assert parity.compare_states(arena.engine.get_state(), o.get_state(), 2, tol=1e-5) == []   # inspection has no side effect
+    arena.dispose()
+
+    class Spin(host.Controller):          # TestMovementController-style scripted controller
+        def computeDesired(self, suite, stepCount):
+            self.pose = suite.getAPS().getPose()
+            self.n = int(suite.getLocalMap()["n_pucks"])
+
+        def getForwards(self):
+            return 300000.0
+
+        def getTorque(self):
+            return 1000000.0
+
+    ctrls = [[Spin() for _ in range(3)] for _ in seeds]
+    a2 = host.Arena(exp, seeds, controllers=ctrls)
+    p0 = a2.robot_poses().copy()
+    for _ in range(5):
+        a2.step()
+    assert a2.getStepCount() == 5
+    assert (np.abs(a2.robot_poses()[..., 2] - p0[..., 2]) > 0.05).all()   # every robot turned
+    assert ctrls[1][2].n >= 0
+    a2.dispose()
