@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(128) k_island_warp(KParams p) {
     int lane = threadIdx.x & 31;
     for (;;) {
         int idx = 0;
-        if (lane == 0) idx = atomicAdd(&p.queue.counts[3], 1);
+        if (lane == 0) idx = atomicAdd(&p.queue.counts[kQueueBuckets], 1);
         idx = __shfl_sync(0xFFFFFFFFu, idx, 0);
         if (idx >= total) break;
         unsigned entry = p.queue.entries[idx];
@@ -185,13 +185,7 @@ __global__ void __launch_bounds__(128) k_island_batch(KParams p, int bucket) {
             islandStageLane(p.env, wk, k, *slots, lane, L);
             L.integ.g = &wk;
         }
-        int iters = 0;
-        // one state-machine step per trip for every lane that still has work; the warp re-converges at every trip
-        bool running = active;
-        while (__any_sync(0xFFFFFFFFu, running)) {
-            if (running) running = islandStepT(L.le, L.lw, st, L.c, &iters, L.integ);
-            __syncwarp();
-        }
+        int iters = islandSolveLanes(p.env, st, L, active);
         if (active) {
             islandFinishLane(p.env, wk, *slots, lane, L);
             atomicMax(&wk.stats[0], iters);
@@ -232,6 +226,8 @@ struct ps_engine {
     // streams; the latency tail of one group's slowest island overlaps with the other groups' work.
     struct Group {
         cudaStream_t s = nullptr, s2 = nullptr;   // s2: the few oversized islands, next to the lane batches
+        cudaStream_t sb[kQueueBuckets] = {};      // the lane batches of the other buckets run side by side as well
+        cudaEvent_t evb[kQueueBuckets] = {};
         cudaEvent_t evPre = nullptr, evBig = nullptr, done = nullptr;
         int a0 = 0, n = 0;
         IslandQueue q;
@@ -367,6 +363,8 @@ int ps_destroy(ps_handle h) {
     for (auto& g : h->groups) {
         if (g.s) cudaStreamSynchronize(g.s);
         if (g.s2) cudaStreamSynchronize(g.s2);
+        for (int b = 0; b < kQueueBuckets; b++)
+            if (g.sb[b]) cudaStreamSynchronize(g.sb[b]);
     }
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->kp.sp.body);
@@ -396,6 +394,10 @@ int ps_destroy(ps_handle h) {
         if (g.evBig) cudaEventDestroy(g.evBig);
         if (g.done) cudaEventDestroy(g.done);
         if (g.s2) cudaStreamDestroy(g.s2);
+        for (int b = 0; b < kQueueBuckets; b++) {
+            if (g.evb[b]) cudaEventDestroy(g.evb[b]);
+            if (g.sb[b]) cudaStreamDestroy(g.sb[b]);
+        }
         if (g.s) cudaStreamDestroy(g.s);
     }
     if (h->evStart) cudaEventDestroy(h->evStart);
@@ -498,19 +500,23 @@ int ps_create(const ps_config* cfg, int device, ps_handle* out) {
         if ((size_t)nGroups > A) nGroups = (int)A;
         size_t perGroup = (A + nGroups - 1) / nGroups;
         int qcap = (int)std::min<size_t>(perGroup * (size_t)pc.d.NB, (size_t)1 << 27);
-        TRY_OR_FREE(cudaMalloc(&e->kp.queue.entries, (size_t)nGroups * 3 * qcap * sizeof(unsigned)));
-        TRY_OR_FREE(cudaMalloc(&e->kp.queue.counts, (size_t)nGroups * 4 * sizeof(int)));
+        TRY_OR_FREE(cudaMalloc(&e->kp.queue.entries, (size_t)nGroups * kQueueBuckets * qcap * sizeof(unsigned)));
+        TRY_OR_FREE(cudaMalloc(&e->kp.queue.counts, (size_t)nGroups * (kQueueBuckets + 1) * sizeof(int)));
         e->kp.queue.cap = qcap;
         e->groups.resize(nGroups);
         for (int g = 0; g < nGroups; g++) {
             ps_engine::Group& G = e->groups[g];
             G.a0 = (int)std::min<size_t>(A, g * perGroup);
             G.n = (int)(std::min<size_t>(A, (g + 1) * perGroup) - G.a0);
-            G.q.entries = e->kp.queue.entries + (size_t)g * 3 * qcap;
-            G.q.counts = e->kp.queue.counts + (size_t)g * 4;
+            G.q.entries = e->kp.queue.entries + (size_t)g * kQueueBuckets * qcap;
+            G.q.counts = e->kp.queue.counts + (size_t)g * (kQueueBuckets + 1);
             G.q.cap = qcap;
             TRY_OR_FREE(cudaStreamCreateWithFlags(&G.s, cudaStreamNonBlocking));
             TRY_OR_FREE(cudaStreamCreateWithFlags(&G.s2, cudaStreamNonBlocking));
+            for (int b = 2; b < kQueueBuckets; b++) {
+                TRY_OR_FREE(cudaStreamCreateWithFlags(&G.sb[b], cudaStreamNonBlocking));
+                TRY_OR_FREE(cudaEventCreateWithFlags(&G.evb[b], cudaEventDisableTiming));
+            }
             TRY_OR_FREE(cudaEventCreateWithFlags(&G.evPre, cudaEventDisableTiming));
             TRY_OR_FREE(cudaEventCreateWithFlags(&G.evBig, cudaEventDisableTiming));
             TRY_OR_FREE(cudaEventCreateWithFlags(&G.done, cudaEventDisableTiming));
@@ -583,7 +589,7 @@ static int launchPhysics(ps_handle h, ps_engine::Group& G, int nTicks) {
     kp.a0 = G.a0;
     kp.queue = G.q;
     for (int t = 0; t < nTicks; ++t) {
-        CUDA_TRY(cudaMemsetAsync(G.q.counts, 0, 4 * sizeof(int), G.s));
+        CUDA_TRY(cudaMemsetAsync(G.q.counts, 0, (kQueueBuckets + 1) * sizeof(int), G.s));
         {
             ScopedTimer t4(h, 4, G.s);
             k_phys_pre<<<G.n, 128, 0, G.s>>>(kp);
@@ -597,14 +603,20 @@ static int launchPhysics(ps_handle h, ps_engine::Group& G, int nTicks) {
             k_island_warp<<<wb, 128, 4 * sizeof(WarpSlot), G.s2>>>(kp);
             CUDA_TRY(cudaEventRecord(G.evBig, G.s2));
             int bb = std::max(1, std::min(h->batchBlocks, (G.n * 12 + 127) / 128));
-            k_island_batch<<<bb, 128, 4 * sizeof(LaneSlots), G.s>>>(kp, 2);
+            for (int bucket = kQueueBuckets - 1; bucket >= 2; --bucket) {
+                CUDA_TRY(cudaStreamWaitEvent(G.sb[bucket], G.evPre, 0));
+                k_island_batch<<<bb, 128, 4 * sizeof(LaneSlots), G.sb[bucket]>>>(kp, bucket);
+                CUDA_TRY(cudaEventRecord(G.evb[bucket], G.sb[bucket]));
+            }
+            k_island_batch<<<bb, 128, 4 * sizeof(LaneSlots), G.s>>>(kp, 1);
+            for (int bucket = 2; bucket < kQueueBuckets; ++bucket) CUDA_TRY(cudaStreamWaitEvent(G.s, G.evb[bucket], 0));
             CUDA_TRY(cudaStreamWaitEvent(G.s, G.evBig, 0));
         }
         {
             ScopedTimer t6(h, 6, G.s);
             k_phys_post<<<G.n, 128, 0, G.s>>>(kp);
         }
-        h->launches += 4;
+        h->launches += 3 + (kQueueBuckets - 1);
         CUDA_TRY(cudaGetLastError());
     }
     return PS_OK;

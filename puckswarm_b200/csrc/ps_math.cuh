@@ -99,7 +99,9 @@ PS_HD float psSin(const Trig& t, float x) {
         if (!(fabsf(x) < kTwoPi)) x = fmodf(x, kTwoPi);
         if (x < 0) x += kTwoPi;
         int idx = (int)(x / kLutPrecision + 0.5f);
-        return t.lut[idx % kLutLength];
+        // idx % LUT_LENGTH: after the reduction x is in [0, 2 pi], so idx <= LUT_LENGTH and the modulo is one subtraction
+        if (idx >= kLutLength) idx = idx < 2 * kLutLength ? idx - kLutLength : idx % kLutLength;
+        return t.lut[idx];
     }
     return (float)sin((double)x);
 }

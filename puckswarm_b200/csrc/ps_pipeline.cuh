@@ -18,12 +18,14 @@
 namespace ps {
 
 struct IslandQueue {
-    unsigned* entries;     // [3][cap]: arena * NB + island; bucket 0 = islands with >= 3 contacts (one warp each),
-                           // bucket 1 unused, bucket 2 = lane batches of islands with 1-2 contacts
-    int* counts;           // [4]: entries per bucket, [3] = consumer head
+    unsigned* entries;     // [kQueueBuckets][cap]: arena * NB + island. Bucket 0: islands that do not fit a lane slot or have
+                           // >= kWarpMinContacts contacts (one warp each, level-parallel sweeps); buckets 1..4: lane batches of
+                           // islands with 1-2, 3-5, 6-12, 13+ contacts (like with like, so that the lanes of a warp finish together)
+    int* counts;           // [kQueueBuckets + 1]: entries per bucket, last = consumer head of bucket 0
     int cap;
 };
-static constexpr int kLaneBodies = 12, kLaneRobots = 4;   // capacity of one lane's shared-memory slot (k_island_batch)
+static constexpr int kLaneBodies = 12, kLaneRobots = 4;
+static constexpr int kQueueBuckets = 5, kWarpMinContacts = 24;   // capacity of one lane's shared-memory slot (k_island_batch)
 
 template <class Ctx>
 PS_HD void physPre(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaState& st, const float* cmdFwd, const float* cmdTorque,
@@ -43,9 +45,7 @@ PS_HD void physPre(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaSt
         int nb = wk.islandBodyStart[k + 1] - wk.islandBodyStart[k], nr = 0;
         for (int i = wk.islandBodyStart[k]; i < wk.islandBodyStart[k + 1]; ++i) nr += wk.ibody[i] >= d.P ? 1 : 0;
         int nc = wk.islandStart[k + 1] - wk.islandStart[k];
-        // islands with one or two contacts nearly always converge at once: 32 of them share a warp (one lane each).
-        // Larger islands mostly run tens of sweeps: each gets a warp that works through the sweep level by level.
-        int bucket = (nc >= 3 || nb > kLaneBodies || nr > kLaneRobots) ? 0 : 2;
+        int bucket = (nc >= kWarpMinContacts || nb > kLaneBodies || nr > kLaneRobots) ? 0 : (nc <= 2 ? 1 : (nc <= 5 ? 2 : (nc <= 12 ? 3 : 4)));
         int pos = ctx.atomicAddI(&q.counts[bucket], 1);
         if (pos < q.cap) q.entries[(size_t)bucket * q.cap + pos] = (unsigned)arena * (unsigned)d.NB + (unsigned)k;
     }
@@ -273,6 +273,71 @@ __device__ __forceinline__ void islandStageLane(const PhysEnv& e, const PhysWork
     L.nb = nb;
     L.nPuck = nPuck;
 }
+// Phase-synchronous solve of up to 32 staged islands, one per lane: the lanes walk warm start, velocity sweeps, integration
+// and position sweeps together (trip counts are the warp maximum, a lane without work at a trip idles), so the warp stays
+// converged and every warp instruction advances all its islands. `has` = this lane holds an island. Returns the lane's
+// position iterations.
+__device__ __forceinline__ int islandSolveLanes(const PhysEnv& e, const ArenaState& st, LaneIsland& L, bool has) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    int nc = has ? L.c.hi - L.c.lo : 0;
+    int lo = L.c.lo;
+    int maxNc = nc;
+    for (int o = 16; o > 0; o >>= 1) maxNc = max(maxNc, __shfl_xor_sync(FULL, maxNc, o));
+    const PhysEnv& le = L.le;
+    const PhysWork& lw = L.lw;
+    for (int i = 0; i < maxNc; ++i) {
+        if (i < nc) warmStartOne(le, lw, lw.tc[lw.order[lo + i]]);
+        __syncwarp();
+    }
+    for (int it = 0; it < e.cfg.velIters; ++it)
+        for (int i = 0; i < maxNc; ++i) {
+            if (i < nc) solveVelocityOne(le, lw, lw.tc[lw.order[lo + i]]);
+            __syncwarp();
+        }
+    if (has) {
+        for (int i = 0; i < nc; ++i) {
+            const TC& t = lw.tc[lw.order[lo + i]];
+            for (int j = 0; j < t.solverPoints; ++j) {
+                st.cimp[4 * t.ci + 2 * j] = t.nImp[j];
+                st.cimp[4 * t.ci + 2 * j + 1] = t.tImp[j];
+            }
+        }
+        for (int b = 0; b < L.nb; ++b) L.integ(le, lw, b);
+    }
+    __syncwarp();
+    int iters = 0;
+    bool running = has && e.cfg.posIters > 0;
+    int P = le.cfg.d.P;
+    while (__any_sync(FULL, running)) {
+        float minSep = 0.0f;
+        bool changed = false;
+        for (int i = 0; i < maxNc; ++i) {
+            if (running && i < nc) {
+                const TC& t = lw.tc[lw.order[lo + i]];
+                int bA = t.bodyA, bB = t.bodyB;
+                float imA = bA < 0 ? 0.0f : (bA < P ? e.hot.pmPuck : e.hot.pmRobot);
+                float iiA = bA < 0 ? 0.0f : (bA < P ? e.hot.piPuck : e.hot.piRobot);
+                float imB = bB < 0 ? 0.0f : (bB < P ? e.hot.pmPuck : e.hot.pmRobot);
+                float iiB = bB < 0 ? 0.0f : (bB < P ? e.hot.piPuck : e.hot.piRobot);
+                for (int j = 0; j < t.solverPoints; ++j) {
+                    float sep = correctPoint(le, lw, bA, bB, t.type, t.localNormal, t.localPoint, t.lp[j], t.radius, kContactBaumgarte, imA, iiA, imB, iiB, &changed);
+                    minSep = fminf_(minSep, sep);
+                }
+            }
+            __syncwarp();
+        }
+        if (running) {
+            ++iters;
+            if (minSep >= -1.5f * kLinearSlop || iters >= e.cfg.posIters) running = false;
+            else if (!changed) {   // fixed point: every later sweep repeats this one
+                iters = e.cfg.posIters;
+                running = false;
+            }
+        }
+    }
+    return iters;
+}
+
 __device__ __forceinline__ void islandFinishLane(const PhysEnv& e, const PhysWork& wk, LaneSlots& s, int lane, const LaneIsland& L) {
     int P = e.cfg.d.P;
     for (int l = 0; l < L.nb; ++l) {

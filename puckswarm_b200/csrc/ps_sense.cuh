@@ -152,6 +152,18 @@ PS_HD SenseWork carveSense(const SenseTables& t, Carver& cv) {
     return w;
 }
 
+// SenseWork whose pointers are byte offsets (carved from a null base on the host) -> pointers into this CTA's shared memory
+PS_HD SenseWork rebaseSense(const SenseWork& o, char* base) {
+    SenseWork w;
+    size_t b = (size_t)base;
+#define RB(f) w.f = (decltype(w.f))((size_t)o.f + b);
+    RB(img) RB(parent) RB(candX) RB(candY) RB(candBody) RB(candLx) RB(candLy) RB(candUx) RB(candUy) RB(candC) RB(candS) RB(candRx) RB(candRy)
+    RB(binCount) RB(binList) RB(blobArea) RB(blobX0) RB(blobX1) RB(blobY0) RB(blobY1) RB(blobSeed) RB(blobRoot) RB(blobOrder) RB(colList)
+    RB(counters) RB(phase)
+#undef RB
+    return w;
+}
+
 PS_HD int ufFind(const int* parent, int i) {
     int p = parent[i];
     while (p != i) {
@@ -518,8 +530,10 @@ PS_HD void senseRobot(Ctx& ctx, const PhysEnv& e, const SenseTables& T, const Se
 // LocalMap.update after the blobs are known: extractPucks (:236-317), extractClusters (:326-370), carriedCluster,
 // filterClusters (:375-437). Short, branchy and sequential -- executed by ONE thread per robot, all robots of the
 // batch in parallel (the working arrays are thread-local).
-PS_HD void localMapFromBlobs(const SenseTables& T, const SenseCfg& sc, const SenseHead& head, const BlobRec* blobs, const uint8_t* occ,
-                             ps_robot_state* rstate, ps_localmap& lm) {
+// Part A (sequential): perceived pucks, carry flag, clusters. Part B (data-parallel over occupancy cells, `first` /
+// `stride` select this caller's share): clusters near ROBOT cells. Part C (sequential): the remaining cluster filters.
+PS_HD void localMapPucksAndClusters(const SenseTables& T, const SenseCfg& sc, const SenseHead& head, const BlobRec* blobs,
+                                    ps_robot_state* rstate, ps_localmap& lm) {
     int nBlobs = head.nBlobs;
     if (nBlobs > kMaxBlobs) nBlobs = kMaxBlobs;
     // blob list order: by colour, then by seed (scan order); blobs that never seed are not found at all
@@ -679,19 +693,25 @@ PS_HD void localMapFromBlobs(const SenseTables& T, const SenseCfg& sc, const Sen
             if (lm.puck_x[p] == carriedX && lm.puck_y[p] == carriedY && (int)lm.puck_cluster[p] > carriedCluster) carriedCluster = lm.puck_cluster[p];
     lm.carried_cluster = carriedCluster;
     lm.overflow = overflow;
-    // ---- LocalMap.filterClusters, part 1: clusters with a puck closer than 10 cm to a ROBOT cell
+}
+
+// LocalMap.filterClusters, part 1: clusters with a puck closer than 10 cm to a ROBOT cell. Handles the 4-cell words
+// first, first + stride, ... of the occupancy grid (the writes are idempotent, so callers may share the work freely).
+PS_HD void localMapRobotFilter(const SenseTables& T, const uint8_t* occ, ps_localmap& lm, int first, int stride) {
+    int nP = lm.n_pucks;
+    if (nP == 0) return;
     int nCells = T.occW * T.occH;
-    if (nP > 0) {
-        for (int c = 0; c < nCells; ++c) {
-            // four cells per load while the pointer is word-aligned; most words hold no ROBOT cell at all
-            if ((c & 3) == 0 && c + 4 <= nCells && (((size_t)(occ + c)) & 3) == 0) {
-                uint32_t wv = *(const uint32_t*)(occ + c);
-                uint32_t xr = wv ^ (0x01010101u * (uint32_t)PS_T_ROBOT);
-                if (((xr - 0x01010101u) & ~xr & 0x80808080u) == 0) {   // no byte equals ROBOT
-                    c += 3;
-                    continue;
-                }
-            }
+    bool aligned = (((size_t)occ) & 3) == 0;
+    int nWords = (nCells + 3) / 4;
+    for (int w = first; w < nWords; w += stride) {
+        int c0 = w * 4;
+        if (aligned && c0 + 4 <= nCells) {
+            // most words hold no ROBOT cell at all
+            uint32_t wv = *(const uint32_t*)(occ + c0);
+            uint32_t xr = wv ^ (0x01010101u * (uint32_t)PS_T_ROBOT);
+            if (((xr - 0x01010101u) & ~xr & 0x80808080u) == 0) continue;
+        }
+        for (int c = c0; c < c0 + 4 && c < nCells; ++c) {
             if (occ[c] != PS_T_ROBOT) continue;
             int i = c / T.occH, j = c - i * T.occH;
             V2 robotV = mk(1.0f * j, T.maxYr - 1.0f * i);
@@ -699,7 +719,12 @@ PS_HD void localMapFromBlobs(const SenseTables& T, const SenseCfg& sc, const Sen
                 if (distSq(robotV, mk(lm.puck_x[p], lm.puck_y[p])) < 100.0f) lm.cluster_kept[lm.puck_cluster[p]] = 0;
         }
     }
-    // part 2: sequential pass over the surviving clusters
+}
+
+// LocalMap.filterClusters, part 2: sequential pass over the surviving clusters
+PS_HD void localMapFinalFilter(const SenseCfg& sc, const SenseHead& head, ps_localmap& lm) {
+    int nP = lm.n_pucks, nC = lm.n_clusters;
+    bool carrying = lm.carrying != 0;
     for (int c = 0; c < nC; ++c) {
         if (!lm.cluster_kept[c]) continue;
         bool remove = false;
@@ -724,6 +749,13 @@ PS_HD void localMapFromBlobs(const SenseTables& T, const SenseCfg& sc, const Sen
     }
     lm.left_sum = head.leftSum;
     lm.right_sum = head.rightSum;
+}
+
+PS_HD void localMapFromBlobs(const SenseTables& T, const SenseCfg& sc, const SenseHead& head, const BlobRec* blobs, const uint8_t* occ,
+                             ps_robot_state* rstate, ps_localmap& lm) {
+    localMapPucksAndClusters(T, sc, head, blobs, rstate, lm);
+    localMapRobotFilter(T, occ, lm, 0, 1);
+    localMapFinalFilter(sc, head, lm);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -15,6 +15,7 @@ struct SenseKParams {
     ObsPtrs obs;
     int nArenas;
     size_t fastCap;
+    SenseWork workOff;   // byte offsets of the camera stage's shared-memory arrays
     int r0;            // first robot (k_sense, k_localmap) / first arena (k_think) of the launch
     int* senseDbg;     // [nRobots][8] phase diagnostics of the last sense
     SenseHead* senseHead;   // [nRobots] camera stage -> local-map stage
@@ -28,13 +29,7 @@ __global__ void __launch_bounds__(256) k_sense(SenseKParams p) {
     __shared__ int scan[40];
     CtaCtx ctx;
     ctx.scanScratch = scan;
-    Carver cv;
-    cv.fast = g_senseSmem;
-    cv.fastCap = p.fastCap;
-    cv.fastUsed = 0;
-    cv.slow = (char*)p.obs.pose;   // never used: the host checked that everything fits in shared memory
-    cv.slowUsed = 0;
-    SenseWork wk = carveSense(p.T, cv);
+    SenseWork wk = rebaseSense(p.workOff, g_senseSmem);
     int R = p.env.cfg.d.R;
     int rg = p.r0 + (int)blockIdx.x;
     int a = rg / R, r = rg - a * R;
@@ -52,20 +47,29 @@ __global__ void __launch_bounds__(256) k_sense(SenseKParams p) {
     if (threadIdx.x < 8) p.senseDbg[ri * 8 + threadIdx.x] = wk.phase[threadIdx.x];
 }
 
-// LocalMap stage: one thread per robot over the whole batch
+// LocalMap stage: one warp per robot over the whole batch. The local map is built in shared memory: lane 0 walks the
+// blob list like LocalMap.extractPucks / extractClusters do, all lanes share the scan of the occupancy grid for ROBOT
+// cells, lane 0 finishes the cluster filter, and the warp writes the struct out coalesced.
 __global__ void __launch_bounds__(128) k_localmap(SenseKParams p, int nRobots) {
-    int ri = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ri >= nRobots) return;
-    ri += p.r0;
+    __shared__ ps_localmap lmS[4];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int idx = blockIdx.x * 4 + warp;
+    if (idx >= nRobots) return;
+    int ri = p.r0 + idx;
     int nCells = p.T.occW * p.T.occH;
-    ps_localmap lm;
+    ps_localmap& lm = lmS[warp];
     uint32_t* w = (uint32_t*)&lm;
-    for (int i = 0; i < (int)(sizeof(ps_localmap) / 4); ++i) w[i] = 0u;
-    long long t0 = clock64();
-    localMapFromBlobs(p.T, p.sc, p.senseHead[ri], p.blobs + (size_t)ri * kMaxBlobs, p.obs.occupancy + (size_t)ri * nCells, p.sp.robot + ri, lm);
-    long long t1 = clock64();
+    for (int i = lane; i < (int)(sizeof(ps_localmap) / 4); i += 32) w[i] = 0u;
+    __syncwarp();
+    const uint8_t* occ = p.obs.occupancy + (size_t)ri * nCells;
+    if (lane == 0) localMapPucksAndClusters(p.T, p.sc, p.senseHead[ri], p.blobs + (size_t)ri * kMaxBlobs, p.sp.robot + ri, lm);
+    __syncwarp();
+    localMapRobotFilter(p.T, occ, lm, lane, 32);
+    __syncwarp();
+    if (lane == 0) localMapFinalFilter(p.sc, p.senseHead[ri], lm);
+    __syncwarp();
     uint32_t* g = (uint32_t*)(p.obs.lm + ri);
-    for (int i = 0; i < (int)(sizeof(ps_localmap) / 4); ++i) g[i] = w[i];
+    for (int i = lane; i < (int)(sizeof(ps_localmap) / 4); i += 32) g[i] = w[i];
 }
 
 // one CTA per arena: controllers in robot order (shared java.util.Random)
@@ -247,7 +251,7 @@ struct SenseDevice {
         kp.obs.camera = nullptr;
         if (haveCamera && (rc = alloc(&kp.obs.camera, nRobotsTotal * nImg)) != PS_OK) return rc;
         Carver m = {nullptr, (size_t)200 * 1024, 0, nullptr, 0};
-        carveSense(kp.T, m);
+        kp.workOff = carveSense(kp.T, m);
         if (m.slowUsed) return fail(PS_E_INVALID, "camera image too large for shared memory");
         senseSmem = m.fastUsed;
         kp.fastCap = senseSmem;
@@ -270,7 +274,7 @@ struct SenseDevice {
         if (!camera) p.obs.camera = nullptr;
         p.r0 = firstRobot;
         k_sense<<<(unsigned)nRobots, threads, senseSmem, stream>>>(p);
-        k_localmap<<<(unsigned)((nRobots + 127) / 128), 128, 0, stream>>>(p, nRobots);
+        k_localmap<<<(unsigned)((nRobots + 3) / 4), 128, 0, stream>>>(p, nRobots);
         (*launches) += 2;
         if (cudaGetLastError() != cudaSuccess) return fail(PS_E_CUDA, "k_sense / k_localmap launch failed");
         return PS_OK;

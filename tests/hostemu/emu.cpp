@@ -117,11 +117,11 @@ int emu_step(Emu* e, int nTicks) {
                 worldStep(ctx, e->env, e->wk, st, fwd.data(), tq.data());
             } else {
                 // the three-stage pipeline of the engine, run for one arena: pre, every queued island, post
-                std::vector<unsigned> qe((size_t)3 * e->hs.phys.d.NB);
-                int qc[4] = {0, 0, 0, 0};
+                std::vector<unsigned> qe((size_t)kQueueBuckets * e->hs.phys.d.NB);
+                int qc[kQueueBuckets + 1] = {0};
                 IslandQueue q = {qe.data(), qc, e->hs.phys.d.NB};
                 physPre(ctx, e->env, e->wk, st, fwd.data(), tq.data(), q, 0);
-                for (int bucket = 0; bucket < 3; bucket++)
+                for (int bucket = 0; bucket < kQueueBuckets; bucket++)
                     for (int i = 0; i < qc[bucket]; i++) {
                         int k = (int)(qe[(size_t)bucket * q.cap + i] % (unsigned)e->hs.phys.d.NB);
                         IslandCursor cur;
