@@ -5,7 +5,9 @@
 #include <vector>
 #include <string>
 #include <cstring>
+#include <cstdlib>
 #include "ps_layout.cuh"
+#include "ps_pipeline.cuh"
 
 namespace ps {
 
@@ -41,6 +43,10 @@ struct HostSetup {
         while (mp < mc / 2) mp <<= 1;
         phys.MPAIR = mp;
         phys.MW = mc / 4 > 256 ? mc / 4 : 256;
+        {
+            const char* wv = getenv("PS_WARP_MIN_CONTACTS");
+            phys.warpMinContacts = wv && *wv ? atoi(wv) : kWarpMinContactsDefault;
+        }
         phys.velIters = c.vel_iters;
         phys.posIters = c.pos_iters;
         phys.toiEnabled = c.toi_enabled;

@@ -19,13 +19,13 @@ namespace ps {
 
 struct IslandQueue {
     unsigned* entries;     // [kQueueBuckets][cap]: arena * NB + island. Bucket 0: islands that do not fit a lane slot or have
-                           // >= kWarpMinContacts contacts (one warp each, level-parallel sweeps); buckets 1..4: lane batches of
+                           // >= PhysCfg::warpMinContacts contacts (one warp each, level-parallel sweeps); buckets 1..4: lane batches of
                            // islands with 1-2, 3-5, 6-12, 13+ contacts (like with like, so that the lanes of a warp finish together)
     int* counts;           // [kQueueBuckets + 1]: entries per bucket, last = consumer head of bucket 0
     int cap;
 };
 static constexpr int kLaneBodies = 12, kLaneRobots = 4;
-static constexpr int kQueueBuckets = 5, kWarpMinContacts = 24;   // capacity of one lane's shared-memory slot (k_island_batch)
+static constexpr int kQueueBuckets = 5, kWarpMinContactsDefault = 16;   // capacity of one lane's shared-memory slot (k_island_batch)
 
 template <class Ctx>
 PS_HD void physPre(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaState& st, const float* cmdFwd, const float* cmdTorque,
@@ -45,7 +45,7 @@ PS_HD void physPre(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaSt
         int nb = wk.islandBodyStart[k + 1] - wk.islandBodyStart[k], nr = 0;
         for (int i = wk.islandBodyStart[k]; i < wk.islandBodyStart[k + 1]; ++i) nr += wk.ibody[i] >= d.P ? 1 : 0;
         int nc = wk.islandStart[k + 1] - wk.islandStart[k];
-        int bucket = (nc >= kWarpMinContacts || nb > kLaneBodies || nr > kLaneRobots) ? 0 : (nc <= 2 ? 1 : (nc <= 5 ? 2 : (nc <= 12 ? 3 : 4)));
+        int bucket = (nc >= e.cfg.warpMinContacts || nb > kLaneBodies || nr > kLaneRobots) ? 0 : (nc <= 2 ? 1 : (nc <= 5 ? 2 : (nc <= 12 ? 3 : 4)));
         int pos = ctx.atomicAddI(&q.counts[bucket], 1);
         if (pos < q.cap) q.entries[(size_t)bucket * q.cap + pos] = (unsigned)arena * (unsigned)d.NB + (unsigned)k;
     }
