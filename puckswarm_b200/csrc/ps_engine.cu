@@ -112,6 +112,22 @@ __global__ void __launch_bounds__(128) k_phys_pre(KParams p) {
     int R = p.env.cfg.d.R;
     PhysWork wk = arenaWork(p, a);
     ArenaState st = arenaState(p.sp, p.env.cfg, a);
+    // the contact graph and the DFS bookkeeping are used by this stage only and are walked by one thread with dependent
+    // loads: keep them in shared memory when the arena is small enough (the usual case)
+    constexpr int kSB = 512, kST = 2304;
+    __shared__ int sAdjOff[kSB + 1], sAdjFill[kSB];
+    __shared__ uint16_t sAdj[2 * kST], sStack[kSB];
+    __shared__ uint32_t sTcPair[kST];
+    __shared__ uint8_t sBodyFlag[kSB], sTcFlag[kST];
+    if (p.env.cfg.d.NB <= kSB && p.env.cfg.MT <= kST) {
+        wk.adjOff = sAdjOff;
+        wk.adjFill = sAdjFill;
+        wk.adj = sAdj;
+        wk.stack = sStack;
+        wk.tcPair = sTcPair;
+        wk.bodyFlag = sBodyFlag;
+        wk.tcFlag = sTcFlag;
+    }
     const ps_robot_state* rs = p.sp.robot + (size_t)a * R;
     for (int r = threadIdx.x; r < R; r += blockDim.x) {
         wk.fx[r] = rs[r].cmd_forwards;

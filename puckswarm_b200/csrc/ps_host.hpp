@@ -37,7 +37,8 @@ struct HostSetup {
         phys.d = d;
         int mc = c.max_contacts > 0 ? c.max_contacts : (24 * c.n_pucks + 256 * c.n_robots + 127) / 128 * 128;
         phys.MC = mc;
-        phys.MT = mc / 2 < 65535 ? mc / 2 : 65535;
+        // touching contacts are a small fraction of the cached ones (a puck pair caches 4 contacts, at most 1 touches)
+        phys.MT = mc / 4 < 65535 ? mc / 4 : 65535;
         if (phys.MT < 64) phys.MT = 64;
         int mp = 256;
         while (mp < mc / 2) mp <<= 1;

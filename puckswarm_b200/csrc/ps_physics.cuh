@@ -72,6 +72,7 @@ struct PhysWork {
     uint16_t* stack;                                     // [NB]
     uint8_t* bodyFlag;                                   // [NB]
     uint8_t* tcFlag;                                     // [MT]
+    uint32_t* tcPair;                                    // [MT] (bodyA + 1) << 16 | (bodyB + 1) of each touching contact (0 = wall)
     uint8_t* moved;                                      // [NP]
     float* bodyFat;                                      // [4][NB] union of the body's fat AABBs
     int* movedList;                                      // [NP]
@@ -572,11 +573,14 @@ PS_HD void physIslands(Ctx& ctx, const PhysEnv& e, const PhysWork& wk) {
             wk.bodyFlag[b] = 0;
         }
     }
-    PS_FOR(t, nT) wk.tcFlag[t] = 0;
+    PS_FOR(t, nT) {
+        wk.tcFlag[t] = 0;
+        wk.tcPair[t] = ((uint32_t)(wk.tc[t].bodyA + 1) << 16) | (uint32_t)(wk.tc[t].bodyB + 1);
+    }
     ctx.sync();
     // degree of every dynamic body in the touching-contact graph
     PS_FOR(t, nT) {
-        int bA = wk.tc[t].bodyA, bB = wk.tc[t].bodyB;
+        int bA = (int)(wk.tcPair[t] >> 16) - 1, bB = (int)(wk.tcPair[t] & 0xFFFFu) - 1;
         if (bA >= 0) ctx.atomicAddI(&wk.adjOff[bA + 1], 1);
         if (bB >= 0) ctx.atomicAddI(&wk.adjOff[bB + 1], 1);
     }
@@ -598,7 +602,7 @@ PS_HD void physIslands(Ctx& ctx, const PhysEnv& e, const PhysWork& wk) {
     }
     // fill, then order every body's list newest contact first (= JBox2D's per-body contact edge list)
     PS_FOR(t, nT) {
-        int bA = wk.tc[t].bodyA, bB = wk.tc[t].bodyB;
+        int bA = (int)(wk.tcPair[t] >> 16) - 1, bB = (int)(wk.tcPair[t] & 0xFFFFu) - 1;
         if (bA >= 0) wk.adj[wk.adjOff[bA] + ctx.atomicAddI(&wk.adjFill[bA], 1)] = (uint16_t)t;
         if (bB >= 0) wk.adj[wk.adjOff[bB] + ctx.atomicAddI(&wk.adjFill[bB], 1)] = (uint16_t)t;
     }
@@ -654,7 +658,7 @@ PS_HD void physIslands(Ctx& ctx, const PhysEnv& e, const PhysWork& wk) {
                     if (wk.tcFlag[t]) continue;
                     wk.tcFlag[t] = 1;
                     wk.order[ordN++] = (uint16_t)t;
-                    int bA = wk.tc[t].bodyA, bB = wk.tc[t].bodyB;
+                    int bA = (int)(wk.tcPair[t] >> 16) - 1, bB = (int)(wk.tcPair[t] & 0xFFFFu) - 1;
                     int other = bA == b ? bB : bA;
                     if (other < 0) continue;   // the wall is static: part of the island, never expanded
                     if (wk.bodyFlag[other]) continue;
@@ -666,7 +670,7 @@ PS_HD void physIslands(Ctx& ctx, const PhysEnv& e, const PhysWork& wk) {
             int i1 = start - 1;
             for (int i2 = start; i2 < ordN; ++i2) {
                 int t = wk.order[i2];
-                bool nonStatic = wk.tc[t].bodyA >= 0 && wk.tc[t].bodyB >= 0;
+                bool nonStatic = (wk.tcPair[t] >> 16) != 0 && (wk.tcPair[t] & 0xFFFFu) != 0;
                 if (nonStatic) {
                     ++i1;
                     uint16_t tmp = wk.order[i1];
@@ -883,15 +887,20 @@ PS_HD void physFindNewContacts(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, c
     const Dims& d = e.cfg.d;
     int NB = d.NB;
     int nMoved = allNew ? d.NP : wk.counters[2];
-    // one thread per moved proxy: its new fat box against every body's box union (then that body's proxies), then the wall
-    PS_FOR(mi, nMoved) {
+    // four work items per moved proxy (each a quarter of the bodies): its new fat box against every body's box union
+    // (then that body's proxies); the first item also tests the wall
+    int quarter = (NB + 3) / 4;
+    PS_FOR(it, nMoved * 4) {
+        int mi = it >> 2, part = it & 3;
         int q = kWallFixtures + (allNew ? mi : wk.movedList[mi]);
         Aabb fatQ = proxyFat(e, st, q);
-        for (int b = 0; b < NB; ++b) {
+        int b1 = (part + 1) * quarter < NB ? (part + 1) * quarter : NB;
+        for (int b = part * quarter; b < b1; ++b) {
             if (!aabbOverlap(loadAabb(wk.bodyFat, NB, b), fatQ)) continue;
             int first = bodyFirstProxy(d, b), cnt = bodyProxyCount(d, b);
             for (int k = 0; k < cnt; ++k) tryPair(ctx, e, wk, st, q, fatQ, first + k, allNew);
         }
+        if (part != 0) continue;
         // wall: only proxies reaching the band where wall boxes live need the 84 tests
         float inner = e.scene->cornerX - 1.0f;
         if (fatQ.lx > -inner && fatQ.ux < inner && fatQ.ly > -inner && fatQ.uy < inner) continue;
