@@ -12,6 +12,7 @@
 #include "ps_host.hpp"
 #include "ps_sense_dev.cuh"
 #include "ps_pipeline.cuh"
+#include "ps_island_lanes.cuh"
 
 using namespace ps;
 
@@ -178,11 +179,13 @@ __global__ void __launch_bounds__(128) k_island_warp(KParams p) {
 // stage B2: all other islands (queue bucket 1): one lane per island, 32 islands per warp, bodies in shared memory
 __global__ void __launch_bounds__(128) k_island_batch(KParams p, int bucket) {
     extern __shared__ __align__(16) char smem[];
-    LaneSlots* slots = reinterpret_cast<LaneSlots*>(smem) + (threadIdx.x >> 5);
+    LaneCtx L;
+    L.S = reinterpret_cast<LaneSlotsU*>(smem) + (threadIdx.x >> 5);
+    L.lane = threadIdx.x & 31;
+    L.nb = L.lo = L.nc = 0;
     int cap = p.queue.cap;
     int total = min(p.queue.counts[bucket], cap);
     unsigned NB = (unsigned)p.env.cfg.d.NB;
-    int lane = threadIdx.x & 31;
     int stride = gridDim.x * blockDim.x;
     int rounds = (total + stride - 1) / stride;
     for (int rnd = 0; rnd < rounds; ++rnd) {
@@ -190,7 +193,6 @@ __global__ void __launch_bounds__(128) k_island_batch(KParams p, int bucket) {
         bool active = idx < total;
         PhysWork wk;
         ArenaState st;
-        LaneIsland L;
         int k = 0;
         if (active) {
             unsigned entry = p.queue.entries[(size_t)bucket * cap + idx];
@@ -198,12 +200,12 @@ __global__ void __launch_bounds__(128) k_island_batch(KParams p, int bucket) {
             k = (int)(entry % NB);
             wk = arenaWork(p, a);
             st = arenaState(p.sp, p.env.cfg, a);
-            islandStageLane(p.env, wk, k, *slots, lane, L);
-            L.integ.g = &wk;
+            lkStage(p.env, wk, k, L);
         }
-        int iters = islandSolveLanes(p.env, st, L, active);
+        __syncwarp();
+        int iters = lkSolve(p.env, wk, st, L, active);
         if (active) {
-            islandFinishLane(p.env, wk, *slots, lane, L);
+            lkFinish(p.env, wk, L);
             atomicMax(&wk.stats[0], iters);
             int nc = wk.islandStart[k + 1] - wk.islandStart[k];
             if (nc >= 3) {
@@ -453,6 +455,9 @@ int ps_create(const ps_config* cfg, int device, ps_handle* out) {
     } while (0)
     TRY_OR_FREE(cudaSetDevice(device));
     TRY_OR_FREE(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    int prioLow = 0, prioHigh = 0;
+    TRY_OR_FREE(cudaDeviceGetStreamPriorityRange(&prioLow, &prioHigh));
+    if (getenv("PS_NO_PRIORITY")) prioHigh = prioLow;
     TRY_OR_FREE(cudaEventCreateWithFlags(&e->evStart, cudaEventDisableTiming));
     const PhysCfg& pc = e->hs.phys;
     size_t A = cfg->n_arenas;
@@ -528,9 +533,10 @@ int ps_create(const ps_config* cfg, int device, ps_handle* out) {
             G.q.counts = e->kp.queue.counts + (size_t)g * (kQueueBuckets + 1);
             G.q.cap = qcap;
             TRY_OR_FREE(cudaStreamCreateWithFlags(&G.s, cudaStreamNonBlocking));
-            TRY_OR_FREE(cudaStreamCreateWithFlags(&G.s2, cudaStreamNonBlocking));
+            // the island kernels are small and latency-bound: their CTAs go ahead of the other groups' wide kernels
+            TRY_OR_FREE(cudaStreamCreateWithPriority(&G.s2, cudaStreamNonBlocking, prioHigh));
             for (int b = 2; b < kQueueBuckets; b++) {
-                TRY_OR_FREE(cudaStreamCreateWithFlags(&G.sb[b], cudaStreamNonBlocking));
+                TRY_OR_FREE(cudaStreamCreateWithPriority(&G.sb[b], cudaStreamNonBlocking, prioHigh));
                 TRY_OR_FREE(cudaEventCreateWithFlags(&G.evb[b], cudaEventDisableTiming));
             }
             TRY_OR_FREE(cudaEventCreateWithFlags(&G.evPre, cudaEventDisableTiming));
@@ -541,7 +547,7 @@ int ps_create(const ps_config* cfg, int device, ps_handle* out) {
         TRY_OR_FREE(cudaMemset(e->kp.islandHist, 0, 64 * sizeof(unsigned long long)));
         e->workerBlocks = prop.multiProcessorCount * (int)envSize("PS_WORKER_BLOCKS_PER_SM", 4);
         TRY_OR_FREE(cudaFuncSetAttribute(k_island_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(WarpSlot))));
-        TRY_OR_FREE(cudaFuncSetAttribute(k_island_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(LaneSlots))));
+        TRY_OR_FREE(cudaFuncSetAttribute(k_island_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(LaneSlotsU))));
         e->batchBlocks = prop.multiProcessorCount * (int)envSize("PS_BATCH_BLOCKS_PER_SM", 4);
     }
     e->kp.env.scene = e->dScene;
@@ -621,10 +627,10 @@ static int launchPhysics(ps_handle h, ps_engine::Group& G, int nTicks) {
             int bb = std::max(1, std::min(h->batchBlocks, (G.n * 12 + 127) / 128));
             for (int bucket = kQueueBuckets - 1; bucket >= 2; --bucket) {
                 CUDA_TRY(cudaStreamWaitEvent(G.sb[bucket], G.evPre, 0));
-                k_island_batch<<<bb, 128, 4 * sizeof(LaneSlots), G.sb[bucket]>>>(kp, bucket);
+                k_island_batch<<<bb, 128, 4 * sizeof(LaneSlotsU), G.sb[bucket]>>>(kp, bucket);
                 CUDA_TRY(cudaEventRecord(G.evb[bucket], G.sb[bucket]));
             }
-            k_island_batch<<<bb, 128, 4 * sizeof(LaneSlots), G.s>>>(kp, 1);
+            k_island_batch<<<bb, 128, 4 * sizeof(LaneSlotsU), G.s>>>(kp, 1);
             for (int bucket = 2; bucket < kQueueBuckets; ++bucket) CUDA_TRY(cudaStreamWaitEvent(G.s, G.evb[bucket], 0));
             CUDA_TRY(cudaStreamWaitEvent(G.s, G.evBig, 0));
         }

@@ -97,6 +97,8 @@ PS_HD PhysWork carveWork(const PhysCfg& c, Carver& cv) {
     w.bodyFat = (float*)cv.take((size_t)4 * NB * sizeof(float));
     w.moved = (uint8_t*)cv.take((size_t)NP);
     w.movedList = (int*)cv.take((size_t)NP * sizeof(int));
+    w.movedBody = (uint16_t*)cv.take((size_t)NB * sizeof(uint16_t));
+    w.bodyPairs = (uint32_t*)cv.take((size_t)4 * NB * sizeof(uint32_t));
     w.pairs = (uint32_t*)cv.take((size_t)c.MPAIR * sizeof(uint32_t));
     w.fatOld = (float*)cv.take((size_t)4 * NP * sizeof(float));
     w.wallList = (int*)cv.take((size_t)c.MW * sizeof(int));
@@ -124,7 +126,7 @@ PS_HD PhysWork rebaseWork(const PhysWork& o, char* base) {
     RB(cx) RB(cy) RB(a) RB(vx) RB(vy) RB(w) RB(c0x) RB(c0y) RB(a0)
     RB(rpx) RB(rpy) RB(rc) RB(rs) RB(r0px) RB(r0py) RB(r0c) RB(r0s) RB(fx) RB(fy) RB(tq)
     RB(adjOff) RB(adjFill) RB(adj) RB(order) RB(islandStart) RB(islandBodyStart) RB(ibody) RB(stack) RB(bodyFlag) RB(tcFlag) RB(tcPair)
-    RB(moved) RB(bodyFat) RB(movedList) RB(fatOld) RB(pairs) RB(wallList) RB(wallBody) RB(wallT) RB(wallState) RB(wallNeed)
+    RB(moved) RB(bodyFat) RB(movedList) RB(movedBody) RB(bodyPairs) RB(fatOld) RB(pairs) RB(wallList) RB(wallBody) RB(wallT) RB(wallState) RB(wallNeed)
     RB(toiT) RB(toiContact) RB(toiCur) RB(toiCount) RB(toiFound) RB(toiIter) RB(toiActive) RB(tc) RB(counters) RB(stats)
 #undef RB
     return w;

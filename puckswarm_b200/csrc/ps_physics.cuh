@@ -76,6 +76,8 @@ struct PhysWork {
     uint8_t* moved;                                      // [NP]
     float* bodyFat;                                      // [4][NB] union of the body's fat AABBs
     int* movedList;                                      // [NP]
+    uint16_t* movedBody;                                 // [NB] bodies with at least one moved proxy
+    uint32_t* bodyPairs;                                 // [4 * NB] (moved body << 16 | body) whose box unions overlap
     float* fatOld;                                       // [4][NP] fat AABB before this step's moveProxy
     uint32_t* pairs;                                     // [MPAIR]
     int* wallList;                                       // [MW] cached contacts with the wall
@@ -837,21 +839,30 @@ PS_HD void physSyncFixtures(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, cons
     ctx.sync();
 }
 
-// Union of each body's fat AABBs (pair-search culling)
+// Union of each body's fat AABBs, and the list of bodies with at least one moved proxy (pair-search culling)
+PS_HD int bodyPairCap(const Dims& d) { return 4 * d.NB; }
 template <class Ctx>
 PS_HD void physBodyFat(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaState& st) {
     const Dims& d = e.cfg.d;
+    if (ctx.tid() == 0) {
+        wk.counters[6] = 0;
+        wk.counters[7] = 0;
+    }
+    ctx.sync();
     PS_FOR(b, d.NB) {
         int first = bodyFirstProxy(d, b) - kWallFixtures, cnt = bodyProxyCount(d, b);
         Aabb u = loadAabb(st.fat, d.NP, first);
+        bool mv = wk.moved[first] != 0;
         for (int k = 1; k < cnt; ++k) {
             Aabb f = loadAabb(st.fat, d.NP, first + k);
             u.lx = fminf_(u.lx, f.lx);
             u.ly = fminf_(u.ly, f.ly);
             u.ux = fmaxf_(u.ux, f.ux);
             u.uy = fmaxf_(u.uy, f.uy);
+            mv = mv || wk.moved[first + k] != 0;
         }
         storeAabb(wk.bodyFat, d.NB, b, u);
+        if (mv) wk.movedBody[ctx.atomicAddI(&wk.counters[6], 1)] = (uint16_t)b;
     }
     ctx.sync();
 }
@@ -887,21 +898,52 @@ PS_HD void physFindNewContacts(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, c
     const Dims& d = e.cfg.d;
     int NB = d.NB;
     int nMoved = allNew ? d.NP : wk.counters[2];
-    // four work items per moved proxy (each a quarter of the bodies): its new fat box against every body's box union
-    // (then that body's proxies); the first item also tests the wall
-    int quarter = (NB + 3) / 4;
-    PS_FOR(it, nMoved * 4) {
-        int mi = it >> 2, part = it & 3;
-        int q = kWallFixtures + (allNew ? mi : wk.movedList[mi]);
-        Aabb fatQ = proxyFat(e, st, q);
-        int b1 = (part + 1) * quarter < NB ? (part + 1) * quarter : NB;
-        for (int b = part * quarter; b < b1; ++b) {
+    // (a) bodies with a moved proxy x bodies: which box unions overlap. The lists only prune: every pair below still goes
+    //     through the reference's tests (tryPair), and the pairs are sorted afterwards, so the order of discovery is free.
+    int nMB = wk.counters[6];
+    int cap = bodyPairCap(d);
+    PS_FOR(it, nMB * NB) {
+        int mi = it / NB, b = it - mi * NB;
+        int mb = wk.movedBody[mi];
+        if (b == mb) continue;
+        if (!aabbOverlap(loadAabb(wk.bodyFat, NB, b), loadAabb(wk.bodyFat, NB, mb))) continue;
+        int slot = ctx.atomicAddI(&wk.counters[7], 1);
+        if (slot < cap) wk.bodyPairs[slot] = ((uint32_t)mb << 16) | (uint32_t)b;
+    }
+    ctx.sync();
+    int nBP = wk.counters[7];
+    if (nBP <= cap) {
+        // (b) one work item per (overlapping body pair, proxy of the moved body): that proxy against the other body's proxies
+        int maxPer = d.R > 0 ? bodyProxyCount(d, d.P) : bodyProxyCount(d, 0);
+        if (d.P > 0 && bodyProxyCount(d, 0) > maxPer) maxPer = bodyProxyCount(d, 0);
+        PS_FOR(it, nBP * maxPer) {
+            int bp = it / maxPer, k = it - bp * maxPer;
+            uint32_t pr = wk.bodyPairs[bp];
+            int mb = (int)(pr >> 16), b = (int)(pr & 0xFFFFu);
+            if (k >= bodyProxyCount(d, mb)) continue;
+            int q = bodyFirstProxy(d, mb) + k;
+            if (!wk.moved[q - kWallFixtures]) continue;
+            Aabb fatQ = proxyFat(e, st, q);
             if (!aabbOverlap(loadAabb(wk.bodyFat, NB, b), fatQ)) continue;
             int first = bodyFirstProxy(d, b), cnt = bodyProxyCount(d, b);
-            for (int k = 0; k < cnt; ++k) tryPair(ctx, e, wk, st, q, fatQ, first + k, allNew);
+            for (int kk = 0; kk < cnt; ++kk) tryPair(ctx, e, wk, st, q, fatQ, first + kk, allNew);
         }
-        if (part != 0) continue;
-        // wall: only proxies reaching the band where wall boxes live need the 84 tests
+    } else {
+        // body-pair list overflow (a very crowded arena): every moved proxy against every body
+        PS_FOR(mi, nMoved) {
+            int q = kWallFixtures + (allNew ? mi : wk.movedList[mi]);
+            Aabb fatQ = proxyFat(e, st, q);
+            for (int b = 0; b < NB; ++b) {
+                if (!aabbOverlap(loadAabb(wk.bodyFat, NB, b), fatQ)) continue;
+                int first = bodyFirstProxy(d, b), cnt = bodyProxyCount(d, b);
+                for (int k = 0; k < cnt; ++k) tryPair(ctx, e, wk, st, q, fatQ, first + k, allNew);
+            }
+        }
+    }
+    // (c) wall: only proxies reaching the band where wall boxes live need the 84 tests
+    PS_FOR(mi, nMoved) {
+        int q = kWallFixtures + (allNew ? mi : wk.movedList[mi]);
+        Aabb fatQ = proxyFat(e, st, q);
         float inner = e.scene->cornerX - 1.0f;
         if (fatQ.lx > -inner && fatQ.ux < inner && fatQ.ly > -inner && fatQ.uy < inner) continue;
         for (int k = 0; k < kWallFixtures; ++k) tryPair(ctx, e, wk, st, q, fatQ, k, allNew);

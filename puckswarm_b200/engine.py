@@ -10,7 +10,7 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libpuckswarm_b200.so")
+LIB_PATH = os.environ.get("PS_ENGINE_LIB") or os.path.join(_HERE, "csrc", "libpuckswarm_b200.so")   # PS_ENGINE_LIB: diagnostic builds
 
 EXPORTS = [
     "ps_last_error", "ps_abi_version", "ps_struct_size", "ps_config_defaults", "ps_create", "ps_destroy", "ps_load_calibration",

@@ -54,6 +54,7 @@ def main():
     hdr = rows[hdr_i]
     ci = {h: i for i, h in enumerate(hdr)}
     lines = sass_lines(kernel)
+    opre = re.compile(os.environ["OP"]) if os.environ.get("OP") else None   # e.g. OP='STL|LDL': local-memory traffic only
     base = None
     inst = collections.Counter()
     stall = collections.Counter()
@@ -64,6 +65,8 @@ def main():
         addr = int(r[ci["Address"]], 16)
         if base is None:
             base = addr
+        if opre and not opre.search(r[ci["Source"]]):
+            continue
         key = lines.get(addr - base, ("?", 0))
         n = int(float(r[ci["Instructions Executed"]] or 0))
         s = int(float(r[ci["# Samples"]] or 0))
