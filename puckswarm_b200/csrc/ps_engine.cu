@@ -103,6 +103,23 @@ __global__ void __launch_bounds__(256) k_physics(KParams p, int nTicks) {
 }
 
 __device__ __forceinline__ PhysWork arenaWork(const KParams& p, int a) { return rebaseWork(p.workOff, p.arenaScratch + (size_t)a * p.arenaScratchStride); }
+// The same into one shared-memory copy per CTA ; the caller synchronises. As per-thread values the ~60 pointers spill to local memory, which is HBM traffic.
+__device__ __forceinline__ void arenaWorkShared(const KParams& p, int a, PhysWork& wk, ArenaState& st) {
+    if (threadIdx.x == 0) rebaseWorkInto(wk, p.workOff, p.arenaScratch + (size_t)a * p.arenaScratchStride);
+    if (threadIdx.x == 32 % blockDim.x) {
+        const PhysCfg& c = p.env.cfg;
+        size_t A = (size_t)a;
+        st.body = p.sp.body + A * 6 * c.d.NB;
+        st.senseAabb = p.sp.senseAabb + A * 4 * c.d.NB;
+        st.fat = p.sp.fat + A * 4 * c.d.NP;
+        st.ckey = p.sp.ckey + A * c.MC;
+        st.cinfo = p.sp.cinfo + A * c.MC;
+        st.cimp = p.sp.cimp + A * c.MC * 4;
+        st.nContacts = &p.sp.arena[a].n_contacts;
+        st.invDt0 = &p.sp.arena[a].inv_dt0;
+        st.errorFlags = &p.sp.arena[a].error_flags;
+    }
+}
 
 // stage A: one CTA per arena
 __global__ void __launch_bounds__(128) k_phys_pre(KParams p) {
@@ -111,8 +128,8 @@ __global__ void __launch_bounds__(128) k_phys_pre(KParams p) {
     ctx.scanScratch = scan;
     int a = p.a0 + blockIdx.x;
     int R = p.env.cfg.d.R;
-    PhysWork wk = arenaWork(p, a);
-    ArenaState st = arenaState(p.sp, p.env.cfg, a);
+    __shared__ PhysWork wk;     // one copy per CTA (see k_phys_post)
+    __shared__ ArenaState st;
     // the contact graph and the DFS bookkeeping are used by this stage only and are walked by one thread with dependent
     // loads: keep them in shared memory when the arena is small enough (the usual case)
     constexpr int kSB = 512, kST = 2304;
@@ -120,7 +137,9 @@ __global__ void __launch_bounds__(128) k_phys_pre(KParams p) {
     __shared__ uint16_t sAdj[2 * kST], sStack[kSB];
     __shared__ uint32_t sTcPair[kST];
     __shared__ uint8_t sBodyFlag[kSB], sTcFlag[kST];
-    if (p.env.cfg.d.NB <= kSB && p.env.cfg.MT <= kST) {
+    arenaWorkShared(p, a, wk, st);
+    __syncthreads();
+    if (threadIdx.x == 0 && p.env.cfg.d.NB <= kSB && p.env.cfg.MT <= kST) {
         wk.adjOff = sAdjOff;
         wk.adjFill = sAdjFill;
         wk.adj = sAdj;
@@ -129,6 +148,7 @@ __global__ void __launch_bounds__(128) k_phys_pre(KParams p) {
         wk.bodyFlag = sBodyFlag;
         wk.tcFlag = sTcFlag;
     }
+    __syncthreads();
     const ps_robot_state* rs = p.sp.robot + (size_t)a * R;
     for (int r = threadIdx.x; r < R; r += blockDim.x) {
         wk.fx[r] = rs[r].cmd_forwards;
@@ -176,8 +196,9 @@ __global__ void __launch_bounds__(128) k_island_warp(KParams p) {
     }
 }
 
+static constexpr int kBatchThreads = 64;   // two lane slots (2 x 32 islands) per CTA: a slot is ~41 KB of shared memory
 // stage B2: all other islands (queue bucket 1): one lane per island, 32 islands per warp, bodies in shared memory
-__global__ void __launch_bounds__(128) k_island_batch(KParams p, int bucket) {
+__global__ void __launch_bounds__(kBatchThreads) k_island_batch(KParams p, int bucket) {
     extern __shared__ __align__(16) char smem[];
     LaneCtx L;
     L.S = reinterpret_cast<LaneSlotsU*>(smem) + (threadIdx.x >> 5);
@@ -224,11 +245,16 @@ __global__ void __launch_bounds__(128) k_phys_post(KParams p) {
     CtaCtx ctx;
     ctx.scanScratch = scan;
     int a = p.a0 + blockIdx.x;
-    PhysWork wk = arenaWork(p, a);
-    ArenaState st = arenaState(p.sp, p.env.cfg, a);
-    // the pair search reads every body's box union once per moved proxy: keep that table in shared memory when it fits
+    // the ~60 array pointers of the arena live in shared memory, one copy per CTA: as per-thread values they spill to
+    // local memory, and local memory goes through L2 to HBM
+    __shared__ PhysWork wk;
+    __shared__ ArenaState st;
+    // the pair search reads every body's box union once per moved body: keep that table in shared memory when it fits
     __shared__ float sBodyFat[4 * 512];
-    if (p.env.cfg.d.NB <= 512) wk.bodyFat = sBodyFat;
+    arenaWorkShared(p, a, wk, st);
+    __syncthreads();
+    if (threadIdx.x == 0 && p.env.cfg.d.NB <= 512) wk.bodyFat = sBodyFat;
+    __syncthreads();
     physPost(ctx, p.env, wk, st);
     if (threadIdx.x == 0) p.sp.arena[a].update_count += 1;
     if (threadIdx.x < 8) p.stepStats[a * 8 + threadIdx.x] = wk.stats[threadIdx.x];
@@ -547,8 +573,8 @@ int ps_create(const ps_config* cfg, int device, ps_handle* out) {
         TRY_OR_FREE(cudaMemset(e->kp.islandHist, 0, 64 * sizeof(unsigned long long)));
         e->workerBlocks = prop.multiProcessorCount * (int)envSize("PS_WORKER_BLOCKS_PER_SM", 4);
         TRY_OR_FREE(cudaFuncSetAttribute(k_island_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(WarpSlot))));
-        TRY_OR_FREE(cudaFuncSetAttribute(k_island_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(LaneSlotsU))));
-        e->batchBlocks = prop.multiProcessorCount * (int)envSize("PS_BATCH_BLOCKS_PER_SM", 4);
+        TRY_OR_FREE(cudaFuncSetAttribute(k_island_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((kBatchThreads / 32) * sizeof(LaneSlotsU))));
+        e->batchBlocks = prop.multiProcessorCount * (int)envSize("PS_BATCH_BLOCKS_PER_SM", 2);
     }
     e->kp.env.scene = e->dScene;
     e->kp.env.trig.lut = e->dLut;
@@ -624,13 +650,13 @@ static int launchPhysics(ps_handle h, ps_engine::Group& G, int nTicks) {
             int wb = std::max(1, std::min(h->workerBlocks, G.n * 3));
             k_island_warp<<<wb, 128, 4 * sizeof(WarpSlot), G.s2>>>(kp);
             CUDA_TRY(cudaEventRecord(G.evBig, G.s2));
-            int bb = std::max(1, std::min(h->batchBlocks, (G.n * 12 + 127) / 128));
+            int bb = std::max(1, std::min(h->batchBlocks, (G.n * 12 + kBatchThreads - 1) / kBatchThreads));
             for (int bucket = kQueueBuckets - 1; bucket >= 2; --bucket) {
                 CUDA_TRY(cudaStreamWaitEvent(G.sb[bucket], G.evPre, 0));
-                k_island_batch<<<bb, 128, 4 * sizeof(LaneSlotsU), G.sb[bucket]>>>(kp, bucket);
+                k_island_batch<<<bb, kBatchThreads, (kBatchThreads / 32) * sizeof(LaneSlotsU), G.sb[bucket]>>>(kp, bucket);
                 CUDA_TRY(cudaEventRecord(G.evb[bucket], G.sb[bucket]));
             }
-            k_island_batch<<<bb, 128, 4 * sizeof(LaneSlotsU), G.s>>>(kp, 1);
+            k_island_batch<<<bb, kBatchThreads, (kBatchThreads / 32) * sizeof(LaneSlotsU), G.s>>>(kp, 1);
             for (int bucket = 2; bucket < kQueueBuckets; ++bucket) CUDA_TRY(cudaStreamWaitEvent(G.s, G.evb[bucket], 0));
             CUDA_TRY(cudaStreamWaitEvent(G.s, G.evBig, 0));
         }

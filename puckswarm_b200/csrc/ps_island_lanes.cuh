@@ -20,8 +20,13 @@ enum { LK_PUCK = 0, LK_ROBOT = 1, LK_WALL = 2 };
 struct LaneSlotsU {
     float cx[kLB][32], cy[kLB][32], a[kLB][32], vx[kLB][32], vy[kLB][32], w[kLB][32];
     float px[kLB][32], py[kLB][32], c[kLB][32], s[kLB][32];
+    float pm[kLB][32], pi[kLB][32];   // position-solver inverse masses (mass * invMass, mass * invI; 0 for the wall)
     uint16_t gidx[kLB][32];
     uint8_t kind[kLB][32];
+    // what the position sweeps read of each constraint: localNormal, localPoint, the two manifold points, radius, and
+    // bodyA | bodyB << 8 | type << 16 | points << 24 (up to 100 sweeps re-read these: shared memory instead of L2 latency)
+    float pc[kLaneContacts][9][32];
+    uint32_t pcHead[kLaneContacts][32];
 };
 
 struct LaneCtx {
@@ -29,26 +34,39 @@ struct LaneCtx {
     int lane;
     int nb;          // staged dynamic bodies; local index nb is the wall
     int lo, nc;      // this island's range in wk.order
+    // body-table accessors (the solver routines below are written against these; WarpBodies in ps_pipeline.cuh is the
+    // other implementation)
+    __device__ __forceinline__ float& cx(int l) const { return S->cx[l][lane]; }
+    __device__ __forceinline__ float& cy(int l) const { return S->cy[l][lane]; }
+    __device__ __forceinline__ float& a(int l) const { return S->a[l][lane]; }
+    __device__ __forceinline__ float& vx(int l) const { return S->vx[l][lane]; }
+    __device__ __forceinline__ float& vy(int l) const { return S->vy[l][lane]; }
+    __device__ __forceinline__ float& w(int l) const { return S->w[l][lane]; }
+    __device__ __forceinline__ float& px(int l) const { return S->px[l][lane]; }
+    __device__ __forceinline__ float& py(int l) const { return S->py[l][lane]; }
+    __device__ __forceinline__ float& c(int l) const { return S->c[l][lane]; }
+    __device__ __forceinline__ float& s(int l) const { return S->s[l][lane]; }
+    __device__ __forceinline__ float pm(int l) const { return S->pm[l][lane]; }
+    __device__ __forceinline__ float pi(int l) const { return S->pi[l][lane]; }
+    __device__ __forceinline__ int kind(int l) const { return S->kind[l][lane]; }
+    __device__ __forceinline__ int gidx(int l) const { return S->gidx[l][lane]; }
 };
 
 __device__ __forceinline__ float lkInvMass(const HotConsts& h, int kind) { return kind == LK_PUCK ? h.puck.invMass : (kind == LK_ROBOT ? h.robot.invMass : 0.0f); }
 __device__ __forceinline__ float lkInvI(const HotConsts& h, int kind) { return kind == LK_PUCK ? h.puck.invI : (kind == LK_ROBOT ? h.robot.invI : 0.0f); }
-__device__ __forceinline__ float lkPosInvMass(const HotConsts& h, int kind) { return kind == LK_PUCK ? h.pmPuck : (kind == LK_ROBOT ? h.pmRobot : 0.0f); }
-__device__ __forceinline__ float lkPosInvI(const HotConsts& h, int kind) { return kind == LK_PUCK ? h.piPuck : (kind == LK_ROBOT ? h.piRobot : 0.0f); }
 
 // Body.synchronizeTransform of staged body l
-__device__ __forceinline__ void lkSyncXf(const PhysEnv& e, const LaneCtx& L, int l) {
-    LaneSlotsU& S = *L.S;
-    int ln = L.lane;
-    if (S.kind[l][ln] == LK_ROBOT) {
-        Xf T = makeXf(e.trig, S.cx[l][ln], S.cy[l][ln], S.a[l][ln], e.hot.robot.lcx, e.hot.robot.lcy);
-        S.px[l][ln] = T.px;
-        S.py[l][ln] = T.py;
-        S.c[l][ln] = T.c;
-        S.s[l][ln] = T.s;
+template <class BT>
+__device__ __forceinline__ void lkSyncXf(const PhysEnv& e, const BT& L, int l) {
+    if (L.kind(l) == LK_ROBOT) {
+        Xf T = makeXf(e.trig, L.cx(l), L.cy(l), L.a(l), e.hot.robot.lcx, e.hot.robot.lcy);
+        L.px(l) = T.px;
+        L.py(l) = T.py;
+        L.c(l) = T.c;
+        L.s(l) = T.s;
     } else {
-        S.px[l][ln] = S.cx[l][ln];
-        S.py[l][ln] = S.cy[l][ln];
+        L.px(l) = L.cx(l);
+        L.py(l) = L.cy(l);
     }
 }
 
@@ -74,12 +92,16 @@ __device__ __forceinline__ void lkStage(const PhysEnv& e, const PhysWork& wk, in
         if (g >= P) {
             int r = g - P;
             S.kind[l][ln] = LK_ROBOT;
+            S.pm[l][ln] = e.hot.pmRobot;
+            S.pi[l][ln] = e.hot.piRobot;
             S.px[l][ln] = wk.rpx[r];
             S.py[l][ln] = wk.rpy[r];
             S.c[l][ln] = wk.rc[r];
             S.s[l][ln] = wk.rs[r];
         } else {
             S.kind[l][ln] = LK_PUCK;
+            S.pm[l][ln] = e.hot.pmPuck;
+            S.pi[l][ln] = e.hot.piPuck;
             S.px[l][ln] = wk.cx[g];
             S.py[l][ln] = wk.cy[g];
             S.c[l][ln] = 1.0f;
@@ -88,6 +110,8 @@ __device__ __forceinline__ void lkStage(const PhysEnv& e, const PhysWork& wk, in
     }
     // the wall: a body that never moves (zero inverse masses), sweep.c = (0, 0), its transform from the scene
     S.kind[nb][ln] = LK_WALL;
+    S.pm[nb][ln] = 0.0f;
+    S.pi[nb][ln] = 0.0f;
     S.cx[nb][ln] = 0.0f;
     S.cy[nb][ln] = 0.0f;
     S.a[nb][ln] = 0.0f;
@@ -109,6 +133,16 @@ __device__ __forceinline__ void lkStage(const PhysEnv& e, const PhysWork& wk, in
         }
         t.bodyA = la;
         t.bodyB = lb;
+        S.pc[i][0][ln] = t.localNormal.x;
+        S.pc[i][1][ln] = t.localNormal.y;
+        S.pc[i][2][ln] = t.localPoint.x;
+        S.pc[i][3][ln] = t.localPoint.y;
+        S.pc[i][4][ln] = t.lp[0].x;
+        S.pc[i][5][ln] = t.lp[0].y;
+        S.pc[i][6][ln] = t.lp[1].x;
+        S.pc[i][7][ln] = t.lp[1].y;
+        S.pc[i][8][ln] = t.radius;
+        S.pcHead[i][ln] = (uint32_t)la | ((uint32_t)lb << 8) | ((uint32_t)t.type << 16) | ((uint32_t)t.solverPoints << 24);
     }
 }
 
@@ -135,13 +169,12 @@ __device__ __forceinline__ void lkFinish(const PhysEnv& e, const PhysWork& wk, c
 }
 
 // ContactSolver.warmStart for one constraint (= warmStartOne)
-__device__ __forceinline__ void lkWarmStart(const PhysEnv& e, const LaneCtx& L, const TC& c) {
-    LaneSlotsU& S = *L.S;
-    int ln = L.lane;
+template <class BT>
+__device__ __forceinline__ void lkWarmStart(const PhysEnv& e, const BT& L, const TC& c) {
     int A = c.bodyA, B = c.bodyB;
-    int kA = S.kind[A][ln], kB = S.kind[B][ln];
-    V2 vA = mk(S.vx[A][ln], S.vy[A][ln]), vB = mk(S.vx[B][ln], S.vy[B][ln]);
-    float wA = S.w[A][ln], wB = S.w[B][ln];
+    int kA = L.kind(A), kB = L.kind(B);
+    V2 vA = mk(L.vx(A), L.vy(A)), vB = mk(L.vx(B), L.vy(B));
+    float wA = L.w(A), wB = L.w(B);
     float invMassA = lkInvMass(e.hot, kA), invIA = lkInvI(e.hot, kA), invMassB = lkInvMass(e.hot, kB), invIB = lkInvI(e.hot, kB);
     V2 normal = c.normal, tangent = crossVS(normal, 1.0f);
     for (int j = 0; j < c.solverPoints; ++j) {
@@ -152,25 +185,24 @@ __device__ __forceinline__ void lkWarmStart(const PhysEnv& e, const LaneCtx& L, 
         vB = vB + invMassB * P;
     }
     if (kA != LK_WALL) {
-        S.vx[A][ln] = vA.x;
-        S.vy[A][ln] = vA.y;
-        S.w[A][ln] = wA;
+        L.vx(A) = vA.x;
+        L.vy(A) = vA.y;
+        L.w(A) = wA;
     }
     if (kB != LK_WALL) {
-        S.vx[B][ln] = vB.x;
-        S.vy[B][ln] = vB.y;
-        S.w[B][ln] = wB;
+        L.vx(B) = vB.x;
+        L.vy(B) = vB.y;
+        L.w(B) = wB;
     }
 }
 
 // ContactSolver.solveVelocityConstraints for one constraint (= solveVelocityOne)
-__device__ __forceinline__ void lkSolveVelocity(const PhysEnv& e, const LaneCtx& L, TC& c) {
-    LaneSlotsU& S = *L.S;
-    int ln = L.lane;
+template <class BT>
+__device__ __forceinline__ void lkSolveVelocity(const PhysEnv& e, const BT& L, TC& c) {
     int A = c.bodyA, B = c.bodyB;
-    int kA = S.kind[A][ln], kB = S.kind[B][ln];
-    V2 vA = mk(S.vx[A][ln], S.vy[A][ln]), vB = mk(S.vx[B][ln], S.vy[B][ln]);
-    float wA = S.w[A][ln], wB = S.w[B][ln];
+    int kA = L.kind(A), kB = L.kind(B);
+    V2 vA = mk(L.vx(A), L.vy(A)), vB = mk(L.vx(B), L.vy(B));
+    float wA = L.w(A), wB = L.w(B);
     float invMassA = lkInvMass(e.hot, kA), invIA = lkInvI(e.hot, kA), invMassB = lkInvMass(e.hot, kB), invIB = lkInvI(e.hot, kB);
     V2 normal = c.normal, tangent = crossVS(normal, 1.0f);
     float friction = e.hot.friction;
@@ -241,31 +273,30 @@ __device__ __forceinline__ void lkSolveVelocity(const PhysEnv& e, const LaneCtx&
         }
     }
     if (kA != LK_WALL) {
-        S.vx[A][ln] = vA.x;
-        S.vy[A][ln] = vA.y;
-        S.w[A][ln] = wA;
+        L.vx(A) = vA.x;
+        L.vy(A) = vA.y;
+        L.w(A) = wA;
     }
     if (kB != LK_WALL) {
-        S.vx[B][ln] = vB.x;
-        S.vy[B][ln] = vB.y;
-        S.w[B][ln] = wB;
+        L.vx(B) = vB.x;
+        L.vy(B) = vB.y;
+        L.w(B) = wB;
     }
 }
 
 // One position correction of one manifold point (= positionManifold + correctPoint). Returns the separation.
-__device__ __forceinline__ float lkCorrectPoint(const PhysEnv& e, const LaneCtx& L, int A, int B, int type, V2 localNormal, V2 localPoint, V2 pointLocal,
+template <class BT>
+__device__ __forceinline__ float lkCorrectPoint(const PhysEnv& e, const BT& L, int A, int B, int type, V2 localNormal, V2 localPoint, V2 pointLocal,
                                                 float radius, bool* changed) {
-    LaneSlotsU& S = *L.S;
-    int ln = L.lane;
     Xf xfA, xfB;
-    xfA.px = S.px[A][ln];
-    xfA.py = S.py[A][ln];
-    xfA.c = S.c[A][ln];
-    xfA.s = S.s[A][ln];
-    xfB.px = S.px[B][ln];
-    xfB.py = S.py[B][ln];
-    xfB.c = S.c[B][ln];
-    xfB.s = S.s[B][ln];
+    xfA.px = L.px(A);
+    xfA.py = L.py(A);
+    xfA.c = L.c(A);
+    xfA.s = L.s(A);
+    xfB.px = L.px(B);
+    xfB.py = L.py(B);
+    xfB.c = L.c(B);
+    xfB.s = L.s(B);
     // circles: pointA = xfA * localPoint, pointB = xfB * pointLocal; face A: plane = xfA * localPoint, clip = xfB * pointLocal;
     // face B: plane = xfB * localPoint, clip = xfA * pointLocal  -> one computation with the reference side selected
     bool faceB = type == MF_FACE_B;
@@ -288,12 +319,12 @@ __device__ __forceinline__ float lkCorrectPoint(const PhysEnv& e, const LaneCtx&
         point = p2;
         if (faceB) normal = -normal;
     }
-    V2 cA = mk(S.cx[A][ln], S.cy[A][ln]), cB = mk(S.cx[B][ln], S.cy[B][ln]);
+    V2 cA = mk(L.cx(A), L.cy(A)), cB = mk(L.cx(B), L.cy(B));
     V2 rA = point - cA, rB = point - cB;
     float C = clampf(kContactBaumgarte * (separation + kLinearSlop), -kMaxLinearCorrection, 0.0f);
     if (C == 0.0f) return separation;
-    int kA = S.kind[A][ln], kB = S.kind[B][ln];
-    float invMassA = lkPosInvMass(e.hot, kA), invIA = lkPosInvI(e.hot, kA), invMassB = lkPosInvMass(e.hot, kB), invIB = lkPosInvI(e.hot, kB);
+    // mass-scaled inverse masses per staged body; the wall's are zero, so it "moves" by -0 * P: never
+    float invMassA = L.pm(A), invIA = L.pi(A), invMassB = L.pm(B), invIB = L.pi(B);
     float rnA = cross(rA, normal), rnB = cross(rB, normal);
     float K = invMassA + invMassB + invIA * rnA * rnA + invIB * rnB * rnB;
     float impulse = K > 0.0f ? -C / K : 0.0f;
@@ -301,24 +332,24 @@ __device__ __forceinline__ float lkCorrectPoint(const PhysEnv& e, const LaneCtx&
     bool moved = false;
     {
         V2 nc = cA - invMassA * P;
-        float oa = S.a[A][ln];
+        float oa = L.a(A);
         float na = oa - invIA * cross(rA, P);
-        if (kA != LK_WALL && (nc.x != cA.x || nc.y != cA.y || na != oa)) {
-            S.cx[A][ln] = nc.x;
-            S.cy[A][ln] = nc.y;
-            S.a[A][ln] = na;
+        if (nc.x != cA.x || nc.y != cA.y || na != oa) {
+            L.cx(A) = nc.x;
+            L.cy(A) = nc.y;
+            L.a(A) = na;
             lkSyncXf(e, L, A);
             moved = true;
         }
     }
     {
         V2 nc = cB + invMassB * P;
-        float oa = S.a[B][ln];
+        float oa = L.a(B);
         float na = oa + invIB * cross(rB, P);
-        if (kB != LK_WALL && (nc.x != cB.x || nc.y != cB.y || na != oa)) {
-            S.cx[B][ln] = nc.x;
-            S.cy[B][ln] = nc.y;
-            S.a[B][ln] = na;
+        if (nc.x != cB.x || nc.y != cB.y || na != oa) {
+            L.cx(B) = nc.x;
+            L.cy(B) = nc.y;
+            L.a(B) = na;
             lkSyncXf(e, L, B);
             moved = true;
         }
@@ -328,13 +359,12 @@ __device__ __forceinline__ float lkCorrectPoint(const PhysEnv& e, const LaneCtx&
 }
 
 // Island.solve step 6 for staged body l (= integrateBody); the start-of-step pose / transform go straight to HBM
-__device__ __forceinline__ void lkIntegrate(const PhysEnv& e, const PhysWork& g, const LaneCtx& L, int l) {
-    LaneSlotsU& S = *L.S;
-    int ln = L.lane;
-    int gb = S.gidx[l][ln];
+template <class BT>
+__device__ __forceinline__ void lkIntegrate(const PhysEnv& e, const PhysWork& g, const BT& L, int l) {
+    int gb = L.gidx(l);
     int P = e.cfg.d.P;
     float dt = e.cfg.dt;
-    float vx = S.vx[l][ln], vy = S.vy[l][ln], w = S.w[l][ln];
+    float vx = L.vx(l), vy = L.vy(l), w = L.w(l);
     V2 tr = mk(dt * vx, dt * vy);
     if (dot(tr, tr) > kMaxTranslationSquared) {
         float ratio = kMaxTranslation / len(tr);
@@ -346,22 +376,22 @@ __device__ __forceinline__ void lkIntegrate(const PhysEnv& e, const PhysWork& g,
         float ratio = kMaxRotation / fabsf(rot);
         w *= ratio;
     }
-    S.vx[l][ln] = vx;
-    S.vy[l][ln] = vy;
-    S.w[l][ln] = w;
-    g.c0x[gb] = S.cx[l][ln];
-    g.c0y[gb] = S.cy[l][ln];
-    g.a0[gb] = S.a[l][ln];
+    L.vx(l) = vx;
+    L.vy(l) = vy;
+    L.w(l) = w;
+    g.c0x[gb] = L.cx(l);
+    g.c0y[gb] = L.cy(l);
+    g.a0[gb] = L.a(l);
     if (gb >= P) {
         int r = gb - P;
-        g.r0px[r] = S.px[l][ln];
-        g.r0py[r] = S.py[l][ln];
-        g.r0c[r] = S.c[l][ln];
-        g.r0s[r] = S.s[l][ln];
+        g.r0px[r] = L.px(l);
+        g.r0py[r] = L.py(l);
+        g.r0c[r] = L.c(l);
+        g.r0s[r] = L.s(l);
     }
-    S.cx[l][ln] += dt * vx;
-    S.cy[l][ln] += dt * vy;
-    S.a[l][ln] += dt * w;
+    L.cx(l) += dt * vx;
+    L.cy(l) += dt * vy;
+    L.a(l) += dt * w;
     lkSyncXf(e, L, l);
 }
 
@@ -398,9 +428,14 @@ __device__ __forceinline__ int lkSolve(const PhysEnv& e, const PhysWork& wk, con
         bool changed = false;
         for (int i = 0; i < maxNc; ++i) {
             if (running && i < nc) {
-                const TC& t = wk.tc[wk.order[L.lo + i]];
-                for (int j = 0; j < t.solverPoints; ++j) {
-                    float sep = lkCorrectPoint(e, L, t.bodyA, t.bodyB, t.type, t.localNormal, t.localPoint, t.lp[j], t.radius, &changed);
+                const LaneSlotsU& S = *L.S;
+                int ln = L.lane;
+                uint32_t hd = S.pcHead[i][ln];
+                int bA = (int)(hd & 255u), bB = (int)((hd >> 8) & 255u), type = (int)((hd >> 16) & 255u), np = (int)(hd >> 24);
+                V2 lnm = mk(S.pc[i][0][ln], S.pc[i][1][ln]), lpt = mk(S.pc[i][2][ln], S.pc[i][3][ln]);
+                float radius = S.pc[i][8][ln];
+                for (int j = 0; j < np; ++j) {
+                    float sep = lkCorrectPoint(e, L, bA, bB, type, lnm, lpt, mk(S.pc[i][4 + 2 * j][ln], S.pc[i][5 + 2 * j][ln]), radius, &changed);
                     minSep = fminf_(minSep, sep);
                 }
             }
@@ -416,6 +451,208 @@ __device__ __forceinline__ int lkSolve(const PhysEnv& e, const PhysWork& wk, con
         }
     }
     return iters;
+}
+
+// Warp-per-island solver for islands of up to kWarpBodies bodies / kWarpContacts contacts. The warp stages the island into
+// its shared-memory slot: one body table (the wall included, as the body after the last dynamic one) and the constraints.
+// A sweep over the constraints is cut into rows: constraint i (in solve order) goes to the row after the last row that
+// holds an earlier constraint sharing a dynamic body with it. The constraints of a row touch disjoint bodies, so the lanes
+// solve them together; rows run in order, so every body still sees its constraints in the reference's order and the
+// sweep is bit-identical to the sequential one. The solver routines are the uniform ones of the lane path.
+static constexpr int kWarpBodies = 48, kWarpContacts = 64;
+static constexpr int kWB = kWarpBodies + 1;
+struct WarpSlot {
+    float cx[kWB], cy[kWB], a[kWB], vx[kWB], vy[kWB], w[kWB];
+    float px[kWB], py[kWB], c[kWB], s[kWB], pm[kWB], pi[kWB];
+    uint16_t gidx[kWB];
+    uint8_t kind[kWB], bodyRow[kWB];
+    TC tc[kWarpContacts];
+    uint8_t row[kWarpContacts];            // row of each constraint
+    uint8_t rowFill[kWarpContacts + 1];
+    alignas(16) uint8_t task[kWarpContacts][32];   // [row][lane] constraint index, 255 = none
+    int nRows;
+};
+struct WarpCtx {
+    WarpSlot* S;
+    __device__ __forceinline__ float& cx(int l) const { return S->cx[l]; }
+    __device__ __forceinline__ float& cy(int l) const { return S->cy[l]; }
+    __device__ __forceinline__ float& a(int l) const { return S->a[l]; }
+    __device__ __forceinline__ float& vx(int l) const { return S->vx[l]; }
+    __device__ __forceinline__ float& vy(int l) const { return S->vy[l]; }
+    __device__ __forceinline__ float& w(int l) const { return S->w[l]; }
+    __device__ __forceinline__ float& px(int l) const { return S->px[l]; }
+    __device__ __forceinline__ float& py(int l) const { return S->py[l]; }
+    __device__ __forceinline__ float& c(int l) const { return S->c[l]; }
+    __device__ __forceinline__ float& s(int l) const { return S->s[l]; }
+    __device__ __forceinline__ float pm(int l) const { return S->pm[l]; }
+    __device__ __forceinline__ float pi(int l) const { return S->pi[l]; }
+    __device__ __forceinline__ int kind(int l) const { return S->kind[l]; }
+    __device__ __forceinline__ int gidx(int l) const { return S->gidx[l]; }
+};
+// Returns false if the island does not fit the slot (the caller falls back to the sequential path).
+__device__ __forceinline__ bool islandSolveWarp(const PhysEnv& e, const PhysWork& wk, const ArenaState& st, int k, WarpSlot& s, int* itersOut) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    int lane = threadIdx.x & 31;
+    int lo = wk.islandStart[k], hi = wk.islandStart[k + 1];
+    int blo = wk.islandBodyStart[k], bhi = wk.islandBodyStart[k + 1];
+    int nb = bhi - blo, nc = hi - lo;
+    int P = e.cfg.d.P;
+    if (nb > kWarpBodies || nc > kWarpContacts) return false;
+    // ---- stage the bodies (island order) and the wall
+    for (int i = lane; i <= nb; i += 32) {
+        if (i < nb) {
+            int g = wk.ibody[blo + i];
+            s.gidx[i] = (uint16_t)g;
+            s.cx[i] = wk.cx[g];
+            s.cy[i] = wk.cy[g];
+            s.a[i] = wk.a[g];
+            s.vx[i] = wk.vx[g];
+            s.vy[i] = wk.vy[g];
+            s.w[i] = wk.w[g];
+            if (g >= P) {
+                int r = g - P;
+                s.kind[i] = LK_ROBOT;
+                s.pm[i] = e.hot.pmRobot;
+                s.pi[i] = e.hot.piRobot;
+                s.px[i] = wk.rpx[r];
+                s.py[i] = wk.rpy[r];
+                s.c[i] = wk.rc[r];
+                s.s[i] = wk.rs[r];
+            } else {
+                s.kind[i] = LK_PUCK;
+                s.pm[i] = e.hot.pmPuck;
+                s.pi[i] = e.hot.piPuck;
+                s.px[i] = wk.cx[g];
+                s.py[i] = wk.cy[g];
+                s.c[i] = 1.0f;
+                s.s[i] = 0.0f;
+            }
+        } else {
+            s.gidx[i] = 0xFFFF;
+            s.kind[i] = LK_WALL;
+            s.cx[i] = s.cy[i] = s.a[i] = s.vx[i] = s.vy[i] = s.w[i] = 0.0f;
+            s.pm[i] = s.pi[i] = 0.0f;
+            s.px[i] = e.hot.wallXf.px;
+            s.py[i] = e.hot.wallXf.py;
+            s.c[i] = e.hot.wallXf.c;
+            s.s[i] = e.hot.wallXf.s;
+        }
+        s.bodyRow[i] = 0;
+    }
+    for (int i = lane; i < kWarpContacts * 8; i += 32) reinterpret_cast<uint32_t*>(&s.task[0][0])[i] = 0xFFFFFFFFu;
+    for (int i = lane; i <= kWarpContacts; i += 32) s.rowFill[i] = 0;
+    __syncwarp();
+    // ---- constraints: body references -> staged indices (wall -> nb)
+    for (int i = lane; i < nc; i += 32) {
+        TC t = wk.tc[wk.order[lo + i]];
+        int la = nb, lb = nb;
+        for (int j = 0; j < nb; ++j) {
+            int g = s.gidx[j];
+            if (g == t.bodyA) la = j;
+            if (g == t.bodyB) lb = j;
+        }
+        t.bodyA = la;
+        t.bodyB = lb;
+        s.tc[i] = t;
+    }
+    __syncwarp();
+    // ---- rows of one Gauss-Seidel sweep
+    if (lane == 0) {
+        int nRows = 0;
+        for (int i = 0; i < nc; ++i) {
+            int a = s.tc[i].bodyA, b = s.tc[i].bodyB;
+            int r = 0;
+            if (a < nb) r = s.bodyRow[a];
+            if (b < nb && s.bodyRow[b] > r) r = s.bodyRow[b];
+            // (row r + 1, 1-based, is the first one after every earlier constraint of these bodies; a full row pushes on)
+            while (s.rowFill[r] >= 32) ++r;
+            int slot = s.rowFill[r]++;
+            s.task[r][slot] = (uint8_t)i;
+            if (a < nb) s.bodyRow[a] = (uint8_t)(r + 1);
+            if (b < nb) s.bodyRow[b] = (uint8_t)(r + 1);
+            if (r + 1 > nRows) nRows = r + 1;
+        }
+        s.nRows = nRows;
+    }
+    __syncwarp();
+    WarpCtx L;
+    L.S = &s;
+    int nRows = s.nRows;
+    // ContactSolver.warmStart
+    for (int r = 0; r < nRows; ++r) {
+        int ci = s.task[r][lane];
+        if (ci != 255) lkWarmStart(e, L, s.tc[ci]);
+        __syncwarp();
+    }
+    // velocity sweeps
+    for (int it = 0; it < e.cfg.velIters; ++it)
+        for (int r = 0; r < nRows; ++r) {
+            int ci = s.task[r][lane];
+            if (ci != 255) lkSolveVelocity(e, L, s.tc[ci]);
+            __syncwarp();
+        }
+    // ContactSolver.storeImpulses
+    for (int i = lane; i < nc; i += 32) {
+        const TC& t = s.tc[i];
+        for (int j2 = 0; j2 < t.solverPoints; ++j2) {
+            st.cimp[4 * t.ci + 2 * j2] = t.nImp[j2];
+            st.cimp[4 * t.ci + 2 * j2 + 1] = t.tImp[j2];
+        }
+    }
+    // integrate the island's bodies
+    for (int b = lane; b < nb; b += 32) lkIntegrate(e, wk, L, b);
+    __syncwarp();
+    // position sweeps
+    int iters = 0;
+    for (int it = 0; it < e.cfg.posIters; ++it) {
+        float minSep = 0.0f;
+        bool changed = false;
+        for (int r = 0; r < nRows; ++r) {
+            int ci = s.task[r][lane];
+            if (ci != 255) {
+                const TC& t = s.tc[ci];
+                int bA = t.bodyA, bB = t.bodyB, type = t.type, np = t.solverPoints;
+                V2 ln = t.localNormal, lp = t.localPoint;
+                float radius = t.radius;
+                for (int j2 = 0; j2 < np; ++j2) {
+                    float sep = lkCorrectPoint(e, L, bA, bB, type, ln, lp, t.lp[j2], radius, &changed);
+                    minSep = fminf_(minSep, sep);
+                }
+            }
+            __syncwarp();
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            float other = __shfl_xor_sync(FULL, minSep, o);
+            minSep = fminf_(minSep, other);
+        }
+        bool anyChanged = __any_sync(FULL, changed);
+        ++iters;
+        if (minSep >= -1.5f * kLinearSlop) break;
+        if (!anyChanged) {   // fixed point: every later sweep repeats this one
+            iters = e.cfg.posIters;
+            break;
+        }
+    }
+    if (lane == 0) *itersOut = iters;
+    __syncwarp();
+    for (int i = lane; i < nb; i += 32) {
+        int g = s.gidx[i];
+        wk.cx[g] = s.cx[i];
+        wk.cy[g] = s.cy[i];
+        wk.a[g] = s.a[i];
+        wk.vx[g] = s.vx[i];
+        wk.vy[g] = s.vy[i];
+        wk.w[g] = s.w[i];
+        if (g >= P) {
+            int r = g - P;
+            wk.rpx[r] = s.px[i];
+            wk.rpy[r] = s.py[i];
+            wk.rc[r] = s.c[i];
+            wk.rs[r] = s.s[i];
+        }
+    }
+    __syncwarp();
+    return true;
 }
 
 }  // namespace ps

@@ -131,5 +131,16 @@ PS_HD PhysWork rebaseWork(const PhysWork& o, char* base) {
 #undef RB
     return w;
 }
+// the same, written member by member into an existing (shared-memory) PhysWork
+PS_HD void rebaseWorkInto(PhysWork& w, const PhysWork& o, char* base) {
+    size_t b = (size_t)base;
+#define RB(f) w.f = (decltype(w.f))((size_t)o.f + b);
+    RB(cx) RB(cy) RB(a) RB(vx) RB(vy) RB(w) RB(c0x) RB(c0y) RB(a0)
+    RB(rpx) RB(rpy) RB(rc) RB(rs) RB(r0px) RB(r0py) RB(r0c) RB(r0s) RB(fx) RB(fy) RB(tq)
+    RB(adjOff) RB(adjFill) RB(adj) RB(order) RB(islandStart) RB(islandBodyStart) RB(ibody) RB(stack) RB(bodyFlag) RB(tcFlag) RB(tcPair)
+    RB(moved) RB(bodyFat) RB(movedList) RB(movedBody) RB(bodyPairs) RB(fatOld) RB(pairs) RB(wallList) RB(wallBody) RB(wallT) RB(wallState) RB(wallNeed)
+    RB(toiT) RB(toiContact) RB(toiCur) RB(toiCount) RB(toiFound) RB(toiIter) RB(toiActive) RB(tc) RB(counters) RB(stats)
+#undef RB
+}
 
 }  // namespace ps

@@ -1035,7 +1035,7 @@ PS_HD Sweep bodySweep(const PhysEnv& e, const PhysWork& wk, int body) {
 }
 
 // TimeOfImpact of one cached wall contact of `body` on [0, tMax]
-PS_HDN void toiEval(const PhysEnv& e, const PhysWork& wk, const ArenaState& st, int body, int ci, float tMax, int& state, float& t) {
+PS_HD void toiEval(const PhysEnv& e, const PhysWork& wk, const ArenaState& st, int body, int ci, float tMax, int& state, float& t) {
     const Dims& d = e.cfg.d;
     uint32_t key = st.ckey[ci];
     int pa = (int)(key >> 16), pb = (int)(key & 0xFFFFu);
@@ -1053,7 +1053,7 @@ PS_HDN void toiEval(const PhysEnv& e, const PhysWork& wk, const ArenaState& st, 
 
 // Second half of World.solveTOI(Body) once the minimum-TOI contact is known: Body.advance(toi), refresh the body's wall
 // contacts (contact-edge order = newest first = descending cache index), then the TOISolver (only this body moves).
-PS_HDN void toiResolve(const PhysEnv& e, const PhysWork& wk, const ArenaState& st, int body, int toiContact, float toi, int nWall) {
+PS_HD void toiResolve(const PhysEnv& e, const PhysWork& wk, const ArenaState& st, int body, int toiContact, float toi, int nWall) {
     const Dims& d = e.cfg.d;
     const BodyConst& k = bodyConst(e, body);
     Sweep sw = bodySweep(e, wk, body);

@@ -52,7 +52,7 @@ PS_HD void sweepAdvance(Sweep& s, float t) {
 
 // DistanceProxy: a circle is one vertex (its centre), a polygon its vertices
 struct DProxy {
-    float vx[kMaxVerts], vy[kMaxVerts];
+    const float *vx, *vy;   // into the scene's shape table (no per-thread copy: a dynamically indexed local array would live in local memory)
     int count;
     float radius;
     PS_HD V2 v(int i) const { return mk(vx[i], vy[i]); }
@@ -72,14 +72,12 @@ struct DProxy {
 PS_HD void proxyFromShape(DProxy& p, const Shape& s) {
     if (s.type == SHAPE_CIRCLE) {
         p.count = 1;
-        p.vx[0] = s.px;
-        p.vy[0] = s.py;
+        p.vx = &s.px;
+        p.vy = &s.py;
     } else {
         p.count = s.count;
-        for (int i = 0; i < s.count; i++) {
-            p.vx[i] = s.vx[i];
-            p.vy[i] = s.vy[i];
-        }
+        p.vx = s.vx;
+        p.vy = s.vy;
     }
     p.radius = s.radius;
 }
@@ -351,7 +349,7 @@ PS_HD float sepEvaluate(const SepFn& f, int indexA, int indexB, const DProxy& pA
 }
 
 // TimeOfImpact.timeOfImpact; kindA / kindB select the exact transform shortcut of each side (see sweepXfKind).
-PS_HDN void timeOfImpact(int& outState, float& outT, const Trig& tr, const DProxy& pA, Sweep sweepA, int kindA, const DProxy& pB, Sweep sweepB, int kindB,
+PS_HDN void timeOfImpact(int& outState, float& outT, Trig tr, const DProxy& pA, Sweep sweepA, int kindA, const DProxy& pB, Sweep sweepB, int kindB,
                          const Xf& staticXf, float tMax) {
     outState = TOI_UNKNOWN;
     outT = tMax;
