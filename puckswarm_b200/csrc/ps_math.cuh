@@ -93,14 +93,28 @@ struct Trig {
     const float* lut;
     int useLut;
 };
+// (int)(x / LUT_PRECISION + 0.5f) for x in [0, 2 pi]. On the device the quotient comes from a multiplication by the
+// rounded reciprocal and one fused residual correction instead of the IEEE division sequence: the index is identical for
+// every float of the domain (exhaustive check: tools/check_lut_index.c, 1.09e9 values, 0 mismatches).
+PS_HD int lutIndex(float x) {
+#if defined(__CUDA_ARCH__)
+    const float rp = 1.0f / kLutPrecision;
+    float q0 = x * rp;
+    float r = __fmaf_rn(-q0, kLutPrecision, x);
+    float q = __fmaf_rn(r, rp, q0);
+    return (int)(q + 0.5f);
+#else
+    return (int)(x / kLutPrecision + 0.5f);
+#endif
+}
 PS_HD float psSin(const Trig& t, float x) {
     if (t.useLut) {
         // x %= TWOPI; fmod is exact, and the identity below 2 pi (the common case) -- skip the slow path there
         if (!(fabsf(x) < kTwoPi)) x = fmodf(x, kTwoPi);
         if (x < 0) x += kTwoPi;
-        int idx = (int)(x / kLutPrecision + 0.5f);
+        int idx = lutIndex(x);
         // idx % LUT_LENGTH: after the reduction x is in [0, 2 pi], so idx <= LUT_LENGTH and the modulo is one subtraction
-        if (idx >= kLutLength) idx = idx < 2 * kLutLength ? idx - kLutLength : idx % kLutLength;
+        if (idx >= kLutLength) idx -= kLutLength;
         return t.lut[idx];
     }
     return (float)sin((double)x);

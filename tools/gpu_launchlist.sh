@@ -14,6 +14,11 @@ for r in rows[1:]:
     if r[ui] == 'ns': v /= 1e3
     elif r[ui] == 'ms': v *= 1e3
     d.setdefault((r[ki][:40], r[gi]), []).append(v)
+b=[v for k,v in d.items() if 'k_island_batch' in k[0]]
+if b:
+    b=b[0]; n=len(b)//4*4; b=b[n//2:n]
+    for j,name in enumerate(['bucket4 (13-15)','bucket3 (6-12)','bucket2 (3-5)','bucket1 (1-2)']):
+        x=b[j::4]; print('   k_island_batch %-16s mean %9.1f us max %9.1f us' % (name, sum(x)/len(x), max(x)))
 for k, v in d.items():
     v2 = v[len(v)//2:]   # second half: after warm-up
     print('%-42s %-14s n=%3d mean %9.1f us  max %9.1f us' % (k[0], k[1], len(v2), sum(v2)/len(v2), max(v2)))
