@@ -35,6 +35,7 @@ struct SenseTables {
     const uint16_t* aRect;       // [nActive] index in the bounding rectangle, x-major: (x - x0) * RH + (y - y0)
     const uint16_t* aImg;        // [nActive] index in the camera image, y * imgW + x
     const uint8_t* aBin;         // [nActive] bin of the pixel's ground point in the robot-frame grid below
+    const struct PixRec* aPix;   // [nActive] the four tables above in one 16-byte record (what the camera stage reads)
     float binSize;               // bins of binSize x binSize cm over [bbXmin, bbXmax] x [bbYmin, bbYmax]
     int binsX, binsY;
     int x0, y0, RW, RH;          // bounding rectangle of the active pixels
@@ -46,6 +47,7 @@ struct SenseTables {
     int occW, occH;
     float maxYr;
     const int16_t* cellSrc;      // [occW * occH] active pixel whose type the cell takes (last writer), -1 = stays NOTHING
+    const uint16_t* cellRect;    // [occW * occH] aRect[cellSrc], 0xFFFF = stays NOTHING
     // VFHPlus.initDataStructures (src/localmap/VFHPlus.java:170-217), per occupancy cell
     const float* vfhBeta;
     const float* vfhMag;
@@ -55,6 +57,12 @@ struct SenseTables {
     float maxRange;              // max distance of an active pixel from the camera
     float bbXmin, bbXmax, bbYmin, bbYmax;
     int nPuckTypes, pucksPerType;
+};
+
+struct alignas(16) PixRec {
+    float xr, yr;
+    uint32_t rectBin;            // aRect | aBin << 16
+    uint32_t img;                // aImg
 };
 
 struct SenseCfg {
@@ -104,6 +112,7 @@ struct SenseWork {
     float* candUy;
     float* candC;         // robots: cos / sin of the body transform
     float* candS;
+    uint8_t* candType;    // pucks: SensedType of the colour (body / pucksPerType)
     float* candRx;        // candidate origin in the sensing robot's frame (binning only, never decides a pixel)
     float* candRy;
     uint8_t* binCount;    // [kMaxBins]
@@ -136,6 +145,7 @@ PS_HD SenseWork carveSense(const SenseTables& t, Carver& cv) {
     w.candUy = (float*)cv.take(kMaxCand * sizeof(float));
     w.candC = (float*)cv.take(kMaxCand * sizeof(float));
     w.candS = (float*)cv.take(kMaxCand * sizeof(float));
+    w.candType = (uint8_t*)cv.take(kMaxCand);
     w.candRx = (float*)cv.take(kMaxCand * sizeof(float));
     w.candRy = (float*)cv.take(kMaxCand * sizeof(float));
     w.binCount = (uint8_t*)cv.take(kMaxBins);
@@ -157,7 +167,7 @@ PS_HD SenseWork rebaseSense(const SenseWork& o, char* base) {
     SenseWork w;
     size_t b = (size_t)base;
 #define RB(f) w.f = (decltype(w.f))((size_t)o.f + b);
-    RB(img) RB(parent) RB(candX) RB(candY) RB(candBody) RB(candLx) RB(candLy) RB(candUx) RB(candUy) RB(candC) RB(candS) RB(candRx) RB(candRy)
+    RB(img) RB(parent) RB(candX) RB(candY) RB(candBody) RB(candLx) RB(candLy) RB(candUx) RB(candUy) RB(candC) RB(candS) RB(candType) RB(candRx) RB(candRy)
     RB(binCount) RB(binList) RB(blobArea) RB(blobX0) RB(blobX1) RB(blobY0) RB(blobY1) RB(blobSeed) RB(blobRoot) RB(blobOrder) RB(colList)
     RB(counters) RB(phase)
 #undef RB
@@ -229,7 +239,11 @@ PS_HD void senseRobot(Ctx& ctx, const PhysEnv& e, const SenseTables& T, const Se
         poseOut[2] = st.body[2 * NB + self];
     }
     int nRect = T.RW * T.RH;
-    PS_FOR(i, nRect) wk.img[i] = PS_T_HIDDEN;
+    {
+        // (the array is 16-byte aligned and padded to a multiple of 4)
+        uint32_t* img4 = (uint32_t*)wk.img;
+        PS_FOR(i, (nRect + 3) / 4) img4[i] = 0x01010101u * (uint32_t)PS_T_HIDDEN;
+    }
     if (camOut) {
         PS_FOR(i, T.imgW * T.imgH) camOut[i] = PS_T_HIDDEN;
     }
@@ -277,6 +291,7 @@ PS_HD void senseRobot(Ctx& ctx, const PhysEnv& e, const SenseTables& T, const Se
                     wk.candX[pos] = bx;
                     wk.candY[pos] = by;
                     wk.candBody[pos] = b;
+                    wk.candType[pos] = (uint8_t)(b < d.P ? b / T.pucksPerType : PS_T_ROBOT);
                     Aabb bb = loadAabb(st.senseAabb, NB, b);
                     wk.candLx[pos] = bb.lx;
                     wk.candLy[pos] = bb.ly;
@@ -299,6 +314,30 @@ PS_HD void senseRobot(Ctx& ctx, const PhysEnv& e, const SenseTables& T, const Se
     // whose sensed fixture could contain a point of the bin: pucks reach 2.1 cm from their origin, robot hulls < 13 cm.
     // The lists only prune the search; every listed candidate still goes through the reference's exact tests.
     int nBins = T.binsX * T.binsY;
+#if defined(__CUDA_ARCH__)
+    // one warp per bin: 32 candidates per ballot, appended in candidate (= body-list) order
+    for (int bin = (int)(threadIdx.x >> 5); bin < nBins; bin += (int)(blockDim.x >> 5)) {
+        int lane = (int)(threadIdx.x & 31u);
+        int bxi = bin / T.binsY, byi = bin - bxi * T.binsY;
+        float x0 = T.bbXmin + bxi * T.binSize, y0 = T.bbYmin + byi * T.binSize;
+        float x1 = x0 + T.binSize, y1 = y0 + T.binSize;
+        int n = 0;
+        for (int base = 0; base < nCand; base += 32) {
+            int c = base + lane;
+            bool in = false;
+            if (c < nCand) {
+                float rad = wk.candBody[c] < d.P ? 2.25f : 13.0f;
+                float cx = wk.candRx[c], cy = wk.candRy[c];
+                in = !(cx + rad < x0 || cx - rad > x1 || cy + rad < y0 || cy - rad > y1);
+            }
+            unsigned m = __ballot_sync(0xFFFFFFFFu, in);
+            int pos = n + __popc(m & ((1u << lane) - 1u));
+            if (in && pos < kBinCap) wk.binList[bin * kBinCap + pos] = (uint8_t)c;
+            n += __popc(m);
+        }
+        if (lane == 0) wk.binCount[bin] = (uint8_t)(n > kBinCap ? 255 : n);
+    }
+#else
     PS_FOR(bin, nBins) {
         int bxi = bin / T.binsY, byi = bin - bxi * T.binsY;
         float x0 = T.bbXmin + bxi * T.binSize, y0 = T.bbYmin + byi * T.binSize;
@@ -313,20 +352,23 @@ PS_HD void senseRobot(Ctx& ctx, const PhysEnv& e, const SenseTables& T, const Se
         }
         wk.binCount[bin] = (uint8_t)(n > kBinCap ? 255 : n);
     }
+#endif
     ctx.sync();
     long long tc1 = phaseClock();
     // ---- PointSensor.pointSense for every active pixel
     const Shape& hull = scene.shapes[kShapeRobot0];
     float innerR = scene.shapes[kShapePuck0 + 1].radius;
     float innerRSq = innerR * innerR;
+    FreeSpace fs = makeFreeSpace(scene, 0.0f);
     PS_FOR(k, T.nActive) {
-        V2 g = mulX(xf, mk(T.aXr[k], T.aYr[k]));
+        PixRec px = T.aPix[k];
+        V2 g = mulX(xf, mk(px.xr, px.yr));
         int type = PS_T_NOTHING;
-        if (!inFreeSpace(scene, g, 0.0f)) {
+        if (!inFreeSpaceFast(fs, g)) {
             type = PS_T_WALL;
         } else {
             bool hit = false;
-            int bin = T.aBin[k];
+            int bin = (int)(px.rectBin >> 16);
             int nList = wk.binCount[bin];
             bool full = nList == 255;   // overfull bin: walk the whole candidate list
             if (full) nList = nCand;
@@ -340,7 +382,7 @@ PS_HD void senseRobot(Ctx& ctx, const PhysEnv& e, const SenseTables& T, const Se
                 if (b < d.P) {
                     // inner disc, centre = body origin: (g - c).(g - c) <= r * r, same magnitude as d2
                     if (d2 <= innerRSq) {
-                        type = b / T.pucksPerType;
+                        type = wk.candType[c];
                         hit = true;
                     }
                 } else {
@@ -369,8 +411,8 @@ PS_HD void senseRobot(Ctx& ctx, const PhysEnv& e, const SenseTables& T, const Se
                 }
             }
         }
-        wk.img[T.aRect[k]] = (uint8_t)type;
-        if (camOut) camOut[T.aImg[k]] = (uint8_t)type;
+        wk.img[px.rectBin & 0xFFFFu] = (uint8_t)type;
+        if (camOut) camOut[px.img] = (uint8_t)type;
     }
     ctx.sync();
     long long tc2 = phaseClock();
@@ -378,8 +420,8 @@ PS_HD void senseRobot(Ctx& ctx, const PhysEnv& e, const SenseTables& T, const Se
     int nCells = T.occW * T.occH;
     int leftSum = 0, rightSum = 0;
     PS_FOR(c, nCells) {
-        int src = T.cellSrc[c];
-        uint8_t t = src < 0 ? (uint8_t)PS_T_NOTHING : wk.img[T.aRect[src]];
+        int src = T.cellRect[c];
+        uint8_t t = src == 0xFFFF ? (uint8_t)PS_T_NOTHING : wk.img[src];
         occOut[c] = t;
         if (t == PS_T_ROBOT || t == PS_T_WALL) {
             // LocalMap.getFreeerSide tallies (src/localmap/LocalMap.java:565-587)
@@ -1389,6 +1431,8 @@ struct SenseSetup {
     std::vector<uint16_t> aRect, aImg;
     std::vector<int16_t> calibIdx, cellSrc, vfhStartK, vfhStopK;
     std::vector<uint8_t> cFlags, vfhSide, aBin;
+    std::vector<PixRec> aPix;
+    std::vector<uint16_t> cellRect;
 
     bool build(const ps_config& cfg, const float* XrYr, const uint16_t* xy, const uint8_t* flags, int n, int w, int h) {
         ready = false;
@@ -1537,6 +1581,17 @@ struct SenseSetup {
         T.aRect = aRect.data();
         T.aImg = aImg.data();
         T.aBin = aBin.data();
+        aPix.resize(aXr.size());
+        for (size_t k = 0; k < aXr.size(); k++) {
+            aPix[k].xr = aXr[k];
+            aPix[k].yr = aYr[k];
+            aPix[k].rectBin = (uint32_t)aRect[k] | ((uint32_t)aBin[k] << 16);
+            aPix[k].img = aImg[k];
+        }
+        T.aPix = aPix.data();
+        cellRect.resize(cellSrc.size());
+        for (size_t c = 0; c < cellSrc.size(); c++) cellRect[c] = cellSrc[c] < 0 ? (uint16_t)0xFFFF : aRect[cellSrc[c]];
+        T.cellRect = cellRect.data();
         T.calibIdx = calibIdx.data();
         T.cXr = cXr.data();
         T.cYr = cYr.data();

@@ -226,6 +226,8 @@ struct SenseDevice {
         UP(aRect, aRect)
         UP(aImg, aImg)
         UP(aBin, aBin)
+        UP(aPix, aPix)
+        UP(cellRect, cellRect)
         UP(calibIdx, calibIdx)
         UP(cXr, cXr)
         UP(cYr, cYr)

@@ -68,6 +68,30 @@ PS_HD bool inFreeSpace(const Scene& sc, V2 v, float minDistance) {
     else if (dist(v, mk(sc.cornerX, -sc.cornerY)) < R - minDistance) return true;
     return false;
 }
+// The same predicate with the constants hoisted and one corner test: of the four corner-arc centres the one in the
+// point's own quadrant is the nearest (|v.x| - cornerX and -(|v.x| - cornerX) square to the same float, and rounding is
+// monotonic), so "within R of any centre" == "within R of that one". Same result for every point.
+struct FreeSpace {
+    float x1, y1, x2lo, x2hi, y2, cx, cy, r;
+};
+PS_HD FreeSpace makeFreeSpace(const Scene& sc, float minDistance) {
+    FreeSpace f;
+    f.x1 = sc.W / 2 - sc.R - minDistance;
+    f.y1 = sc.H / 2 - minDistance;
+    f.x2lo = sc.W / 2 - sc.R;
+    f.x2hi = sc.W / 2 - minDistance;
+    f.y2 = sc.H / 2 - sc.R - minDistance;
+    f.cx = sc.cornerX;
+    f.cy = sc.cornerY;
+    f.r = sc.R - minDistance;
+    return f;
+}
+PS_HD bool inFreeSpaceFast(const FreeSpace& f, V2 v) {
+    float ax = fabsf(v.x), ay = fabsf(v.y);
+    if (ax < f.x1 && ay < f.y1) return true;
+    if (ax > f.x2lo && ax < f.x2hi && ay < f.y2) return true;
+    return dist(mk(ax, ay), mk(f.cx, f.cy)) < f.r;
+}
 PS_HD bool randomInside(const Scene& sc, JRandom& rng, float minDistance, V2& out) {
     for (int i = 0; i < 100000; i++) {
         float fx = jrNextFloat(rng);
