@@ -129,36 +129,50 @@ struct SenseWork {
     int* counters;        // [8]
     int* phase;           // [8] diagnostics: cycles / 16 of the phases of senseRobot (thread 0)
 };
-PS_HD SenseWork carveSense(const SenseTables& t, Carver& cv) {
+inline SenseWork carveSense(const SenseTables& t, Carver& cv) {   // host only
     SenseWork w;
     int n = t.RW * t.RH;
     w.counters = (int*)cv.take(8 * sizeof(int));
     w.phase = (int*)cv.take(8 * sizeof(int));
     w.img = (uint8_t*)cv.take((size_t)n);
     w.parent = (int*)cv.take((size_t)n * sizeof(int));
-    w.candX = (float*)cv.take(kMaxCand * sizeof(float));
-    w.candY = (float*)cv.take(kMaxCand * sizeof(float));
-    w.candBody = (int*)cv.take(kMaxCand * sizeof(int));
-    w.candLx = (float*)cv.take(kMaxCand * sizeof(float));
-    w.candLy = (float*)cv.take(kMaxCand * sizeof(float));
-    w.candUx = (float*)cv.take(kMaxCand * sizeof(float));
-    w.candUy = (float*)cv.take(kMaxCand * sizeof(float));
-    w.candC = (float*)cv.take(kMaxCand * sizeof(float));
-    w.candS = (float*)cv.take(kMaxCand * sizeof(float));
-    w.candType = (uint8_t*)cv.take(kMaxCand);
-    w.candRx = (float*)cv.take(kMaxCand * sizeof(float));
-    w.candRy = (float*)cv.take(kMaxCand * sizeof(float));
-    w.binCount = (uint8_t*)cv.take(kMaxBins);
-    w.binList = (uint8_t*)cv.take(kMaxBins * kBinCap);
-    w.blobArea = (int*)cv.take(kMaxBlobs * sizeof(int));
-    w.blobX0 = (int*)cv.take(kMaxBlobs * sizeof(int));
-    w.blobX1 = (int*)cv.take(kMaxBlobs * sizeof(int));
-    w.blobY0 = (int*)cv.take(kMaxBlobs * sizeof(int));
-    w.blobY1 = (int*)cv.take(kMaxBlobs * sizeof(int));
-    w.blobSeed = (int*)cv.take(kMaxBlobs * sizeof(int));
-    w.blobRoot = (int*)cv.take(kMaxBlobs * sizeof(int));
-    w.blobOrder = (int*)cv.take(kMaxBlobs * sizeof(int));
-    w.colList = (uint16_t*)cv.take(kMaxColPix * sizeof(uint16_t));
+    // the candidate / bin arrays (camera stage) and the blob / colour-pixel arrays (blob labelling, afterwards) share
+    // one block: the two stages never overlap
+    auto up16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
+    size_t szA = 11 * up16(kMaxCand * sizeof(float)) + up16(kMaxCand) + up16(kMaxBins) + up16(kMaxBins * kBinCap);
+    size_t szB = 8 * up16(kMaxBlobs * sizeof(int)) + up16(kMaxColPix * sizeof(uint16_t));
+    char* blk = (char*)cv.take(szA > szB ? szA : szB);
+    {
+        char* q = blk;
+        auto sub = [&](size_t b) { char* r = q; q += up16(b); return (void*)r; };
+        w.candX = (float*)sub(kMaxCand * sizeof(float));
+        w.candY = (float*)sub(kMaxCand * sizeof(float));
+        w.candBody = (int*)sub(kMaxCand * sizeof(int));
+        w.candLx = (float*)sub(kMaxCand * sizeof(float));
+        w.candLy = (float*)sub(kMaxCand * sizeof(float));
+        w.candUx = (float*)sub(kMaxCand * sizeof(float));
+        w.candUy = (float*)sub(kMaxCand * sizeof(float));
+        w.candC = (float*)sub(kMaxCand * sizeof(float));
+        w.candS = (float*)sub(kMaxCand * sizeof(float));
+        w.candType = (uint8_t*)sub(kMaxCand);
+        w.candRx = (float*)sub(kMaxCand * sizeof(float));
+        w.candRy = (float*)sub(kMaxCand * sizeof(float));
+        w.binCount = (uint8_t*)sub(kMaxBins);
+        w.binList = (uint8_t*)sub(kMaxBins * kBinCap);
+    }
+    {
+        char* q = blk;
+        auto sub = [&](size_t b) { char* r = q; q += up16(b); return (void*)r; };
+        w.blobArea = (int*)sub(kMaxBlobs * sizeof(int));
+        w.blobX0 = (int*)sub(kMaxBlobs * sizeof(int));
+        w.blobX1 = (int*)sub(kMaxBlobs * sizeof(int));
+        w.blobY0 = (int*)sub(kMaxBlobs * sizeof(int));
+        w.blobY1 = (int*)sub(kMaxBlobs * sizeof(int));
+        w.blobSeed = (int*)sub(kMaxBlobs * sizeof(int));
+        w.blobRoot = (int*)sub(kMaxBlobs * sizeof(int));
+        w.blobOrder = (int*)sub(kMaxBlobs * sizeof(int));
+        w.colList = (uint16_t*)sub(kMaxColPix * sizeof(uint16_t));
+    }
     return w;
 }
 
@@ -360,8 +374,7 @@ PS_HD void senseRobot(Ctx& ctx, const PhysEnv& e, const SenseTables& T, const Se
     float innerR = scene.shapes[kShapePuck0 + 1].radius;
     float innerRSq = innerR * innerR;
     FreeSpace fs = makeFreeSpace(scene, 0.0f);
-    PS_FOR(k, T.nActive) {
-        PixRec px = T.aPix[k];
+    auto sensePixel = [&](const PixRec& px) {
         V2 g = mulX(xf, mk(px.xr, px.yr));
         int type = PS_T_NOTHING;
         if (!inFreeSpaceFast(fs, g)) {
@@ -413,6 +426,18 @@ PS_HD void senseRobot(Ctx& ctx, const PhysEnv& e, const SenseTables& T, const Se
         }
         wk.img[px.rectBin & 0xFFFFu] = (uint8_t)type;
         if (camOut) camOut[px.img] = (uint8_t)type;
+    };
+    {
+        // two pixels per trip: both table records are in flight before the first is used
+        int nT = ctx.nthreads();
+        for (int k0 = ctx.tid(); k0 < T.nActive; k0 += 2 * nT) {
+            int k1 = k0 + nT;
+            bool two = k1 < T.nActive;
+            PixRec pa = T.aPix[k0];
+            PixRec pb = T.aPix[two ? k1 : k0];
+            sensePixel(pa);
+            if (two) sensePixel(pb);
+        }
     }
     ctx.sync();
     long long tc2 = phaseClock();
