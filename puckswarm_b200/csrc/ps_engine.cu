@@ -198,19 +198,26 @@ __global__ void __launch_bounds__(128) k_island_warp(KParams p) {
 
 static constexpr int kBatchThreads = 64;   // two lane slots (2 x 32 islands) per CTA: a slot is ~41 KB of shared memory
 // stage B2: all other islands (queue bucket 1): one lane per island, 32 islands per warp, bodies in shared memory
-__global__ void __launch_bounds__(kBatchThreads) k_island_batch(KParams p, int bucket) {
+// bucket < 0: one launch for all lane buckets, segBlocks CTAs each, the buckets of the largest islands first
+__global__ void __launch_bounds__(kBatchThreads) k_island_batch(KParams p, int bucket, int segBlocks) {
     extern __shared__ __align__(16) char smem[];
     LaneCtx L;
     L.S = reinterpret_cast<LaneSlotsU*>(smem) + (threadIdx.x >> 5);
     L.lane = threadIdx.x & 31;
     L.nb = L.lo = L.nc = 0;
     int cap = p.queue.cap;
+    int blk = blockIdx.x, nBlk = gridDim.x;
+    if (bucket < 0) {
+        bucket = kQueueBuckets - 1 - blk / segBlocks;
+        blk = blk % segBlocks;
+        nBlk = segBlocks;
+    }
     int total = min(p.queue.counts[bucket], cap);
     unsigned NB = (unsigned)p.env.cfg.d.NB;
-    int stride = gridDim.x * blockDim.x;
+    int stride = nBlk * blockDim.x;
     int rounds = (total + stride - 1) / stride;
     for (int rnd = 0; rnd < rounds; ++rnd) {
-        int idx = rnd * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        int idx = rnd * stride + blk * blockDim.x + threadIdx.x;
         bool active = idx < total;
         PhysWork wk;
         ArenaState st;
@@ -289,6 +296,7 @@ struct ps_engine {
     int nSlots = 0, threads = 128;
     bool fused = false;      // PS_FUSED=1: the single-kernel World.step (kept for comparison)
     int workerBlocks = 0, batchBlocks = 0;
+    bool mergeBatch = true;    // one launch for all lane buckets (PS_MERGE_BATCH=0: one launch and stream per bucket)
     size_t smemBytes = 0;
     int64_t launches = 0;
     int updateCount = 0;     // all arenas advance in lock step
@@ -574,6 +582,7 @@ int ps_create(const ps_config* cfg, int device, ps_handle* out) {
         e->workerBlocks = prop.multiProcessorCount * (int)envSize("PS_WORKER_BLOCKS_PER_SM", 4);
         TRY_OR_FREE(cudaFuncSetAttribute(k_island_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(WarpSlot))));
         TRY_OR_FREE(cudaFuncSetAttribute(k_island_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((kBatchThreads / 32) * sizeof(LaneSlotsU))));
+        e->mergeBatch = envSize("PS_MERGE_BATCH", 1) != 0;
         e->batchBlocks = prop.multiProcessorCount * (int)envSize("PS_BATCH_BLOCKS_PER_SM", 2);
     }
     e->kp.env.scene = e->dScene;
@@ -651,20 +660,24 @@ static int launchPhysics(ps_handle h, ps_engine::Group& G, int nTicks) {
             k_island_warp<<<wb, 128, 4 * sizeof(WarpSlot), G.s2>>>(kp);
             CUDA_TRY(cudaEventRecord(G.evBig, G.s2));
             int bb = std::max(1, std::min(h->batchBlocks, (G.n * 12 + kBatchThreads - 1) / kBatchThreads));
-            for (int bucket = kQueueBuckets - 1; bucket >= 2; --bucket) {
-                CUDA_TRY(cudaStreamWaitEvent(G.sb[bucket], G.evPre, 0));
-                k_island_batch<<<bb, kBatchThreads, (kBatchThreads / 32) * sizeof(LaneSlotsU), G.sb[bucket]>>>(kp, bucket);
-                CUDA_TRY(cudaEventRecord(G.evb[bucket], G.sb[bucket]));
+            if (h->mergeBatch) {
+                k_island_batch<<<bb * (kQueueBuckets - 1), kBatchThreads, (kBatchThreads / 32) * sizeof(LaneSlotsU), G.s>>>(kp, -1, bb);
+            } else {
+                for (int bucket = kQueueBuckets - 1; bucket >= 2; --bucket) {
+                    CUDA_TRY(cudaStreamWaitEvent(G.sb[bucket], G.evPre, 0));
+                    k_island_batch<<<bb, kBatchThreads, (kBatchThreads / 32) * sizeof(LaneSlotsU), G.sb[bucket]>>>(kp, bucket, bb);
+                    CUDA_TRY(cudaEventRecord(G.evb[bucket], G.sb[bucket]));
+                }
+                k_island_batch<<<bb, kBatchThreads, (kBatchThreads / 32) * sizeof(LaneSlotsU), G.s>>>(kp, 1, bb);
+                for (int bucket = 2; bucket < kQueueBuckets; ++bucket) CUDA_TRY(cudaStreamWaitEvent(G.s, G.evb[bucket], 0));
             }
-            k_island_batch<<<bb, kBatchThreads, (kBatchThreads / 32) * sizeof(LaneSlotsU), G.s>>>(kp, 1);
-            for (int bucket = 2; bucket < kQueueBuckets; ++bucket) CUDA_TRY(cudaStreamWaitEvent(G.s, G.evb[bucket], 0));
             CUDA_TRY(cudaStreamWaitEvent(G.s, G.evBig, 0));
         }
         {
             ScopedTimer t6(h, 6, G.s);
             k_phys_post<<<G.n, 128, 0, G.s>>>(kp);
         }
-        h->launches += 3 + (kQueueBuckets - 1);
+        h->launches += 3 + (h->mergeBatch ? 1 : kQueueBuckets - 1);
         CUDA_TRY(cudaGetLastError());
     }
     return PS_OK;
