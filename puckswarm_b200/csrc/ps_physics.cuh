@@ -114,6 +114,15 @@ struct PhysEnv {
     HotConsts hot;
 };
 
+// Phase clock for the per-step diagnostics (stats[3..7]: cycles of collide, islands, velocity, position, broadphase + TOI)
+PS_HD long long phaseClock() {
+#if defined(__CUDA_ARCH__) && defined(PS_PHASE_CLOCKS)
+    return clock64();
+#else
+    return 0;
+#endif
+}
+
 PS_HD bool isRobot(const Dims& d, int b) { return b >= d.P; }
 
 PS_HD Xf bodyXf(const PhysEnv& e, const PhysWork& wk, int b) {
@@ -1274,14 +1283,6 @@ PS_HD void physStore(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const Arena
     ctx.sync();
 }
 
-// Phase clock for the per-step diagnostics (stats[3..7]: cycles of collide, islands, velocity, position, broadphase + TOI)
-PS_HD long long phaseClock() {
-#if defined(__CUDA_ARCH__) && defined(PS_PHASE_CLOCKS)
-    return clock64();
-#else
-    return 0;
-#endif
-}
 
 // World.step
 template <class Ctx>
