@@ -260,7 +260,11 @@ __global__ void __launch_bounds__(128) k_phys_post(KParams p) {
     __shared__ float sBodyFat[4 * 512];
     arenaWorkShared(p, a, wk, st);
     __syncthreads();
-    if (threadIdx.x == 0 && p.env.cfg.d.NB <= 512) wk.bodyFat = sBodyFat;
+    __shared__ float sFatNow[4 * 1024];   // this step's fat boxes of every proxy (pair search)
+    if (threadIdx.x == 0) {
+        if (p.env.cfg.d.NB <= 512) wk.bodyFat = sBodyFat;
+        if (p.env.cfg.d.NP <= 1024) wk.fatNow = sFatNow;
+    }
     __syncthreads();
     physPost(ctx, p.env, wk, st);
     if (threadIdx.x == 0) p.sp.arena[a].update_count += 1;

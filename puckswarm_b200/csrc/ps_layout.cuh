@@ -59,6 +59,7 @@ struct Carver {
 PS_HD PhysWork carveWork(const PhysCfg& c, Carver& cv) {
     PhysWork w;
     int NB = c.d.NB, R = c.d.R, NP = c.d.NP;
+    w.fatNow = nullptr;
     w.counters = (int*)cv.take(8 * sizeof(int));
     w.stats = (int*)cv.take(8 * sizeof(int));
     float* bodyArr = (float*)cv.take((size_t)9 * NB * sizeof(float));
@@ -129,6 +130,7 @@ PS_HD PhysWork rebaseWork(const PhysWork& o, char* base) {
     RB(moved) RB(bodyFat) RB(movedList) RB(movedBody) RB(bodyPairs) RB(fatOld) RB(pairs) RB(wallList) RB(wallBody) RB(wallT) RB(wallState) RB(wallNeed)
     RB(toiT) RB(toiContact) RB(toiCur) RB(toiCount) RB(toiFound) RB(toiIter) RB(toiActive) RB(tc) RB(counters) RB(stats)
 #undef RB
+    w.fatNow = nullptr;
     return w;
 }
 // the same, written member by member into an existing (shared-memory) PhysWork
@@ -141,6 +143,7 @@ PS_HD void rebaseWorkInto(PhysWork& w, const PhysWork& o, char* base) {
     RB(moved) RB(bodyFat) RB(movedList) RB(movedBody) RB(bodyPairs) RB(fatOld) RB(pairs) RB(wallList) RB(wallBody) RB(wallT) RB(wallState) RB(wallNeed)
     RB(toiT) RB(toiContact) RB(toiCur) RB(toiCount) RB(toiFound) RB(toiIter) RB(toiActive) RB(tc) RB(counters) RB(stats)
 #undef RB
+    w.fatNow = nullptr;
 }
 
 }  // namespace ps

@@ -133,6 +133,14 @@ PS_HD Xf makeXf(const Trig& t, float cx, float cy, float a, float lcx, float lcy
     return T;
 }
 
+PS_HD int ctz32(uint32_t v) {   // v != 0
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)v) - 1;
+#else
+    return __builtin_ctz(v);
+#endif
+}
+
 struct Aabb {
     float lx, ly, ux, uy;
 };

@@ -76,6 +76,7 @@ struct PhysWork {
     uint8_t* moved;                                      // [NP]
     float* bodyFat;                                      // [4][NB] union of the body's fat AABBs
     int* movedList;                                      // [NP]
+    float* fatNow;                                       // [4][NP] the fat AABBs of this step for the pair search: a shared-memory copy, or null = st.fat
     uint16_t* movedBody;                                 // [NB] bodies with at least one moved proxy
     uint32_t* bodyPairs;                                 // [4 * NB] (moved body << 16 | body) whose box unions overlap
     float* fatOld;                                       // [4][NP] fat AABB before this step's moveProxy
@@ -190,6 +191,7 @@ PS_HD Aabb proxyFat(const PhysEnv& e, const ArenaState& st, int proxy) {
     if (proxy < kWallFixtures) return e.scene->wallFat[proxy];
     return loadAabb(st.fat, e.cfg.d.NP, proxy - kWallFixtures);
 }
+PS_HD const float* fatNowOf(const PhysWork& wk, const ArenaState& st) { return wk.fatNow ? wk.fatNow : st.fat; }
 
 // Contact.update: evaluate the manifold at the current transforms and carry the impulses of points whose id survived.
 PS_HD void updateContact(const PhysEnv& e, const PhysWork& wk, const ArenaState& st, int ci, Manifold& m, float* imp /*[4]*/) {
@@ -835,8 +837,10 @@ PS_HD void physSyncFixtures(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, cons
                 if (ddx < 0.0f) nb.lx += ddx; else nb.ux += ddx;
                 if (ddy < 0.0f) nb.ly += ddy; else nb.uy += ddy;
                 storeAabb(st.fat, NP, i, nb);
+                fat = nb;
                 mv = true;
             }
+            if (wk.fatNow) storeAabb(wk.fatNow, NP, i, fat);
             wk.moved[i] = mv ? 1 : 0;
         }
         int total;
@@ -860,10 +864,11 @@ PS_HD void physBodyFat(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const Are
     ctx.sync();
     PS_FOR(b, d.NB) {
         int first = bodyFirstProxy(d, b) - kWallFixtures, cnt = bodyProxyCount(d, b);
-        Aabb u = loadAabb(st.fat, d.NP, first);
+        const float* fatNow = fatNowOf(wk, st);
+        Aabb u = loadAabb(fatNow, d.NP, first);
         bool mv = wk.moved[first] != 0;
         for (int k = 1; k < cnt; ++k) {
-            Aabb f = loadAabb(st.fat, d.NP, first + k);
+            Aabb f = loadAabb(fatNow, d.NP, first + k);
             u.lx = fminf_(u.lx, f.lx);
             u.ly = fminf_(u.ly, f.ly);
             u.ux = fmaxf_(u.ux, f.ux);
@@ -880,16 +885,14 @@ PS_HD void physBodyFat(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const Are
 // A pair is new iff the fat AABBs overlap now and did not overlap before this step's moveProxy calls: the contact cache
 // always equals the set of filtered pairs with overlapping fat AABBs (contacts die in collide() exactly when they stop
 // overlapping, and are born here exactly when they start), so "already has a contact" == "overlapped before".
+// Callers pass proxies of different bodies only. filtQ / shapeP: the Filter word of q's shape, the shape index of p.
 template <class Ctx>
-PS_HD void tryPair(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaState& st, int q, const Aabb& fatQ, int p, bool allNew) {
+PS_HD void tryPair(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaState& st, int q, uint32_t filtQ, const Aabb& fatQ, int p, int shapeP,
+                   bool allNew) {
     const Dims& d = e.cfg.d;
-    if (p == q) return;
-    int bq = proxyBody(d, q), bp = proxyBody(d, p);
-    if (bq == bp) return;
-    const Shape& sq = e.scene->shapes[proxyShape(d, q)];
-    const Shape& sp = e.scene->shapes[proxyShape(d, p)];
-    if (!shouldCollide(sq, sp)) return;
-    Aabb fatP = proxyFat(e, st, p);
+    if (!filtCollide(filtQ, e.scene->filt[shapeP])) return;
+    const float* fatNow = fatNowOf(wk, st);
+    Aabb fatP = p < kWallFixtures ? e.scene->wallFat[p] : loadAabb(fatNow, d.NP, p - kWallFixtures);
     if (!aabbOverlap(fatP, fatQ)) return;
     if (!allNew) {
         Aabb oq = loadAabb(wk.fatOld, d.NP, q - kWallFixtures);   // q moved: its old box was saved
@@ -911,13 +914,23 @@ PS_HD void physFindNewContacts(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, c
     //     through the reference's tests (tryPair), and the pairs are sorted afterwards, so the order of discovery is free.
     int nMB = wk.counters[6];
     int cap = bodyPairCap(d);
-    PS_FOR(it, nMB * NB) {
-        int mi = it / NB, b = it - mi * NB;
-        int mb = wk.movedBody[mi];
-        if (b == mb) continue;
-        if (!aabbOverlap(loadAabb(wk.bodyFat, NB, b), loadAabb(wk.bodyFat, NB, mb))) continue;
-        int slot = ctx.atomicAddI(&wk.counters[7], 1);
-        if (slot < cap) wk.bodyPairs[slot] = ((uint32_t)mb << 16) | (uint32_t)b;
+    const float* fatNow = fatNowOf(wk, st);
+    {
+        // flat index it = mi * NB + b, advanced without divisions
+        int nT = ctx.nthreads();
+        int mi = ctx.tid() / NB, b = ctx.tid() - mi * NB;
+        for (int it = ctx.tid(); it < nMB * NB; it += nT) {
+            int mb = wk.movedBody[mi];
+            if (b != mb && aabbOverlap(loadAabb(wk.bodyFat, NB, b), loadAabb(wk.bodyFat, NB, mb))) {
+                int slot = ctx.atomicAddI(&wk.counters[7], 1);
+                if (slot < cap) wk.bodyPairs[slot] = ((uint32_t)mb << 16) | (uint32_t)b;
+            }
+            b += nT;
+            while (b >= NB) {
+                b -= NB;
+                ++mi;
+            }
+        }
     }
     ctx.sync();
     int nBP = wk.counters[7];
@@ -925,37 +938,68 @@ PS_HD void physFindNewContacts(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, c
         // (b) one work item per (overlapping body pair, proxy of the moved body): that proxy against the other body's proxies
         int maxPer = d.R > 0 ? bodyProxyCount(d, d.P) : bodyProxyCount(d, 0);
         if (d.P > 0 && bodyProxyCount(d, 0) > maxPer) maxPer = bodyProxyCount(d, 0);
-        PS_FOR(it, nBP * maxPer) {
-            int bp = it / maxPer, k = it - bp * maxPer;
+        int nT = ctx.nthreads();
+        int bp = ctx.tid() / maxPer, k = ctx.tid() - bp * maxPer;
+        for (int it = ctx.tid(); it < nBP * maxPer; it += nT) {
             uint32_t pr = wk.bodyPairs[bp];
             int mb = (int)(pr >> 16), b = (int)(pr & 0xFFFFu);
-            if (k >= bodyProxyCount(d, mb)) continue;
-            int q = bodyFirstProxy(d, mb) + k;
-            if (!wk.moved[q - kWallFixtures]) continue;
-            Aabb fatQ = proxyFat(e, st, q);
-            if (!aabbOverlap(loadAabb(wk.bodyFat, NB, b), fatQ)) continue;
-            int first = bodyFirstProxy(d, b), cnt = bodyProxyCount(d, b);
-            for (int kk = 0; kk < cnt; ++kk) tryPair(ctx, e, wk, st, q, fatQ, first + kk, allNew);
+            if (k < bodyProxyCount(d, mb)) {
+                int q = bodyFirstProxy(d, mb) + k;
+                if (wk.moved[q - kWallFixtures]) {
+                    Aabb fatQ = loadAabb(fatNow, d.NP, q - kWallFixtures);
+                    if (aabbOverlap(loadAabb(wk.bodyFat, NB, b), fatQ)) {
+                        uint32_t filtQ = e.scene->filt[bodyFirstShape(d, mb) + k];
+                        int first = bodyFirstProxy(d, b), cnt = bodyProxyCount(d, b), shape0 = bodyFirstShape(d, b);
+                        for (int kk = 0; kk < cnt; ++kk) tryPair(ctx, e, wk, st, q, filtQ, fatQ, first + kk, shape0 + kk, allNew);
+                    }
+                }
+            }
+            k += nT;
+            while (k >= maxPer) {
+                k -= maxPer;
+                ++bp;
+            }
         }
     } else {
         // body-pair list overflow (a very crowded arena): every moved proxy against every body
         PS_FOR(mi, nMoved) {
             int q = kWallFixtures + (allNew ? mi : wk.movedList[mi]);
-            Aabb fatQ = proxyFat(e, st, q);
+            Aabb fatQ = loadAabb(fatNow, d.NP, q - kWallFixtures);
+            int bq = proxyBody(d, q);
+            uint32_t filtQ = e.scene->filt[proxyShape(d, q)];
             for (int b = 0; b < NB; ++b) {
-                if (!aabbOverlap(loadAabb(wk.bodyFat, NB, b), fatQ)) continue;
-                int first = bodyFirstProxy(d, b), cnt = bodyProxyCount(d, b);
-                for (int k = 0; k < cnt; ++k) tryPair(ctx, e, wk, st, q, fatQ, first + k, allNew);
+                if (b == bq || !aabbOverlap(loadAabb(wk.bodyFat, NB, b), fatQ)) continue;
+                int first = bodyFirstProxy(d, b), cnt = bodyProxyCount(d, b), shape0 = bodyFirstShape(d, b);
+                for (int k = 0; k < cnt; ++k) tryPair(ctx, e, wk, st, q, filtQ, fatQ, first + k, shape0 + k, allNew);
             }
         }
     }
-    // (c) wall: only proxies reaching the band where wall boxes live need the 84 tests
+    // (c) wall: the grid names the wall proxies whose boxes come near the moved proxy's box
     PS_FOR(mi, nMoved) {
         int q = kWallFixtures + (allNew ? mi : wk.movedList[mi]);
-        Aabb fatQ = proxyFat(e, st, q);
+        Aabb fatQ = loadAabb(fatNow, d.NP, q - kWallFixtures);
         float inner = e.scene->cornerX - 1.0f;
         if (fatQ.lx > -inner && fatQ.ux < inner && fatQ.ly > -inner && fatQ.uy < inner) continue;
-        for (int k = 0; k < kWallFixtures; ++k) tryPair(ctx, e, wk, st, q, fatQ, k, allNew);
+        const Scene& sc = *e.scene;
+        int ix0 = wallGridIndex(fatQ.lx, sc.wgX0, sc.wgInvX), ix1 = wallGridIndex(fatQ.ux, sc.wgX0, sc.wgInvX);
+        int iy0 = wallGridIndex(fatQ.ly, sc.wgY0, sc.wgInvY), iy1 = wallGridIndex(fatQ.uy, sc.wgY0, sc.wgInvY);
+        uint32_t m[3] = {0u, 0u, 0u};
+        for (int ix = ix0; ix <= ix1; ++ix)
+            for (int iy = iy0; iy <= iy1; ++iy) {
+                const uint32_t* c = sc.wallGrid[ix * kWallGrid + iy];
+                m[0] |= c[0];
+                m[1] |= c[1];
+                m[2] |= c[2];
+            }
+        uint32_t filtQ = sc.filt[proxyShape(d, q)];
+        for (int w = 0; w < 3; ++w) {
+            uint32_t bits = m[w];
+            while (bits) {
+                int k = w * 32 + ctz32(bits);
+                bits &= bits - 1u;
+                tryPair(ctx, e, wk, st, q, filtQ, fatQ, k, k, allNew);
+            }
+        }
     }
     ctx.sync();
     int nPairs = wk.counters[3];

@@ -17,6 +17,7 @@ static constexpr int kRobotFixtures = 14;
 static constexpr int kShapePuck0 = kWallFixtures;
 static constexpr int kShapeRobot0 = kWallFixtures + kPuckFixtures;
 static constexpr int kNumShapes = kShapeRobot0 + kRobotFixtures;
+static constexpr int kWallGrid = 16;
 static constexpr int kMaxVerts = 5;
 
 enum { SHAPE_CIRCLE = 0, SHAPE_POLYGON = 1 };
@@ -46,7 +47,16 @@ struct Scene {
     float cornerX, cornerY;        // |x|, |y| of the corner-arc centres
     float friction;                // sqrt(0.2 * 0.2): every fixture keeps FixtureDef's default friction
     int wallSensable;              // any wall fixture AABB within 22 cm of the origin (PointSensor body filter)
+    uint32_t filt[kNumShapes];     // Filter of every shape: category | mask << 16
+    // pair-search pruning: which wall proxies' fat boxes reach each cell of a kWallGrid x kWallGrid grid over the arena
+    uint32_t wallGrid[kWallGrid * kWallGrid][3];
+    float wgX0, wgY0, wgInvX, wgInvY;
 };
+PS_HD bool filtCollide(uint32_t a, uint32_t b) { return ((a >> 16) & (b & 0xFFFFu)) != 0 && ((a & 0xFFFFu) & (b >> 16)) != 0; }
+PS_HD int wallGridIndex(float v, float v0, float inv) {
+    int i = (int)floorf((v - v0) * inv);
+    return i < 0 ? 0 : (i > kWallGrid - 1 ? kWallGrid - 1 : i);
+}
 
 // ---- proxy id <-> (body, shape) mapping; ids are fixture creation order ----
 struct Dims {
@@ -309,6 +319,26 @@ inline void scene(Scene* sc, float scale, const Trig& trig) {
         a.uy += kAabbExtension;
         sc->wallFat[i] = a;
     }
+    for (int i = 0; i < kNumShapes; i++) sc->filt[i] = (uint32_t)s[i].category | ((uint32_t)s[i].mask << 16);
+    // wall grid over [-W/2 - 1, W/2 + 1] x [-H/2 - 1, H/2 + 1]; a cell lists every wall box within 0.05 of it (the margin
+    // absorbs the rounding of the cell-index computation)
+    float gx0 = -W / 2 - 1.0f, gy0 = -H / 2 - 1.0f, csx = (W + 2.0f) / kWallGrid, csy = (H + 2.0f) / kWallGrid;
+    sc->wgX0 = gx0;
+    sc->wgY0 = gy0;
+    sc->wgInvX = 1.0f / csx;
+    sc->wgInvY = 1.0f / csy;
+    for (int ix = 0; ix < kWallGrid; ix++)
+        for (int iy = 0; iy < kWallGrid; iy++) {
+            Aabb c;
+            c.lx = gx0 + ix * csx - 0.05f;
+            c.ux = gx0 + (ix + 1) * csx + 0.05f;
+            c.ly = gy0 + iy * csy - 0.05f;
+            c.uy = gy0 + (iy + 1) * csy + 0.05f;
+            uint32_t* m = sc->wallGrid[ix * kWallGrid + iy];
+            m[0] = m[1] = m[2] = 0;
+            for (int i = 0; i < kWallFixtures; i++)
+                if (aabbOverlap(sc->wallFat[i], c)) m[i >> 5] |= 1u << (i & 31);
+        }
 }
 
 }  // namespace build
