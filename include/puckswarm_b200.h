@@ -270,7 +270,8 @@ int ps_get_dims(ps_handle h, int32_t* n_bodies, int32_t* n_proxies, int32_t* max
  * 1 = TOI events, 2 = islands with contacts. */
 int ps_get_step_stats(ps_handle h, int32_t* out);
 /* Diagnostics of the last sense of every robot, [n_arenas][n_robots][8] int32: cycles / 16 of 0 = candidate cull, 1 = camera,
- * 2 = occupancy + blob labelling, 3 = pucks + clusters, 4 = cluster filter; 5 = perceived pucks, 6 = candidate bodies, 7 = blobs. */
+ * 2 = occupancy + blob labelling, 3 = occupancy (cycle counts are zero unless the library is built with PS_PHASE_CLOCKS);
+ * 4 = candidate bodies examined summed over the robot's pixels, 5 = puck-coloured pixels, 6 = candidate bodies, 7 = blobs. */
 int ps_get_sense_stats(ps_handle h, int32_t* out);
 /* Diagnostics: islands with >= 3 contacts solved since the last reset, as an 8 x 8 histogram [position-iteration bucket][contact
  * bucket]; iterations <=1, <=3, <=6, <=12, <=25, <=50, <100, 100; contacts <=3, <=5, <=8, <=12, <=16, <=32, <=64, >64. */

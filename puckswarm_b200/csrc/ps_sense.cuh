@@ -374,6 +374,7 @@ PS_HD void senseRobot(Ctx& ctx, const PhysEnv& e, const SenseTables& T, const Se
     float innerR = scene.shapes[kShapePuck0 + 1].radius;
     float innerRSq = innerR * innerR;
     FreeSpace fs = makeFreeSpace(scene, 0.0f);
+    int visited = 0;   // candidate bodies examined by this thread's pixels (diagnostic: K of SURVEY 8(d))
     auto sensePixel = [&](const PixRec& px) {
         V2 g = mulX(xf, mk(px.xr, px.yr));
         int type = PS_T_NOTHING;
@@ -387,6 +388,7 @@ PS_HD void senseRobot(Ctx& ctx, const PhysEnv& e, const SenseTables& T, const Se
             if (full) nList = nCand;
             for (int li = 0; li < nList && !hit; ++li) {
                 int c = full ? li : (int)wk.binList[bin * kBinCap + li];
+                ++visited;
                 V2 bp = mk(wk.candX[c], wk.candY[c]);
                 float d2 = distSq(bp, g);
                 if (d2 > 484.0f) continue;
@@ -439,6 +441,7 @@ PS_HD void senseRobot(Ctx& ctx, const PhysEnv& e, const SenseTables& T, const Se
             if (two) sensePixel(pb);
         }
     }
+    if (visited) ctx.atomicAddI(&wk.counters[7], visited);
     ctx.sync();
     long long tc2 = phaseClock();
     // ---- LocalMap.extractOccupancy: every cell takes the type of its last writer in (x, y) scan order
@@ -585,7 +588,7 @@ PS_HD void senseRobot(Ctx& ctx, const PhysEnv& e, const SenseTables& T, const Se
         wk.phase[2] = (int)((tc3 - tc2) >> 4);   // occupancy + blob labelling
         wk.phase[3] = (int)((tc4 - tc3) >> 4);   // blob table
         wk.phase[3] = (int)((tq0 - tc2) >> 4);   // occupancy
-        wk.phase[4] = 0;
+        wk.phase[4] = wk.counters[7];            // candidate bodies examined, summed over the pixels
         wk.phase[5] = wk.counters[6];            // puck-coloured pixels
         wk.phase[6] = nCand;
         wk.phase[7] = nBlobs;
