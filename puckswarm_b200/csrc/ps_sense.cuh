@@ -602,8 +602,8 @@ PS_HD void senseRobot(Ctx& ctx, const PhysEnv& e, const SenseTables& T, const Se
 // batch in parallel (the working arrays are thread-local).
 // Part A (sequential): perceived pucks, carry flag, clusters. Part B (data-parallel over occupancy cells, `first` /
 // `stride` select this caller's share): clusters near ROBOT cells. Part C (sequential): the remaining cluster filters.
-PS_HD void localMapPucksAndClusters(const SenseTables& T, const SenseCfg& sc, const SenseHead& head, const BlobRec* blobs,
-                                    ps_robot_state* rstate, ps_localmap& lm) {
+PS_HD void localMapPucks(const SenseTables& T, const SenseCfg& sc, const SenseHead& head, const BlobRec* blobs, ps_robot_state* rstate,
+                         ps_localmap& lm) {
     int nBlobs = head.nBlobs;
     if (nBlobs > kMaxBlobs) nBlobs = kMaxBlobs;
     // blob list order: by colour, then by seed (scan order); blobs that never seed are not found at all
@@ -691,8 +691,15 @@ PS_HD void localMapPucksAndClusters(const SenseTables& T, const SenseCfg& sc, co
     lm.carried_x = carrying ? carriedX : 0.0f;
     lm.carried_y = carrying ? carriedY : 0.0f;
     rstate->lm_carrying = carrying ? 1 : 0;
-    // ---- LocalMap.extractClusters per colour: graph over distinct positions, edge if distance < threshold,
-    // connected components in first-vertex order, members in insertion order
+    lm.overflow = overflow;
+}
+
+// LocalMap.extractClusters per colour: graph over distinct positions, edge if distance < threshold, connected components
+// in first-vertex order, members in insertion order; then carriedCluster. Sequential version (one thread).
+PS_HD void localMapClusters(const SenseCfg& sc, ps_localmap& lm) {
+    int nP = lm.n_pucks;
+    bool carrying = lm.carrying != 0;
+    float carriedX = lm.carried_x, carriedY = lm.carried_y;
     // rep[p] = first puck of the same colour at the bitwise-same position (the graph vertex p stands for)
     uint8_t rep[PS_MAX_LM_PUCKS];
     for (int p = 0; p < nP; ++p) {
@@ -762,8 +769,88 @@ PS_HD void localMapPucksAndClusters(const SenseTables& T, const SenseCfg& sc, co
         for (int p = 0; p < nP; ++p)
             if (lm.puck_x[p] == carriedX && lm.puck_y[p] == carriedY && (int)lm.puck_cluster[p] > carriedCluster) carriedCluster = lm.puck_cluster[p];
     lm.carried_cluster = carriedCluster;
-    lm.overflow = overflow;
 }
+
+PS_HD void localMapPucksAndClusters(const SenseTables& T, const SenseCfg& sc, const SenseHead& head, const BlobRec* blobs,
+                                    ps_robot_state* rstate, ps_localmap& lm) {
+    localMapPucks(T, sc, head, blobs, rstate, lm);
+    localMapClusters(sc, lm);
+}
+
+#if defined(__CUDACC__)
+// The same by one warp for up to 32 perceived pucks: lane p owns puck p; adjacency as one 32-bit mask per lane, components
+// by OR-reduction over the member lanes, cluster ids in first-vertex order, centroids summed by lane 0 in insertion order
+// (same float order as the sequential version). Every lane of the warp must call it; lm is in shared memory.
+__device__ __forceinline__ void localMapClustersWarp(const SenseCfg& sc, ps_localmap& lm, int lane) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    int nP = lm.n_pucks;
+    bool valid = lane < nP;
+    float x = valid ? lm.puck_x[lane] : 0.0f, y = valid ? lm.puck_y[lane] : 0.0f;
+    int type = valid ? (int)lm.puck_type[lane] : -1;
+    int rep = lane;
+    if (valid)
+        for (int q = 0; q < lane; ++q)
+            if ((int)lm.puck_type[q] == type && lm.puck_x[q] == x && lm.puck_y[q] == y) {
+                rep = q;
+                break;
+            }
+    bool isRep = valid && rep == lane;
+    unsigned repMask = __ballot_sync(FULL, isRep);
+    unsigned adj = 0;
+    if (isRep)
+        for (int q = 0; q < nP; ++q) {
+            if (q == lane || !((repMask >> q) & 1u) || (int)lm.puck_type[q] != type) continue;
+            if (dist(mk(x, y), mk(lm.puck_x[q], lm.puck_y[q])) < sc.clusterThreshold) adj |= 1u << q;
+        }
+    int deg = __popc(adj);
+    int cluster = 255;
+    int nC = 0;
+    unsigned remaining = repMask;
+    while (remaining) {
+        int seed = __ffs((int)remaining) - 1;
+        unsigned comp = 1u << seed;
+        for (;;) {
+            unsigned grown = comp | __reduce_or_sync(FULL, ((comp >> lane) & 1u) ? adj : 0u);
+            if (grown == comp) break;
+            comp = grown;
+        }
+        if ((comp >> lane) & 1u) cluster = nC;
+        if (lane == 0) {
+            float sx = 0.0f, sy = 0.0f;
+            int size = 0;
+            for (unsigned m = comp; m; m &= m - 1u) {
+                int a = __ffs((int)m) - 1;
+                sx += lm.puck_x[a];
+                sy += lm.puck_y[a];
+                ++size;
+            }
+            float inv = 1.0f / size;
+            lm.cluster_x[nC] = sx * inv;
+            lm.cluster_y[nC] = sy * inv;
+            lm.cluster_type[nC] = lm.puck_type[seed];
+            lm.cluster_size[nC] = (uint8_t)size;
+            lm.cluster_kept[nC] = 1;
+        }
+        remaining &= ~comp;
+        ++nC;
+    }
+    // duplicates share the cluster and degree of their first occurrence
+    int repCluster = __shfl_sync(FULL, cluster, rep & 31);
+    int repDeg = __shfl_sync(FULL, deg, rep & 31);
+    if (valid) {
+        lm.puck_cluster[lane] = (uint8_t)(isRep ? cluster : repCluster);
+        lm.puck_degree[lane] = (uint8_t)(isRep ? deg : repDeg);
+    }
+    // carriedCluster: the last cluster (any colour) holding a vertex equal to carriedV
+    int mine = -1;
+    if (lm.carrying != 0 && valid && x == lm.carried_x && y == lm.carried_y) mine = isRep ? cluster : repCluster;
+    for (int o = 16; o > 0; o >>= 1) mine = max(mine, __shfl_xor_sync(FULL, mine, o));
+    if (lane == 0) {
+        lm.n_clusters = nC;
+        lm.carried_cluster = mine;
+    }
+}
+#endif
 
 // LocalMap.filterClusters, part 1: clusters with a puck closer than 10 cm to a ROBOT cell. Handles the 4-cell words
 // first, first + stride, ... of the occupancy grid (the writes are idempotent, so callers may share the work freely).

@@ -62,7 +62,10 @@ __global__ void __launch_bounds__(128) k_localmap(SenseKParams p, int nRobots) {
     for (int i = lane; i < (int)(sizeof(ps_localmap) / 4); i += 32) w[i] = 0u;
     __syncwarp();
     const uint8_t* occ = p.obs.occupancy + (size_t)ri * nCells;
-    if (lane == 0) localMapPucksAndClusters(p.T, p.sc, p.senseHead[ri], p.blobs + (size_t)ri * kMaxBlobs, p.sp.robot + ri, lm);
+    if (lane == 0) localMapPucks(p.T, p.sc, p.senseHead[ri], p.blobs + (size_t)ri * kMaxBlobs, p.sp.robot + ri, lm);
+    __syncwarp();
+    if (lm.n_pucks <= 32) localMapClustersWarp(p.sc, lm, lane);
+    else if (lane == 0) localMapClusters(p.sc, lm);
     __syncwarp();
     localMapRobotFilter(p.T, occ, lm, lane, 32);
     __syncwarp();
