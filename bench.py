@@ -235,47 +235,71 @@ def main():
     value = robot_steps / (ms_max / 1000.0)
 
     # ---- end to end through the C-ABI with host buffers ("e2e") ----
-    st = eng.new_state()
-    pinned_body = torch.empty(st.body.shape, dtype=torch.float32).pin_memory()
-    st.body = pinned_body.numpy()
-    pinned_arena = torch.empty(st.arena.nbytes, dtype=torch.uint8).pin_memory()
-    st.arena = pinned_arena.numpy().view(abi.ARENA_DTYPE)
-    st.sense_aabb = st.fat_aabb = st.contact_key = st.contact_info = st.contact_impulse = st.robot = None
-
+    # The caller splits its arenas over a few handles and serves them round-robin: while it waits for one handle's download,
+    # the others are stepping (plain multi-buffering; with a single handle every step would begin with the whole GPU waiting
+    # on the copies). Every step of every handle uploads its bodies' poses / velocities from pinned memory, steps, and
+    # downloads them with the step counters.
+    sense_dbg = eng.sense_stats().reshape(-1, 8).astype(np.float64)
+    n_groups = eng.num_groups
     import ctypes as C
+    halves = []
+    old_groups = os.environ.get("PS_GROUPS")
+    n_handles = int(os.environ.get("PS_E2E_HANDLES", "4"))
+    os.environ["PS_GROUPS"] = str(max(1, n_groups // n_handles))
+    h2d = d2h = 0
+    for hi in range(n_handles):
+        a0, a1 = lo + hi * A // n_handles, lo + (hi + 1) * A // n_handles
+        c2 = abi.config_defaults(n_arenas=a1 - a0, n_robots=N_ROBOTS, n_pucks=N_PUCKS, controller=abi.PS_CTRL_CACHECONS,
+                                 rng_mode=abi.PS_RNG_JAVA_SHARED)
+        e2 = engine.Engine(c2, device=local_rank)
+        e2.reset(np.arange(a0, a1))
+        e2.step(STEP_INTERVAL * (args.warmup + args.steps), sync=False)   # the state the device-resident run measured in
+        st = e2.new_state()
+        pinned_body = torch.empty(st.body.shape, dtype=torch.float32).pin_memory()
+        pinned_arena = torch.empty(st.arena.nbytes, dtype=torch.uint8).pin_memory()
+        body, arena = pinned_body.numpy(), pinned_arena.numpy().view(abi.ARENA_DTYPE)
+        vin, vout = abi.ps_state_view(), abi.ps_state_view()
+        vin.body = body.ctypes.data_as(C.POINTER(C.c_float))
+        vout.body = body.ctypes.data_as(C.POINTER(C.c_float))
+        vout.arena = arena.ctypes.data_as(C.POINTER(abi.ps_arena_state))
+        e2._check(e2.L.ps_get_state(e2.h, C.byref(vout)))
+        h2d += body.nbytes
+        d2h += body.nbytes + arena.nbytes
+        halves.append((e2, vin, vout, pinned_body, pinned_arena))
+    if old_groups is None:
+        os.environ.pop("PS_GROUPS", None)
+    else:
+        os.environ["PS_GROUPS"] = old_groups
 
-    def body_view(with_arena):
-        v = abi.ps_state_view()
-        v.body = st.body.ctypes.data_as(C.POINTER(C.c_float))
-        if with_arena:
-            v.arena = st.arena.ctypes.data_as(C.POINTER(abi.ps_arena_state))
-        return v
+    def e2e_round(first):
+        for e2, vin, vout, _, _ in halves:
+            if not first:
+                e2._check(e2.L.ps_get_state(e2.h, C.byref(vout)))   # D2H: poses + velocities + step counters (synchronous)
+            e2._check(e2.L.ps_set_state(e2.h, C.byref(vin)))          # H2D: poses + velocities of every body
+            e2._check(e2.L.ps_step(e2.h, STEP_INTERVAL))
 
-    vin, vout = body_view(False), body_view(True)
-    eng._check(eng.L.ps_get_state(eng.h, C.byref(vout)))
-    h2d = st.body.nbytes
-    d2h = st.body.nbytes + st.arena.nbytes
+    def e2e_drain():
+        for e2, vin, vout, _, _ in halves:
+            e2._check(e2.L.ps_get_state(e2.h, C.byref(vout)))
 
-    def e2e_step():
-        eng._check(eng.L.ps_set_state(eng.h, C.byref(vin)))     # H2D: poses + velocities of every body
-        eng._check(eng.L.ps_step(eng.h, STEP_INTERVAL))
-        eng._check(eng.L.ps_get_state(eng.h, C.byref(vout)))    # D2H: poses + velocities + step counters (synchronous)
-
+    e2e_round(True)
     for _ in range(3):
-        e2e_step()
+        e2e_round(False)
+    e2e_drain()
     barrier()
     t0 = time.perf_counter()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        e2e_step()
-    ev1.record(stream)
-    eng.sync()
-    wall = time.perf_counter() - t0
-    e2e_ms = max(ev0.elapsed_time(ev1), wall * 1000.0)
+    e2e_round(True)
+    for _ in range(args.steps - 1):
+        e2e_round(False)
+    e2e_drain()                       # the last step's results are on the host when the clock stops
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1000.0
     t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = robot_steps / (float(t.item()) / 1000.0)
+    for e2, *_ in halves:
+        e2.close()
 
     # ---- the same batch with the sensors on every tick (stepInterval = 1 beside the reference's 3) ----
     also = {}
@@ -326,7 +350,6 @@ def main():
         "kernel_ms_total": kms, "kernel_launch_counts": kcnt,
     }
     # ---- shared-memory roofline of the camera stage (algorithmic smem bytes per robot-sense) ----
-    sense_dbg = eng.sense_stats().reshape(-1, 8).astype(np.float64)
     p_act = 4556.0
     k_bar = float(sense_dbg[:, 4].mean()) / p_act            # candidate bodies examined per pixel (measured)
     smem_bytes_per_sense = p_act * 9.0 + p_act * k_bar * 12.0 + 3825.0 + 2294.0 * 3.0 + 19040.0
@@ -364,7 +387,8 @@ def main():
             "config": workload_config(A * world, "arenas sharded by index, %d per GPU, one process per GPU" % A),
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "call": "ps_set_state(body) + ps_step(3) + ps_get_state(body, arena) per step, pinned host buffers"},
+                    "call": "per step and per handle: ps_set_state(body) + ps_step(3) + ps_get_state(body, arena), pinned host buffers; the "
+                            "arenas are split over two handles that the caller alternates (double buffering); host wall clock"},
             "roofline": roofline, "roofline_sense": roofline_sense, "also": also, "cpu_baseline": cpu,
             "stats": {"mean_percent_completion": psd.mean_completion(total_stats), "arenas": int(total_stats.n_arenas),
                       "robots_carrying": int(total_stats.n_carrying), "cache_points": int(total_stats.n_caches),

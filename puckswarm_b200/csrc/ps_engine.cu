@@ -791,39 +791,59 @@ int ps_step_external(ps_handle h, const float* forwards, const float* torque) {
     return PS_OK;
 }
 
+// State copies run group by group on the groups' own streams (the arrays are arena-major, so a group's share is one
+// slice of each): a group's upload does not wait for the others to finish their step, and its download starts when it is done.
 static int copyState(ps_handle h, const ps_state_view* v, bool toHost) {
     const PhysCfg& pc = h->hs.phys;
-    size_t A = h->kp.nArenas;
     cudaMemcpyKind kind = toHost ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice;
-#define CP(field, dptr, bytes)                                                                          \
-    if (v->field) {                                                                                     \
-        if (toHost) CUDA_TRY(cudaMemcpyAsync((void*)v->field, dptr, bytes, kind, h->stream));           \
-        else CUDA_TRY(cudaMemcpyAsync(dptr, (const void*)v->field, bytes, kind, h->stream));            \
+    bool grouped = !h->fused && !h->groups.empty();
+    if (grouped) {
+        int rc = forkGroups(h);
+        if (rc != PS_OK) return rc;
+    } else {
+        int jr = joinGroups(h);
+        if (jr != PS_OK) return jr;
     }
-    CP(body, h->kp.sp.body, A * 6 * pc.d.NB * sizeof(float))
-    CP(sense_aabb, h->kp.sp.senseAabb, A * 4 * pc.d.NB * sizeof(float))
-    CP(fat_aabb, h->kp.sp.fat, A * 4 * pc.d.NP * sizeof(float))
-    CP(contact_key, h->kp.sp.ckey, A * pc.MC * sizeof(uint32_t))
-    CP(contact_info, h->kp.sp.cinfo, A * pc.MC * sizeof(uint32_t))
-    CP(contact_impulse, h->kp.sp.cimp, A * pc.MC * 4 * sizeof(float))
-    CP(robot, h->kp.sp.robot, A * pc.d.R * sizeof(ps_robot_state))
-    CP(arena, h->kp.sp.arena, A * sizeof(ps_arena_state))
+    size_t nSlices = grouped ? h->groups.size() : 1;
+    for (size_t g = 0; g < nSlices; ++g) {
+        size_t a0 = grouped ? (size_t)h->groups[g].a0 : 0, n = grouped ? (size_t)h->groups[g].n : (size_t)h->kp.nArenas;
+        cudaStream_t s = grouped ? h->groups[g].s : h->stream;
+        if (n == 0) continue;
+#define CP(field, dptr, perArena)                                                                                              \
+    if (v->field) {                                                                                                            \
+        size_t off = a0 * (size_t)(perArena), bytes = n * (size_t)(perArena);                                                  \
+        if (toHost) CUDA_TRY(cudaMemcpyAsync((char*)v->field + off, (const char*)(dptr) + off, bytes, kind, s));              \
+        else CUDA_TRY(cudaMemcpyAsync((char*)(dptr) + off, (const char*)v->field + off, bytes, kind, s));                      \
+    }
+        CP(body, h->kp.sp.body, 6 * pc.d.NB * sizeof(float))
+        CP(sense_aabb, h->kp.sp.senseAabb, 4 * pc.d.NB * sizeof(float))
+        CP(fat_aabb, h->kp.sp.fat, 4 * pc.d.NP * sizeof(float))
+        CP(contact_key, h->kp.sp.ckey, pc.MC * sizeof(uint32_t))
+        CP(contact_info, h->kp.sp.cinfo, pc.MC * sizeof(uint32_t))
+        CP(contact_impulse, h->kp.sp.cimp, pc.MC * 4 * sizeof(float))
+        CP(robot, h->kp.sp.robot, pc.d.R * sizeof(ps_robot_state))
+        CP(arena, h->kp.sp.arena, sizeof(ps_arena_state))
 #undef CP
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    if (grouped) {
+        h->groupsDirty = true;
+        for (auto& G : h->groups)
+            if (G.n) CUDA_TRY(cudaStreamSynchronize(G.s));
+    } else {
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
     return PS_OK;
 }
 
 int ps_get_state(ps_handle h, ps_state_view* v) {
     if (!h || !v) return setError(PS_E_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(h->device));
-    { int jr = joinGroups(h); if (jr != PS_OK) return jr; }
     return copyState(h, v, true);
 }
 
 int ps_set_state(ps_handle h, const ps_state_view* v) {
     if (!h || !v) return setError(PS_E_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(h->device));
-    { int jr = joinGroups(h); if (jr != PS_OK) return jr; }
     int rc = copyState(h, v, false);
     if (rc != PS_OK) return rc;
     if (v->arena) h->updateCount = v->arena[0].update_count;
