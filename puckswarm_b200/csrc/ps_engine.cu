@@ -178,6 +178,7 @@ __global__ void __launch_bounds__(128) k_island_warp(KParams p) {
         long long tw0 = clock64();
         bool ok = islandSolveWarp(p.env, wk, st, k, *slot, &iters);
         if (!ok && lane == 0) {
+            atomicAdd(&p.islandHist[62], 1ULL);   // diagnostic: islands that did not fit a slot
             // too large for a slot: lane 0 runs the island straight from HBM / L2
             IslandCursor cur;
             islandBegin(cur, wk, k);
@@ -187,6 +188,41 @@ __global__ void __launch_bounds__(128) k_island_warp(KParams p) {
         if (lane == 0) {
             atomicMax(&wk.stats[0], iters);
             // diagnostic: the slowest oversized island of the run: kilo-cycles << 32 | contacts << 20 | bodies << 10 | sweeps
+            unsigned long long kc = (unsigned long long)((clock64() - tw0) >> 10);
+            unsigned long long nc = (unsigned long long)(wk.islandStart[k + 1] - wk.islandStart[k]);
+            unsigned long long nb = (unsigned long long)(wk.islandBodyStart[k + 1] - wk.islandBodyStart[k]);
+            atomicMax(&p.islandHist[63], (kc << 32) | ((nc & 0xFFF) << 20) | ((nb & 0x3FF) << 10) | (unsigned long long)(iters & 0x3FF) | (ok ? 0ULL : (1ULL << 31)));
+        }
+        __syncwarp();
+    }
+}
+
+// stage B0: the islands that outgrow a WarpSlot (queue bucket kBucketBig): one warp (= one CTA) per island
+__global__ void __launch_bounds__(32) k_island_big(KParams p) {
+    extern __shared__ __align__(16) char smem[];
+    BigSlot* slot = reinterpret_cast<BigSlot*>(smem);
+    int cap = p.queue.cap;
+    int total = min(p.queue.counts[kBucketBig], cap);
+    unsigned NB = (unsigned)p.env.cfg.d.NB;
+    int lane = threadIdx.x & 31;
+    for (int idx = blockIdx.x; idx < total; idx += gridDim.x) {
+        unsigned entry = p.queue.entries[(size_t)kBucketBig * cap + idx];
+        int a = (int)(entry / NB), k = (int)(entry % NB);
+        PhysWork wk = arenaWork(p, a);
+        ArenaState st = arenaState(p.sp, p.env.cfg, a);
+        int iters = 0;
+        long long tw0 = clock64();
+        bool ok = islandSolveBig(p.env, wk, st, k, *slot, &iters);
+        if (!ok && lane == 0) {
+            atomicAdd(&p.islandHist[62], 1ULL);   // diagnostic: islands that did not fit any slot
+            // lane 0 runs the island straight from HBM / L2
+            IslandCursor cur;
+            islandBegin(cur, wk, k);
+            while (islandStep(p.env, wk, st, cur, &iters)) {
+            }
+        }
+        if (lane == 0) {
+            atomicMax(&wk.stats[0], iters);
             unsigned long long kc = (unsigned long long)((clock64() - tw0) >> 10);
             unsigned long long nc = (unsigned long long)(wk.islandStart[k + 1] - wk.islandStart[k]);
             unsigned long long nb = (unsigned long long)(wk.islandBodyStart[k + 1] - wk.islandBodyStart[k]);
@@ -208,7 +244,7 @@ __global__ void __launch_bounds__(kBatchThreads) k_island_batch(KParams p, int b
     int cap = p.queue.cap;
     int blk = blockIdx.x, nBlk = gridDim.x;
     if (bucket < 0) {
-        bucket = kQueueBuckets - 1 - blk / segBlocks;
+        bucket = kLaneBuckets - blk / segBlocks;
         blk = blk % segBlocks;
         nBlk = segBlocks;
     }
@@ -299,7 +335,7 @@ struct ps_engine {
     int* dStepStats = nullptr;
     int nSlots = 0, threads = 128;
     bool fused = false;      // PS_FUSED=1: the single-kernel World.step (kept for comparison)
-    int workerBlocks = 0, batchBlocks = 0;
+    int workerBlocks = 0, batchBlocks = 0, bigBlocks = 0;
     bool mergeBatch = true;    // one launch for all lane buckets (PS_MERGE_BATCH=0: one launch and stream per bucket)
     size_t smemBytes = 0;
     int64_t launches = 0;
@@ -587,6 +623,8 @@ int ps_create(const ps_config* cfg, int device, ps_handle* out) {
         TRY_OR_FREE(cudaFuncSetAttribute(k_island_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(WarpSlot))));
         TRY_OR_FREE(cudaFuncSetAttribute(k_island_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((kBatchThreads / 32) * sizeof(LaneSlotsU))));
         e->mergeBatch = envSize("PS_MERGE_BATCH", 1) != 0;
+        e->bigBlocks = prop.multiProcessorCount * 4;
+        TRY_OR_FREE(cudaFuncSetAttribute(k_island_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BigSlot)));
         e->batchBlocks = prop.multiProcessorCount * (int)envSize("PS_BATCH_BLOCKS_PER_SM", 2);
     }
     e->kp.env.scene = e->dScene;
@@ -660,28 +698,33 @@ static int launchPhysics(ps_handle h, ps_engine::Group& G, int nTicks) {
             // islands are independent: the oversized ones (one warp each) run beside the lane batches
             CUDA_TRY(cudaEventRecord(G.evPre, G.s));
             CUDA_TRY(cudaStreamWaitEvent(G.s2, G.evPre, 0));
+            // the largest islands start first, on a stream of their own
+            CUDA_TRY(cudaStreamWaitEvent(G.sb[kBucketBig], G.evPre, 0));
+            k_island_big<<<std::max(1, std::min(h->bigBlocks, G.n)), 32, sizeof(BigSlot), G.sb[kBucketBig]>>>(kp);
+            CUDA_TRY(cudaEventRecord(G.evb[kBucketBig], G.sb[kBucketBig]));
             int wb = std::max(1, std::min(h->workerBlocks, G.n * 3));
             k_island_warp<<<wb, 128, 4 * sizeof(WarpSlot), G.s2>>>(kp);
             CUDA_TRY(cudaEventRecord(G.evBig, G.s2));
             int bb = std::max(1, std::min(h->batchBlocks, (G.n * 12 + kBatchThreads - 1) / kBatchThreads));
             if (h->mergeBatch) {
-                k_island_batch<<<bb * (kQueueBuckets - 1), kBatchThreads, (kBatchThreads / 32) * sizeof(LaneSlotsU), G.s>>>(kp, -1, bb);
+                k_island_batch<<<bb * kLaneBuckets, kBatchThreads, (kBatchThreads / 32) * sizeof(LaneSlotsU), G.s>>>(kp, -1, bb);
             } else {
-                for (int bucket = kQueueBuckets - 1; bucket >= 2; --bucket) {
+                for (int bucket = kLaneBuckets; bucket >= 2; --bucket) {
                     CUDA_TRY(cudaStreamWaitEvent(G.sb[bucket], G.evPre, 0));
                     k_island_batch<<<bb, kBatchThreads, (kBatchThreads / 32) * sizeof(LaneSlotsU), G.sb[bucket]>>>(kp, bucket, bb);
                     CUDA_TRY(cudaEventRecord(G.evb[bucket], G.sb[bucket]));
                 }
                 k_island_batch<<<bb, kBatchThreads, (kBatchThreads / 32) * sizeof(LaneSlotsU), G.s>>>(kp, 1, bb);
-                for (int bucket = 2; bucket < kQueueBuckets; ++bucket) CUDA_TRY(cudaStreamWaitEvent(G.s, G.evb[bucket], 0));
+                for (int bucket = 2; bucket <= kLaneBuckets; ++bucket) CUDA_TRY(cudaStreamWaitEvent(G.s, G.evb[bucket], 0));
             }
             CUDA_TRY(cudaStreamWaitEvent(G.s, G.evBig, 0));
+            CUDA_TRY(cudaStreamWaitEvent(G.s, G.evb[kBucketBig], 0));
         }
         {
             ScopedTimer t6(h, 6, G.s);
             k_phys_post<<<G.n, 128, 0, G.s>>>(kp);
         }
-        h->launches += 3 + (h->mergeBatch ? 1 : kQueueBuckets - 1);
+        h->launches += 4 + (h->mergeBatch ? 1 : kLaneBuckets);
         CUDA_TRY(cudaGetLastError());
     }
     return PS_OK;

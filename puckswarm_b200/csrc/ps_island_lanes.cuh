@@ -459,7 +459,7 @@ __device__ __forceinline__ int lkSolve(const PhysEnv& e, const PhysWork& wk, con
 // holds an earlier constraint sharing a dynamic body with it. The constraints of a row touch disjoint bodies, so the lanes
 // solve them together; rows run in order, so every body still sees its constraints in the reference's order and the
 // sweep is bit-identical to the sequential one. The solver routines are the uniform ones of the lane path.
-static constexpr int kWarpBodies = 48, kWarpContacts = 64;
+static constexpr int kWarpBodies = kQueueWarpBodies, kWarpContacts = kQueueWarpContacts;
 static constexpr int kWB = kWarpBodies + 1;
 struct WarpSlot {
     float cx[kWB], cy[kWB], a[kWB], vx[kWB], vy[kWB], w[kWB];
@@ -629,6 +629,207 @@ __device__ __forceinline__ bool islandSolveWarp(const PhysEnv& e, const PhysWork
         ++iters;
         if (minSep >= -1.5f * kLinearSlop) break;
         if (!anyChanged) {   // fixed point: every later sweep repeats this one
+            iters = e.cfg.posIters;
+            break;
+        }
+    }
+    if (lane == 0) *itersOut = iters;
+    __syncwarp();
+    for (int i = lane; i < nb; i += 32) {
+        int g = s.gidx[i];
+        wk.cx[g] = s.cx[i];
+        wk.cy[g] = s.cy[i];
+        wk.a[g] = s.a[i];
+        wk.vx[g] = s.vx[i];
+        wk.vy[g] = s.vy[i];
+        wk.w[g] = s.w[i];
+        if (g >= P) {
+            int r = g - P;
+            wk.rpx[r] = s.px[i];
+            wk.rpy[r] = s.py[i];
+            wk.rc[r] = s.c[i];
+            wk.rs[r] = s.s[i];
+        }
+    }
+    __syncwarp();
+    return true;
+}
+
+// Warp-per-island solver for the islands that outgrow a WarpSlot (puck caches of 50+ bodies, 100+ contacts): the body
+// table and what the position sweeps read of each constraint live in shared memory, the constraints themselves stay in
+// HBM / L2 (the four velocity-phase passes read them there, many lanes at a time), and a sweep is the same row schedule
+// in CSR form (rows may be wider than the warp).
+static constexpr int kBigBodies = 254, kBigContacts = 640;
+static constexpr int kBB = kBigBodies + 1;
+struct BigSlot {
+    float cx[kBB], cy[kBB], a[kBB], vx[kBB], vy[kBB], w[kBB];
+    float px[kBB], py[kBB], c[kBB], s[kBB], pm[kBB], pi[kBB];
+    uint16_t gidx[kBB], bodyRow[kBB];
+    uint8_t kind[kBB];
+    float pc[kBigContacts][9];             // localNormal, localPoint, two manifold points, radius
+    uint32_t pcHead[kBigContacts];         // bodyA | bodyB << 8 | type << 16 | points << 24
+    uint16_t row[kBigContacts], sched[kBigContacts], rowStart[kBigContacts + 2];
+    int nRows;
+};
+struct BigCtx {
+    BigSlot* S;
+    __device__ __forceinline__ float& cx(int l) const { return S->cx[l]; }
+    __device__ __forceinline__ float& cy(int l) const { return S->cy[l]; }
+    __device__ __forceinline__ float& a(int l) const { return S->a[l]; }
+    __device__ __forceinline__ float& vx(int l) const { return S->vx[l]; }
+    __device__ __forceinline__ float& vy(int l) const { return S->vy[l]; }
+    __device__ __forceinline__ float& w(int l) const { return S->w[l]; }
+    __device__ __forceinline__ float& px(int l) const { return S->px[l]; }
+    __device__ __forceinline__ float& py(int l) const { return S->py[l]; }
+    __device__ __forceinline__ float& c(int l) const { return S->c[l]; }
+    __device__ __forceinline__ float& s(int l) const { return S->s[l]; }
+    __device__ __forceinline__ float pm(int l) const { return S->pm[l]; }
+    __device__ __forceinline__ float pi(int l) const { return S->pi[l]; }
+    __device__ __forceinline__ int kind(int l) const { return S->kind[l]; }
+    __device__ __forceinline__ int gidx(int l) const { return S->gidx[l]; }
+};
+// Returns false if the island does not fit (the caller falls back to the sequential path).
+__device__ __forceinline__ bool islandSolveBig(const PhysEnv& e, const PhysWork& wk, const ArenaState& st, int k, BigSlot& s, int* itersOut) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    int lane = threadIdx.x & 31;
+    int lo = wk.islandStart[k], hi = wk.islandStart[k + 1];
+    int blo = wk.islandBodyStart[k], bhi = wk.islandBodyStart[k + 1];
+    int nb = bhi - blo, nc = hi - lo;
+    int P = e.cfg.d.P;
+    if (nb > kBigBodies || nc > kBigContacts) return false;
+    for (int i = lane; i <= nb; i += 32) {
+        if (i < nb) {
+            int g = wk.ibody[blo + i];
+            s.gidx[i] = (uint16_t)g;
+            s.cx[i] = wk.cx[g];
+            s.cy[i] = wk.cy[g];
+            s.a[i] = wk.a[g];
+            s.vx[i] = wk.vx[g];
+            s.vy[i] = wk.vy[g];
+            s.w[i] = wk.w[g];
+            if (g >= P) {
+                int r = g - P;
+                s.kind[i] = LK_ROBOT;
+                s.pm[i] = e.hot.pmRobot;
+                s.pi[i] = e.hot.piRobot;
+                s.px[i] = wk.rpx[r];
+                s.py[i] = wk.rpy[r];
+                s.c[i] = wk.rc[r];
+                s.s[i] = wk.rs[r];
+            } else {
+                s.kind[i] = LK_PUCK;
+                s.pm[i] = e.hot.pmPuck;
+                s.pi[i] = e.hot.piPuck;
+                s.px[i] = wk.cx[g];
+                s.py[i] = wk.cy[g];
+                s.c[i] = 1.0f;
+                s.s[i] = 0.0f;
+            }
+        } else {
+            s.gidx[i] = 0xFFFF;
+            s.kind[i] = LK_WALL;
+            s.cx[i] = s.cy[i] = s.a[i] = s.vx[i] = s.vy[i] = s.w[i] = 0.0f;
+            s.pm[i] = s.pi[i] = 0.0f;
+            s.px[i] = e.hot.wallXf.px;
+            s.py[i] = e.hot.wallXf.py;
+            s.c[i] = e.hot.wallXf.c;
+            s.s[i] = e.hot.wallXf.s;
+        }
+        s.bodyRow[i] = 0;
+    }
+    for (int i = lane; i < nc + 2; i += 32) s.rowStart[i] = 0;
+    __syncwarp();
+    // constraints: body references -> staged indices (wall -> nb), in place; position data -> shared memory
+    for (int i = lane; i < nc; i += 32) {
+        TC& t = wk.tc[wk.order[lo + i]];
+        int a = t.bodyA, b = t.bodyB;
+        int la = nb, lb = nb;
+        for (int j = 0; j < nb; ++j) {
+            int g = s.gidx[j];
+            if (g == a) la = j;
+            if (g == b) lb = j;
+        }
+        t.bodyA = la;
+        t.bodyB = lb;
+        s.pc[i][0] = t.localNormal.x;
+        s.pc[i][1] = t.localNormal.y;
+        s.pc[i][2] = t.localPoint.x;
+        s.pc[i][3] = t.localPoint.y;
+        s.pc[i][4] = t.lp[0].x;
+        s.pc[i][5] = t.lp[0].y;
+        s.pc[i][6] = t.lp[1].x;
+        s.pc[i][7] = t.lp[1].y;
+        s.pc[i][8] = t.radius;
+        s.pcHead[i] = (uint32_t)la | ((uint32_t)lb << 8) | ((uint32_t)t.type << 16) | ((uint32_t)t.solverPoints << 24);
+    }
+    __syncwarp();
+    // rows: constraint i goes to the row after the last row holding an earlier constraint on one of its bodies
+    if (lane == 0) {
+        int nRows = 0;
+        for (int i = 0; i < nc; ++i) {
+            uint32_t hd = s.pcHead[i];
+            int a = (int)(hd & 255u), b = (int)((hd >> 8) & 255u);
+            int r = 0;
+            if (a < nb) r = s.bodyRow[a];
+            if (b < nb && s.bodyRow[b] > r) r = s.bodyRow[b];
+            s.row[i] = (uint16_t)r;
+            s.rowStart[r + 2]++;                       // counts, shifted by two for the in-place prefix sum below
+            if (a < nb) s.bodyRow[a] = (uint16_t)(r + 1);
+            if (b < nb) s.bodyRow[b] = (uint16_t)(r + 1);
+            if (r + 1 > nRows) nRows = r + 1;
+        }
+        for (int r = 0; r < nRows; ++r) s.rowStart[r + 2] += s.rowStart[r + 1];   // rowStart[r + 1] = start of row r, for now
+        for (int i = 0; i < nc; ++i) s.sched[s.rowStart[s.row[i] + 1]++] = (uint16_t)i;   // ... and becomes its end = start of row r + 1
+        s.nRows = nRows;
+    }
+    __syncwarp();
+    BigCtx L;
+    L.S = &s;
+    int nRows = s.nRows;
+    for (int r = 0; r < nRows; ++r) {
+        for (int q = s.rowStart[r] + lane; q < s.rowStart[r + 1]; q += 32) lkWarmStart(e, L, wk.tc[wk.order[lo + s.sched[q]]]);
+        __syncwarp();
+    }
+    for (int it = 0; it < e.cfg.velIters; ++it)
+        for (int r = 0; r < nRows; ++r) {
+            for (int q = s.rowStart[r] + lane; q < s.rowStart[r + 1]; q += 32) lkSolveVelocity(e, L, wk.tc[wk.order[lo + s.sched[q]]]);
+            __syncwarp();
+        }
+    for (int i = lane; i < nc; i += 32) {
+        const TC& t = wk.tc[wk.order[lo + i]];
+        for (int j2 = 0; j2 < t.solverPoints; ++j2) {
+            st.cimp[4 * t.ci + 2 * j2] = t.nImp[j2];
+            st.cimp[4 * t.ci + 2 * j2 + 1] = t.tImp[j2];
+        }
+    }
+    for (int b = lane; b < nb; b += 32) lkIntegrate(e, wk, L, b);
+    __syncwarp();
+    int iters = 0;
+    for (int it = 0; it < e.cfg.posIters; ++it) {
+        float minSep = 0.0f;
+        bool changed = false;
+        for (int r = 0; r < nRows; ++r) {
+            for (int q = s.rowStart[r] + lane; q < s.rowStart[r + 1]; q += 32) {
+                int ci = s.sched[q];
+                uint32_t hd = s.pcHead[ci];
+                int bA = (int)(hd & 255u), bB = (int)((hd >> 8) & 255u), type = (int)((hd >> 16) & 255u), np = (int)(hd >> 24);
+                V2 ln = mk(s.pc[ci][0], s.pc[ci][1]), lp = mk(s.pc[ci][2], s.pc[ci][3]);
+                float radius = s.pc[ci][8];
+                for (int j2 = 0; j2 < np; ++j2) {
+                    float sep = lkCorrectPoint(e, L, bA, bB, type, ln, lp, mk(s.pc[ci][4 + 2 * j2], s.pc[ci][5 + 2 * j2]), radius, &changed);
+                    minSep = fminf_(minSep, sep);
+                }
+            }
+            __syncwarp();
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            float other = __shfl_xor_sync(FULL, minSep, o);
+            minSep = fminf_(minSep, other);
+        }
+        bool anyChanged = __any_sync(FULL, changed);
+        ++iters;
+        if (minSep >= -1.5f * kLinearSlop) break;
+        if (!anyChanged) {
             iters = e.cfg.posIters;
             break;
         }

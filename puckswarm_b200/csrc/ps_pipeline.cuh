@@ -24,8 +24,9 @@ struct IslandQueue {
     int* counts;           // [kQueueBuckets + 1]: entries per bucket, last = consumer head of bucket 0
     int cap;
 };
+static constexpr int kQueueWarpBodies = 48, kQueueWarpContacts = 64;   // = kWarpBodies, kWarpContacts of ps_island_lanes.cuh
 static constexpr int kLaneBodies = 12, kLaneContacts = 16;   // what a lane slot of the lane-per-island solver holds
-static constexpr int kQueueBuckets = 5, kWarpMinContactsDefault = 16;   // capacity of one lane's shared-memory slot (k_island_batch)
+static constexpr int kQueueBuckets = 6, kLaneBuckets = 4, kBucketBig = 5, kWarpMinContactsDefault = 16;   // capacity of one lane's shared-memory slot (k_island_batch)
 
 template <class Ctx>
 PS_HD void physPre(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaState& st, const float* cmdFwd, const float* cmdTorque,
@@ -44,7 +45,9 @@ PS_HD void physPre(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaSt
     PS_FOR(k, nIsl) {
         int nb = wk.islandBodyStart[k + 1] - wk.islandBodyStart[k];
         int nc = wk.islandStart[k + 1] - wk.islandStart[k];
-        int bucket = (nc >= e.cfg.warpMinContacts || nc > kLaneContacts || nb > kLaneBodies) ? 0 : (nc <= 2 ? 1 : (nc <= 5 ? 2 : (nc <= 12 ? 3 : 4)));
+        // 0: a warp each (WarpSlot); kBucketBig: what outgrows that (BigSlot); 1..4: a lane each, by contact count
+        int bucket = (nc >= e.cfg.warpMinContacts || nc > kLaneContacts || nb > kLaneBodies) ? ((nb > kQueueWarpBodies || nc > kQueueWarpContacts) ? kBucketBig : 0)
+                                                                                               : (nc <= 2 ? 1 : (nc <= 5 ? 2 : (nc <= 12 ? 3 : 4)));
         int pos = ctx.atomicAddI(&q.counts[bucket], 1);
         if (pos < q.cap) q.entries[(size_t)bucket * q.cap + pos] = (unsigned)arena * (unsigned)d.NB + (unsigned)k;
     }
