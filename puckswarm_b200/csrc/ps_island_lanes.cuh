@@ -453,27 +453,42 @@ __device__ __forceinline__ int lkSolve(const PhysEnv& e, const PhysWork& wk, con
     return iters;
 }
 
-// Warp-per-island solver for islands of up to kWarpBodies bodies / kWarpContacts contacts. The warp stages the island into
-// its shared-memory slot: one body table (the wall included, as the body after the last dynamic one) and the constraints.
-// A sweep over the constraints is cut into rows: constraint i (in solve order) goes to the row after the last row that
-// holds an earlier constraint sharing a dynamic body with it. The constraints of a row touch disjoint bodies, so the lanes
-// solve them together; rows run in order, so every body still sees its constraints in the reference's order and the
-// sweep is bit-identical to the sequential one. The solver routines are the uniform ones of the lane path.
+// Warp-per-island solver. The warp stages the island into its shared-memory slot: one body table (the wall included, as
+// the body after the last dynamic one), what the position sweeps read of each constraint, and -- when the slot is
+// built with STAGE_TC -- the constraints themselves (otherwise the four velocity-phase passes read them from HBM / L2).
+//
+// Rows. A sweep over the constraints is cut into rows: constraint i (in solve order) goes to the row after the last row
+// that holds an earlier constraint sharing a dynamic body with it. The constraints of a row touch disjoint bodies, so
+// the lanes solve them together; rows run in order, so every body still sees its constraints in the reference's order
+// and the sweep is bit-identical to the sequential one.
+//
+// (Two ways of running corrections of different sweeps side by side -- a modulo schedule over the rows, and a dataflow
+// order driven by per-body correction counters -- were built, verified bit-exact, and measured slower: the solve order of
+// real islands leaves ~2 independent corrections per step, less than the bookkeeping costs. The plain row schedule stays.)
 static constexpr int kWarpBodies = kQueueWarpBodies, kWarpContacts = kQueueWarpContacts;
-static constexpr int kWB = kWarpBodies + 1;
-struct WarpSlot {
-    float cx[kWB], cy[kWB], a[kWB], vx[kWB], vy[kWB], w[kWB];
-    float px[kWB], py[kWB], c[kWB], s[kWB], pm[kWB], pi[kWB];
-    uint16_t gidx[kWB];
-    uint8_t kind[kWB], bodyRow[kWB];
-    TC tc[kWarpContacts];
-    uint8_t row[kWarpContacts];            // row of each constraint
-    uint8_t rowFill[kWarpContacts + 1];
-    alignas(16) uint8_t task[kWarpContacts][32];   // [row][lane] constraint index, 255 = none
+static constexpr int kBigBodies = 254, kBigContacts = 640;
+template <int NB_, int NC_, bool STAGE_TC>
+struct IslandSlot {
+    static constexpr int NBX = NB_ + 1;
+    static constexpr int kBodies = NB_, kContacts = NC_;
+    static constexpr bool kStageTC = STAGE_TC;
+    float cx[NBX], cy[NBX], a[NBX], vx[NBX], vy[NBX], w[NBX];
+    float px[NBX], py[NBX], c[NBX], s[NBX], pm[NBX], pi[NBX];
+    uint16_t gidx[NBX], bodyRow[NBX];
+    uint8_t kind[NBX];
+    float pc[NC_][9];                      // localNormal, localPoint, two manifold points, radius
+    uint32_t pcHead[NC_];                  // bodyA | bodyB << 8 | type << 16 | points << 24
+    uint16_t row[NC_], sched[NC_], rowStart[NC_ + 2];
     int nRows;
+    TC tc[STAGE_TC ? NC_ : 1];
+    __device__ __forceinline__ float& CX(int l) { return cx[l]; }
 };
-struct WarpCtx {
-    WarpSlot* S;
+typedef IslandSlot<kWarpBodies, kWarpContacts, true> WarpSlot;
+typedef IslandSlot<kBigBodies, kBigContacts, false> BigSlot;
+
+template <class Slot>
+struct SlotCtx {
+    Slot* S;
     __device__ __forceinline__ float& cx(int l) const { return S->cx[l]; }
     __device__ __forceinline__ float& cy(int l) const { return S->cy[l]; }
     __device__ __forceinline__ float& a(int l) const { return S->a[l]; }
@@ -489,214 +504,33 @@ struct WarpCtx {
     __device__ __forceinline__ int kind(int l) const { return S->kind[l]; }
     __device__ __forceinline__ int gidx(int l) const { return S->gidx[l]; }
 };
-// Returns false if the island does not fit the slot (the caller falls back to the sequential path).
-__device__ __forceinline__ bool islandSolveWarp(const PhysEnv& e, const PhysWork& wk, const ArenaState& st, int k, WarpSlot& s, int* itersOut) {
-    const unsigned FULL = 0xFFFFFFFFu;
-    int lane = threadIdx.x & 31;
-    int lo = wk.islandStart[k], hi = wk.islandStart[k + 1];
-    int blo = wk.islandBodyStart[k], bhi = wk.islandBodyStart[k + 1];
-    int nb = bhi - blo, nc = hi - lo;
-    int P = e.cfg.d.P;
-    if (nb > kWarpBodies || nc > kWarpContacts) return false;
-    // ---- stage the bodies (island order) and the wall
-    for (int i = lane; i <= nb; i += 32) {
-        if (i < nb) {
-            int g = wk.ibody[blo + i];
-            s.gidx[i] = (uint16_t)g;
-            s.cx[i] = wk.cx[g];
-            s.cy[i] = wk.cy[g];
-            s.a[i] = wk.a[g];
-            s.vx[i] = wk.vx[g];
-            s.vy[i] = wk.vy[g];
-            s.w[i] = wk.w[g];
-            if (g >= P) {
-                int r = g - P;
-                s.kind[i] = LK_ROBOT;
-                s.pm[i] = e.hot.pmRobot;
-                s.pi[i] = e.hot.piRobot;
-                s.px[i] = wk.rpx[r];
-                s.py[i] = wk.rpy[r];
-                s.c[i] = wk.rc[r];
-                s.s[i] = wk.rs[r];
-            } else {
-                s.kind[i] = LK_PUCK;
-                s.pm[i] = e.hot.pmPuck;
-                s.pi[i] = e.hot.piPuck;
-                s.px[i] = wk.cx[g];
-                s.py[i] = wk.cy[g];
-                s.c[i] = 1.0f;
-                s.s[i] = 0.0f;
-            }
-        } else {
-            s.gidx[i] = 0xFFFF;
-            s.kind[i] = LK_WALL;
-            s.cx[i] = s.cy[i] = s.a[i] = s.vx[i] = s.vy[i] = s.w[i] = 0.0f;
-            s.pm[i] = s.pi[i] = 0.0f;
-            s.px[i] = e.hot.wallXf.px;
-            s.py[i] = e.hot.wallXf.py;
-            s.c[i] = e.hot.wallXf.c;
-            s.s[i] = e.hot.wallXf.s;
-        }
-        s.bodyRow[i] = 0;
+
+// position correction of both points of staged constraint ci; returns the smaller separation
+template <class Slot>
+__device__ __forceinline__ float slotCorrect(const PhysEnv& e, const SlotCtx<Slot>& L, Slot& s, int ci, bool* changed) {
+    uint32_t hd = s.pcHead[ci];
+    int bA = (int)(hd & 255u), bB = (int)((hd >> 8) & 255u), type = (int)((hd >> 16) & 255u), np = (int)(hd >> 24);
+    V2 ln = mk(s.pc[ci][0], s.pc[ci][1]), lp = mk(s.pc[ci][2], s.pc[ci][3]);
+    float radius = s.pc[ci][8];
+    float minSep = 0.0f;
+    for (int j2 = 0; j2 < np; ++j2) {
+        float sep = lkCorrectPoint(e, L, bA, bB, type, ln, lp, mk(s.pc[ci][4 + 2 * j2], s.pc[ci][5 + 2 * j2]), radius, changed);
+        minSep = fminf_(minSep, sep);
     }
-    for (int i = lane; i < kWarpContacts * 8; i += 32) reinterpret_cast<uint32_t*>(&s.task[0][0])[i] = 0xFFFFFFFFu;
-    for (int i = lane; i <= kWarpContacts; i += 32) s.rowFill[i] = 0;
-    __syncwarp();
-    // ---- constraints: body references -> staged indices (wall -> nb)
-    for (int i = lane; i < nc; i += 32) {
-        TC t = wk.tc[wk.order[lo + i]];
-        int la = nb, lb = nb;
-        for (int j = 0; j < nb; ++j) {
-            int g = s.gidx[j];
-            if (g == t.bodyA) la = j;
-            if (g == t.bodyB) lb = j;
-        }
-        t.bodyA = la;
-        t.bodyB = lb;
-        s.tc[i] = t;
-    }
-    __syncwarp();
-    // ---- rows of one Gauss-Seidel sweep
-    if (lane == 0) {
-        int nRows = 0;
-        for (int i = 0; i < nc; ++i) {
-            int a = s.tc[i].bodyA, b = s.tc[i].bodyB;
-            int r = 0;
-            if (a < nb) r = s.bodyRow[a];
-            if (b < nb && s.bodyRow[b] > r) r = s.bodyRow[b];
-            // (row r + 1, 1-based, is the first one after every earlier constraint of these bodies; a full row pushes on)
-            while (s.rowFill[r] >= 32) ++r;
-            int slot = s.rowFill[r]++;
-            s.task[r][slot] = (uint8_t)i;
-            if (a < nb) s.bodyRow[a] = (uint8_t)(r + 1);
-            if (b < nb) s.bodyRow[b] = (uint8_t)(r + 1);
-            if (r + 1 > nRows) nRows = r + 1;
-        }
-        s.nRows = nRows;
-    }
-    __syncwarp();
-    WarpCtx L;
-    L.S = &s;
-    int nRows = s.nRows;
-    // ContactSolver.warmStart
-    for (int r = 0; r < nRows; ++r) {
-        int ci = s.task[r][lane];
-        if (ci != 255) lkWarmStart(e, L, s.tc[ci]);
-        __syncwarp();
-    }
-    // velocity sweeps
-    for (int it = 0; it < e.cfg.velIters; ++it)
-        for (int r = 0; r < nRows; ++r) {
-            int ci = s.task[r][lane];
-            if (ci != 255) lkSolveVelocity(e, L, s.tc[ci]);
-            __syncwarp();
-        }
-    // ContactSolver.storeImpulses
-    for (int i = lane; i < nc; i += 32) {
-        const TC& t = s.tc[i];
-        for (int j2 = 0; j2 < t.solverPoints; ++j2) {
-            st.cimp[4 * t.ci + 2 * j2] = t.nImp[j2];
-            st.cimp[4 * t.ci + 2 * j2 + 1] = t.tImp[j2];
-        }
-    }
-    // integrate the island's bodies
-    for (int b = lane; b < nb; b += 32) lkIntegrate(e, wk, L, b);
-    __syncwarp();
-    // position sweeps
-    int iters = 0;
-    for (int it = 0; it < e.cfg.posIters; ++it) {
-        float minSep = 0.0f;
-        bool changed = false;
-        for (int r = 0; r < nRows; ++r) {
-            int ci = s.task[r][lane];
-            if (ci != 255) {
-                const TC& t = s.tc[ci];
-                int bA = t.bodyA, bB = t.bodyB, type = t.type, np = t.solverPoints;
-                V2 ln = t.localNormal, lp = t.localPoint;
-                float radius = t.radius;
-                for (int j2 = 0; j2 < np; ++j2) {
-                    float sep = lkCorrectPoint(e, L, bA, bB, type, ln, lp, t.lp[j2], radius, &changed);
-                    minSep = fminf_(minSep, sep);
-                }
-            }
-            __syncwarp();
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-            float other = __shfl_xor_sync(FULL, minSep, o);
-            minSep = fminf_(minSep, other);
-        }
-        bool anyChanged = __any_sync(FULL, changed);
-        ++iters;
-        if (minSep >= -1.5f * kLinearSlop) break;
-        if (!anyChanged) {   // fixed point: every later sweep repeats this one
-            iters = e.cfg.posIters;
-            break;
-        }
-    }
-    if (lane == 0) *itersOut = iters;
-    __syncwarp();
-    for (int i = lane; i < nb; i += 32) {
-        int g = s.gidx[i];
-        wk.cx[g] = s.cx[i];
-        wk.cy[g] = s.cy[i];
-        wk.a[g] = s.a[i];
-        wk.vx[g] = s.vx[i];
-        wk.vy[g] = s.vy[i];
-        wk.w[g] = s.w[i];
-        if (g >= P) {
-            int r = g - P;
-            wk.rpx[r] = s.px[i];
-            wk.rpy[r] = s.py[i];
-            wk.rc[r] = s.c[i];
-            wk.rs[r] = s.s[i];
-        }
-    }
-    __syncwarp();
-    return true;
+    return minSep;
 }
 
-// Warp-per-island solver for the islands that outgrow a WarpSlot (puck caches of 50+ bodies, 100+ contacts): the body
-// table and what the position sweeps read of each constraint live in shared memory, the constraints themselves stay in
-// HBM / L2 (the four velocity-phase passes read them there, many lanes at a time), and a sweep is the same row schedule
-// in CSR form (rows may be wider than the warp).
-static constexpr int kBigBodies = 254, kBigContacts = 640;
-static constexpr int kBB = kBigBodies + 1;
-struct BigSlot {
-    float cx[kBB], cy[kBB], a[kBB], vx[kBB], vy[kBB], w[kBB];
-    float px[kBB], py[kBB], c[kBB], s[kBB], pm[kBB], pi[kBB];
-    uint16_t gidx[kBB], bodyRow[kBB];
-    uint8_t kind[kBB];
-    float pc[kBigContacts][9];             // localNormal, localPoint, two manifold points, radius
-    uint32_t pcHead[kBigContacts];         // bodyA | bodyB << 8 | type << 16 | points << 24
-    uint16_t row[kBigContacts], sched[kBigContacts], rowStart[kBigContacts + 2];
-    int nRows;
-};
-struct BigCtx {
-    BigSlot* S;
-    __device__ __forceinline__ float& cx(int l) const { return S->cx[l]; }
-    __device__ __forceinline__ float& cy(int l) const { return S->cy[l]; }
-    __device__ __forceinline__ float& a(int l) const { return S->a[l]; }
-    __device__ __forceinline__ float& vx(int l) const { return S->vx[l]; }
-    __device__ __forceinline__ float& vy(int l) const { return S->vy[l]; }
-    __device__ __forceinline__ float& w(int l) const { return S->w[l]; }
-    __device__ __forceinline__ float& px(int l) const { return S->px[l]; }
-    __device__ __forceinline__ float& py(int l) const { return S->py[l]; }
-    __device__ __forceinline__ float& c(int l) const { return S->c[l]; }
-    __device__ __forceinline__ float& s(int l) const { return S->s[l]; }
-    __device__ __forceinline__ float pm(int l) const { return S->pm[l]; }
-    __device__ __forceinline__ float pi(int l) const { return S->pi[l]; }
-    __device__ __forceinline__ int kind(int l) const { return S->kind[l]; }
-    __device__ __forceinline__ int gidx(int l) const { return S->gidx[l]; }
-};
-// Returns false if the island does not fit (the caller falls back to the sequential path).
-__device__ __forceinline__ bool islandSolveBig(const PhysEnv& e, const PhysWork& wk, const ArenaState& st, int k, BigSlot& s, int* itersOut) {
+// Returns false if the island does not fit the slot (the caller falls back to the sequential path).
+template <class Slot>
+__device__ __forceinline__ bool islandSolveSlot(const PhysEnv& e, const PhysWork& wk, const ArenaState& st, int k, Slot& s, int* itersOut) {
     const unsigned FULL = 0xFFFFFFFFu;
     int lane = threadIdx.x & 31;
     int lo = wk.islandStart[k], hi = wk.islandStart[k + 1];
     int blo = wk.islandBodyStart[k], bhi = wk.islandBodyStart[k + 1];
     int nb = bhi - blo, nc = hi - lo;
     int P = e.cfg.d.P;
-    if (nb > kBigBodies || nc > kBigContacts) return false;
+    if (nb > Slot::kBodies || nc > Slot::kContacts) return false;
+    // ---- stage the bodies (island order) and the wall
     for (int i = lane; i <= nb; i += 32) {
         if (i < nb) {
             int g = wk.ibody[blo + i];
@@ -739,18 +573,24 @@ __device__ __forceinline__ bool islandSolveBig(const PhysEnv& e, const PhysWork&
     }
     for (int i = lane; i < nc + 2; i += 32) s.rowStart[i] = 0;
     __syncwarp();
-    // constraints: body references -> staged indices (wall -> nb), in place; position data -> shared memory
+    // ---- constraints: body references -> staged indices (wall -> nb); position data -> shared memory
     for (int i = lane; i < nc; i += 32) {
-        TC& t = wk.tc[wk.order[lo + i]];
-        int a = t.bodyA, b = t.bodyB;
+        TC& g = wk.tc[wk.order[lo + i]];
+        TC t = g;
         int la = nb, lb = nb;
         for (int j = 0; j < nb; ++j) {
-            int g = s.gidx[j];
-            if (g == a) la = j;
-            if (g == b) lb = j;
+            int gi = s.gidx[j];
+            if (gi == t.bodyA) la = j;
+            if (gi == t.bodyB) lb = j;
         }
         t.bodyA = la;
         t.bodyB = lb;
+        if (Slot::kStageTC) {
+            s.tc[i] = t;
+        } else {
+            g.bodyA = la;
+            g.bodyB = lb;
+        }
         s.pc[i][0] = t.localNormal.x;
         s.pc[i][1] = t.localNormal.y;
         s.pc[i][2] = t.localPoint.x;
@@ -763,7 +603,7 @@ __device__ __forceinline__ bool islandSolveBig(const PhysEnv& e, const PhysWork&
         s.pcHead[i] = (uint32_t)la | ((uint32_t)lb << 8) | ((uint32_t)t.type << 16) | ((uint32_t)t.solverPoints << 24);
     }
     __syncwarp();
-    // rows: constraint i goes to the row after the last row holding an earlier constraint on one of its bodies
+    // ---- rows of one Gauss-Seidel sweep (CSR: rowStart / sched) and the sweep distance D
     if (lane == 0) {
         int nRows = 0;
         for (int i = 0; i < nc; ++i) {
@@ -778,48 +618,46 @@ __device__ __forceinline__ bool islandSolveBig(const PhysEnv& e, const PhysWork&
             if (b < nb) s.bodyRow[b] = (uint16_t)(r + 1);
             if (r + 1 > nRows) nRows = r + 1;
         }
-        for (int r = 0; r < nRows; ++r) s.rowStart[r + 2] += s.rowStart[r + 1];   // rowStart[r + 1] = start of row r, for now
+        for (int r = 0; r < nRows; ++r) s.rowStart[r + 2] += s.rowStart[r + 1];             // rowStart[r + 1] = start of row r, for now
         for (int i = 0; i < nc; ++i) s.sched[s.rowStart[s.row[i] + 1]++] = (uint16_t)i;   // ... and becomes its end = start of row r + 1
         s.nRows = nRows;
     }
     __syncwarp();
-    BigCtx L;
+    SlotCtx<Slot> L;
     L.S = &s;
     int nRows = s.nRows;
+    auto constraint = [&](int ci) -> TC& { return Slot::kStageTC ? s.tc[ci] : wk.tc[wk.order[lo + ci]]; };
+    // ContactSolver.warmStart
     for (int r = 0; r < nRows; ++r) {
-        for (int q = s.rowStart[r] + lane; q < s.rowStart[r + 1]; q += 32) lkWarmStart(e, L, wk.tc[wk.order[lo + s.sched[q]]]);
+        for (int q = s.rowStart[r] + lane; q < s.rowStart[r + 1]; q += 32) lkWarmStart(e, L, constraint(s.sched[q]));
         __syncwarp();
     }
+    // velocity sweeps
     for (int it = 0; it < e.cfg.velIters; ++it)
         for (int r = 0; r < nRows; ++r) {
-            for (int q = s.rowStart[r] + lane; q < s.rowStart[r + 1]; q += 32) lkSolveVelocity(e, L, wk.tc[wk.order[lo + s.sched[q]]]);
+            for (int q = s.rowStart[r] + lane; q < s.rowStart[r + 1]; q += 32) lkSolveVelocity(e, L, constraint(s.sched[q]));
             __syncwarp();
         }
+    // ContactSolver.storeImpulses
     for (int i = lane; i < nc; i += 32) {
-        const TC& t = wk.tc[wk.order[lo + i]];
+        const TC& t = constraint(i);
         for (int j2 = 0; j2 < t.solverPoints; ++j2) {
             st.cimp[4 * t.ci + 2 * j2] = t.nImp[j2];
             st.cimp[4 * t.ci + 2 * j2 + 1] = t.tImp[j2];
         }
     }
+    // integrate the island's bodies
     for (int b = lane; b < nb; b += 32) lkIntegrate(e, wk, L, b);
     __syncwarp();
+    // ---- position sweeps
+    int posIters = e.cfg.posIters;
     int iters = 0;
-    for (int it = 0; it < e.cfg.posIters; ++it) {
+    bool done = posIters <= 0;
+    while (!done) {
         float minSep = 0.0f;
         bool changed = false;
         for (int r = 0; r < nRows; ++r) {
-            for (int q = s.rowStart[r] + lane; q < s.rowStart[r + 1]; q += 32) {
-                int ci = s.sched[q];
-                uint32_t hd = s.pcHead[ci];
-                int bA = (int)(hd & 255u), bB = (int)((hd >> 8) & 255u), type = (int)((hd >> 16) & 255u), np = (int)(hd >> 24);
-                V2 ln = mk(s.pc[ci][0], s.pc[ci][1]), lp = mk(s.pc[ci][2], s.pc[ci][3]);
-                float radius = s.pc[ci][8];
-                for (int j2 = 0; j2 < np; ++j2) {
-                    float sep = lkCorrectPoint(e, L, bA, bB, type, ln, lp, mk(s.pc[ci][4 + 2 * j2], s.pc[ci][5 + 2 * j2]), radius, &changed);
-                    minSep = fminf_(minSep, sep);
-                }
-            }
+            for (int q = s.rowStart[r] + lane; q < s.rowStart[r + 1]; q += 32) minSep = fminf_(minSep, slotCorrect(e, L, s, s.sched[q], &changed));
             __syncwarp();
         }
         for (int o = 16; o > 0; o >>= 1) {
@@ -828,10 +666,10 @@ __device__ __forceinline__ bool islandSolveBig(const PhysEnv& e, const PhysWork&
         }
         bool anyChanged = __any_sync(FULL, changed);
         ++iters;
-        if (minSep >= -1.5f * kLinearSlop) break;
-        if (!anyChanged) {
-            iters = e.cfg.posIters;
-            break;
+        if (minSep >= -1.5f * kLinearSlop || iters >= posIters) done = true;
+        else if (!anyChanged) {   // fixed point: every later sweep repeats this one
+            iters = posIters;
+            done = true;
         }
     }
     if (lane == 0) *itersOut = iters;
@@ -854,6 +692,12 @@ __device__ __forceinline__ bool islandSolveBig(const PhysEnv& e, const PhysWork&
     }
     __syncwarp();
     return true;
+}
+__device__ __forceinline__ bool islandSolveWarp(const PhysEnv& e, const PhysWork& wk, const ArenaState& st, int k, WarpSlot& s, int* itersOut) {
+    return islandSolveSlot(e, wk, st, k, s, itersOut);
+}
+__device__ __forceinline__ bool islandSolveBig(const PhysEnv& e, const PhysWork& wk, const ArenaState& st, int k, BigSlot& s, int* itersOut) {
+    return islandSolveSlot(e, wk, st, k, s, itersOut);
 }
 
 }  // namespace ps
