@@ -60,7 +60,7 @@ enum {
 };
 
 /* controllerType property, src/controllers/ControllerUtils.java:6-41 */
-enum { PS_CTRL_CACHECONS = 0, PS_CTRL_BHD = 1, PS_CTRL_EXTERNAL = 2 };
+enum { PS_CTRL_CACHECONS = 0, PS_CTRL_BHD = 1, PS_CTRL_EXTERNAL = 2, PS_CTRL_PROBSEEK = 3 };
 /* shared java.util.Random per experiment (src/experiment/Experiment.java:22) or one stream per robot */
 enum { PS_RNG_JAVA_SHARED = 0, PS_RNG_PER_ROBOT = 1 };
 /* CacheConsController.CacheSelectionOption / CacheSeparationOption, CacheConsController.java:136-177 */
@@ -69,6 +69,8 @@ enum { PS_SEP_IGNORE = 0, PS_SEP_NULLIFY_OLD = 1, PS_SEP_ACCEPT_ISOLATED = 2, PS
 /* CacheConsController.State / BHDController.State ordinals */
 enum { PS_CC_PU_SCAN = 0, PS_CC_PU_TARGET, PS_CC_HOMING, PS_CC_DE_PUSH, PS_CC_DE_BACKUP, PS_CC_EXILE, PS_CC_SPIT_OUT };
 enum { PS_BHD_FORWARD = 0, PS_BHD_PUSH, PS_BHD_BACKUP, PS_BHD_TURN };
+/* ProbSeekController.State ordinals, src/controllers/ProbSeekController.java:27-34 */
+enum { PS_PS_PU_SCAN = 0, PS_PS_PU_TARGET, PS_PS_DE_SCAN, PS_PS_DE_TARGET, PS_PS_DE_PUSH, PS_PS_DE_BACKUP, PS_PS_DE_TURN };
 
 /*
  * Configuration: one POD filled from the .properties keys. ps_config_defaults()
@@ -118,6 +120,10 @@ typedef struct ps_config {
     /* BHDController.* (src/controllers/BHDController.java:76-79) */
     int32_t bhd_push_in_time;     /* 1 */
     int32_t bhd_backup_time;      /* 5 */
+    /* ProbSeekController.* (src/controllers/ProbSeekController.java:98-121): K1, K2, PICK_UP_TIME, PUSH_IN_TIME, BACKUP_TIME,
+     * PREDICTION_DISTANCE_SQD and ST_DEV have the names and defaults of the CacheCons keys and travel in the cc_* fields above
+     * when controller == PS_CTRL_PROBSEEK; the one key of its own: */
+    int32_t ps_placement_time;    /* PLACEMENT_TIME (40) */
 } ps_config;
 
 /*

@@ -173,6 +173,11 @@ static void packRobot(const Robot& r, ps_robot_state* o, int controller) {
         o->target_x = cc->haveTarget ? cc->target.centroid.x : 0;
         o->target_y = cc->haveTarget ? cc->target.centroid.y : 0;
         o->last_carried_type = cc->lastCarriedType;
+        if (controller == PS_CTRL_PROBSEEK) {
+            const ProbSeekController* pc = static_cast<const ProbSeekController*>(c);
+            o->bhd_turn_dir = pc->randomTurnDir;
+            o->bhd_turn_time = pc->randomTurnTime;
+        }
     }
 }
 static void unpackRobot(Robot& r, const ps_robot_state* o, int controller) {
@@ -202,6 +207,11 @@ static void unpackRobot(Robot& r, const ps_robot_state* o, int controller) {
         cc->haveTarget = o->has_target != 0;
         if (cc->haveTarget) cc->target = Cluster::single(Vec2(o->target_x, o->target_y), o->target_type);
         cc->lastCarriedType = o->last_carried_type;
+        if (controller == PS_CTRL_PROBSEEK) {
+            ProbSeekController* pc = static_cast<ProbSeekController*>(c);
+            pc->randomTurnDir = o->bhd_turn_dir;
+            pc->randomTurnTime = o->bhd_turn_time;
+        }
     }
 }
 

@@ -1019,6 +1019,85 @@ struct CacheConsController : Controller {  // src/controllers/CacheConsControlle
     }
 };
 
+// src/controllers/ProbSeekController.java:176-308. Shares ExtremaSelector / ClusterTargetSelector / matchTarget with
+// CacheCons (inherited); its property keys (ProbSeekController.K1, K2, PICK_UP_TIME, PUSH_IN_TIME, BACKUP_TIME,
+// PREDICTION_DISTANCE_SQD, ST_DEV) have the CacheCons names and defaults and travel in the cc_* fields.
+struct ProbSeekController : CacheConsController {
+    int randomTurnDir = 0, randomTurnTime = 0;
+    static const int TURNTIME_MIN = ONE_EIGHTY_TIME / 2;
+    ProbSeekController(const ps_config* cfg, JavaRandom* rng) : CacheConsController(cfg, rng, false) {}
+    void initiateRandomTurn(const LocalMap& lm) {  // :303-308
+        randomTurnDir = lm.getFreeerSide();
+        randomTurnTime = TURNTIME_MIN + random->nextInt(ONE_EIGHTY_TIME - TURNTIME_MIN + 1);
+    }
+    void computeDesired(LocalMap& lm, const Pose&, int stepCount_) override {  // :176-279
+        bool carrying = lm.carrying;
+        stepCount = stepCount_;
+        switch (state) {
+            case PS_PS_PU_SCAN:
+                if (carrying) transition(PS_PS_DE_SCAN);
+                else {
+                    haveTarget = selectTarget(lm, carrying, !carrying, &target);
+                    if (haveTarget) transition(PS_PS_PU_TARGET);
+                }
+                break;
+            case PS_PS_PU_TARGET:
+                if (carrying) transition(PS_PS_DE_SCAN);
+                else {
+                    Cluster nt;
+                    haveTarget = matchTarget(lm, target, P->cc_prediction_distance_sqd, &nt);
+                    if (haveTarget) target = nt;
+                    if (!haveTarget) transition(PS_PS_PU_SCAN);
+                    else if (stepCount - startCount > P->cc_pick_up_time) transition(PS_PS_PU_SCAN);
+                }
+                break;
+            case PS_PS_DE_SCAN:
+                if (!carrying) transition(PS_PS_PU_SCAN);
+                else {
+                    haveTarget = selectTarget(lm, carrying, !carrying, &target);
+                    if (haveTarget) transition(PS_PS_DE_TARGET);
+                }
+                break;
+            case PS_PS_DE_TARGET:
+                if (!carrying) transition(PS_PS_PU_SCAN);
+                else if (lm.carriedCluster >= 0 && lm.rawClusters[lm.carriedCluster].size > 1) transition(PS_PS_DE_PUSH);
+                else {
+                    Cluster nt;
+                    haveTarget = matchTarget(lm, target, P->cc_prediction_distance_sqd, &nt);
+                    if (haveTarget) target = nt;
+                    if (!haveTarget) transition(PS_PS_DE_SCAN);
+                    else if (stepCount - startCount > P->ps_placement_time) transition(PS_PS_DE_SCAN);
+                }
+                break;
+            case PS_PS_DE_PUSH:
+                if (stepCount - startCount >= P->cc_push_in_time) transition(PS_PS_DE_BACKUP);
+                break;
+            case PS_PS_DE_BACKUP:
+                if (stepCount - startCount >= P->cc_backup_time) {
+                    transition(PS_PS_DE_TURN);
+                    initiateRandomTurn(lm);
+                }
+                break;
+            case PS_PS_DE_TURN:
+                if (stepCount - startCount >= randomTurnTime) transition(PS_PS_PU_SCAN);
+                break;
+        }
+        if (state == PS_PS_PU_SCAN || state == PS_PS_DE_SCAN) {
+            float randomTurn = P->cc_st_dev * (float)random->nextGaussian();
+            movement = applyVFH(vfh, lm, randomTurn, false);
+        } else if (state == PS_PS_PU_TARGET || state == PS_PS_DE_TARGET) {
+            movement = MovementCommand(1, (float)std::atan2((double)target.centroid.y, (double)target.centroid.x));
+        } else if (state == PS_PS_DE_PUSH) {
+            movement = MovementCommand(1, 0);
+        } else if (state == PS_PS_DE_BACKUP) {
+            movement = MovementCommand(-1, 0);
+        } else if (state == PS_PS_DE_TURN) {
+            movement = MovementCommand(0, (float)(M_PI / 2 * randomTurnDir));
+        }
+        updateStateCounts(stepCount);
+    }
+};
+
 struct BHDController : Controller {  // src/controllers/BHDController.java:126-191
     const ps_config* P;
     int stepCount = 0;
@@ -1199,6 +1278,7 @@ struct Arena {
         r.localMap.CARRY_THRESHOLD_HI = cfg.carry_threshold_hi;
         r.image.assign((size_t)calib->imageWidth * calib->imageHeight, PS_T_NOTHING);
         if (cfg.controller == PS_CTRL_BHD) r.controller.reset(new BHDController(&cfg, &rng));
+        else if (cfg.controller == PS_CTRL_PROBSEEK) r.controller.reset(new ProbSeekController(&cfg, &rng));
         else r.controller.reset(new CacheConsController(&cfg, &rng, presetCaches));
         // VFHPlus re-runs initDataStructures on its first computeTurnAngle (propertiesUpdated is set by the
         // constructor, VFHPlus.java:167,227-230); nothing touches the histograms before that, so doing it here

@@ -19,13 +19,14 @@ PS_T_NOTHING, PS_T_WALL, PS_T_ROBOT, PS_T_HIDDEN = 8, 9, 10, 11
 PS_OK = 0
 PS_E_INVALID, PS_E_NODEVICE, PS_E_CUDA, PS_E_NOCALIB, PS_E_CAPACITY, PS_E_NOMEM = -1, -2, -3, -4, -5, -6
 
-PS_CTRL_CACHECONS, PS_CTRL_BHD, PS_CTRL_EXTERNAL = 0, 1, 2
+PS_CTRL_CACHECONS, PS_CTRL_BHD, PS_CTRL_EXTERNAL, PS_CTRL_PROBSEEK = 0, 1, 2, 3
 PS_RNG_JAVA_SHARED, PS_RNG_PER_ROBOT = 0, 1
 PS_SEL_PROB_ABSOLUTE, PS_SEL_PROB_RELATIVE, PS_SEL_RELATIVE, PS_SEL_RELATIVE_FORGET = 0, 1, 2, 3
 PS_SEP_IGNORE, PS_SEP_NULLIFY_OLD, PS_SEP_ACCEPT_ISOLATED, PS_SEP_ACCEPT_LARGER = 0, 1, 2, 3
 
 CC_STATES = ["PU_SCAN", "PU_TARGET", "HOMING", "DE_PUSH", "DE_BACKUP", "EXILE", "SPIT_OUT"]
 BHD_STATES = ["FORWARD", "PUSH", "BACKUP", "TURN"]
+PROBSEEK_STATES = ["PU_SCAN", "PU_TARGET", "DE_SCAN", "DE_TARGET", "DE_PUSH", "DE_BACKUP", "DE_TURN"]
 
 
 class ps_config(C.Structure):
@@ -42,7 +43,7 @@ class ps_config(C.Structure):
         ("cc_spit_out_time", C.c_int32), ("cc_cache_selection", C.c_int32), ("cc_k_absolute", C.c_float),
         ("cc_k_relative", C.c_float), ("cc_forget_prob", C.c_float), ("cc_cache_separation", C.c_int32),
         ("cc_home_separation_distance", C.c_float), ("cc_ignore_pucks", C.c_int32),
-        ("bhd_push_in_time", C.c_int32), ("bhd_backup_time", C.c_int32),
+        ("bhd_push_in_time", C.c_int32), ("bhd_backup_time", C.c_int32), ("ps_placement_time", C.c_int32),
     ]
 
 
@@ -90,6 +91,7 @@ def config_defaults(**kw):
     c.cc_ignore_pucks = 0
     c.bhd_push_in_time = 1
     c.bhd_backup_time = 5
+    c.ps_placement_time = 40
     for k, v in kw.items():
         if not hasattr(c, k):
             raise AttributeError("ps_config has no field %r" % k)

@@ -447,6 +447,7 @@ void ps_config_defaults(ps_config* c) {
     c->cc_ignore_pucks = 0;
     c->bhd_push_in_time = 1;
     c->bhd_backup_time = 5;
+    c->ps_placement_time = 40;
 }
 
 int ps_destroy(ps_handle h) {

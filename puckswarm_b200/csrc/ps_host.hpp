@@ -26,7 +26,7 @@ struct HostSetup {
         if (c.n_arenas < 1 || c.n_robots < 1 || c.n_pucks < 0 || c.n_puck_types < 1 || c.n_puck_types > PS_MAX_COLOURS)
             return fail("bad arena shape");
         if (c.step_interval < 1 || c.vel_iters < 0 || c.pos_iters < 0 || !(c.dt > 0)) return fail("bad step parameters");
-        if (c.controller < PS_CTRL_CACHECONS || c.controller > PS_CTRL_EXTERNAL) return fail("bad controller");
+        if (c.controller < PS_CTRL_CACHECONS || c.controller > PS_CTRL_PROBSEEK) return fail("bad controller");
         int P = c.n_pucks / c.n_puck_types * c.n_puck_types;   // Arena.java:91-95: nPucks / nPuckTypes per colour
         Dims d;
         d.P = P;

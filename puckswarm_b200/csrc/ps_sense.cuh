@@ -73,6 +73,7 @@ struct SenseCfg {
     float k1, k2, predictionDistSqd, stDev, kAbsolute, kRelative, forgetProb, homeSeparation;
     int pickUpTime, pushInTime, backupTime, exileTime, spitOutTime, cacheSelection, cacheSeparation, ignorePucks;
     int bhdPushInTime, bhdBackupTime;
+    int placementTime;   // ProbSeekController.PLACEMENT_TIME
     int nInformed;
 };
 
@@ -1490,6 +1491,203 @@ PS_HD void thinkBHD(Ctx& ctx, const SenseTables& T, const SenseCfg& sc, const Th
     ctx.sync();
 }
 
+// ProbSeekController.computeDesired (src/controllers/ProbSeekController.java:176-279): the SI-2012 benchmark controller.
+// Same selector (ExtremaSelector over ClusterTargetSelector), matchTarget and VFH+ as CacheCons; no caches.
+// The ProbSeekController.* property keys travel in the cc_* fields of ps_config (same names, same defaults) plus
+// ps_placement_time; ALWAYS_TARGET_ISOLATED is false (the reference reads it from the K2 key as a boolean, :107).
+template <class Ctx>
+PS_HD void thinkProbSeek(Ctx& ctx, const SenseTables& T, const SenseCfg& sc, const ThinkWork& tw, uint8_t* occ, ps_localmap* lm, ps_robot_state* rs,
+                         JRandom* rng, int stepCount) {
+    ctx.sync();
+    if (ctx.tid() == 0) {
+        int nP = lm->n_pucks, nC = lm->n_clusters;
+        bool carrying = lm->carrying != 0;
+        int state = rs->ctrl_state;
+        int startCount = rs->start_count;
+#define TRANSITION(s)           \
+    do {                        \
+        state = (s);            \
+        startCount = stepCount; \
+    } while (0)
+        // ClusterTargetSelector.selectTarget(carrying, !carrying): ExtremaSelector.selectCluster, then (pick-up only) the
+        // extreme-Yr member of lower degree, if reachable (ClusterTargetSelector.java:48-101, ExtremaSelector.java:36-59)
+        auto selectTarget = [&](bool preferLargest, bool isolatePuck) {
+            int hasTarget = 0;
+            float tx = 0, ty = 0;
+            int ttype = 0;
+            int extreme = -1;
+            for (int c = 0; c < nC; ++c) {
+                if (!lm->cluster_kept[c]) continue;
+                if (extreme < 0) {
+                    extreme = c;
+                    continue;
+                }
+                if (preferLargest && lm->cluster_size[c] > lm->cluster_size[extreme]) extreme = c;
+                else if (!preferLargest && lm->cluster_size[c] < lm->cluster_size[extreme]) extreme = c;
+                else if (lm->cluster_size[c] == lm->cluster_size[extreme] && fabsf(lm->cluster_y[c]) < fabsf(lm->cluster_y[extreme])) extreme = c;
+            }
+            if (extreme >= 0) {
+                float prob;
+                if (preferLargest) prob = sc.k2 < 0 ? 1.0f : depositProb((float)lm->cluster_size[extreme], sc.k2);
+                else prob = sc.k1 < 0 ? 1.0f : pickupProb((float)lm->cluster_size[extreme], sc.k1);
+                if (jrNextFloat(*rng) < prob) {
+                    if (!isolatePuck) {
+                        hasTarget = 1;
+                        tx = lm->cluster_x[extreme];
+                        ty = lm->cluster_y[extreme];
+                        ttype = lm->cluster_type[extreme];
+                    } else {
+                        float largestYr = -INFINITY, smallestYr = INFINITY;
+                        int li = -1, si = -1;
+                        for (int p = 0; p < nP; ++p) {
+                            if (lm->puck_cluster[p] != extreme) continue;
+                            bool dup = false;   // the subgraph holds each position once
+                            for (int q = 0; q < p; ++q)
+                                if (lm->puck_cluster[q] == extreme && lm->puck_x[q] == lm->puck_x[p] && lm->puck_y[q] == lm->puck_y[p]) dup = true;
+                            if (dup) continue;
+                            if (lm->puck_y[p] > largestYr) {
+                                largestYr = lm->puck_y[p];
+                                li = p;
+                            }
+                            if (lm->puck_y[p] < smallestYr) {
+                                smallestYr = lm->puck_y[p];
+                                si = p;
+                            }
+                        }
+                        int pick = lm->puck_degree[li] <= lm->puck_degree[si] ? li : si;
+                        if (lmReachable(lm->puck_x[pick], lm->puck_y[pick])) {
+                            hasTarget = 1;
+                            tx = lm->puck_x[pick];
+                            ty = lm->puck_y[pick];
+                            ttype = lm->cluster_type[extreme];
+                        }
+                    }
+                }
+            }
+            rs->has_target = hasTarget;
+            rs->target_x = hasTarget ? tx : 0.0f;
+            rs->target_y = hasTarget ? ty : 0.0f;
+            rs->target_type = hasTarget ? ttype : 0;
+            return hasTarget != 0;
+        };
+        // ProbSeekController.matchTarget (:286-301): the closest cluster centroid (carrying; never the carried cluster)
+        // or the closest puck of the kept clusters (not carrying) to the last target, within the prediction distance
+        auto matchTarget = [&]() {
+            int have = 0;
+            float bx = 0, by = 0, smallest = INFINITY;
+            int btype = -1;
+            V2 last = mk(rs->target_x, rs->target_y);
+            for (int c = 0; c < nC; ++c) {
+                if (!lm->cluster_kept[c]) continue;
+                if (carrying) {
+                    if (c == lm->carried_cluster) continue;
+                    float ds = distSq(last, mk(lm->cluster_x[c], lm->cluster_y[c]));
+                    if (ds < sc.predictionDistSqd && ds < smallest) {
+                        smallest = ds;
+                        bx = lm->cluster_x[c];
+                        by = lm->cluster_y[c];
+                        btype = lm->cluster_type[c];
+                        have = 1;
+                    }
+                } else {
+                    for (int p = 0; p < nP; ++p) {
+                        if (lm->puck_cluster[p] != c) continue;
+                        float ds = distSq(last, mk(lm->puck_x[p], lm->puck_y[p]));
+                        if (ds < sc.predictionDistSqd && ds < smallest) {
+                            smallest = ds;
+                            bx = lm->puck_x[p];
+                            by = lm->puck_y[p];
+                            btype = lm->cluster_type[c];
+                            have = 1;
+                        }
+                    }
+                }
+            }
+            if (have && !lmReachable(bx, by)) have = 0;
+            rs->has_target = have;
+            rs->target_x = have ? bx : 0.0f;
+            rs->target_y = have ? by : 0.0f;
+            rs->target_type = have ? btype : 0;
+            return have != 0;
+        };
+        switch (state) {
+            case PS_PS_PU_SCAN:
+                if (carrying) TRANSITION(PS_PS_DE_SCAN);
+                else if (selectTarget(false, true)) TRANSITION(PS_PS_PU_TARGET);
+                break;
+            case PS_PS_PU_TARGET:
+                if (carrying) TRANSITION(PS_PS_DE_SCAN);
+                else if (!matchTarget()) TRANSITION(PS_PS_PU_SCAN);
+                else if (stepCount - startCount > sc.pickUpTime) TRANSITION(PS_PS_PU_SCAN);
+                break;
+            case PS_PS_DE_SCAN:
+                if (!carrying) TRANSITION(PS_PS_PU_SCAN);
+                else if (selectTarget(true, false)) TRANSITION(PS_PS_DE_TARGET);
+                break;
+            case PS_PS_DE_TARGET:
+                if (!carrying) TRANSITION(PS_PS_PU_SCAN);
+                else if (lm->carried_cluster >= 0 && lm->cluster_size[lm->carried_cluster] > 1) TRANSITION(PS_PS_DE_PUSH);
+                else if (!matchTarget()) TRANSITION(PS_PS_DE_SCAN);
+                else if (stepCount - startCount > sc.placementTime) TRANSITION(PS_PS_DE_SCAN);
+                break;
+            case PS_PS_DE_PUSH:
+                if (stepCount - startCount >= sc.pushInTime) TRANSITION(PS_PS_DE_BACKUP);
+                break;
+            case PS_PS_DE_BACKUP:
+                if (stepCount - startCount >= sc.backupTime) {
+                    TRANSITION(PS_PS_DE_TURN);
+                    // initiateRandomTurn (:303-308)
+                    const int TURNTIME_MIN = 10 / 2, ONE_EIGHTY_TIME = 10;
+                    rs->bhd_turn_dir = lm->left_sum <= lm->right_sum ? 1 : -1;
+                    rs->bhd_turn_time = TURNTIME_MIN + jrNextInt(*rng, ONE_EIGHTY_TIME - TURNTIME_MIN + 1);
+                }
+                break;
+            case PS_PS_DE_TURN:
+                if (stepCount - startCount >= rs->bhd_turn_time) TRANSITION(PS_PS_PU_SCAN);
+                break;
+        }
+#undef TRANSITION
+        rs->ctrl_state = state;
+        rs->start_count = startCount;
+        int useVfh = 0;
+        float angle = 0.0f, fwd = 0.0f, tq = 0.0f;
+        if (state == PS_PS_PU_SCAN || state == PS_PS_DE_SCAN) {
+            angle = sc.stDev * (float)jrNextGaussian(*rng);   // wander
+            useVfh = 1;
+        } else if (state == PS_PS_PU_TARGET || state == PS_PS_DE_TARGET) {
+            movementCommand(1.0f, (float)atan2((double)rs->target_y, (double)rs->target_x), fwd, tq);
+        } else if (state == PS_PS_DE_PUSH) {
+            movementCommand(1.0f, 0.0f, fwd, tq);
+        } else if (state == PS_PS_DE_BACKUP) {
+            movementCommand(-1.0f, 0.0f, fwd, tq);
+        } else {
+            movementCommand(0.0f, (float)(3.14159265358979323846 / 2 * rs->bhd_turn_dir), fwd, tq);
+        }
+        rs->cmd_forwards = fwd;
+        rs->cmd_torque = tq;
+        tw.flag[1] = useVfh;
+        tw.limits[0] = fbits(angle);
+    }
+    ctx.sync();
+    int useVfh = tw.flag[1];
+    float angle = bitsf(tw.limits[0]);
+    ctx.sync();
+    if (useVfh) {
+        float fwd, tq;
+        applyVFH(ctx, T, sc, tw, occ, lm, rs, angle, false, fwd, tq);
+        if (ctx.tid() == 0) {
+            rs->cmd_forwards = fwd;
+            rs->cmd_torque = tq;
+        }
+    }
+    if (ctx.tid() == 0) {
+        rs->state_counts[rs->ctrl_state & 7]++;
+        if (stepCount % 100 == 0)
+            for (int i = 0; i < 8; i++) rs->state_counts[i] = 0;
+    }
+    ctx.sync();
+}
+
 // Arena.step's think loop for one arena (sense already done): robots in creation order, shared or per-robot RNG
 template <class Ctx>
 PS_HD void thinkArena(Ctx& ctx, const SenseTables& T, const SenseCfg& sc, const ThinkWork& tw, int R, uint8_t* occ /*[R][cells]*/,
@@ -1514,6 +1712,7 @@ PS_HD void thinkArena(Ctx& ctx, const SenseTables& T, const SenseCfg& sc, const 
             ctx.sync();
         }
         if (sc.controller == PS_CTRL_BHD) thinkBHD(ctx, T, sc, tw, occ + (size_t)r * nCells, lm + r, rs + r, rng, stepCount);
+        else if (sc.controller == PS_CTRL_PROBSEEK) thinkProbSeek(ctx, T, sc, tw, occ + (size_t)r * nCells, lm + r, rs + r, rng, stepCount);
         else thinkCacheCons(ctx, T, sc, tw, occ + (size_t)r * nCells, lm + r, rs + r, rng, pose + 3 * r, stepCount, r < sc.nInformed);
         if (sc.rngMode == PS_RNG_PER_ROBOT) {
             if (ctx.tid() == 0) {
@@ -1724,6 +1923,7 @@ struct SenseSetup {
         sc.tauHi = cfg.vfh_tau_hi * A;
         sc.controller = cfg.controller;
         sc.rngMode = cfg.rng_mode;
+        sc.placementTime = cfg.ps_placement_time;
         sc.k1 = cfg.cc_k1;
         sc.k2 = cfg.cc_k2;
         sc.predictionDistSqd = cfg.cc_prediction_distance_sqd;

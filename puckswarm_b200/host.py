@@ -28,7 +28,7 @@ _SEL = {"PROB_ABSOLUTE": abi.PS_SEL_PROB_ABSOLUTE, "PROB_RELATIVE": abi.PS_SEL_P
         "RELATIVE_FORGET": abi.PS_SEL_RELATIVE_FORGET}
 _SEP = {"IGNORE": abi.PS_SEP_IGNORE, "NULLIFY_OLD": abi.PS_SEP_NULLIFY_OLD, "ACCEPT_ISOLATED": abi.PS_SEP_ACCEPT_ISOLATED,
         "ACCEPT_LARGER": abi.PS_SEP_ACCEPT_LARGER}
-_CTRL = {"CacheCons": abi.PS_CTRL_CACHECONS, "BHD": abi.PS_CTRL_BHD}
+_CTRL = {"CacheCons": abi.PS_CTRL_CACHECONS, "BHD": abi.PS_CTRL_BHD, "ProbSeek": abi.PS_CTRL_PROBSEEK}
 PROPERTY_MAP = {
     "controllerType": ("controller", str, _CTRL),
     "Arena.nPucks": ("n_pucks", int, None), "Arena.nPuckTypes": ("n_puck_types", int, None),
@@ -50,6 +50,15 @@ PROPERTY_MAP = {
     "CacheConsController.HOME_SEPARATION_DISTANCE": ("cc_home_separation_distance", float, None),
     "CacheConsController.IGNORE_PUCKS": ("cc_ignore_pucks", bool, None),
     "BHDController.PUSH_IN_TIME": ("bhd_push_in_time", int, None), "BHDController.BACKUP_TIME": ("bhd_backup_time", int, None),
+    "ProbSeekController.PLACEMENT_TIME": ("ps_placement_time", int, None),
+}
+# ProbSeekController's other keys have the CacheCons names and defaults (ProbSeekController.java:98-121) and use the same
+# ps_config fields; they apply when controllerType = ProbSeek
+PROBSEEK_SHARED = {
+    "ProbSeekController.K1": ("cc_k1", float), "ProbSeekController.K2": ("cc_k2", float),
+    "ProbSeekController.PICK_UP_TIME": ("cc_pick_up_time", int), "ProbSeekController.PUSH_IN_TIME": ("cc_push_in_time", int),
+    "ProbSeekController.BACKUP_TIME": ("cc_backup_time", int),
+    "ProbSeekController.PREDICTION_DISTANCE_SQD": ("cc_prediction_distance_sqd", float), "ProbSeekController.ST_DEV": ("cc_st_dev", float),
 }
 
 
@@ -114,6 +123,10 @@ class Experiment:
             else:
                 val = typ(raw)
             setattr(cfg, field, val)
+        if cfg.controller == abi.PS_CTRL_PROBSEEK:
+            d = abi.config_defaults()
+            for key, (field, typ) in PROBSEEK_SHARED.items():
+                setattr(cfg, field, typ(self.properties[key]) if key in self.properties else getattr(d, field))
         for k, v in overrides.items():
             setattr(cfg, k, v)
         return cfg

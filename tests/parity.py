@@ -41,8 +41,11 @@ def compare_states(sa, sb, n_arenas, tol=0.0, what=("body", "sense_aabb", "fat_a
                     out.append("arena %d: %s differs at %s (%d entries): %r vs %r" % (a, name, tuple(idx), int(bad.sum()), x[tuple(idx)], y[tuple(idx)]))
         if "arena" in what:
             for f in ("rng_seed", "rng_have_gaussian", "update_count", "step_count", "inv_dt0", "rng_next_gaussian"):
-                if sa.arena[a][f] != sb.arena[a][f]:
-                    out.append("arena %d: arena.%s %r vs %r" % (a, f, sa.arena[a][f], sb.arena[a][f]))
+                x, y = sa.arena[a][f], sb.arena[a][f]
+                # the cached second Gaussian comes out of a double log / sqrt: device libm vs glibc may differ in the last place
+                same = x == y or (f == "rng_next_gaussian" and tol > 0 and abs(float(x) - float(y)) <= 4e-16 * max(1.0, abs(float(y))))
+                if not same:
+                    out.append("arena %d: arena.%s %r vs %r" % (a, f, x, y))
         if "robot" in what:
             for r in range(sa.robot.shape[1]):
                 ra, rb = sa.robot[a, r], sb.robot[a, r]

@@ -86,7 +86,7 @@ def test_camera_and_localmap_bit_exact():
     assert seen_puck > 0 and seen_robot > 0 and seen_carry > 0
 
 
-@pytest.mark.parametrize("controller", [abi.PS_CTRL_CACHECONS, abi.PS_CTRL_BHD])
+@pytest.mark.parametrize("controller", [abi.PS_CTRL_CACHECONS, abi.PS_CTRL_BHD, abi.PS_CTRL_PROBSEEK])
 def test_full_tick_lockstep(controller):
     """Stepping the reference restatement and the engine one think interval from identical states."""
     import parity
@@ -106,7 +106,7 @@ def test_full_tick_lockstep(controller):
     print("bit-exact think steps: %d / 150" % exact)
 
 
-@pytest.mark.parametrize("controller", [abi.PS_CTRL_CACHECONS, abi.PS_CTRL_BHD])
+@pytest.mark.parametrize("controller", [abi.PS_CTRL_CACHECONS, abi.PS_CTRL_BHD, abi.PS_CTRL_PROBSEEK])
 def test_full_tick_free_running(controller):
     """No re-synchronisation: both sides run 100 think steps (300 ticks) from the same seeds."""
     import parity
@@ -119,6 +119,29 @@ def test_full_tick_free_running(controller):
     o.step(300)
     bad = parity.compare_states(e.get_state(), o.get_state(), A, tol=TOL)
     assert bad == [], bad[:5]
+
+
+@pytest.mark.parametrize("controller", [abi.PS_CTRL_CACHECONS, abi.PS_CTRL_BHD, abi.PS_CTRL_PROBSEEK])
+def test_lockstep_with_wide_cluster_threshold(controller):
+    """LocalMap.CLUSTER_DISTANCE_THRESHOLD = 8 (touching pucks cluster): multi-puck clusters form, so the deposit states
+    (PUSH / BACKUP / TURN, carried-cluster logic, the warp-built cluster lists) are exercised, which the default 1.5 never does."""
+    import parity
+    A, R, P = 4, 8, 120
+    cfg = abi.config_defaults(n_arenas=A, n_robots=R, n_pucks=P, controller=controller, cluster_distance_threshold=8.0)
+    e, o = _engine(cfg), _oracle(cfg)
+    o.reset(np.arange(A))
+    seen = np.zeros(8, int)
+    for k in range(240):
+        e.set_state(o.get_state())
+        e.step(3)
+        o.step(3)
+        se, so = e.get_state(), o.get_state()
+        bad = parity.compare_states(se, so, A, tol=TOL)
+        assert bad == [], "think step %d: %s" % (k, bad[:5])
+        for st in so.robot["ctrl_state"].ravel():
+            seen[st] += 1
+    n_states = {abi.PS_CTRL_CACHECONS: 5, abi.PS_CTRL_BHD: 4, abi.PS_CTRL_PROBSEEK: 7}[controller]
+    assert (seen[:n_states] > 0).all(), seen
 
 
 def test_c3_shape_against_oracle():

@@ -43,7 +43,7 @@ def test_world_step_external(shape, steps):
         assert np.array_equal(e.solve_order(0), o.solve_order(0))
 
 
-@pytest.mark.parametrize("controller", [abi.PS_CTRL_CACHECONS, abi.PS_CTRL_BHD])
+@pytest.mark.parametrize("controller", [abi.PS_CTRL_CACHECONS, abi.PS_CTRL_BHD, abi.PS_CTRL_PROBSEEK])
 def test_sense_think_step(controller):
     A, R, P = 2, 4, 40
     cfg = abi.config_defaults(n_arenas=A, n_robots=R, n_pucks=P, controller=controller)
@@ -63,6 +63,26 @@ def test_sense_think_step(controller):
         e.step(3)
         bad = parity.compare_states(e.get_state(), o.get_state(), A)
         assert bad == [], "think step %d: %s" % (k, bad[:4])
+
+
+@pytest.mark.parametrize("controller", [abi.PS_CTRL_CACHECONS, abi.PS_CTRL_PROBSEEK])
+def test_think_with_wide_cluster_threshold(controller):
+    """Cluster threshold 8 (touching pucks cluster): the deposit states and the carried-cluster logic run, bit-exact."""
+    A, R, P = 2, 6, 90
+    cfg = abi.config_defaults(n_arenas=A, n_robots=R, n_pucks=P, controller=controller, cluster_distance_threshold=8.0)
+    e, o = emu.Emu(cfg), oracle.Oracle(cfg)
+    e.reset([0, 1])
+    o.reset([0, 1])
+    seen = np.zeros(8, int)
+    for k in range(150):
+        o.step(3)
+        e.step(3)
+        so = o.get_state()
+        bad = parity.compare_states(e.get_state(), so, A)
+        assert bad == [], "think step %d: %s" % (k, bad[:4])
+        for st in so.robot["ctrl_state"].ravel():
+            seen[st] += 1
+    assert (seen[:4] > 0).all(), seen
 
 
 def test_narrow_phase_samples():
