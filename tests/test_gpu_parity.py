@@ -144,6 +144,28 @@ def test_lockstep_with_wide_cluster_threshold(controller):
     assert (seen[:n_states] > 0).all(), seen
 
 
+def test_dense_arena_big_islands():
+    """A crowded arena (150 pucks, 6 robots, enclosure scale 0.6): puck clusters grow past the warp slot (48 bodies / 64
+    contacts), so the big-island solver runs; lock-step parity with the oracle every think step."""
+    import parity
+    A = 2
+    cfg = abi.config_defaults(n_arenas=A, n_robots=6, n_pucks=150, enclosure_scale=0.6)
+    e, o = _engine(cfg), _oracle(cfg)
+    o.reset(np.arange(A))
+    e.island_hist()
+    most_bodies = most_contacts = 0
+    for k in range(100):
+        e.set_state(o.get_state())
+        e.step(3)
+        o.step(3)
+        bad = parity.compare_states(e.get_state(), o.get_state(), A, tol=TOL)
+        assert bad == [], "think step %d: %s" % (k, bad[:5])
+        if k % 10 == 9:
+            w = int(e.island_hist()[7, 7])   # slowest warp-solved island since the last read: contacts << 20 | bodies << 10 | sweeps
+            most_contacts, most_bodies = max(most_contacts, (w >> 20) & 0xFFF), max(most_bodies, (w >> 10) & 0x3FF)
+    assert most_bodies > 48 or most_contacts > 64, (most_bodies, most_contacts)
+
+
 def test_c3_shape_against_oracle():
     """16 robots / 200 pucks (the shape of the headline config), CacheCons on device, 20 think steps free-running."""
     import parity
