@@ -253,7 +253,6 @@ def main():
                                  rng_mode=abi.PS_RNG_JAVA_SHARED)
         e2 = engine.Engine(c2, device=local_rank)
         e2.reset(np.arange(a0, a1))
-        e2.step(STEP_INTERVAL * (args.warmup + args.steps), sync=False)   # the state the device-resident run measured in
         st = e2.new_state()
         pinned_body = torch.empty(st.body.shape, dtype=torch.float32).pin_memory()
         pinned_arena = torch.empty(st.arena.nbytes, dtype=torch.uint8).pin_memory()
@@ -282,8 +281,9 @@ def main():
         for e2, vin, vout, _, _ in halves:
             e2._check(e2.L.ps_get_state(e2.h, C.byref(vout)))
 
+    # the same simulated interval as the device-resident run: W warm-up steps after the reset, then K timed steps
     e2e_round(True)
-    for _ in range(3):
+    for _ in range(args.warmup - 1):
         e2e_round(False)
     e2e_drain()
     barrier()

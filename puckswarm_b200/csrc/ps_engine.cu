@@ -9,6 +9,8 @@
 #include <cstdlib>
 #include <string>
 #include <vector>
+#include <map>
+#include <mutex>
 #include "ps_host.hpp"
 #include "ps_sense_dev.cuh"
 #include "ps_pipeline.cuh"
@@ -307,6 +309,38 @@ __global__ void __launch_bounds__(128) k_phys_post(KParams p) {
     if (threadIdx.x < 8) p.stepStats[a * 8 + threadIdx.x] = wk.stats[threadIdx.x];
 }
 
+// The MathUtils sin table (228 KB) is the same for every handle: one device copy per GPU, shared by the handles of the
+// process, so that several engines on one GPU do not multiply its L1 / L2 footprint (it sits on the solver's critical path).
+struct SharedLut {
+    float* ptr = nullptr;
+    int refs = 0;
+};
+static std::mutex g_lutMutex;
+static std::map<int, SharedLut> g_lut;
+static float* acquireSharedLut(int device, const float* host) {
+    std::lock_guard<std::mutex> lock(g_lutMutex);
+    SharedLut& L = g_lut[device];
+    if (!L.ptr) {
+        if (cudaMalloc(&L.ptr, kLutLength * sizeof(float)) != cudaSuccess) return nullptr;
+        if (cudaMemcpy(L.ptr, host, kLutLength * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaFree(L.ptr);
+            L.ptr = nullptr;
+            return nullptr;
+        }
+    }
+    L.refs++;
+    return L.ptr;
+}
+static void releaseSharedLut(int device) {
+    std::lock_guard<std::mutex> lock(g_lutMutex);
+    auto it = g_lut.find(device);
+    if (it == g_lut.end() || it->second.refs <= 0) return;
+    if (--it->second.refs == 0) {
+        cudaFree(it->second.ptr);
+        it->second.ptr = nullptr;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 struct ps_engine {
     HostSetup hs;
@@ -474,7 +508,7 @@ int ps_destroy(ps_handle h) {
     cudaFree(h->kp.queue.counts);
     cudaFree(h->kp.islandHist);
     cudaFree(h->dScene);
-    cudaFree(h->dLut);
+    if (h->dLut) releaseSharedLut(h->device);
     cudaFree(h->dRobotInit);
     cudaFree(h->dSeeds);
     cudaFree(h->dStepStats);
@@ -554,8 +588,11 @@ int ps_create(const ps_config* cfg, int device, ps_handle* out) {
     TRY_OR_FREE(cudaMemset(e->kp.sp.arena, 0, A * sizeof(ps_arena_state)));
     TRY_OR_FREE(cudaMalloc(&e->dScene, sizeof(Scene)));
     TRY_OR_FREE(cudaMemcpy(e->dScene, &e->hs.scene, sizeof(Scene), cudaMemcpyHostToDevice));
-    TRY_OR_FREE(cudaMalloc(&e->dLut, kLutLength * sizeof(float)));
-    TRY_OR_FREE(cudaMemcpy(e->dLut, e->hs.sinLut.data(), kLutLength * sizeof(float), cudaMemcpyHostToDevice));
+    e->dLut = acquireSharedLut(device, e->hs.sinLut.data());
+    if (!e->dLut) {
+        ps_destroy(e);
+        return setError(PS_E_NOMEM, "cudaMalloc (sin table)");
+    }
     TRY_OR_FREE(cudaMalloc(&e->dRobotInit, 2 * sizeof(ps_robot_state)));
     TRY_OR_FREE(cudaMemcpy(e->dRobotInit, e->hs.robotInit, 2 * sizeof(ps_robot_state), cudaMemcpyHostToDevice));
     TRY_OR_FREE(cudaMalloc(&e->dSeeds, A * sizeof(int64_t)));
