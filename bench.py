@@ -108,41 +108,40 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_port_run(n_threads, budget_s, warm_ticks=30):
-    """The oracle (CPU restatement) on n_threads arenas of the benchmark shape, one arena per thread. Returns robot-steps/s."""
+def cpu_port_run(n_threads, warm_ticks, ticks, budget_s):
+    """The oracle (CPU restatement) on n_threads arenas of the benchmark shape, one arena per thread, over the same simulated
+    interval as the GPU arm (warm_ticks after the reset, then `ticks`), cut short when budget_s runs out. Returns robot-steps/s."""
     from puckswarm_b200 import abi
     import oracle_binding
     cfg = abi.config_defaults(n_arenas=n_threads, n_robots=N_ROBOTS, n_pucks=N_PUCKS, controller=abi.PS_CTRL_CACHECONS)
     o = oracle_binding.Oracle(cfg, threads=n_threads)
     o.reset(np.arange(n_threads))
-    o.step(warm_ticks)
     t0 = time.perf_counter()
-    o.step(9)
-    per_tick = (time.perf_counter() - t0) / 9
-    ticks = int(max(9, min(3000, budget_s / max(per_tick, 1e-6)))) // 3 * 3
+    done_warm = 0
+    while done_warm < warm_ticks and time.perf_counter() - t0 < budget_s:
+        n = min(30, warm_ticks - done_warm)
+        o.step(n)
+        done_warm += n
     t0 = time.perf_counter()
-    o.step(ticks)
+    done = 0
+    while done < ticks and (done == 0 or time.perf_counter() - t0 < budget_s):
+        n = min(30, ticks - done)
+        o.step(n)
+        done += n
     dt = time.perf_counter() - t0
-    return n_threads * N_ROBOTS * ticks / dt, ticks, dt
+    return n_threads * N_ROBOTS * done / dt, done, dt, done_warm
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path on the host cores (rank 0 only)."""
+    """--impl reference: the reference's CPU implementation of the path on the host cores (rank 0 only). A step is one think
+    interval (3 ticks) of one arena per host thread; the same W warm-up and K timed steps as the GPU arm, within a time budget."""
     if rank != 0:
         return
     import __graft_entry__ as g
     g.build_oracle()
     cores = os.cpu_count() or 1
-    per_step_budget = 8.0
-    vals = []
-    total_ticks = 0
-    for i in range(args.warmup + args.steps):
-        v, ticks, dt = cpu_port_run(cores, per_step_budget, warm_ticks=30)
-        if i >= args.warmup:
-            vals.append(v)
-            total_ticks += ticks
-    value = float(np.mean(vals))
-    sample = "%d arenas (one per host thread) x 16 robots x 200 pucks, %d timed ticks per step after 30 warm-up ticks" % (cores, total_ticks // max(1, len(vals)))
+    value, ticks, dt, warm = cpu_port_run(cores, STEP_INTERVAL * args.warmup, STEP_INTERVAL * args.steps, 90.0)
+    sample = "%d arenas (one per host thread) x 16 robots x 200 pucks, %d timed ticks after %d warm-up ticks (%.1f s)" % (cores, ticks, warm, dt)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * cores * N_ROBOTS * STEP_INTERVAL / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -157,8 +156,9 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    # defaults follow the metric's definition: >= 300 warm-up ticks, then a few hundred think steps
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--arenas", type=int, default=ARENAS_PER_GPU, help="arenas per GPU (default: BASELINE config[2])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -377,9 +377,9 @@ def main():
         if not args.no_cpu_baseline:
             g.build_oracle()
             cores = os.cpu_count() or 1
-            v, ticks, dt = cpu_port_run(cores, 15.0)
+            v, ticks, dt, warm = cpu_port_run(cores, STEP_INTERVAL * args.warmup, STEP_INTERVAL * args.steps, 25.0)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": "%d arenas (one per host thread) x 16 robots x 200 pucks, CacheCons, %d ticks after 30 warm-up ticks (%.1f s)" % (cores, ticks, dt)}
+                   "sample": "%d arenas (one per host thread) x 16 robots x 200 pucks, CacheCons, %d ticks after %d warm-up ticks (%.1f s)" % (cores, ticks, warm, dt)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -164,7 +164,9 @@ __global__ void __launch_bounds__(128) k_phys_pre(KParams p) {
 __global__ void __launch_bounds__(128) k_island_warp(KParams p) {
     extern __shared__ __align__(16) char smem[];
     WarpSlot* slot = reinterpret_cast<WarpSlot*>(smem) + (threadIdx.x >> 5);
-    int total = min(p.queue.counts[0], p.queue.cap);
+    // the islands with the most contacts (bucket kBucketLarge) are handed out first, then bucket 0
+    int nLarge = min(p.queue.counts[kBucketLarge], p.queue.cap);
+    int total = nLarge + min(p.queue.counts[0], p.queue.cap);
     unsigned NB = (unsigned)p.env.cfg.d.NB;
     int lane = threadIdx.x & 31;
     for (;;) {
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(128) k_island_warp(KParams p) {
         if (lane == 0) idx = atomicAdd(&p.queue.counts[kQueueBuckets], 1);
         idx = __shfl_sync(0xFFFFFFFFu, idx, 0);
         if (idx >= total) break;
-        unsigned entry = p.queue.entries[idx];
+        unsigned entry = idx < nLarge ? p.queue.entries[(size_t)kBucketLarge * p.queue.cap + idx] : p.queue.entries[idx - nLarge];
         int a = (int)(entry / NB), k = (int)(entry % NB);
         PhysWork wk = arenaWork(p, a);
         ArenaState st = arenaState(p.sp, p.env.cfg, a);

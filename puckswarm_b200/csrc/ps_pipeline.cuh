@@ -26,7 +26,8 @@ struct IslandQueue {
 };
 static constexpr int kQueueWarpBodies = 48, kQueueWarpContacts = 64;   // = kWarpBodies, kWarpContacts of ps_island_lanes.cuh
 static constexpr int kLaneBodies = 12, kLaneContacts = 16;   // what a lane slot of the lane-per-island solver holds
-static constexpr int kQueueBuckets = 6, kLaneBuckets = 4, kBucketBig = 5, kWarpMinContactsDefault = 16;   // capacity of one lane's shared-memory slot (k_island_batch)
+static constexpr int kQueueBuckets = 7, kLaneBuckets = 4, kBucketBig = 5, kBucketLarge = 6, kWarpMinContactsDefault = 16;
+static constexpr int kLargeContacts = 28;   // warp-slot islands with at least this many contacts are handed out first (they are the tail)   // capacity of one lane's shared-memory slot (k_island_batch)
 
 template <class Ctx>
 PS_HD void physPre(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaState& st, const float* cmdFwd, const float* cmdTorque,
@@ -46,7 +47,7 @@ PS_HD void physPre(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaSt
         int nb = wk.islandBodyStart[k + 1] - wk.islandBodyStart[k];
         int nc = wk.islandStart[k + 1] - wk.islandStart[k];
         // 0: a warp each (WarpSlot); kBucketBig: what outgrows that (BigSlot); 1..4: a lane each, by contact count
-        int bucket = (nc >= e.cfg.warpMinContacts || nc > kLaneContacts || nb > kLaneBodies) ? ((nb > kQueueWarpBodies || nc > kQueueWarpContacts) ? kBucketBig : 0)
+        int bucket = (nc >= e.cfg.warpMinContacts || nc > kLaneContacts || nb > kLaneBodies) ? ((nb > kQueueWarpBodies || nc > kQueueWarpContacts) ? kBucketBig : (nc >= kLargeContacts ? kBucketLarge : 0))
                                                                                                : (nc <= 2 ? 1 : (nc <= 5 ? 2 : (nc <= 12 ? 3 : 4)));
         int pos = ctx.atomicAddI(&q.counts[bucket], 1);
         if (pos < q.cap) q.entries[(size_t)bucket * q.cap + pos] = (unsigned)arena * (unsigned)d.NB + (unsigned)k;
