@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(kBatchThreads) k_island_batch(KParams p, int b
 }
 
 // stage C: one CTA per arena
-__global__ void __launch_bounds__(128) k_phys_post(KParams p) {
+__global__ void __launch_bounds__(128, 6) k_phys_post(KParams p) {
     __shared__ int scan[40];
     CtaCtx ctx;
     ctx.scanScratch = scan;
