@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define PS_ABI_VERSION 1
+#define PS_ABI_VERSION 2
 
 /* ---- fixed sizes of the scene ---- */
 #define PS_MAX_COLOURS      8    /* SensedType.NPUCK_COLOURS, src/sensors/SensedType.java:39 */
@@ -124,6 +124,10 @@ typedef struct ps_config {
      * PREDICTION_DISTANCE_SQD and ST_DEV have the names and defaults of the CacheCons keys and travel in the cc_* fields above
      * when controller == PS_CTRL_PROBSEEK; the one key of its own: */
     int32_t ps_placement_time;    /* PLACEMENT_TIME (40) */
+    /* Perturbations at the start of Arena.step, every think step whose stepCount is a multiple of the value; -1 = never
+     * (src/arena/Arena.java:186-192, 318-373: shiftPucksThroughCentre / shufflePucks through Body.setTransform) */
+    int32_t puck_shift_step;      /* Arena.puckShiftStep (-1) */
+    int32_t puck_shuffle_step;    /* Arena.puckShuffleStep (-1) */
 } ps_config;
 
 /*

@@ -1466,28 +1466,43 @@ struct World {
             c = c->next;
         }
     }
+    // Fixture.synchronize(broadPhase, xf1, xf2) + BroadPhase.moveProxy / DynamicTree.moveProxy
+    void synchronizeFixture(Fixture* f, const Transform& xf1, const Transform& xf2) {
+        AABB aabb1, aabb2;
+        f->shape.computeAABB(&aabb1, xf1);
+        f->shape.computeAABB(&aabb2, xf2);
+        f->aabb.combine(aabb1, aabb2);
+        Vec2 displacement = xf2.position - xf1.position;
+        // DynamicTree.moveProxy
+        if (f->fat.contains(f->aabb)) return;
+        AABB nb = f->aabb;
+        Vec2 r(kAabbExtension, kAabbExtension);
+        nb.lower = nb.lower - r;
+        nb.upper = nb.upper + r;
+        Vec2 d = kAabbMultiplier * displacement;
+        if (d.x < 0.0f) nb.lower.x += d.x; else nb.upper.x += d.x;
+        if (d.y < 0.0f) nb.lower.y += d.y; else nb.upper.y += d.y;
+        f->fat = nb;
+        moveBuffer.push_back(f->proxyId);
+    }
     void synchronizeFixtures(Body* b) {
         Transform xf1;
         xf1.R.set(b->sweep.a0, tr);
         xf1.position = b->sweep.c0 - mul(xf1.R, b->sweep.localCenter);
-        for (Fixture* f = b->fixtureList; f; f = f->next) {
-            AABB aabb1, aabb2;
-            f->shape.computeAABB(&aabb1, xf1);
-            f->shape.computeAABB(&aabb2, b->xf);
-            f->aabb.combine(aabb1, aabb2);
-            Vec2 displacement = b->xf.position - xf1.position;
-            // DynamicTree.moveProxy
-            if (f->fat.contains(f->aabb)) continue;
-            AABB nb = f->aabb;
-            Vec2 r(kAabbExtension, kAabbExtension);
-            nb.lower = nb.lower - r;
-            nb.upper = nb.upper + r;
-            Vec2 d = kAabbMultiplier * displacement;
-            if (d.x < 0.0f) nb.lower.x += d.x; else nb.upper.x += d.x;
-            if (d.y < 0.0f) nb.lower.y += d.y; else nb.upper.y += d.y;
-            f->fat = nb;
-            moveBuffer.push_back(f->proxyId);
-        }
+        for (Fixture* f = b->fixtureList; f; f = f->next) synchronizeFixture(f, xf1, b->xf);
+    }
+    // Body.setTransform (JBox2D 2.1.2.2 Body.setTransform == Box2D v2.1.2 b2Body::SetTransform; called by
+    // src/arena/Arena.java:346,360,369,371 outside World.step, so the world is not locked): new transform, sweep
+    // collapsed onto it (c0 = c, a0 = a), every fixture re-synchronised with xf1 == xf2 (zero displacement, so a
+    // proxy that left its fat AABB gets the tight box + aabbExtension), then ContactManager.findNewContacts.
+    // Velocities and the cached contacts stay: contacts whose fat AABBs no longer overlap die in the next collide().
+    void setTransform(Body* b, const Vec2& position, float angle) {
+        b->xf.R.set(angle, tr);
+        b->xf.position = position;
+        b->sweep.c0 = b->sweep.c = mul(b->xf, b->sweep.localCenter);
+        b->sweep.a0 = b->sweep.a = angle;
+        for (Fixture* f = b->fixtureList; f; f = f->next) synchronizeFixture(f, b->xf, b->xf);
+        findNewContacts();
     }
 
     // ---- ContactSolver + Island.solve (A.6) ----

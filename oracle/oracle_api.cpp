@@ -132,6 +132,7 @@ int orc_step_external(orc_batch* b, const float* fwd, const float* torque, int n
             a.robots[r].controller->movement.forwards = fwd[(size_t)i * R + r];
             a.robots[r].controller->movement.torque = torque[(size_t)i * R + r];
         }
+        a.perturb();
         a.stepCount++;
         for (int t = 0; t < a.cfg.step_interval; t++) {
             a.coast();

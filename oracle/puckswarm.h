@@ -1361,7 +1361,53 @@ struct Arena {
             r.localMap.update(r.image);
         }
     }
+    // Arena.getRandomPuckPos (Arena.java:318-329): a free-space point at least one puck width from every robot origin
+    bool getRandomPuckPos(Vec2* out) {
+        float closest = 0;
+        Vec2 pos;
+        do {
+            if (!enclosure.getRandomInside(PUCK_MIN_BOUNDARY_DISTANCE, &pos)) return false;   // null: the arena is blocked full
+            closest = INFINITY;
+            for (const Robot& r : robots)
+                if (jb::distance(r.body->xf.position, pos) < closest) closest = jb::distance(r.body->xf.position, pos);
+        } while (closest < PUCK_WIDTH);
+        *out = pos;
+        return true;
+    }
+    void teleportPuckRandomly(Puck& p) {
+        Vec2 pos;
+        if (getRandomPuckPos(&pos)) world->setTransform(p.body, pos, 0);
+    }
+    // Arena.shiftPucksThroughCentre + shiftPucks (Arena.java:334-343, 354-373)
+    void shiftPucksThroughCentre() {
+        Vec2 centroid;
+        for (Puck& p : pucks) centroid += p.body->xf.position;
+        centroid.normalize();
+        centroid *= -100;
+        for (Puck& p : pucks) {
+            Vec2 pos = p.body->xf.position + centroid;
+            if (!enclosure.inFreeSpace(pos, PUCK_MIN_BOUNDARY_DISTANCE)) {
+                teleportPuckRandomly(p);
+            } else {
+                float closest = INFINITY;
+                for (const Robot& r : robots)
+                    if (jb::distance(r.body->xf.position, pos) < closest) closest = jb::distance(r.body->xf.position, pos);
+                if (closest < PUCK_WIDTH) teleportPuckRandomly(p);
+                else world->setTransform(p.body, pos, 0);
+            }
+        }
+    }
+    // Arena.shufflePucks (Arena.java:345-348)
+    void shufflePucks() {
+        for (Puck& p : pucks) teleportPuckRandomly(p);
+    }
+    // the head of Arena.step (Arena.java:185-192)
+    void perturb() {
+        if (cfg.puck_shift_step != -1 && stepCount % cfg.puck_shift_step == 0) shiftPucksThroughCentre();
+        if (cfg.puck_shuffle_step != -1 && stepCount % cfg.puck_shuffle_step == 0) shufflePucks();
+    }
     void arenaStep() {  // Arena.java:183-267 with (true,true,true,false,0,false)
+        perturb();
         for (Robot& r : robots) {
             cameraSense(r);
             r.localMap.update(r.image);

@@ -6,7 +6,7 @@ arrays the ABI exchanges. Nothing in this module computes simulation results.
 import ctypes as C
 import numpy as np
 
-PS_ABI_VERSION = 1
+PS_ABI_VERSION = 2
 PS_MAX_COLOURS = 8
 PS_ROBOT_FIXTURES = 14
 PS_PUCK_FIXTURES = 2
@@ -44,6 +44,7 @@ class ps_config(C.Structure):
         ("cc_k_relative", C.c_float), ("cc_forget_prob", C.c_float), ("cc_cache_separation", C.c_int32),
         ("cc_home_separation_distance", C.c_float), ("cc_ignore_pucks", C.c_int32),
         ("bhd_push_in_time", C.c_int32), ("bhd_backup_time", C.c_int32), ("ps_placement_time", C.c_int32),
+        ("puck_shift_step", C.c_int32), ("puck_shuffle_step", C.c_int32),
     ]
 
 
@@ -92,6 +93,8 @@ def config_defaults(**kw):
     c.bhd_push_in_time = 1
     c.bhd_backup_time = 5
     c.ps_placement_time = 40
+    c.puck_shift_step = -1
+    c.puck_shuffle_step = -1
     for k, v in kw.items():
         if not hasattr(c, k):
             raise AttributeError("ps_config has no field %r" % k)

@@ -41,6 +41,7 @@ struct KParams {
     const int64_t* seeds;
     const ps_robot_state* robotInit;
     int nInformed;
+    int puckShiftStep, puckShuffleStep;   // Arena.puckShiftStep / puckShuffleStep (-1 = never)
     int* stepStats;          // [nArenas][8] diagnostics of the last World.step
     // three-stage pipeline (ps_pipeline.cuh): per-arena scratch blocks in HBM + the batch-wide island queue
     PhysWork workOff;        // byte offsets of the working arrays inside one arena's scratch block
@@ -74,6 +75,23 @@ __global__ void __launch_bounds__(256) k_reset(KParams p) {
         out.robot = p.sp.robot + (size_t)a * p.env.cfg.d.R;
         out.arena = p.sp.arena + a;
         arenaReset(ctx, p.env, wk, st, out, p.seeds[a], p.robotInit, p.nInformed);
+        __syncthreads();
+    }
+}
+
+// The head of Arena.step (puck shift / shuffle perturbations, ps_spawn.cuh) for arenas [a0, a0 + n): launched before every
+// think step when either perturbation is configured; an arena whose stepCount is not due returns at once
+__global__ void __launch_bounds__(256) k_perturb(KParams p, int a0, int n, int perArenaScratch) {
+    __shared__ int scan[40];
+    CtaCtx ctx;
+    ctx.scanScratch = scan;
+    // arena groups run this concurrently on their own streams, so the working arrays come from the arenas' own scratch
+    // blocks (HBM / L2: the perturbations are rare); the fused single-stream mode has CTA slots only
+    PhysWork slotWork = ctaWork(p);
+    for (int a = a0 + blockIdx.x; a < a0 + n; a += gridDim.x) {
+        ArenaState st = arenaState(p.sp, p.env.cfg, a);
+        PhysWork wk = perArenaScratch ? rebaseWork(p.workOff, p.arenaScratch + (size_t)a * p.arenaScratchStride) : slotWork;
+        arenaPerturb(ctx, p.env, wk, st, p.sp.arena + a, p.puckShiftStep, p.puckShuffleStep);
         __syncthreads();
     }
 }
@@ -484,6 +502,8 @@ void ps_config_defaults(ps_config* c) {
     c->bhd_push_in_time = 1;
     c->bhd_backup_time = 5;
     c->ps_placement_time = 40;
+    c->puck_shift_step = -1;
+    c->puck_shuffle_step = -1;
 }
 
 int ps_destroy(ps_handle h) {
@@ -619,6 +639,7 @@ int ps_create(const ps_config* cfg, int device, ps_handle* out) {
     TRY_OR_FREE(cudaMalloc(&e->kp.slow, (size_t)e->nSlots * slowStride + 256));
     TRY_OR_FREE(cudaMemset(e->kp.slow, 0, (size_t)e->nSlots * slowStride + 256));
     TRY_OR_FREE(cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smemBytes));
+    TRY_OR_FREE(cudaFuncSetAttribute(k_perturb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smemBytes));
     TRY_OR_FREE(cudaFuncSetAttribute(k_physics, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smemBytes));
     // pipeline: one scratch block per arena (all working arrays in HBM / L2), island queue
     {
@@ -679,6 +700,8 @@ int ps_create(const ps_config* cfg, int device, ps_handle* out) {
     e->kp.seeds = e->dSeeds;
     e->kp.robotInit = e->dRobotInit;
     e->kp.nInformed = cfg->n_informed_robots;
+    e->kp.puckShiftStep = cfg->puck_shift_step;
+    e->kp.puckShuffleStep = cfg->puck_shuffle_step;
     e->kp.stepStats = e->dStepStats;
     *out = e;
     return PS_OK;
@@ -791,6 +814,15 @@ static int joinGroups(ps_handle h) {
     return PS_OK;
 }
 
+// Arena.step's perturbations for arenas [a0, a0 + n) on stream s (nothing is launched when none is configured)
+static int launchPerturb(ps_handle h, int a0, int n, cudaStream_t s) {
+    if (h->kp.puckShiftStep == -1 && h->kp.puckShuffleStep == -1) return PS_OK;
+    k_perturb<<<std::max(1, std::min(h->nSlots, n)), h->threads, h->smemBytes, s>>>(h->kp, a0, n, h->fused ? 0 : 1);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PS_OK;
+}
+
 int ps_step(ps_handle h, int n_ticks) {
     if (!h || n_ticks < 0) return setError(PS_E_INVALID, "bad argument");
     if (!h->isReset) return setError(PS_E_INVALID, "ps_reset or ps_set_state first");
@@ -807,6 +839,8 @@ int ps_step(ps_handle h, int n_ticks) {
         int t = 0;
         while (t < n_ticks) {
             if (uc % interval == 0) {
+                rc = launchPerturb(h, G.a0, G.n, G.s);
+                if (rc != PS_OK) return rc;
                 if (onDevice) {
                     {
                         ScopedTimer timer(h, 0, G.s);
@@ -857,6 +891,7 @@ int ps_step_external(ps_handle h, const float* forwards, const float* torque) {
     CUDA_TRY(cudaMemcpyAsync(h->dCmd, forwards, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->dCmd + n, torque, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     k_set_commands<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->kp.sp.robot, h->dCmd, h->dCmd + n, n);
+    { int pr = launchPerturb(h, 0, h->kp.nArenas, h->stream); if (pr != PS_OK) return pr; }
     k_count_step<<<(h->kp.nArenas + 127) / 128, 128, 0, h->stream>>>(h->kp.sp.arena, h->kp.nArenas);
     h->launches += 2;
     CUDA_TRY(cudaGetLastError());

@@ -27,6 +27,8 @@ struct HostSetup {
             return fail("bad arena shape");
         if (c.step_interval < 1 || c.vel_iters < 0 || c.pos_iters < 0 || !(c.dt > 0)) return fail("bad step parameters");
         if (c.controller < PS_CTRL_CACHECONS || c.controller > PS_CTRL_PROBSEEK) return fail("bad controller");
+        // stepCount % 0 throws in the reference (Arena.java:189-191); negative periods other than the "never" value are refused
+        if (c.puck_shift_step == 0 || c.puck_shift_step < -1 || c.puck_shuffle_step == 0 || c.puck_shuffle_step < -1) return fail("bad perturbation period");
         int P = c.n_pucks / c.n_puck_types * c.n_puck_types;   // Arena.java:91-95: nPucks / nPuckTypes per colour
         Dims d;
         d.P = P;

@@ -904,6 +904,97 @@ PS_HD void tryPair(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaSt
     if (slot < e.cfg.MPAIR) wk.pairs[slot] = ((uint32_t)lo << 16) | (uint32_t)hi;
 }
 
+// BroadPhase.updatePairs' tail + ContactManager.addPair over the candidate keys in wk.pairs[0 .. counters[3]): sort,
+// drop duplicates (and, with checkCache, pairs that already have a contact), append the rest in sorted proxy order.
+template <class Ctx>
+PS_HD void physAppendPairs(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaState& st, bool checkCache) {
+    const Dims& d = e.cfg.d;
+    int nPairs = wk.counters[3];
+    if (nPairs > e.cfg.MPAIR) {
+        if (ctx.tid() == 0) *st.errorFlags |= ERR_PAIR_CAP;
+        nPairs = e.cfg.MPAIR;
+    }
+    // bitonic sort of the pair keys (padded with 0xFFFFFFFF), then unique -> append in sorted order
+    int n2 = 1;
+    while (n2 < nPairs) n2 <<= 1;
+    PS_FOR(i, n2) if (i >= nPairs) wk.pairs[i] = 0xFFFFFFFFu;
+    ctx.sync();
+    for (int k = 2; k <= n2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            PS_FOR(i, n2) {
+                int l = i ^ j;
+                if (l > i) {
+                    uint32_t a = wk.pairs[i], b = wk.pairs[l];
+                    bool up = (i & k) == 0;
+                    if ((a > b) == up) {
+                        wk.pairs[i] = b;
+                        wk.pairs[l] = a;
+                    }
+                }
+            }
+            ctx.sync();
+        }
+    int nOld = *st.nContacts;
+    int nNew = 0;
+    uint8_t* cached = (uint8_t*)wk.tc;   // [MPAIR] flags; the constraint table is idle whenever pairs are appended (MT * sizeof(TC) >= MPAIR)
+    if (checkCache) {
+        // ContactManager.addPair's "does a contact between these two fixtures exist already" walk, for callers whose cache
+        // may hold contacts of separated boxes (Body.setTransform outside World.step): every cached key looks itself up
+        // in the sorted pair list and flags the first occurrence
+        PS_FOR(i, nPairs) cached[i] = 0;
+        ctx.sync();
+        PS_FOR(ci, nOld) {
+            uint32_t k = st.ckey[ci];
+            uint32_t a = k >> 16, b = k & 0xFFFFu;
+            uint32_t canon = a < b ? k : ((b << 16) | a);
+            int lo = 0, hi = nPairs;
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if (wk.pairs[mid] < canon) lo = mid + 1;
+                else hi = mid;
+            }
+            if (lo < nPairs && wk.pairs[lo] == canon) cached[lo] = 1;
+        }
+        ctx.sync();
+    }
+    int nRound = roundUpThreads(ctx, nPairs);
+    for (int base = 0; base < nRound; base += ctx.nthreads()) {
+        int i = base + ctx.tid();
+        bool uniq = false;
+        uint32_t key = 0;
+        if (i < nPairs) {
+            key = wk.pairs[i];
+            uniq = (i == 0 || wk.pairs[i - 1] != key) && !(checkCache && cached[i]);
+        }
+        int total;
+        int pos = nOld + nNew + ctx.exscanFlag(uniq, total);
+        if (uniq) {
+            if (pos < e.cfg.MC) {
+                int pa = (int)(key >> 16), pb = (int)(key & 0xFFFFu);
+                // Contact.create: the polygon is fixture A of a polygon-circle contact
+                const Shape& sA = e.scene->shapes[proxyShape(d, pa)];
+                const Shape& sB = e.scene->shapes[proxyShape(d, pb)];
+                if (sA.type == SHAPE_CIRCLE && sB.type == SHAPE_POLYGON) key = ((uint32_t)pb << 16) | (uint32_t)pa;
+                st.ckey[pos] = key;
+                st.cinfo[pos] = 0;
+                st.cimp[4 * pos + 0] = 0.0f;
+                st.cimp[4 * pos + 1] = 0.0f;
+                st.cimp[4 * pos + 2] = 0.0f;
+                st.cimp[4 * pos + 3] = 0.0f;
+            } else {
+                *st.errorFlags |= ERR_CONTACT_CAP;
+            }
+        }
+        nNew += total;
+    }
+    ctx.sync();
+    if (ctx.tid() == 0) {
+        int nc = nOld + nNew;
+        *st.nContacts = nc > e.cfg.MC ? e.cfg.MC : nc;
+    }
+    ctx.sync();
+}
+
 // Phase H: ContactManager.findNewContacts. allNew = every proxy counts as moved and there is no previous cache (reset).
 template <class Ctx>
 PS_HD void physFindNewContacts(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaState& st, bool allNew) {
@@ -1002,69 +1093,7 @@ PS_HD void physFindNewContacts(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, c
         }
     }
     ctx.sync();
-    int nPairs = wk.counters[3];
-    if (nPairs > e.cfg.MPAIR) {
-        if (ctx.tid() == 0) *st.errorFlags |= ERR_PAIR_CAP;
-        nPairs = e.cfg.MPAIR;
-    }
-    // bitonic sort of the pair keys (padded with 0xFFFFFFFF), then unique -> append in sorted order
-    int n2 = 1;
-    while (n2 < nPairs) n2 <<= 1;
-    PS_FOR(i, n2) if (i >= nPairs) wk.pairs[i] = 0xFFFFFFFFu;
-    ctx.sync();
-    for (int k = 2; k <= n2; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            PS_FOR(i, n2) {
-                int l = i ^ j;
-                if (l > i) {
-                    uint32_t a = wk.pairs[i], b = wk.pairs[l];
-                    bool up = (i & k) == 0;
-                    if ((a > b) == up) {
-                        wk.pairs[i] = b;
-                        wk.pairs[l] = a;
-                    }
-                }
-            }
-            ctx.sync();
-        }
-    int nOld = *st.nContacts;
-    int nNew = 0;
-    int nRound = roundUpThreads(ctx, nPairs);
-    for (int base = 0; base < nRound; base += ctx.nthreads()) {
-        int i = base + ctx.tid();
-        bool uniq = false;
-        uint32_t key = 0;
-        if (i < nPairs) {
-            key = wk.pairs[i];
-            uniq = i == 0 || wk.pairs[i - 1] != key;
-        }
-        int total;
-        int pos = nOld + nNew + ctx.exscanFlag(uniq, total);
-        if (uniq) {
-            if (pos < e.cfg.MC) {
-                int pa = (int)(key >> 16), pb = (int)(key & 0xFFFFu);
-                // Contact.create: the polygon is fixture A of a polygon-circle contact
-                const Shape& sA = e.scene->shapes[proxyShape(d, pa)];
-                const Shape& sB = e.scene->shapes[proxyShape(d, pb)];
-                if (sA.type == SHAPE_CIRCLE && sB.type == SHAPE_POLYGON) key = ((uint32_t)pb << 16) | (uint32_t)pa;
-                st.ckey[pos] = key;
-                st.cinfo[pos] = 0;
-                st.cimp[4 * pos + 0] = 0.0f;
-                st.cimp[4 * pos + 1] = 0.0f;
-                st.cimp[4 * pos + 2] = 0.0f;
-                st.cimp[4 * pos + 3] = 0.0f;
-            } else {
-                *st.errorFlags |= ERR_CONTACT_CAP;
-            }
-        }
-        nNew += total;
-    }
-    ctx.sync();
-    if (ctx.tid() == 0) {
-        int nc = nOld + nNew;
-        *st.nContacts = nc > e.cfg.MC ? e.cfg.MC : nc;
-    }
-    ctx.sync();
+    physAppendPairs(ctx, e, wk, st, false);
 }
 
 // Sweep of a body over the current step. Pucks carry no rotation that anything reads (circle fixtures centred on the

@@ -219,4 +219,146 @@ PS_HD void arenaReset(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const Aren
     physFindNewContacts(ctx, e, wk, st, true);
 }
 
+// ---- Arena.step's puck perturbations (src/arena/Arena.java:185-192, 318-373) ----
+//
+// Body.setTransform(pos, 0) of one puck (JBox2D 2.1.2.2 Body.setTransform: sweep collapsed onto the new transform, both
+// fixtures re-synchronised with zero displacement, then ContactManager.findNewContacts), by the whole CTA. The puck keeps
+// its velocity and its cached contacts: those whose fat AABBs separated die in the next World.step's collide(). Because
+// of them "overlapped before" no longer means "has a contact", so the pairs go through the explicit cache check.
+template <class Ctx>
+PS_HD void teleportPuck(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaState& st, int b, float x, float y) {
+    const Dims& d = e.cfg.d;
+    const Scene& sc = *e.scene;
+    int NB = d.NB, NP = d.NP;
+    int first = bodyFirstProxy(d, b);
+    ctx.sync();
+    if (ctx.tid() == 0) {
+        st.body[0 * NB + b] = x;
+        st.body[1 * NB + b] = y;
+        st.body[2 * NB + b] = 0.0f;
+        Xf T;
+        T.px = x;
+        T.py = y;
+        T.c = 1.0f;
+        T.s = 0.0f;
+        for (int k = 0; k < kPuckFixtures; ++k) {
+            int i = first - kWallFixtures + k;
+            Aabb a = shapeAabb(sc.shapes[kShapePuck0 + k], T);   // combine(aabb1, aabb2) of two equal boxes
+            if (k == 1) storeAabb(st.senseAabb, NB, b, a);
+            Aabb fat = loadAabb(st.fat, NP, i);
+            bool mv = !aabbContains(fat, a);
+            if (mv) {
+                a.lx -= kAabbExtension;
+                a.ly -= kAabbExtension;
+                a.ux += kAabbExtension;
+                a.uy += kAabbExtension;   // the displacement prediction adds 2 * (0, 0)
+                storeAabb(st.fat, NP, i, a);
+            }
+            wk.counters[4 + k] = mv ? 1 : 0;
+        }
+        wk.counters[3] = 0;
+    }
+    ctx.sync();
+    // BroadPhase.updatePairs: each moved proxy queries every fat AABB; addPair's same-body and Filter tests are applied
+    // here (they only drop pairs, so their place in the order is free)
+    for (int k = 0; k < kPuckFixtures; ++k) {
+        if (!wk.counters[4 + k]) continue;
+        int q = first + k;
+        Aabb fatQ = loadAabb(st.fat, NP, q - kWallFixtures);
+        uint32_t filtQ = sc.filt[kShapePuck0 + k];
+        PS_FOR(p, kWallFixtures + NP) {
+            if (proxyBody(d, p) == b) continue;
+            if (!filtCollide(filtQ, sc.filt[proxyShape(d, p)])) continue;
+            if (!aabbOverlap(proxyFat(e, st, p), fatQ)) continue;
+            int lo = p < q ? p : q, hi = p < q ? q : p;
+            int slot = ctx.atomicAddI(&wk.counters[3], 1);
+            if (slot < e.cfg.MPAIR) wk.pairs[slot] = ((uint32_t)lo << 16) | (uint32_t)hi;
+        }
+    }
+    ctx.sync();
+    if (wk.counters[3] > 0) physAppendPairs(ctx, e, wk, st, true);
+}
+
+// The head of Arena.step: shiftPucksThroughCentre when stepCount % puckShiftStep == 0, then shufflePucks when
+// stepCount % puckShuffleStep == 0 (a step of -1 = never). Thread 0 draws the new positions in puck order from the arena's
+// java.util.Random (a puck's new position depends on the robots and on its own old position only); the pucks are
+// then moved one after the other, because each setTransform ends with its own findNewContacts.
+template <class Ctx>
+PS_HD void arenaPerturb(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaState& st, ps_arena_state* as, int shiftStep, int shuffleStep) {
+    const Dims& d = e.cfg.d;
+    const Scene& sc = *e.scene;
+    int NB = d.NB;
+    const float PUCK_WIDTH = 6.3f, MIN_BOUNDARY = PUCK_WIDTH / 2;
+    int stepCount = as->step_count;
+    for (int mode = 0; mode < 2; ++mode) {
+        int every = mode == 0 ? shiftStep : shuffleStep;
+        if (every == -1 || stepCount % every != 0) continue;
+        ctx.sync();
+        PS_FOR(r, d.R) {   // robot.body.m_xf.position
+            int b = d.P + r;
+            Xf T = makeXf(e.trig, st.body[0 * NB + b], st.body[1 * NB + b], st.body[2 * NB + b], sc.robot.lcx, sc.robot.lcy);
+            wk.rpx[r] = T.px;
+            wk.rpy[r] = T.py;
+        }
+        ctx.sync();
+        if (ctx.tid() == 0) {
+            JRandom rng;
+            rng.seed = as->rng_seed;
+            rng.haveNextNextGaussian = as->rng_have_gaussian;
+            rng.nextNextGaussian = as->rng_next_gaussian;
+            V2 shift = mk(0.0f, 0.0f);
+            if (mode == 0) {
+                for (int p = 0; p < d.P; ++p) shift = shift + mk(st.body[0 * NB + p], st.body[1 * NB + p]);
+                float l = len(shift);   // Vec2.normalize
+                if (!(l < kEpsilon)) {
+                    float inv = 1.0f / l;
+                    shift.x *= inv;
+                    shift.y *= inv;
+                }
+                shift.x *= -100.0f;
+                shift.y *= -100.0f;
+            }
+            for (int p = 0; p < d.P; ++p) {
+                V2 pos = mk(0.0f, 0.0f);
+                bool random = true, ok = true;
+                if (mode == 0) {
+                    pos = mk(st.body[0 * NB + p], st.body[1 * NB + p]) + shift;
+                    if (inFreeSpace(sc, pos, MIN_BOUNDARY)) {
+                        float closest = INFINITY;
+                        for (int r = 0; r < d.R; ++r) {
+                            float dd = dist(mk(wk.rpx[r], wk.rpy[r]), pos);
+                            if (dd < closest) closest = dd;
+                        }
+                        random = closest < PUCK_WIDTH;
+                    }
+                }
+                if (random) {   // Arena.getRandomPuckPos
+                    float closest = 0.0f;
+                    do {
+                        if (!randomInside(sc, rng, MIN_BOUNDARY, pos)) {
+                            ok = false;
+                            break;
+                        }
+                        closest = INFINITY;
+                        for (int r = 0; r < d.R; ++r) {
+                            float dd = dist(mk(wk.rpx[r], wk.rpy[r]), pos);
+                            if (dd < closest) closest = dd;
+                        }
+                    } while (closest < PUCK_WIDTH);
+                }
+                wk.cx[p] = pos.x;
+                wk.cy[p] = pos.y;
+                wk.bodyFlag[p] = ok ? 1 : 0;
+            }
+            as->rng_seed = rng.seed;
+            as->rng_have_gaussian = rng.haveNextNextGaussian;
+            as->rng_next_gaussian = rng.nextNextGaussian;
+        }
+        ctx.sync();
+        for (int p = 0; p < d.P; ++p)
+            if (wk.bodyFlag[p]) teleportPuck(ctx, e, wk, st, p, wk.cx[p], wk.cy[p]);
+        ctx.sync();
+    }
+}
+
 }  // namespace ps

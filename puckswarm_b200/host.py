@@ -33,6 +33,7 @@ PROPERTY_MAP = {
     "controllerType": ("controller", str, _CTRL),
     "Arena.nPucks": ("n_pucks", int, None), "Arena.nPuckTypes": ("n_puck_types", int, None),
     "Arena.nRobots": ("n_robots", int, None), "Arena.nInformedRobots": ("n_informed_robots", int, None),
+    "Arena.puckShiftStep": ("puck_shift_step", int, None), "Arena.puckShuffleStep": ("puck_shuffle_step", int, None),
     "RoundedRectangleEnclosure.scale": ("enclosure_scale", float, None),
     "LocalMap.CARRY_THRESHOLD_LO": ("carry_threshold_lo", float, None), "LocalMap.CARRY_THRESHOLD_HI": ("carry_threshold_hi", float, None),
     "VFHPlus.SAFETY_DISTANCE_GAMMA": ("vfh_safety_gamma", float, None), "VFHPlus.SAFETY_DISTANCE_MASK": ("vfh_safety_mask", float, None),

@@ -101,6 +101,7 @@ int emu_step(Emu* e, int nTicks) {
         ps_arena_state* as = e->sp.arena + a;
         for (int t = 0; t < nTicks; t++) {
             if (as->update_count % e->hs.cfg.step_interval == 0) {
+                arenaPerturb(ctx, e->env, e->wk, st, as, e->hs.cfg.puck_shift_step, e->hs.cfg.puck_shuffle_step);
                 if (e->hs.cfg.controller != PS_CTRL_EXTERNAL) {
                     if (!e->sense.ready) return PS_E_NOCALIB;
                     senseAndThinkArena(ctx, e->env, e->sense, e->senseBuf, st, rs, as, nullptr);   // counts the think step

@@ -352,3 +352,33 @@ def test_ensemble_statistics_match():
         assert list(se.ctrl_state_hist) == list(so.ctrl_state_hist)
         assert se.n_carrying == so.n_carrying and se.n_caches == so.n_caches
         assert abs(se.sum_completion - so.sum_completion) < 1e-9 * max(1.0, so.sum_completion)
+
+
+@pytest.mark.parametrize("controller,shift,shuffle,shape", [(abi.PS_CTRL_EXTERNAL, 4, 6, (3, 4, 60)), (abi.PS_CTRL_CACHECONS, 5, -1, (5, 4, 60)),
+                                                            (abi.PS_CTRL_BHD, 1, 1, (6, 3, 200)), (abi.PS_CTRL_CACHECONS, 3, 4, (4, 16, 200))])
+def test_puck_shift_and_shuffle(controller, shift, shuffle, shape):
+    """Arena.puckShiftStep / puckShuffleStep (Arena.java:185-192, 318-373) on the device: pucks teleported through
+    Body.setTransform + findNewContacts at the head of the due think steps, arena groups perturbing concurrently; state
+    incl. contact cache order and the shared RNG bit-exact. The (1, 1) case re-teleports 200 pucks twice per think step,
+    which exercises addPair's "contact exists already" walk against stale contacts."""
+    import parity
+    A, R, P = shape
+    cfg = abi.config_defaults(n_arenas=A, n_robots=R, n_pucks=P, controller=controller, puck_shift_step=shift, puck_shuffle_step=shuffle)
+    e, o = _engine(cfg), _oracle(cfg)
+    seeds = np.arange(20, 20 + A)
+    e.reset(seeds)
+    o.reset(seeds)
+    rng = np.random.RandomState(1)
+    for k in range(9):
+        if controller == abi.PS_CTRL_EXTERNAL:
+            fwd = ((rng.rand(A, R) * 1.5) * 750000).astype(np.float32)
+            tq = ((rng.rand(A, R) * 2 - 1) * 2375000).astype(np.float32)
+            o.step_external(fwd, tq)
+            e.step_external(fwd, tq)
+        else:
+            o.step(3)
+            e.step(3)
+        # on-device controllers: double-precision libm may differ in the last ulp (see TOL above); the rest is bit-exact
+        bad = parity.compare_states(e.get_state(), o.get_state(), A, tol=0.0 if controller == abi.PS_CTRL_EXTERNAL else TOL)
+        assert bad == [], "think step %d: %s" % (k, bad[:4])
+    assert (e.get_state().arena["error_flags"] == 0).all()

@@ -112,3 +112,52 @@ def test_narrow_phase_samples():
                 if n == 2:
                     assert np.array_equal(me[8:10].view(np.uint32), mo[8:10].view(np.uint32)) and me[11] == mo[11]
     assert hits > 100
+
+
+@pytest.mark.parametrize("controller,shift,shuffle", [(abi.PS_CTRL_EXTERNAL, 4, 6), (abi.PS_CTRL_CACHECONS, 5, -1), (abi.PS_CTRL_BHD, -1, 7)])
+def test_puck_shift_and_shuffle(controller, shift, shuffle):
+    """Arena.puckShiftStep / puckShuffleStep (Arena.java:185-192, 318-373): every puck teleported through
+    Body.setTransform + findNewContacts at the head of the due think steps; state (incl. the contact cache, its order and
+    the shared RNG) stays bit-exact through the perturbations and the World.steps that clean up after them."""
+    A, R, P = 2, 4, 60
+    cfg = abi.config_defaults(n_arenas=A, n_robots=R, n_pucks=P, controller=controller, puck_shift_step=shift, puck_shuffle_step=shuffle)
+    e, o = emu.Emu(cfg), oracle.Oracle(cfg)
+    e.reset([3, 4])
+    o.reset([3, 4])
+    rng = np.random.RandomState(1)
+    moved = 0
+    for k in range(16):
+        before = o.get_state().body[:, 0:2, :P].copy()
+        if controller == abi.PS_CTRL_EXTERNAL:
+            fwd = ((rng.rand(A, R) * 1.5) * 750000).astype(np.float32)
+            tq = ((rng.rand(A, R) * 2 - 1) * 2375000).astype(np.float32)
+            o.step_external(fwd, tq)
+            se = e.get_state()
+            se.robot["cmd_forwards"], se.robot["cmd_torque"] = fwd, tq
+            e.set_state(se)
+            e.step(3)
+        else:
+            o.step(3)
+            e.step(3)
+        so = o.get_state()
+        bad = parity.compare_states(e.get_state(), so, A)
+        assert bad == [], "think step %d: %s" % (k, bad[:4])
+        if np.abs(so.body[:, 0:2, :P] - before).max() > 20:
+            moved += 1
+    due = sum(1 for k in range(16) if (shift != -1 and k % shift == 0) or (shuffle != -1 and k % shuffle == 0))
+    assert moved == due, (moved, due)
+
+
+def test_puck_shuffle_every_step_dense():
+    """200 pucks re-teleported twice per think step: stale contacts of earlier moves meet new overlaps, so addPair's
+    "contact exists already" walk decides (without it the cache grows duplicates on the first step)."""
+    A, R, P = 2, 3, 200
+    cfg = abi.config_defaults(n_arenas=A, n_robots=R, n_pucks=P, controller=abi.PS_CTRL_BHD, puck_shift_step=1, puck_shuffle_step=1)
+    e, o = emu.Emu(cfg), oracle.Oracle(cfg)
+    e.reset([3, 4])
+    o.reset([3, 4])
+    for k in range(6):
+        o.step(3)
+        e.step(3)
+        bad = parity.compare_states(e.get_state(), o.get_state(), A)
+        assert bad == [], "think step %d: %s" % (k, bad[:4])
