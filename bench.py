@@ -150,7 +150,28 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "CPU restatement of JBox2D 2.1.2.2 + PuckSwarm sensing/controllers (oracle/), not the JVM reference: no JDK / JBox2D jar in this image",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def claim_stdout():
+    """Only the JSON line may reach stdout: libraries that print there (NCCL's version banner) are sent to stderr."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
@@ -165,6 +186,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the stepInterval = 1 side measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    claim_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -388,13 +410,13 @@ def main():
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "call": "per step and per handle: ps_set_state(body) + ps_step(3) + ps_get_state(body, arena), pinned host buffers; the "
-                            "arenas are split over two handles that the caller alternates (double buffering); host wall clock"},
+                            "arenas are split over %d handles that the caller serves round-robin (multi-buffering); host wall clock" % n_handles},
             "roofline": roofline, "roofline_sense": roofline_sense, "also": also, "cpu_baseline": cpu,
             "stats": {"mean_percent_completion": psd.mean_completion(total_stats), "arenas": int(total_stats.n_arenas),
                       "robots_carrying": int(total_stats.n_carrying), "cache_points": int(total_stats.n_caches),
                       "cached_contacts_per_arena": total_stats.n_contacts / max(1, total_stats.n_arenas)},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
