@@ -483,7 +483,13 @@ struct IslandSlot {
     TC tc[STAGE_TC ? NC_ : 1];
     __device__ __forceinline__ float& CX(int l) { return cx[l]; }
 };
-typedef IslandSlot<kWarpBodies, kWarpContacts, true> WarpSlot;
+// The velocity-phase constraints (TC, 164 B each) stay in HBM / L2 for both slot sizes: staging them made a warp slot 17.7 KB
+// instead of 5.6 KB, and the shared memory the island kernels hold is what keeps the other arena groups' wide kernels off the
+// SMs while an island tail runs (measured: +8.5 % on the whole step in the steady state, profiles/r01_summary.md).
+#ifndef PS_WARP_STAGE_TC
+#define PS_WARP_STAGE_TC 0
+#endif
+typedef IslandSlot<kWarpBodies, kWarpContacts, PS_WARP_STAGE_TC != 0> WarpSlot;
 typedef IslandSlot<kBigBodies, kBigContacts, false> BigSlot;
 
 template <class Slot>
