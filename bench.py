@@ -353,9 +353,10 @@ def main():
     peak, peak_src = measured_peaks()
     c_hat = total_stats.n_touching_points / max(1, total_stats.n_arenas)   # live touching manifold points per arena
     bytes_per_arena_tick = 2.0 * (24.0 * (N_ROBOTS + N_PUCKS) + 24.0 * c_hat + 96.0 * N_ROBOTS)
-    n_phys = max(1, kcnt["physics"])
-    phys_ms = kms["physics"] / n_phys
+    # one World.step launch sequence of one arena group = k_phys_pre + island kernels + k_phys_post, each timed by its own
+    # event pair on the group's stream (the turn-taking wait between the island phase and k_phys_post is outside all three)
     ticks_per_launch = STEP_INTERVAL
+    phys_ms = ticks_per_launch * sum(kms[k] / max(1, kcnt[k]) for k in ("phys_pre", "phys_islands", "phys_post"))
     arenas_per_launch = A / max(1, eng.num_groups)   # every arena group launches its own kernel sequence
     alg_bytes_per_launch = bytes_per_arena_tick * arenas_per_launch * ticks_per_launch
     achieved = alg_bytes_per_launch / (phys_ms / 1000.0) / 1e9 if phys_ms > 0 else 0.0

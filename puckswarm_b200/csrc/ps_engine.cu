@@ -738,57 +738,137 @@ int ps_reset(ps_handle h, const int64_t* seeds) {
     return PS_OK;
 }
 
-// World.step x nTicks for one arena group on its stream
-static int launchPhysics(ps_handle h, ps_engine::Group& G, int nTicks) {
-    ScopedTimer timer(h, 2, G.s);
-    if (h->fused) {
-        k_physics<<<h->nSlots, h->threads, h->smemBytes, G.s>>>(h->kp, nTicks);
+// Arena.step's perturbations for arenas [a0, a0 + n) on stream s (nothing is launched when none is configured)
+static int launchPerturb(ps_handle h, int a0, int n, cudaStream_t s) {
+    if (h->kp.puckShiftStep == -1 && h->kp.puckShuffleStep == -1) return PS_OK;
+    k_perturb<<<std::max(1, std::min(h->nSlots, n)), h->threads, h->smemBytes, s>>>(h->kp, a0, n, h->fused ? 0 : 1);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PS_OK;
+}
+
+// Arena.step of one group on a think tick: perturbations, then on-device sense + think (think == 1) or the step counter alone
+static int launchThinkStage(ps_handle h, ps_engine::Group& G, int think) {
+    int rc = launchPerturb(h, G.a0, G.n, G.s);
+    if (rc != PS_OK) return rc;
+    int R = h->hs.phys.d.R;
+    if (think == 1) {
+        {
+            ScopedTimer timer(h, 0, G.s);
+            rc = h->sd.launchSense(h->kp.env, h->kp.sp, G.s, &h->launches, false, G.a0 * R, G.n * R);
+        }
+        if (rc != PS_OK) return setError(rc, h->sd.error);
+        {
+            ScopedTimer timer(h, 1, G.s);
+            rc = h->sd.launchThink(G.a0, G.n, G.s, &h->launches);
+        }
+        if (rc != PS_OK) return setError(rc, h->sd.error);
+    } else {
+        k_count_step<<<(G.n + 127) / 128, 128, 0, G.s>>>(h->kp.sp.arena + G.a0, G.n);
         h->launches++;
         CUDA_TRY(cudaGetLastError());
-        return PS_OK;
     }
+    return PS_OK;
+}
+
+// Stages A and B of one World.step for one arena group: k_phys_pre on the group's stream, the island kernels beside each
+// other on the group's island streams; the group's stream is left waiting for them.
+static int enqueuePreIslands(ps_handle h, ps_engine::Group& G) {
+    ScopedTimer timer(h, 2, G.s);
     KParams kp = h->kp;
     kp.a0 = G.a0;
     kp.queue = G.q;
-    for (int t = 0; t < nTicks; ++t) {
-        CUDA_TRY(cudaMemsetAsync(G.q.counts, 0, (kQueueBuckets + 1) * sizeof(int), G.s));
-        {
-            ScopedTimer t4(h, 4, G.s);
-            k_phys_pre<<<G.n, 128, 0, G.s>>>(kp);
-        }
-        {
-            ScopedTimer t5(h, 5, G.s);
-            // islands are independent: the oversized ones (one warp each) run beside the lane batches
-            CUDA_TRY(cudaEventRecord(G.evPre, G.s));
-            CUDA_TRY(cudaStreamWaitEvent(G.s2, G.evPre, 0));
-            // the largest islands start first, on a stream of their own
-            CUDA_TRY(cudaStreamWaitEvent(G.sb[kBucketBig], G.evPre, 0));
-            k_island_big<<<std::max(1, std::min(h->bigBlocks, G.n)), 32, sizeof(BigSlot), G.sb[kBucketBig]>>>(kp);
-            CUDA_TRY(cudaEventRecord(G.evb[kBucketBig], G.sb[kBucketBig]));
-            int wb = std::max(1, std::min(h->workerBlocks, G.n * 3));
-            k_island_warp<<<wb, 128, 4 * sizeof(WarpSlot), G.s2>>>(kp);
-            CUDA_TRY(cudaEventRecord(G.evBig, G.s2));
-            int bb = std::max(1, std::min(h->batchBlocks, (G.n * 12 + kBatchThreads - 1) / kBatchThreads));
-            if (h->mergeBatch) {
-                k_island_batch<<<bb * kLaneBuckets, kBatchThreads, (kBatchThreads / 32) * sizeof(LaneSlotsU), G.s>>>(kp, -1, bb);
-            } else {
-                for (int bucket = kLaneBuckets; bucket >= 2; --bucket) {
-                    CUDA_TRY(cudaStreamWaitEvent(G.sb[bucket], G.evPre, 0));
-                    k_island_batch<<<bb, kBatchThreads, (kBatchThreads / 32) * sizeof(LaneSlotsU), G.sb[bucket]>>>(kp, bucket, bb);
-                    CUDA_TRY(cudaEventRecord(G.evb[bucket], G.sb[bucket]));
-                }
-                k_island_batch<<<bb, kBatchThreads, (kBatchThreads / 32) * sizeof(LaneSlotsU), G.s>>>(kp, 1, bb);
-                for (int bucket = 2; bucket <= kLaneBuckets; ++bucket) CUDA_TRY(cudaStreamWaitEvent(G.s, G.evb[bucket], 0));
+    CUDA_TRY(cudaMemsetAsync(G.q.counts, 0, (kQueueBuckets + 1) * sizeof(int), G.s));
+    {
+        ScopedTimer t4(h, 4, G.s);
+        k_phys_pre<<<G.n, 128, 0, G.s>>>(kp);
+    }
+    CUDA_TRY(cudaEventRecord(G.evPre, G.s));
+    {
+        ScopedTimer t5(h, 5, G.s);
+        // islands are independent: the oversized ones (one warp each) run beside the lane batches
+        CUDA_TRY(cudaStreamWaitEvent(G.s2, G.evPre, 0));
+        // the largest islands start first, on a stream of their own
+        CUDA_TRY(cudaStreamWaitEvent(G.sb[kBucketBig], G.evPre, 0));
+        k_island_big<<<std::max(1, std::min(h->bigBlocks, G.n)), 32, sizeof(BigSlot), G.sb[kBucketBig]>>>(kp);
+        CUDA_TRY(cudaEventRecord(G.evb[kBucketBig], G.sb[kBucketBig]));
+        int wb = std::max(1, std::min(h->workerBlocks, G.n * 3));
+        k_island_warp<<<wb, 128, 4 * sizeof(WarpSlot), G.s2>>>(kp);
+        CUDA_TRY(cudaEventRecord(G.evBig, G.s2));
+        int bb = std::max(1, std::min(h->batchBlocks, (G.n * 12 + kBatchThreads - 1) / kBatchThreads));
+        if (h->mergeBatch) {
+            k_island_batch<<<bb * kLaneBuckets, kBatchThreads, (kBatchThreads / 32) * sizeof(LaneSlotsU), G.s>>>(kp, -1, bb);
+        } else {
+            for (int bucket = kLaneBuckets; bucket >= 2; --bucket) {
+                CUDA_TRY(cudaStreamWaitEvent(G.sb[bucket], G.evPre, 0));
+                k_island_batch<<<bb, kBatchThreads, (kBatchThreads / 32) * sizeof(LaneSlotsU), G.sb[bucket]>>>(kp, bucket, bb);
+                CUDA_TRY(cudaEventRecord(G.evb[bucket], G.sb[bucket]));
             }
-            CUDA_TRY(cudaStreamWaitEvent(G.s, G.evBig, 0));
-            CUDA_TRY(cudaStreamWaitEvent(G.s, G.evb[kBucketBig], 0));
+            k_island_batch<<<bb, kBatchThreads, (kBatchThreads / 32) * sizeof(LaneSlotsU), G.s>>>(kp, 1, bb);
+            for (int bucket = 2; bucket <= kLaneBuckets; ++bucket) CUDA_TRY(cudaStreamWaitEvent(G.s, G.evb[bucket], 0));
         }
-        {
-            ScopedTimer t6(h, 6, G.s);
-            k_phys_post<<<G.n, 128, 0, G.s>>>(kp);
+        CUDA_TRY(cudaStreamWaitEvent(G.s, G.evBig, 0));
+        CUDA_TRY(cudaStreamWaitEvent(G.s, G.evb[kBucketBig], 0));
+    }
+    h->launches += 3 + (h->mergeBatch ? 1 : kLaneBuckets);
+    CUDA_TRY(cudaGetLastError());
+    return PS_OK;
+}
+// Stage C (k_phys_post)
+static int enqueuePost(ps_handle h, ps_engine::Group& G) {
+    KParams kp = h->kp;
+    kp.a0 = G.a0;
+    kp.queue = G.q;
+    {
+        ScopedTimer timer(h, 2, G.s);
+        ScopedTimer t6(h, 6, G.s);
+        k_phys_post<<<G.n, 128, 0, G.s>>>(kp);
+    }
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PS_OK;
+}
+
+// RunOffline.step x nTicks for every arena group: {Arena.step on think ticks | nothing} + World.step.
+// (Two ways of steering how the groups overlap were built and measured in the steady state. Chaining the groups'
+// CTA-per-arena sections by events, so that one group's wide kernels run beside the others' island tails instead of beside
+// their wide kernels: slower at every group count -- a wide kernel beside island kernels runs ~2x slower (the island
+// kernels hold the SMs' shared memory), and serialised wide sections then bound the step. Starting the groups out of phase
+// after a fork, by one k_phys_pre or by a whole lane-batch kernel: no measurable difference.)
+// think = 0: no Arena.step (the caller has set the commands and counted the think step), 1: on-device sense + think,
+// 2: perturbations + step counter only (external controller)
+static int enqueueTicks(ps_handle h, int nTicks, int think) {
+    if (h->fused) {
+        ps_engine::Group& G = h->groups[0];
+        int uc = h->updateCount, interval = h->hs.cfg.step_interval, t = 0;
+        while (t < nTicks) {
+            if (think && uc % interval == 0) {
+                int rc = launchThinkStage(h, G, think);
+                if (rc != PS_OK) return rc;
+            }
+            int run = think ? interval - uc % interval : nTicks;
+            if (run > nTicks - t) run = nTicks - t;
+            ScopedTimer timer(h, 2, G.s);
+            k_physics<<<h->nSlots, h->threads, h->smemBytes, G.s>>>(h->kp, run);
+            h->launches++;
+            CUDA_TRY(cudaGetLastError());
+            t += run;
+            uc += run;
         }
-        h->launches += 4 + (h->mergeBatch ? 1 : kLaneBuckets);
-        CUDA_TRY(cudaGetLastError());
+        return PS_OK;
+    }
+    // group-major: a group's whole sequence is enqueued before the next group's. Measured against tick-major enqueueing
+    // (all groups' tick t, then tick t + 1): 36.1 vs 39.8 ms per think step in the steady state -- the head start keeps the
+    // groups out of phase, so one group's CTA-per-arena kernels run beside the other's island tail
+    int interval = h->hs.cfg.step_interval;
+    for (auto& G : h->groups) {
+        if (G.n == 0) continue;
+        for (int t = 0; t < nTicks; ++t) {
+            int uc = h->updateCount + t, rc;
+            if (think && uc % interval == 0 && (rc = launchThinkStage(h, G, think)) != PS_OK) return rc;
+            if ((rc = enqueuePreIslands(h, G)) != PS_OK) return rc;
+            if ((rc = enqueuePost(h, G)) != PS_OK) return rc;
+        }
     }
     return PS_OK;
 }
@@ -814,59 +894,16 @@ static int joinGroups(ps_handle h) {
     return PS_OK;
 }
 
-// Arena.step's perturbations for arenas [a0, a0 + n) on stream s (nothing is launched when none is configured)
-static int launchPerturb(ps_handle h, int a0, int n, cudaStream_t s) {
-    if (h->kp.puckShiftStep == -1 && h->kp.puckShuffleStep == -1) return PS_OK;
-    k_perturb<<<std::max(1, std::min(h->nSlots, n)), h->threads, h->smemBytes, s>>>(h->kp, a0, n, h->fused ? 0 : 1);
-    h->launches++;
-    CUDA_TRY(cudaGetLastError());
-    return PS_OK;
-}
-
 int ps_step(ps_handle h, int n_ticks) {
     if (!h || n_ticks < 0) return setError(PS_E_INVALID, "bad argument");
     if (!h->isReset) return setError(PS_E_INVALID, "ps_reset or ps_set_state first");
     CUDA_TRY(cudaSetDevice(h->device));
-    int interval = h->hs.cfg.step_interval;
     bool onDevice = h->hs.cfg.controller != PS_CTRL_EXTERNAL;
     if (onDevice && !h->sd.ready) return setError(PS_E_NOCALIB, "ps_load_calibration has not been called");
     int rc = forkGroups(h);
     if (rc != PS_OK) return rc;
-    int R = h->hs.phys.d.R;
-    for (auto& G : h->groups) {
-        if (G.n == 0) continue;
-        int uc = h->updateCount;
-        int t = 0;
-        while (t < n_ticks) {
-            if (uc % interval == 0) {
-                rc = launchPerturb(h, G.a0, G.n, G.s);
-                if (rc != PS_OK) return rc;
-                if (onDevice) {
-                    {
-                        ScopedTimer timer(h, 0, G.s);
-                        rc = h->sd.launchSense(h->kp.env, h->kp.sp, G.s, &h->launches, false, G.a0 * R, G.n * R);
-                    }
-                    if (rc != PS_OK) return setError(rc, h->sd.error);
-                    {
-                        ScopedTimer timer(h, 1, G.s);
-                        rc = h->sd.launchThink(G.a0, G.n, G.s, &h->launches);
-                    }
-                    if (rc != PS_OK) return setError(rc, h->sd.error);
-                } else {
-                    k_count_step<<<(G.n + 127) / 128, 128, 0, G.s>>>(h->kp.sp.arena + G.a0, G.n);
-                    h->launches++;
-                    CUDA_TRY(cudaGetLastError());
-                }
-            }
-            // run up to the next think tick
-            int run = interval - uc % interval;
-            if (run > n_ticks - t) run = n_ticks - t;
-            rc = launchPhysics(h, G, run);
-            if (rc != PS_OK) return rc;
-            t += run;
-            uc += run;
-        }
-    }
+    rc = enqueueTicks(h, n_ticks, onDevice ? 1 : 2);
+    if (rc != PS_OK) return rc;
     h->updateCount += n_ticks;
     h->groupsDirty = true;
     return PS_OK;
@@ -899,11 +936,8 @@ int ps_step_external(ps_handle h, const float* forwards, const float* torque) {
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     int rc = forkGroups(h);
     if (rc != PS_OK) return rc;
-    for (auto& G : h->groups) {
-        if (G.n == 0) continue;
-        rc = launchPhysics(h, G, h->hs.cfg.step_interval);
-        if (rc != PS_OK) return rc;
-    }
+    rc = enqueueTicks(h, h->hs.cfg.step_interval, 0);
+    if (rc != PS_OK) return rc;
     h->updateCount += h->hs.cfg.step_interval;
     h->groupsDirty = true;
     return PS_OK;

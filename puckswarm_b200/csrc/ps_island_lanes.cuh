@@ -358,6 +358,78 @@ __device__ __forceinline__ float lkCorrectPoint(const PhysEnv& e, const BT& L, i
     return separation;
 }
 
+// The same correction by a PAIR of lanes (warp-per-island solver): both lanes evaluate the point identically, then lane
+// `side` 0 moves body A and lane `side` 1 moves body B, so the two bodies' updates (for a robot: the transform with its two
+// table look-ups) leave each other's dependency chain. x - y == x + (-y) and (-m) * P == -(m * P) exactly, so "own body,
+// signed inverse masses" is the reference's arithmetic bit for bit. Every lane of the warp calls this together (inactive
+// lanes with on = false): the reads of a point are separated from its writes, and the writes from the next reads, by
+// warp barriers.
+template <class BT>
+__device__ __forceinline__ float lkCorrectPointPair(const PhysEnv& e, const BT& L, bool on, int side, int A, int B, int type, V2 localNormal, V2 localPoint,
+                                                    V2 pointLocal, float radius, bool* changed) {
+    float separation = 0.0f;
+    bool write = false;
+    int me = side ? B : A;
+    V2 nc = mk(0.0f, 0.0f);
+    float na = 0.0f;
+    if (on) {
+        Xf xfA, xfB;
+        xfA.px = L.px(A);
+        xfA.py = L.py(A);
+        xfA.c = L.c(A);
+        xfA.s = L.s(A);
+        xfB.px = L.px(B);
+        xfB.py = L.py(B);
+        xfB.c = L.c(B);
+        xfB.s = L.s(B);
+        bool faceB = type == MF_FACE_B;
+        Xf xfRef = faceB ? xfB : xfA, xfInc = faceB ? xfA : xfB;
+        V2 p1 = mulX(xfRef, localPoint), p2 = mulX(xfInc, pointLocal);
+        V2 normal, point;
+        if (type == MF_CIRCLES) {
+            if (distSq(p1, p2) > kEpsilon * kEpsilon) {
+                normal = p2 - p1;
+                normalize(normal);
+            } else {
+                normal = mk(1.0f, 0.0f);
+            }
+            point = 0.5f * (p1 + p2);
+            separation = dot(p2 - p1, normal) - radius;
+        } else {
+            normal = mulR(xfRef, localNormal);
+            separation = dot(p2 - p1, normal) - radius;
+            point = p2;
+            if (faceB) normal = -normal;
+        }
+        float C = clampf(kContactBaumgarte * (separation + kLinearSlop), -kMaxLinearCorrection, 0.0f);
+        if (C != 0.0f) {
+            V2 cA = mk(L.cx(A), L.cy(A)), cB = mk(L.cx(B), L.cy(B));
+            V2 rA = point - cA, rB = point - cB;
+            float invMassA = L.pm(A), invIA = L.pi(A), invMassB = L.pm(B), invIB = L.pi(B);
+            float rnA = cross(rA, normal), rnB = cross(rB, normal);
+            float K = invMassA + invMassB + invIA * rnA * rnA + invIB * rnB * rnB;
+            float impulse = K > 0.0f ? -C / K : 0.0f;
+            V2 P = impulse * normal;
+            V2 cM = side ? cB : cA, rM = side ? rB : rA;
+            float sm = side ? invMassB : -invMassA, si = side ? invIB : -invIA;
+            float oa = L.a(me);
+            nc = cM + sm * P;
+            na = oa + si * cross(rM, P);
+            write = nc.x != cM.x || nc.y != cM.y || na != oa;
+        }
+    }
+    __syncwarp();
+    if (write) {
+        L.cx(me) = nc.x;
+        L.cy(me) = nc.y;
+        L.a(me) = na;
+        lkSyncXf(e, L, me);
+        *changed = true;
+    }
+    __syncwarp();
+    return separation;
+}
+
 // Island.solve step 6 for staged body l (= integrateBody); the start-of-step pose / transform go straight to HBM
 template <class BT>
 __device__ __forceinline__ void lkIntegrate(const PhysEnv& e, const PhysWork& g, const BT& L, int l) {
@@ -511,21 +583,6 @@ struct SlotCtx {
     __device__ __forceinline__ int gidx(int l) const { return S->gidx[l]; }
 };
 
-// position correction of both points of staged constraint ci; returns the smaller separation
-template <class Slot>
-__device__ __forceinline__ float slotCorrect(const PhysEnv& e, const SlotCtx<Slot>& L, Slot& s, int ci, bool* changed) {
-    uint32_t hd = s.pcHead[ci];
-    int bA = (int)(hd & 255u), bB = (int)((hd >> 8) & 255u), type = (int)((hd >> 16) & 255u), np = (int)(hd >> 24);
-    V2 ln = mk(s.pc[ci][0], s.pc[ci][1]), lp = mk(s.pc[ci][2], s.pc[ci][3]);
-    float radius = s.pc[ci][8];
-    float minSep = 0.0f;
-    for (int j2 = 0; j2 < np; ++j2) {
-        float sep = lkCorrectPoint(e, L, bA, bB, type, ln, lp, mk(s.pc[ci][4 + 2 * j2], s.pc[ci][5 + 2 * j2]), radius, changed);
-        minSep = fminf_(minSep, sep);
-    }
-    return minSep;
-}
-
 // Returns false if the island does not fit the slot (the caller falls back to the sequential path).
 template <class Slot>
 __device__ __forceinline__ bool islandSolveSlot(const PhysEnv& e, const PhysWork& wk, const ArenaState& st, int k, Slot& s, int* itersOut) {
@@ -663,8 +720,23 @@ __device__ __forceinline__ bool islandSolveSlot(const PhysEnv& e, const PhysWork
         float minSep = 0.0f;
         bool changed = false;
         for (int r = 0; r < nRows; ++r) {
-            for (int q = s.rowStart[r] + lane; q < s.rowStart[r + 1]; q += 32) minSep = fminf_(minSep, slotCorrect(e, L, s, s.sched[q], &changed));
-            __syncwarp();
+            // a lane pair per constraint of the row (16 constraints per pass; a row rarely holds more than three)
+            int rowEnd = s.rowStart[r + 1];
+            for (int base = s.rowStart[r]; base < rowEnd; base += 16) {
+                int q = base + (lane >> 1);
+                bool on = q < rowEnd;
+                int ci = on ? s.sched[q] : 0;
+                uint32_t hd = on ? s.pcHead[ci] : 0u;
+                int bA = (int)(hd & 255u), bB = (int)((hd >> 8) & 255u), type = (int)((hd >> 16) & 255u), np = (int)(hd >> 24);
+                V2 ln = mk(s.pc[ci][0], s.pc[ci][1]), lp = mk(s.pc[ci][2], s.pc[ci][3]);
+                float radius = s.pc[ci][8];
+                float sep0 = lkCorrectPointPair(e, L, on && np > 0, lane & 1, bA, bB, type, ln, lp, mk(s.pc[ci][4], s.pc[ci][5]), radius, &changed);
+                minSep = fminf_(minSep, sep0);
+                if (__any_sync(FULL, np > 1)) {
+                    float sep1 = lkCorrectPointPair(e, L, on && np > 1, lane & 1, bA, bB, type, ln, lp, mk(s.pc[ci][6], s.pc[ci][7]), radius, &changed);
+                    minSep = fminf_(minSep, sep1);
+                }
+            }
         }
         for (int o = 16; o > 0; o >>= 1) {
             float other = __shfl_xor_sync(FULL, minSep, o);

@@ -12,8 +12,9 @@ e.step(warm)
 e.island_hist()
 t = time.time(); e.step(30); e.get_state(); dt = time.time() - t
 print('robot-steps/s', A * 16 * 30 / dt)
-h = e.island_hist().astype(np.float64)
-worst = int(h[7, 7]); h[7, 7] = 0
+h = e.island_hist()
+worst = int(h[7, 7]); h[7, 7] = 0; h = h.astype(np.float64)
+print('slowest warp / big island: kcycles', worst >> 32, 'contacts', (worst >> 20) & 0xFFF, 'bodies', (worst >> 10) & 0x3FF, 'sweeps', worst & 0x3FF, 'fit_slot', not bool(worst & (1 << 31)), 'unfit islands', int(h[7, 6]))
 print('islands (>=3 contacts) per arena-tick by [iterations x contacts]; rows iters <=1,<=3,<=6,<=12,<=25,<=50,<100,100; cols contacts <=3,5,8,12,16,32,64,>64')
 np.set_printoptions(linewidth=200, suppress=True)
 print(np.round(h / (A * 30.0), 3))
