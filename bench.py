@@ -391,7 +391,10 @@ def main():
     ncu_traffic = os.path.join(ROOT, "profiles", "k_physics_traffic.json")
     if os.path.exists(ncu_traffic):
         try:
-            roofline["traffic"] = json.load(open(ncu_traffic)).get("dram_bytes_per_launch")
+            # per launch like `achieved`: the ncu capture's DRAM bytes per arena-tick x the arenas and ticks of one launch sequence
+            per_arena_tick = json.load(open(ncu_traffic)).get("dram_bytes_per_arena_tick")
+            roofline["traffic"] = per_arena_tick * arenas_per_launch * ticks_per_launch
+            roofline["traffic_bytes_per_arena_tick"] = per_arena_tick
         except Exception:
             pass
 
