@@ -49,7 +49,7 @@ public final class ArenaB200 {
     public static final class Config {
         public int nArenas = 1, nRobots = 4, nPucks = 10, nPuckTypes = 2, stepInterval = 3;
         public java.util.Properties properties = new java.util.Properties();
-        public ByteBuffer toBuffer() { throw new UnsupportedOperationException("fill the 42 fields of ps_config in header order; ps_struct_size(0) gives the size to check against"); }
+        public ByteBuffer toBuffer() { throw new UnsupportedOperationException("fill the 44 fields of ps_config in header order; ps_struct_size(0) gives the size to check against"); }
     }
     public static final class Calibration { public ByteBuffer xrYr, xy, flags; public int n, width, height; }
 }

@@ -270,6 +270,8 @@ def test_errors_are_loud():
     bad = abi.config_defaults(n_arenas=0)
     with pytest.raises(engine.EngineError):
         engine.Engine(bad, device=0)
+    with pytest.raises(engine.EngineError):      # stepCount % 0 throws in the reference
+        engine.Engine(abi.config_defaults(n_arenas=1, puck_shift_step=0), device=0)
 
 
 def test_baseline_config_1_and_2():

@@ -34,6 +34,10 @@ def test_properties_to_config(tmp_path):
         host.Experiment(0, {"Arena.nRobots": "four"}).getProperty("Arena.nRobots", 4)
     with pytest.raises(ValueError):
         host.Experiment(0, {"controllerType": "Nope"}).to_config()
+    # perturbation periods (Arena.java:187-188): absent = -1 = never
+    assert (cfg.puck_shift_step, cfg.puck_shuffle_step, cfg.n_informed_robots) == (-1, -1, 0)
+    c2 = host.Experiment(0, {"Arena.puckShiftStep": "5000", "Arena.puckShuffleStep": "2500", "Arena.nInformedRobots": "2"}).to_config()
+    assert (c2.puck_shift_step, c2.puck_shuffle_step, c2.n_informed_robots) == (5000, 2500, 2)
 
 
 @pytest.mark.gpu
