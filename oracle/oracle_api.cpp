@@ -288,7 +288,13 @@ int orc_get_state(orc_batch* b, ps_state_view* v) {
             }
         }
         if (v->robot)
-            for (int r = 0; r < R; r++) packRobot(a.robots[r], v->robot + ai * R + r, b->cfg.controller);
+            for (int r = 0; r < R; r++) {
+                ps_robot_state* o = v->robot + ai * R + r;
+                packRobot(a.robots[r], o, b->cfg.controller);
+                o->rng_seed = a.robots[r].rng->seed;
+                o->rng_have_gaussian = a.robots[r].rng->haveNextNextGaussian ? 1 : 0;
+                o->rng_next_gaussian = a.robots[r].rng->nextNextGaussian;
+            }
         if (v->arena) {
             ps_arena_state* s = v->arena + ai;
             std::memset(s, 0, sizeof(*s));
@@ -364,7 +370,13 @@ int orc_set_state(orc_batch* b, const ps_state_view* v) {
             }
         }
         if (v->robot)
-            for (int r = 0; r < R; r++) unpackRobot(a.robots[r], v->robot + ai * R + r, b->cfg.controller);
+            for (int r = 0; r < R; r++) {
+                const ps_robot_state* o = v->robot + ai * R + r;
+                unpackRobot(a.robots[r], o, b->cfg.controller);
+                a.robots[r].rng->seed = o->rng_seed;
+                a.robots[r].rng->haveNextNextGaussian = o->rng_have_gaussian != 0;
+                a.robots[r].rng->nextNextGaussian = o->rng_next_gaussian;
+            }
         if (v->arena) {
             const ps_arena_state* s = v->arena + ai;
             a.rng.seed = s->rng_seed;

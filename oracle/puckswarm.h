@@ -1156,6 +1156,9 @@ struct BHDController : Controller {  // src/controllers/BHDController.java:126-1
 // ---- arena.Robot / arena.Puck / arena.DotPuck ----
 struct Robot {
     jb::Body* body = nullptr;
+    // PS_RNG_PER_ROBOT: the robot's own java.util.Random(seed * 1000003 + 7919 * (index + 1)) (an engine option for throughput
+    // runs; the reference shares one Random per experiment, Experiment.java:22). On the heap: controllers keep a pointer to it.
+    std::unique_ptr<JavaRandom> rng;
     std::unique_ptr<Controller> controller;
     LocalMap localMap;
     std::vector<uint8_t> image;  // STCameraImage.pixels[x][y] at x*H + y
@@ -1198,6 +1201,7 @@ struct Arena {
     ps_config cfg;
     const Calibration* calib;
     JavaRandom rng;
+    int64_t episodeSeed = 0;
     std::unique_ptr<jb::World> world;
     Enclosure enclosure;
     std::vector<Robot> robots;
@@ -1277,9 +1281,11 @@ struct Arena {
         r.localMap.CARRY_THRESHOLD_LO = cfg.carry_threshold_lo;
         r.localMap.CARRY_THRESHOLD_HI = cfg.carry_threshold_hi;
         r.image.assign((size_t)calib->imageWidth * calib->imageHeight, PS_T_NOTHING);
-        if (cfg.controller == PS_CTRL_BHD) r.controller.reset(new BHDController(&cfg, &rng));
-        else if (cfg.controller == PS_CTRL_PROBSEEK) r.controller.reset(new ProbSeekController(&cfg, &rng));
-        else r.controller.reset(new CacheConsController(&cfg, &rng, presetCaches));
+        r.rng.reset(new JavaRandom(episodeSeed * 1000003LL + 7919LL * (int64_t)robots.size()));
+        JavaRandom* stream = cfg.rng_mode == PS_RNG_PER_ROBOT ? r.rng.get() : &rng;
+        if (cfg.controller == PS_CTRL_BHD) r.controller.reset(new BHDController(&cfg, stream));
+        else if (cfg.controller == PS_CTRL_PROBSEEK) r.controller.reset(new ProbSeekController(&cfg, stream));
+        else r.controller.reset(new CacheConsController(&cfg, stream, presetCaches));
         // VFHPlus re-runs initDataStructures on its first computeTurnAngle (propertiesUpdated is set by the
         // constructor, VFHPlus.java:167,227-230); nothing touches the histograms before that, so doing it here
         // is equivalent and lets set_state restore binaryHistogram at any time.
@@ -1299,6 +1305,7 @@ struct Arena {
     }
     // RunOffline.recreateArena (:97-113) + new Arena(world, null, false) (Arena.java:45-120) for Experiment(seed)
     void reset(int64_t seed) {
+        episodeSeed = seed;
         rng.setSeed(seed);
         newWorld();
         robots.reserve(cfg.n_robots);

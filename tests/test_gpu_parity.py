@@ -384,3 +384,19 @@ def test_puck_shift_and_shuffle(controller, shift, shuffle, shape):
         bad = parity.compare_states(e.get_state(), o.get_state(), A, tol=0.0 if controller == abi.PS_CTRL_EXTERNAL else TOL)
         assert bad == [], "think step %d: %s" % (k, bad[:4])
     assert (e.get_state().arena["error_flags"] == 0).all()
+
+
+@pytest.mark.parametrize("controller", [abi.PS_CTRL_CACHECONS, abi.PS_CTRL_BHD])
+def test_per_robot_rng_streams(controller):
+    """PS_RNG_PER_ROBOT: one java.util.Random per robot (the engine's throughput option) -- the oracle runs the same streams."""
+    import parity
+    A, R, P = 4, 6, 80
+    cfg = abi.config_defaults(n_arenas=A, n_robots=R, n_pucks=P, controller=controller, rng_mode=abi.PS_RNG_PER_ROBOT)
+    e, o = _engine(cfg), _oracle(cfg)
+    e.reset(np.arange(A))
+    o.reset(np.arange(A))
+    for k in range(40):
+        o.step(3)
+        e.step(3)
+        bad = parity.compare_states(e.get_state(), o.get_state(), A, tol=TOL)
+        assert bad == [], "think step %d: %s" % (k, bad[:4])

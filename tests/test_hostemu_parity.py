@@ -161,3 +161,23 @@ def test_puck_shuffle_every_step_dense():
         e.step(3)
         bad = parity.compare_states(e.get_state(), o.get_state(), A)
         assert bad == [], "think step %d: %s" % (k, bad[:4])
+
+
+@pytest.mark.parametrize("controller", [abi.PS_CTRL_CACHECONS, abi.PS_CTRL_BHD, abi.PS_CTRL_PROBSEEK])
+def test_per_robot_rng_streams(controller):
+    """PS_RNG_PER_ROBOT (the engine's throughput option: one java.util.Random per robot instead of the experiment's shared
+    one): same streams, same draws, the arena's generator untouched by the controllers."""
+    A, R, P = 2, 5, 60
+    cfg = abi.config_defaults(n_arenas=A, n_robots=R, n_pucks=P, controller=controller, rng_mode=abi.PS_RNG_PER_ROBOT)
+    e, o = emu.Emu(cfg), oracle.Oracle(cfg)
+    e.reset([7, 8])
+    o.reset([7, 8])
+    arena_seed = o.get_state().arena["rng_seed"].copy()
+    for k in range(60):
+        o.step(3)
+        e.step(3)
+        so = o.get_state()
+        bad = parity.compare_states(e.get_state(), so, A)
+        assert bad == [], "think step %d: %s" % (k, bad[:4])
+    assert np.array_equal(so.arena["rng_seed"], arena_seed)
+    assert len(np.unique(so.robot["rng_seed"])) == A * R
