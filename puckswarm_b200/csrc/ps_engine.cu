@@ -651,7 +651,7 @@ int ps_create(const ps_config* cfg, int device, ps_handle* out) {
         TRY_OR_FREE(cudaMalloc(&e->kp.arenaScratch, nBlocks * e->kp.arenaScratchStride + 256));
         TRY_OR_FREE(cudaMemset(e->kp.arenaScratch, 0, nBlocks * e->kp.arenaScratchStride + 256));
         // arena groups, each with its own streams, events and island queue
-        int nGroups = (int)envSize("PS_GROUPS", 2);
+        int nGroups = (int)envSize("PS_GROUPS", 1);
         if (e->fused || nGroups < 1) nGroups = 1;
         if ((size_t)nGroups > A) nGroups = (int)A;
         size_t perGroup = (A + nGroups - 1) / nGroups;

@@ -287,7 +287,17 @@ struct SenseDevice {
     int launchThink(int firstArena, int nArenas, cudaStream_t stream, int64_t* launches) {
         SenseKParams p = kp;
         p.r0 = firstArena;
-        k_think<<<nArenas, 128, 0, stream>>>(p);
+        // CTA width by batch size. The stage is the robots' controllers one after the other (shared java.util.Random), with a
+        // barrier between every parallel piece and the serial state machine. When the launch fills the GPU, one warp per arena
+        // wins (a one-warp barrier costs nothing and four times as many arenas are resident: 2.60 / 1.92 / 1.51 ms per 4096
+        // arenas with 128 / 64 / 32 threads); a small launch is one arena's latency, which 128 threads cut (1024 arenas:
+        // 0.72 ms with 128 threads, 1.19 ms with 32). PS_THINK_THREADS overrides.
+        int thinkThreads = nArenas >= 2368 ? 32 : (nArenas >= 1184 ? 64 : 128);
+        {
+            const char* v = getenv("PS_THINK_THREADS");
+            if (v && *v) thinkThreads = atoi(v) < 64 ? 32 : (atoi(v) < 128 ? 64 : 128);
+        }
+        k_think<<<nArenas, thinkThreads, 0, stream>>>(p);
         (*launches)++;
         if (cudaGetLastError() != cudaSuccess) return fail(PS_E_CUDA, "k_think launch failed");
         return PS_OK;

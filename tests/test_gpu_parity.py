@@ -400,3 +400,21 @@ def test_per_robot_rng_streams(controller):
         e.step(3)
         bad = parity.compare_states(e.get_state(), o.get_state(), A, tol=TOL)
         assert bad == [], "think step %d: %s" % (k, bad[:4])
+
+
+@pytest.mark.parametrize("threads", ["32", "64"])
+def test_think_stage_cta_widths(threads, monkeypatch):
+    """k_think picks its CTA width by batch size (one warp per arena for launches that fill the GPU); the narrow widths,
+    which small test batches would not reach, forced here."""
+    import parity
+    monkeypatch.setenv("PS_THINK_THREADS", threads)
+    A, R, P = 3, 8, 100
+    cfg = abi.config_defaults(n_arenas=A, n_robots=R, n_pucks=P, controller=abi.PS_CTRL_CACHECONS)
+    e, o = _engine(cfg), _oracle(cfg)
+    e.reset(np.arange(A))
+    o.reset(np.arange(A))
+    for k in range(40):
+        o.step(3)
+        e.step(3)
+        bad = parity.compare_states(e.get_state(), o.get_state(), A, tol=TOL)
+        assert bad == [], "think step %d: %s" % (k, bad[:4])

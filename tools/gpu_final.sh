@@ -9,7 +9,7 @@ python bench.py --steps 20 --warmup 5 > gpurun_out/bench_early.json 2>> gpurun_o
 python bench.py --impl reference > gpurun_out/bench_reference.json 2>> gpurun_out/bench.err; echo "ref rc=$?"; cut -c1-200 gpurun_out/bench_reference.json
 CMD="python bench.py --steps 2 --warmup 100 --no-cpu-baseline --no-extras"
 $CMD > gpurun_out/plain.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 3500 --launch-count 300 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 1750 --launch-count 150 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
 echo "ncu list rc=$?"
 CMD2="python bench.py --steps 2 --warmup 100 --no-cpu-baseline --no-extras --arenas 1024"
 PS_GROUPS=1 $CMD2 > gpurun_out/plain2.log 2>&1 && \
