@@ -363,7 +363,7 @@ def main():
     top = ("sense", "think", "physics", "other")
     total_k = sum(kms[k] for k in top)
     roofline = {
-        "kernel": "World.step pipeline (k_phys_pre + k_island_worker + k_phys_post) x %d ticks" % ticks_per_launch,
+        "kernel": "World.step pipeline (k_phys_pre + k_island_big | k_island_warp | k_island_batch + k_phys_post) x %d ticks" % ticks_per_launch,
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
         "traffic": None,
         "algorithmic_bytes_per_arena_tick": bytes_per_arena_tick, "touching_points_per_arena": c_hat,
