@@ -257,16 +257,16 @@ def main():
     value = robot_steps / (ms_max / 1000.0)
 
     # ---- end to end through the C-ABI with host buffers ("e2e") ----
-    # The caller splits its arenas over a few handles and serves them round-robin: while it waits for one handle's download,
-    # the others are stepping (plain multi-buffering; with a single handle every step would begin with the whole GPU waiting
-    # on the copies). Every step of every handle uploads its bodies' poses / velocities from pinned memory, steps, and
-    # downloads them with the step counters.
+    # Every step uploads the bodies' poses / velocities from pinned memory, steps, and downloads them with the step counters.
+    # PS_E2E_HANDLES > 1 splits the arenas over several handles served round-robin, so that one handle's copies overlap the
+    # others' stepping; measured in the steady state the copies (2 x 21 MB per step) cost less than what kernels of several
+    # handles running side by side lose: 5.64 / 5.37 / 5.22 M robot-steps/s with 1 / 2 / 4 handles. One handle is the default.
     sense_dbg = eng.sense_stats().reshape(-1, 8).astype(np.float64)
     n_groups = eng.num_groups
     import ctypes as C
     halves = []
     old_groups = os.environ.get("PS_GROUPS")
-    n_handles = int(os.environ.get("PS_E2E_HANDLES", "4"))
+    n_handles = int(os.environ.get("PS_E2E_HANDLES", "1"))
     os.environ["PS_GROUPS"] = str(max(1, n_groups // n_handles))
     h2d = d2h = 0
     for hi in range(n_handles):
@@ -413,8 +413,8 @@ def main():
             "config": workload_config(A * world, "arenas sharded by index, %d per GPU, one process per GPU" % A),
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "call": "per step and per handle: ps_set_state(body) + ps_step(3) + ps_get_state(body, arena), pinned host buffers; the "
-                            "arenas are split over %d handles that the caller serves round-robin (multi-buffering); host wall clock" % n_handles},
+                    "call": "per step and per handle: ps_set_state(body) + ps_step(3) + ps_get_state(body, arena), pinned host buffers; "
+                            "%d handle(s) served round-robin; host wall clock" % n_handles},
             "roofline": roofline, "roofline_sense": roofline_sense, "also": also, "cpu_baseline": cpu,
             "stats": {"mean_percent_completion": psd.mean_completion(total_stats), "arenas": int(total_stats.n_arenas),
                       "robots_carrying": int(total_stats.n_carrying), "cache_points": int(total_stats.n_caches),
