@@ -392,16 +392,19 @@ PS_HD void senseRobot(Ctx& ctx, const PhysEnv& e, const SenseTables& T, const Se
                 ++visited;
                 V2 bp = mk(wk.candX[c], wk.candY[c]);
                 float d2 = distSq(bp, g);
-                if (d2 > 484.0f) continue;
                 int b = wk.candBody[c];
-                if (!(g.x <= wk.candUx[c] && g.x >= wk.candLx[c] && g.y <= wk.candUy[c] && g.y >= wk.candLy[c])) continue;
                 if (b < d.P) {
-                    // inner disc, centre = body origin: (g - c).(g - c) <= r * r, same magnitude as d2
-                    if (d2 <= innerRSq) {
+                    // inner disc, centre = body origin: (g - c).(g - c) <= r * r, same magnitude as d2. The reference tests the
+                    // 22 cm body radius and the fixture's AABB first; all three are pure predicates, so the cheap, rarely true
+                    // one goes first here (it implies d2 <= 484: the disc radius is 2.1), and the box (four loads) is only
+                    // looked at for the few pixels inside the disc
+                    if (d2 <= innerRSq && g.x <= wk.candUx[c] && g.x >= wk.candLx[c] && g.y <= wk.candUy[c] && g.y >= wk.candLy[c]) {
                         type = wk.candType[c];
                         hit = true;
                     }
                 } else {
+                    if (d2 > 484.0f) continue;
+                    if (!(g.x <= wk.candUx[c] && g.x >= wk.candLx[c] && g.y <= wk.candUy[c] && g.y >= wk.candLy[c])) continue;
                     Xf o;
                     o.px = bp.x;
                     o.py = bp.y;
