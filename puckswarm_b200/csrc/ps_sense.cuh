@@ -912,6 +912,43 @@ PS_HD void localMapFinalFilter(const SenseCfg& sc, const SenseHead& head, ps_loc
     lm.right_sum = head.rightSum;
 }
 
+#if defined(__CUDACC__)
+// localMapFinalFilter by one warp. The clusters are still visited one after the other (a cluster removed earlier no longer
+// counts as a neighbour of the later ones), but "some puck of c lies within the threshold of some puck of a kept cluster
+// of another colour" is an existence test over puck pairs, so the lanes share the pairs and vote.
+__device__ __forceinline__ void localMapFinalFilterWarp(const SenseCfg& sc, const SenseHead& head, ps_localmap& lm, int lane) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    int nP = lm.n_pucks, nC = lm.n_clusters;
+    bool carrying = lm.carrying != 0;
+    for (int c = 0; c < nC; ++c) {
+        if (!lm.cluster_kept[c]) continue;   // shared memory, same for every lane
+        bool remove = false;
+        if (carrying && c == lm.carried_cluster) remove = true;
+        else if (!lmReachable(lm.cluster_x[c], lm.cluster_y[c])) remove = true;
+        else if (carrying && lm.carried_type != lm.cluster_type[c]) remove = true;
+        else if (carrying) {
+            bool found = false;
+            int typeC = lm.cluster_type[c];
+            for (int idx = lane; idx < nP * nP && !found; idx += 32) {
+                int pi = idx / nP, q = idx - pi * nP;
+                if (lm.puck_cluster[pi] != c) continue;
+                int o = lm.puck_cluster[q];
+                if (o == c || !lm.cluster_kept[o] || lm.cluster_type[o] == typeC) continue;
+                if (dist(mk(lm.puck_x[pi], lm.puck_y[pi]), mk(lm.puck_x[q], lm.puck_y[q])) < sc.clusterThreshold) found = true;
+            }
+            remove = __any_sync(FULL, found);
+        }
+        __syncwarp();
+        if (remove && lane == 0) lm.cluster_kept[c] = 0;
+        __syncwarp();
+    }
+    if (lane == 0) {
+        lm.left_sum = head.leftSum;
+        lm.right_sum = head.rightSum;
+    }
+}
+#endif
+
 PS_HD void localMapFromBlobs(const SenseTables& T, const SenseCfg& sc, const SenseHead& head, const BlobRec* blobs, const uint8_t* occ,
                              ps_robot_state* rstate, ps_localmap& lm) {
     localMapPucksAndClusters(T, sc, head, blobs, rstate, lm);

@@ -49,7 +49,8 @@ __global__ void __launch_bounds__(256) k_sense(SenseKParams p) {
 
 // LocalMap stage: one warp per robot over the whole batch. The local map is built in shared memory: lane 0 walks the
 // blob list like LocalMap.extractPucks / extractClusters do, all lanes share the scan of the occupancy grid for ROBOT
-// cells, lane 0 finishes the cluster filter, and the warp writes the struct out coalesced.
+// cells, the warp finishes the cluster filter (clusters in order, the puck pairs of a cluster shared by the lanes), and
+// the warp writes the struct out coalesced.
 __global__ void __launch_bounds__(128) k_localmap(SenseKParams p, int nRobots) {
     __shared__ ps_localmap lmS[4];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(128) k_localmap(SenseKParams p, int nRobots) {
     __syncwarp();
     localMapRobotFilter(p.T, occ, lm, lane, 32);
     __syncwarp();
-    if (lane == 0) localMapFinalFilter(p.sc, p.senseHead[ri], lm);
+    localMapFinalFilterWarp(p.sc, p.senseHead[ri], lm, lane);
     __syncwarp();
     uint32_t* g = (uint32_t*)(p.obs.lm + ri);
     for (int i = lane; i < (int)(sizeof(ps_localmap) / 4); i += 32) g[i] = w[i];
