@@ -418,3 +418,22 @@ def test_think_stage_cta_widths(threads, monkeypatch):
         e.step(3)
         bad = parity.compare_states(e.get_state(), o.get_state(), A, tol=TOL)
         assert bad == [], "think step %d: %s" % (k, bad[:4])
+
+
+@pytest.mark.parametrize("shape", [(1, 2, 0, 2, abi.PS_CTRL_BHD), (2, 3, 7, 2, abi.PS_CTRL_CACHECONS), (1, 1, 5, 5, abi.PS_CTRL_PROBSEEK),
+                                   (1, 6, 3, 3, abi.PS_CTRL_CACHECONS), (1, 2, 16, 8, abi.PS_CTRL_CACHECONS)])
+def test_edge_shapes(shape):
+    """Empty and ragged inputs on the device: no pucks, a puck count the colours do not divide, a single robot, more robots
+    than pucks, all eight colours."""
+    import parity
+    A, R, P, K, ctrl = shape
+    cfg = abi.config_defaults(n_arenas=A, n_robots=R, n_pucks=P, n_puck_types=K, controller=ctrl)
+    e, o = _engine(cfg), _oracle(cfg)
+    e.reset(np.arange(A))
+    o.reset(np.arange(A))
+    for k in range(30):
+        o.step(3)
+        e.step(3)
+        bad = parity.compare_states(e.get_state(), o.get_state(), A, tol=TOL)
+        assert bad == [], "think step %d: %s" % (k, bad[:4])
+    assert (e.get_state().arena["error_flags"] == 0).all()

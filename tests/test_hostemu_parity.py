@@ -181,3 +181,21 @@ def test_per_robot_rng_streams(controller):
         assert bad == [], "think step %d: %s" % (k, bad[:4])
     assert np.array_equal(so.arena["rng_seed"], arena_seed)
     assert len(np.unique(so.robot["rng_seed"])) == A * R
+
+
+@pytest.mark.parametrize("shape", [(1, 2, 0, 2, abi.PS_CTRL_BHD), (2, 3, 7, 2, abi.PS_CTRL_CACHECONS), (1, 1, 5, 5, abi.PS_CTRL_PROBSEEK),
+                                   (1, 6, 3, 3, abi.PS_CTRL_CACHECONS), (1, 2, 16, 8, abi.PS_CTRL_CACHECONS)])
+def test_edge_shapes(shape):
+    """Empty and ragged inputs: no pucks at all, a puck count the colours do not divide (Arena.java:91-95 drops the remainder),
+    a single robot, more robots than pucks, all eight colours."""
+    A, R, P, K, ctrl = shape
+    cfg = abi.config_defaults(n_arenas=A, n_robots=R, n_pucks=P, n_puck_types=K, controller=ctrl)
+    e, o = emu.Emu(cfg), oracle.Oracle(cfg)
+    e.reset(np.arange(A))
+    o.reset(np.arange(A))
+    assert e.get_state().body.shape[2] == P // K * K + R
+    for k in range(30):
+        o.step(3)
+        e.step(3)
+        bad = parity.compare_states(e.get_state(), o.get_state(), A)
+        assert bad == [], "think step %d: %s" % (k, bad[:4])
