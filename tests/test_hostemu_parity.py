@@ -199,3 +199,12 @@ def test_edge_shapes(shape):
         e.step(3)
         bad = parity.compare_states(e.get_state(), o.get_state(), A)
         assert bad == [], "think step %d: %s" % (k, bad[:4])
+
+
+@pytest.mark.parametrize("bad", [dict(puck_shift_step=0), dict(puck_shuffle_step=-3), dict(n_arenas=0), dict(n_puck_types=9), dict(step_interval=0),
+                                 dict(controller=7)])
+def test_config_validation(bad):
+    """The host-side set-up shared by the engine and this harness (ps_host.hpp) refuses what the reference would crash on
+    (stepCount % 0, Arena.java:189-191) or cannot represent."""
+    with pytest.raises(RuntimeError):
+        emu.Emu(abi.config_defaults(**bad))
