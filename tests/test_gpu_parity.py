@@ -437,3 +437,19 @@ def test_edge_shapes(shape):
         bad = parity.compare_states(e.get_state(), o.get_state(), A, tol=TOL)
         assert bad == [], "think step %d: %s" % (k, bad[:4])
     assert (e.get_state().arena["error_flags"] == 0).all()
+
+
+def test_informed_robots():
+    """Arena.nInformedRobots: the first robots run CacheCons with preset cache points (CacheConsController.java:209-243)."""
+    import parity
+    A, R, P = 3, 4, 40
+    cfg = abi.config_defaults(n_arenas=A, n_robots=R, n_pucks=P, controller=abi.PS_CTRL_CACHECONS, n_informed_robots=2, cc_ignore_pucks=1)
+    e, o = _engine(cfg), _oracle(cfg)
+    e.reset(np.arange(5, 5 + A))
+    o.reset(np.arange(5, 5 + A))
+    assert (e.get_state().robot["cache_valid"][:, :2, :2] == 1).all()
+    for k in range(60):
+        o.step(3)
+        e.step(3)
+        bad = parity.compare_states(e.get_state(), o.get_state(), A, tol=TOL)
+        assert bad == [], "think step %d: %s" % (k, bad[:4])

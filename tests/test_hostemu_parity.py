@@ -208,3 +208,21 @@ def test_config_validation(bad):
     (stepCount % 0, Arena.java:189-191) or cannot represent."""
     with pytest.raises(RuntimeError):
         emu.Emu(abi.config_defaults(**bad))
+
+
+def test_informed_robots():
+    """Arena.nInformedRobots (Arena.java:101-106): the first robots get CacheConsController(presetCaches = true) -- two preset
+    cache points, remembered sizes 1000, IGNORE_PUCKS forced off, no forgetting (CacheConsController.java:209-243, :558)."""
+    A, R, P = 2, 4, 40
+    cfg = abi.config_defaults(n_arenas=A, n_robots=R, n_pucks=P, controller=abi.PS_CTRL_CACHECONS, n_informed_robots=2, cc_ignore_pucks=1)
+    e, o = emu.Emu(cfg), oracle.Oracle(cfg)
+    e.reset([5, 6])
+    o.reset([5, 6])
+    s0 = o.get_state()
+    assert (s0.robot["cache_valid"][:, :2, :2] == 1).all() and (s0.robot["cache_valid"][:, 2:, :] == 0).all()
+    assert (s0.robot["remembered"][:, :2, :2] == 1000).all()
+    for k in range(80):
+        o.step(3)
+        e.step(3)
+        bad = parity.compare_states(e.get_state(), o.get_state(), A)
+        assert bad == [], "think step %d: %s" % (k, bad[:4])
