@@ -453,3 +453,25 @@ def test_informed_robots():
         e.step(3)
         bad = parity.compare_states(e.get_state(), o.get_state(), A, tol=TOL)
         assert bad == [], "think step %d: %s" % (k, bad[:4])
+
+
+@pytest.mark.parametrize("kw", [dict(cc_cache_selection=abi.PS_SEL_PROB_ABSOLUTE, cc_cache_separation=abi.PS_SEP_NULLIFY_OLD, cc_forget_prob=0.05),
+                                dict(cc_cache_selection=abi.PS_SEL_RELATIVE_FORGET, cc_cache_separation=abi.PS_SEP_ACCEPT_ISOLATED, cc_forget_prob=0.05),
+                                dict(cc_cache_selection=abi.PS_SEL_PROB_RELATIVE, cc_cache_separation=abi.PS_SEP_IGNORE),
+                                dict(sincos_lut=0), dict(toi_enabled=0), dict(n_puck_types=3, n_pucks=60), dict(step_interval=1),
+                                dict(vel_iters=1, pos_iters=7), dict(enclosure_scale=2.0)],
+                         ids=lambda kw: ",".join("%s=%s" % it for it in kw.items()))
+def test_config_option_sweep(kw):
+    """A sample of the option space of tests/test_hostemu_parity.py::test_config_option_sweep on the device."""
+    import parity
+    base = dict(n_arenas=3, n_robots=4, n_pucks=50, controller=abi.PS_CTRL_CACHECONS, cluster_distance_threshold=8.0)
+    base.update(kw)
+    cfg = abi.config_defaults(**base)
+    e, o = _engine(cfg), _oracle(cfg)
+    e.reset([1, 2, 3])
+    o.reset([1, 2, 3])
+    for k in range(50):
+        o.step(cfg.step_interval)
+        e.step(cfg.step_interval)
+        bad = parity.compare_states(e.get_state(), o.get_state(), 3, tol=TOL)
+        assert bad == [], "think step %d: %s" % (k, bad[:4])

@@ -226,3 +226,29 @@ def test_informed_robots():
         e.step(3)
         bad = parity.compare_states(e.get_state(), o.get_state(), A)
         assert bad == [], "think step %d: %s" % (k, bad[:4])
+
+
+_OPTION_CASES = (
+    [dict(cc_cache_selection=sel, cc_cache_separation=sep, cc_forget_prob=0.05)
+     for sel in (abi.PS_SEL_PROB_ABSOLUTE, abi.PS_SEL_PROB_RELATIVE, abi.PS_SEL_RELATIVE, abi.PS_SEL_RELATIVE_FORGET)
+     for sep in (abi.PS_SEP_IGNORE, abi.PS_SEP_NULLIFY_OLD, abi.PS_SEP_ACCEPT_ISOLATED, abi.PS_SEP_ACCEPT_LARGER)]
+    + [dict(sincos_lut=0), dict(toi_enabled=0), dict(n_puck_types=3, n_pucks=60), dict(cc_ignore_pucks=1), dict(step_interval=1),
+       dict(step_interval=5), dict(vel_iters=1, pos_iters=7), dict(enclosure_scale=2.0)])
+
+
+@pytest.mark.parametrize("kw", _OPTION_CASES, ids=lambda kw: ",".join("%s=%s" % it for it in kw.items()))
+def test_config_option_sweep(kw):
+    """Every CacheCons cache-selection x cache-separation option (CacheConsController.java:136-177, with forgetting switched
+    up so that it happens), the JBox2D switches (trig table, TOI), three colours, IGNORE_PUCKS, other think intervals, iteration
+    counts and a larger enclosure: lock-step with the oracle at a cluster threshold that lets caches form."""
+    base = dict(n_arenas=2, n_robots=4, n_pucks=50, controller=abi.PS_CTRL_CACHECONS, cluster_distance_threshold=8.0)
+    base.update(kw)
+    cfg = abi.config_defaults(**base)
+    e, o = emu.Emu(cfg), oracle.Oracle(cfg)
+    e.reset([1, 2])
+    o.reset([1, 2])
+    for k in range(60):
+        o.step(cfg.step_interval)
+        e.step(cfg.step_interval)
+        bad = parity.compare_states(e.get_state(), o.get_state(), 2)
+        assert bad == [], "think step %d: %s" % (k, bad[:4])
