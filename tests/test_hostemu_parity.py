@@ -252,3 +252,30 @@ def test_config_option_sweep(kw):
         e.step(cfg.step_interval)
         bad = parity.compare_states(e.get_state(), o.get_state(), 2)
         assert bad == [], "think step %d: %s" % (k, bad[:4])
+
+
+@pytest.mark.parametrize("ctrl,kw", [
+    (abi.PS_CTRL_BHD, dict(bhd_push_in_time=3, bhd_backup_time=2)),
+    (abi.PS_CTRL_PROBSEEK, dict(ps_placement_time=5, cc_k1=0.3, cc_k2=2.0, cc_pick_up_time=5, cc_backup_time=2)),
+    (abi.PS_CTRL_CACHECONS, dict(cc_k1=0.2, cc_k2=3.0, cc_pick_up_time=4, cc_push_in_time=3, cc_backup_time=2, cc_exile_time=5, cc_spit_out_time=3)),
+    (abi.PS_CTRL_CACHECONS, dict(cc_k_absolute=5.0, cc_k_relative=2.0, cc_cache_selection=abi.PS_SEL_PROB_ABSOLUTE, cc_home_separation_distance=20.0,
+                                 cc_prediction_distance_sqd=25.0, cc_st_dev=2.0)),
+    (abi.PS_CTRL_CACHECONS, dict(vfh_safety_gamma=4.0, vfh_safety_mask=2.0, vfh_tau_lo=0.5, vfh_tau_hi=0.6)),
+    (abi.PS_CTRL_BHD, dict(carry_threshold_lo=0.05, carry_threshold_hi=0.2)),
+    (abi.PS_CTRL_CACHECONS, dict(dt=1 / 30.0)),
+    (abi.PS_CTRL_CACHECONS, dict(max_contacts=2048)),
+], ids=lambda v: v if isinstance(v, int) else ",".join(v))
+def test_numeric_property_keys(ctrl, kw):
+    """The numeric keys of SURVEY App. C.8 away from their defaults (controller timers and constants, VFH+ safety distances and
+    hysteresis, carry thresholds, time step, cache capacity): each reaches the device program and the oracle alike."""
+    base = dict(n_arenas=2, n_robots=4, n_pucks=50, controller=ctrl, cluster_distance_threshold=8.0)
+    base.update(kw)
+    cfg = abi.config_defaults(**base)
+    e, o = emu.Emu(cfg), oracle.Oracle(cfg)
+    e.reset([1, 2])
+    o.reset([1, 2])
+    for k in range(60):
+        o.step(3)
+        e.step(3)
+        bad = parity.compare_states(e.get_state(), o.get_state(), 2)
+        assert bad == [], "think step %d: %s" % (k, bad[:4])
