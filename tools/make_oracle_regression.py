@@ -21,11 +21,17 @@ CASES = [
     dict(name="C1_cachecons_2robots_10pucks", n_arenas=1, n_robots=2, n_pucks=10, controller=abi.PS_CTRL_CACHECONS, seeds=[0], ticks=300),
     dict(name="C2_bhd_4robots_40pucks", n_arenas=2, n_robots=4, n_pucks=40, controller=abi.PS_CTRL_BHD, seeds=[0, 1], ticks=300),
     dict(name="C3shape_cachecons_16robots_200pucks", n_arenas=1, n_robots=16, n_pucks=200, controller=abi.PS_CTRL_CACHECONS, seeds=[7], ticks=60),
+    dict(name="probseek_4robots_40pucks", n_arenas=1, n_robots=4, n_pucks=40, controller=abi.PS_CTRL_PROBSEEK, seeds=[3], ticks=240),
+    dict(name="shift_shuffle_informed", n_arenas=1, n_robots=4, n_pucks=40, controller=abi.PS_CTRL_CACHECONS, seeds=[2], ticks=150,
+         extra=dict(puck_shift_step=10, puck_shuffle_step=25, n_informed_robots=1)),
+    dict(name="per_robot_rng_bhd", n_arenas=1, n_robots=4, n_pucks=40, controller=abi.PS_CTRL_BHD, seeds=[4], ticks=150,
+         extra=dict(rng_mode=abi.PS_RNG_PER_ROBOT)),
 ]
 
 
 def digest(case):
-    cfg = abi.config_defaults(n_arenas=case["n_arenas"], n_robots=case["n_robots"], n_pucks=case["n_pucks"], controller=case["controller"])
+    cfg = abi.config_defaults(n_arenas=case["n_arenas"], n_robots=case["n_robots"], n_pucks=case["n_pucks"], controller=case["controller"],
+                              **case.get("extra", {}))
     o = oracle.Oracle(cfg)
     o.reset(case["seeds"])
     o.step(case["ticks"])
