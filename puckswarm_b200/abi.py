@@ -230,3 +230,15 @@ def load_calibration_arrays(path=None):
     z = np.load(path)
     return (np.ascontiguousarray(z["XrYr"], np.float32), np.ascontiguousarray(z["xy"], np.uint16),
             np.ascontiguousarray(z["flags"], np.uint8), int(z["size"][0]), int(z["size"][1]))
+
+
+def write_calibration_bin(path, calib=None):
+    """The packed calibration as the flat file the C++ host reads (puckswarm_b200/host/puckswarm_host.hpp: Calibration::load):
+    int32 n, w, h; float32 XrYr[n][2]; uint16 xy[n][2]; uint8 flags[n]."""
+    XrYr, xy, flags, w, h = calib if calib is not None else load_calibration_arrays()
+    with open(path, "wb") as f:
+        f.write(np.array([len(flags), w, h], np.int32).tobytes())
+        f.write(np.ascontiguousarray(XrYr, np.float32).tobytes())
+        f.write(np.ascontiguousarray(xy, np.uint16).tobytes())
+        f.write(np.ascontiguousarray(flags, np.uint8).tobytes())
+    return path
