@@ -317,8 +317,15 @@ class Arena:
         return Suite(self, arena, robot)
 
     def robot_poses(self):
-        """[n_arenas][n_robots][3]: body.m_xf.position.x, .y, body.getAngle() (what Arena.java:231-233 stores)."""
-        return self._obs().pose.copy()
+        """[n_arenas][n_robots][3]: body.m_xf.position.x, .y, body.getAngle() NOW (what Arena.java:231-233 stores at the head
+        of Arena.step). The poses the engine keeps are those of the last sense, one think interval old, so a sense is run on
+        the current state and the state put back (sensing moves nothing but the LocalMap.carrying hysteresis)."""
+        st = self.engine.get_state()
+        self.engine.sense()
+        pose = self.engine.get_observations(camera=False).pose.copy()
+        self.engine.set_state(st)
+        self._obs_cache = None
+        return pose
 
     def puck_positions(self):
         """[n_arenas][n_pucks][2] (pucks are circles about their origin: m_xf.position == sweep.c)."""

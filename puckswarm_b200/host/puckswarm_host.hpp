@@ -15,10 +15,14 @@
 // path (ps_create fails with PS_E_NODEVICE without a B200).
 #pragma once
 #include <cctype>
+#include <charconv>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <fstream>
+#include <sys/stat.h>
 #include <map>
+#include <algorithm>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -56,6 +60,44 @@ inline std::map<std::string, std::string> loadProperties(const std::string& path
     }
     return out;
 }
+
+// Float.toString(float) / Double.toString(double): the shortest decimal that round-trips, in Java's layout -- plain notation
+// with at least one digit after the point for 1e-3 <= |x| < 1e7, otherwise d.dddE<exp> (FileUtils / PositionList.save /
+// PoseList.save write their numbers this way: PositionList.java:36-49, PoseList.java:32-46)
+template <class T>
+inline std::string javaNumberStr(T x) {
+    if (std::isnan(x)) return "NaN";
+    if (std::isinf(x)) return x > 0 ? "Infinity" : "-Infinity";
+    if (x == 0) return std::signbit(x) ? "-0.0" : "0.0";
+    char buf[64];
+    auto res = std::to_chars(buf, buf + sizeof(buf), x, std::chars_format::scientific);   // shortest round-trip digits: d[.ddd]e[+-]XX
+    std::string sci(buf, res.ptr);
+    size_t e = sci.find('e');
+    std::string mant = sci.substr(0, e);
+    int exp10 = std::stoi(sci.substr(e + 1));
+    bool neg = mant[0] == '-';
+    if (neg) mant = mant.substr(1);
+    std::string digits;
+    for (char c : mant)
+        if (c != '.') digits.push_back(c);
+    double a = std::fabs((double)x);
+    std::string out;
+    if (a >= 1e-3 && a < 1e7) {
+        if (exp10 >= 0) {
+            std::string ip = digits.substr(0, std::min(digits.size(), (size_t)exp10 + 1));
+            while ((int)ip.size() < exp10 + 1) ip.push_back('0');
+            std::string fp = digits.size() > (size_t)exp10 + 1 ? digits.substr(exp10 + 1) : "0";
+            out = ip + "." + fp;
+        } else {
+            out = "0." + std::string((size_t)(-exp10 - 1), '0') + digits;
+        }
+    } else {
+        out = digits.substr(0, 1) + "." + (digits.size() > 1 ? digits.substr(1) : "0") + "E" + std::to_string(exp10);
+    }
+    return neg ? "-" + out : out;
+}
+inline std::string javaFloatStr(float x) { return javaNumberStr<float>(x); }
+inline std::string javaDoubleStr(double x) { return javaNumberStr<double>(x); }
 
 // experiment.Experiment: one (code, seed)
 class Experiment {
@@ -252,14 +294,14 @@ public:
     typedef std::vector<std::vector<std::shared_ptr<Controller>>> Controllers;   // [n_arenas][n_robots]
 
     Arena(const Experiment& e, const std::vector<int64_t>& seeds, const Calibration& calib, int device = 0, Controllers controllers = {})
-        : cfg_(e.toConfig((int)seeds.size())), controllers_(std::move(controllers)), imgW_(calib.width), imgH_(calib.height) {
+        : cfg_(e.toConfig((int)seeds.size())), controllers_(std::move(controllers)), seeds_(seeds), code_(e.code()), imgW_(calib.width),
+          imgH_(calib.height) {
         if (!controllers_.empty()) cfg_.controller = PS_CTRL_EXTERNAL;   // host controllers: the batched per-think-step callback path
         check(ps_create(&cfg_, device, &h_));
         try {
             check(ps_load_calibration(h_, calib.XrYr.data(), calib.xy.data(), calib.flags.data(), calib.n, calib.width, calib.height));
             check(ps_reset(h_, seeds.data()));
-            int32_t np = 0, mc = 0;
-            check(ps_get_dims(h_, &nBodies_, &np, &mc, &occW_, &occH_));
+            check(ps_get_dims(h_, &nBodies_, &nProxies_, &maxContacts_, &occW_, &occH_));
         } catch (...) {
             ps_destroy(h_);
             h_ = nullptr;
@@ -323,6 +365,72 @@ public:
         return b;
     }
 
+    // [n_arenas][n_robots][3]: body.m_xf.position.x, .y, body.getAngle() NOW (what Arena.java:231-233 stores at the head of
+    // Arena.step). The poses the engine keeps are those of the last sense, one think interval old, so a sense is run on the
+    // current state and the state put back (sensing moves nothing but the LocalMap.carrying hysteresis).
+    std::vector<float> robotPoses() {
+        size_t A = (size_t)cfg_.n_arenas, NB = (size_t)nBodies_, NP = (size_t)nProxies_, MC = (size_t)maxContacts_, R = (size_t)cfg_.n_robots;
+        std::vector<float> body(A * 6 * NB), saabb(A * 4 * NB), fat(A * 4 * NP), cimp(A * MC * 4);
+        std::vector<uint32_t> ckey(A * MC), cinfo(A * MC);
+        std::vector<ps_robot_state> rs(A * R);
+        std::vector<ps_arena_state> as(A);
+        ps_state_view v = {};
+        v.body = body.data();
+        v.sense_aabb = saabb.data();
+        v.fat_aabb = fat.data();
+        v.contact_key = ckey.data();
+        v.contact_info = cinfo.data();
+        v.contact_impulse = cimp.data();
+        v.robot = rs.data();
+        v.arena = as.data();
+        check(ps_get_state(h_, &v));
+        check(ps_sense(h_));
+        obsValid_ = false;
+        fetchObservations(false);
+        std::vector<float> pose = pose_;
+        check(ps_set_state(h_, &v));
+        obsValid_ = false;
+        return pose;
+    }
+    // The reference's snapshot files (Arena.java:223-243): step%07d_robots.txt ("x, y, theta" as doubles) and
+    // step%07d_<COLOUR>_pucks.txt ("x, y" as floats) per arena under <outputDir>/<code>/<seed>/, so that analysis.Analyze
+    // reads GPU runs unchanged. Returns the files written.
+    std::vector<std::string> saveSnapshot(const std::string& outputDir) {
+        static const char* kColours[PS_MAX_COLOURS] = {"RED", "GREEN", "MAGENTA", "CYAN", "ORANGE", "GRAY", "YELLOW", "PINK"};   // SensedType.java:9-23
+        int step = getStepCount();
+        std::vector<float> pose = robotPoses(), body = bodies();
+        int R = cfg_.n_robots, NB = nBodies_, P = NB - R, K = cfg_.n_puck_types;
+        int perType = std::max(1, P / std::max(1, K));
+        std::vector<std::string> written;
+        char name[32];
+        std::snprintf(name, sizeof(name), "step%07d", step);
+        ::mkdir(outputDir.c_str(), 0777);
+        ::mkdir((outputDir + "/" + code_).c_str(), 0777);
+        for (int a = 0; a < cfg_.n_arenas; ++a) {
+            std::string d = outputDir + "/" + code_ + "/" + std::to_string(seeds_[a]);
+            ::mkdir(d.c_str(), 0777);
+            std::string base = d + "/" + name;
+            {
+                std::ofstream f(base + "_robots.txt");
+                for (int r = 0; r < R; ++r) {
+                    const float* p = pose.data() + ((size_t)a * R + r) * 3;
+                    f << javaDoubleStr(p[0]) << ", " << javaDoubleStr(p[1]) << ", " << javaDoubleStr(p[2]) << "\n";
+                }
+                written.push_back(base + "_robots.txt");
+            }
+            const float* b = body.data() + (size_t)a * 6 * NB;
+            for (int k = 0; k < K; ++k) {
+                int lo = k * perType, hi = std::min(P, (k + 1) * perType);
+                if (hi <= lo) continue;
+                std::string fn = base + "_" + kColours[k] + "_pucks.txt";
+                std::ofstream f(fn);
+                for (int p = lo; p < hi; ++p) f << javaFloatStr(b[0 * NB + p]) << ", " << javaFloatStr(b[1 * NB + p]) << "\n";
+                written.push_back(fn);
+            }
+        }
+        return written;
+    }
+
 private:
     friend class Suite;
     void fetchObservations(bool camera) {
@@ -343,8 +451,10 @@ private:
     }
     ps_config cfg_;
     Controllers controllers_;
+    std::vector<int64_t> seeds_;
+    std::string code_;
     ps_handle h_ = nullptr;
-    int32_t nBodies_ = 0, occW_ = 0, occH_ = 0;
+    int32_t nBodies_ = 0, nProxies_ = 0, maxContacts_ = 0, occW_ = 0, occH_ = 0;
     int imgW_ = 0, imgH_ = 0;
     bool obsValid_ = false, obsCamera_ = false;
     std::vector<ps_localmap> lm_;

@@ -4,6 +4,7 @@
 // with the Python binding. Usage: host_demo <properties dir> <code> <calibration.bin> <n arenas> <ticks> [external]
 #include <cinttypes>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../puckswarm_b200/host/puckswarm_host.hpp"
@@ -41,6 +42,11 @@ int main(int argc, char** argv) {
             return 4;
         }
     }
+    if (argc == 2 && std::strcmp(argv[1], "--format") == 0) {   // numbers on stdin -> Float.toString / Double.toString of the float
+        double d;
+        while (std::scanf("%lf", &d) == 1) std::printf("%s %s\n", javaFloatStr((float)d).c_str(), javaDoubleStr((double)(float)d).c_str());
+        return 0;
+    }
     if (argc < 6) {
         std::fprintf(stderr, "usage: host_demo <dir> <code> <calib.bin> <arenas> <ticks> [external]\n");
         return 2;
@@ -62,6 +68,7 @@ int main(int argc, char** argv) {
         Arena arena(exp, seeds, calib, 0, ctrls);
         RunOffline run(arena);
         for (int t = 0; t < ticks; ++t) run.step();
+        if (const char* snap = std::getenv("HOST_DEMO_SNAPSHOT_DIR")) arena.saveSnapshot(snap);
         std::vector<float> b = arena.bodies();
         int NB = arena.nBodies();
         std::printf("code %s stepCount %d nBodies %d robot0 %s pucksSeen %d\n", exp.code().c_str(), arena.getStepCount(), NB,

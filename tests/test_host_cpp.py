@@ -46,6 +46,19 @@ def test_property_mapping_matches_python_mirror(demo, tmp_path):
     assert bad.returncode == 4 and "four" in bad.stderr      # NumberFormatException of the reference
 
 
+def test_java_number_formatting_matches_python_mirror(demo):
+    """Float.toString / Double.toString as the snapshot files need them: the C++ and the Python mirror agree on 3 000 values."""
+    rng = np.random.RandomState(0)
+    vals = np.concatenate([rng.uniform(-100, 100, 2000), rng.uniform(-1, 1, 500) * 1e-4, rng.uniform(-1, 1, 500) * 1e8,
+                           [0.0, 1.5, 100.0, 1e-4, 1.25e7, 1e-3, 1e7, 9999999.0, 123456.7, -38.847805, 3.0e-5, 1.0e10]]).astype(np.float32)
+    out = subprocess.run([demo, "--format"], input="\n".join(repr(float(v)) for v in vals), capture_output=True, text=True)
+    lines = out.stdout.strip().split("\n")
+    assert len(lines) == len(vals)
+    for v, l in zip(vals, lines):
+        f, d = l.split()
+        assert f == host.java_float_str(v) and d == host.java_double_str(np.float32(v)), (v, l)
+
+
 def test_no_device_is_loud(demo, tmp_path):
     import torch
     if torch.cuda.is_available():
@@ -63,7 +76,8 @@ def test_cpp_host_matches_ctypes_binding(demo, tmp_path, external):
     _write_props(tmp_path)
     calib = abi.write_calibration_bin(str(tmp_path / "calib.bin"))
     A, ticks = 3, 30
-    out = subprocess.run([demo, str(tmp_path), "X", calib, str(A), str(ticks)] + (["external"] if external else []), capture_output=True, text=True)
+    env = dict(os.environ, HOST_DEMO_SNAPSHOT_DIR=str(tmp_path / "snap_cpp"))
+    out = subprocess.run([demo, str(tmp_path), "X", calib, str(A), str(ticks)] + (["external"] if external else []), capture_output=True, text=True, env=env)
     assert out.returncode == 0, out.stderr
     lines = out.stdout.strip().split("\n")
     assert lines[0].startswith("code X stepCount %d nBodies 43 robot0 R0" % (ticks // 3))
@@ -84,3 +98,15 @@ def test_cpp_host_matches_ctypes_binding(demo, tmp_path, external):
         want = np.array([body[a, 0, NB - 3], body[a, 1, NB - 3], body[a, 2, NB - 3], body[a, 0, 0], body[a, 1, 0]], np.float32).view(np.uint32)
         got = [int(x, 16) for x in lines[1 + a].split()[2:]]
         assert got == [int(x) for x in want], (a, lines[1 + a])
+    if not external:
+        # the reference's snapshot files, written by the C++ mirror and by the Python mirror after the same run
+        e.close()
+        arena = host.Arena(host.Experiment.from_files(str(tmp_path), "X", 0), list(range(A)))
+        for _ in range(ticks // 3):
+            arena.step()
+        written = arena.save_snapshot(str(tmp_path / "snap_py"))
+        arena.dispose()
+        assert len(written) == A * 3
+        for f in written:
+            rel = os.path.relpath(f, str(tmp_path / "snap_py"))
+            assert open(f).read() == open(os.path.join(str(tmp_path / "snap_cpp"), rel)).read(), rel

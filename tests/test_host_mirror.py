@@ -57,6 +57,13 @@ def test_arena_runoffline_snapshot_and_host_controllers(tmp_path):
     assert files == ["step0000000_GREEN_pucks.txt", "step0000000_RED_pucks.txt", "step0000000_robots.txt"]
     rows = (tmp_path / "T" / "1" / "step0000000_robots.txt").read_text().strip().split("\n")
     assert len(rows) == 3 and all(len(r.split(", ")) == 3 for r in rows)
+    # the poses of the snapshot are the spawn poses (Arena.java:231-233 stores them at the head of the first Arena.step)
+    o0 = oracle.Oracle(arena.cfg)
+    o0.reset(seeds)
+    o0.sense()
+    want = o0.get_observations().pose[1]
+    got = np.array([[float(x) for x in r.split(", ")] for r in rows], np.float32)
+    assert np.array_equal(got, want.astype(np.float32)), (got, want)
     # same trajectory as the oracle stepping the same experiment
     o = oracle.Oracle(arena.cfg)
     o.reset(seeds)
