@@ -35,6 +35,8 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 N_ROBOTS, N_PUCKS, ARENAS_PER_GPU, STEP_INTERVAL = 16, 200, 4096, 3
+STEADY_STEPS = 200      # think steps timed for also.steady_state (600 ticks) after >= 300 warm-up ticks
+PARITY_ARENAS = 8       # arenas of the timed batch replayed by the oracle after the clocks stop
 METRIC = "robot-steps/sec, 16 robots/200 pucks x N arenas"
 UNIT = "robot-steps/s"
 
@@ -183,7 +185,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--arenas", type=int, default=ARENAS_PER_GPU, help="arenas per GPU (default: BASELINE config[2])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the stepInterval = 1 side measurement")
+    ap.add_argument("--no-extras", action="store_true", help="skip the side measurements (stepInterval = 1, external controller, configs[3] / [4])")
+    ap.add_argument("--no-steady", action="store_true", help="skip also.steady_state (the >= 300 warm-up ticks regime) when W / K are shorter")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle replay of arenas of the timed batch")
+    ap.add_argument("--no-config4", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     claim_stdout()
@@ -212,11 +217,7 @@ def main():
 
     A = args.arenas
     lo = rank * A   # arenas shard by index: rank r owns [r * A, (r + 1) * A)
-    cfg = abi.config_defaults(n_arenas=A, n_robots=N_ROBOTS, n_pucks=N_PUCKS, controller=abi.PS_CTRL_CACHECONS,
-                              rng_mode=abi.PS_RNG_JAVA_SHARED)
-    eng = engine.Engine(cfg, device=local_rank)
-    eng.reset(np.arange(lo, lo + A))
-    stream = torch.cuda.ExternalStream(eng.stream, device=local_rank)
+    dev = torch.device("cuda", local_rank)
 
     def barrier():
         torch.cuda.synchronize()
@@ -224,179 +225,319 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput ("value") ----
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def make_engine(n_arenas, first_seed, **kw):
+        c = abi.config_defaults(n_arenas=n_arenas, n_robots=kw.pop("n_robots", N_ROBOTS), n_pucks=kw.pop("n_pucks", N_PUCKS),
+                                controller=kw.pop("controller", abi.PS_CTRL_CACHECONS), rng_mode=abi.PS_RNG_JAVA_SHARED, **kw)
+        e = engine.Engine(c, device=local_rank)
+        e.reset(np.arange(first_seed, first_seed + n_arenas))
+        return e
+
+    def timed_steps(e, n_steps, ticks_per_step=STEP_INTERVAL, sample_clocks=False):
+        """n_steps think intervals with device-resident state: CUDA events on the engine's stream, barrier + synchronize on both
+        sides, max over ranks. Returns (ms, launches, per-kernel ms, per-kernel launch counts, clocks)."""
+        stream = torch.cuda.ExternalStream(e.stream, device=local_rank)
+        e.sync()
+        e.profile(True)
+        e.kernel_ms()
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        barrier()
+        if sampler:
+            sampler.start()
+        l0 = e.kernel_launches
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(n_steps):
+            e.step(ticks_per_step, sync=False)
+        e.join()
+        ev1.record(stream)
+        e.sync()   # raises on a capacity flag in any arena: a degraded batch is not a measurement
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        ms = max_over_ranks(ev0.elapsed_time(ev1))
+        launches = e.kernel_launches - l0
+        kms, kcnt = e.kernel_ms()
+        e.profile(False)
+        return ms, launches, kms, kcnt, clocks
+
+    def rooflines(e, kms, kcnt, stats, clocks, regime):
+        """roofline (World.step pipeline, HBM) and roofline_sense (camera stage, shared memory) of one timed region."""
+        peak, peak_src = measured_peaks()
+        c_hat = stats.n_touching_points / max(1, stats.n_arenas)   # live touching manifold points per arena
+        bytes_per_arena_tick = 2.0 * (24.0 * (N_ROBOTS + N_PUCKS) + 24.0 * c_hat + 96.0 * N_ROBOTS)   # SURVEY 8(d)
+        # one World.step launch sequence of one arena group = k_phys_pre + island kernels + k_phys_post, each timed by its own
+        # event pair on the group's stream
+        phys_ms = STEP_INTERVAL * sum(kms[k] / max(1, kcnt[k]) for k in ("phys_pre", "phys_islands", "phys_post"))
+        arenas_per_launch = e.cfg.n_arenas / max(1, e.num_groups)   # every arena group launches its own kernel sequence
+        alg_bytes_per_launch = bytes_per_arena_tick * arenas_per_launch * STEP_INTERVAL
+        achieved = alg_bytes_per_launch / (phys_ms / 1000.0) / 1e9 if phys_ms > 0 else 0.0
+        top = ("sense", "think", "physics", "other")
+        total_k = sum(kms[k] for k in top)
+        roofline = {
+            "kernel": "World.step pipeline (k_phys_pre + island kernels + k_phys_post) x %d ticks" % STEP_INTERVAL,
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+            "traffic": None, "regime": regime,
+            "algorithmic_bytes_per_arena_tick": bytes_per_arena_tick, "touching_points_per_arena": c_hat,
+            "kernel_ms_per_launch": phys_ms, "arenas_per_launch": arenas_per_launch, "arena_groups": e.num_groups,
+            "kernel_share_of_step": {k: (kms[k] / total_k if total_k > 0 else 0.0) for k in top},
+            "world_step_stage_ms_per_tick": {k: kms[k] / max(1, kcnt[k]) for k in ("phys_pre", "phys_islands", "phys_post")},
+            "kernel_ms_total": kms, "kernel_launch_counts": kcnt,
+        }
+        # DRAM bytes the World.step kernels move: cannot be counted outside a profiler, so it comes from the ncu capture of
+        # the same regime (profiles/k_physics_traffic.json names the capture), scaled to this launch like `achieved`
+        ncu_traffic = os.path.join(ROOT, "profiles", "k_physics_traffic.json")
+        if os.path.exists(ncu_traffic):
+            try:
+                j = json.load(open(ncu_traffic))
+                per_arena_tick = (j.get("by_regime") or {}).get(regime, {}).get("dram_bytes_per_arena_tick")
+                if per_arena_tick is not None:
+                    roofline["traffic"] = per_arena_tick * arenas_per_launch * STEP_INTERVAL
+                    roofline["traffic_bytes_per_arena_tick"] = per_arena_tick
+                    roofline["traffic_source"] = (j.get("by_regime") or {}).get(regime, {}).get("source")
+            except Exception:
+                pass
+        # shared-memory roofline of the camera stage (SURVEY 8(d): algorithmic smem bytes per robot-sense)
+        sense_dbg = e.sense_stats().reshape(-1, 8).astype(np.float64)
+        p_act = 4556.0
+        k_bar = float(sense_dbg[:, 4].mean()) / p_act            # candidate bodies examined per pixel (measured)
+        smem_bytes_per_sense = p_act * 9.0 + p_act * k_bar * 12.0 + 3825.0 + 2294.0 * 3.0 + 19040.0
+        sense_ms = kms["sense"] / max(1, kcnt["sense"])             # the camera + local-map stage of one arena group
+        robots_per_launch = arenas_per_launch * N_ROBOTS
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        smem_peak = 148 * 128 * sm_mhz * 1e6 / 1e9   # GB/s: 148 SMs x 128 B/clk x SM clock
+        smem_achieved = smem_bytes_per_sense * robots_per_launch / (sense_ms / 1000.0) / 1e9 if sense_ms > 0 else 0.0
+        roofline_sense = {
+            "kernel": "camera + local-map stage (camera, occupancy, blobs, local map) per arena group", "bound": "smem",
+            "achieved": smem_achieved, "peak": smem_peak, "unit": "GB/s", "frac": smem_achieved / smem_peak,
+            "peak_source": "148 SMs x 128 B/clk x sampled SM clock", "candidates_per_pixel": k_bar,
+            "algorithmic_bytes_per_robot_sense": smem_bytes_per_sense, "kernel_ms_per_launch": sense_ms, "robots_per_launch": robots_per_launch,
+            "note": "candidate binning cuts K from the ~12 the survey assumed to the measured value, so the algorithmic byte count (and this fraction) "
+                    "shrinks with it; the stage is issue/latency bound (profiles/)",
+        }
+        return roofline, roofline_sense
+
+    def e2e_run(n_arenas, first_seed, warm_steps, timed_steps_n):
+        """The same steps through the C-ABI with HOST buffers: per step ps_set_state(body) from pinned memory, ps_step(3),
+        ps_get_state(body, arena) into pinned memory; host wall clock around the timed steps, max over ranks."""
+        # PS_E2E_HANDLES > 1 splits the arenas over several handles served round-robin (their copies overlap the others' steps)
+        n_handles = int(os.environ.get("PS_E2E_HANDLES", "1"))
+        halves, h2d, d2h = [], 0, 0
+        for hi in range(n_handles):
+            a0, a1 = hi * n_arenas // n_handles, (hi + 1) * n_arenas // n_handles
+            e2 = make_engine(a1 - a0, first_seed + a0)
+            st = e2.new_state()
+            pinned_body = torch.empty(st.body.shape, dtype=torch.float32).pin_memory()
+            pinned_arena = torch.empty(st.arena.nbytes, dtype=torch.uint8).pin_memory()
+            del st
+            body, arena = pinned_body.numpy(), pinned_arena.numpy().view(abi.ARENA_DTYPE)
+            vin, vout = abi.ps_state_view(), abi.ps_state_view()
+            vin.body = body.ctypes.data_as(C.POINTER(C.c_float))
+            vout.body = body.ctypes.data_as(C.POINTER(C.c_float))
+            vout.arena = arena.ctypes.data_as(C.POINTER(abi.ps_arena_state))
+            e2._check(e2.L.ps_get_state(e2.h, C.byref(vout)))
+            h2d += body.nbytes
+            d2h += body.nbytes + arena.nbytes
+            halves.append((e2, vin, vout, pinned_body, pinned_arena))
+
+        def e2e_round(first):
+            for e2, vin, vout, _, _ in halves:
+                if not first:
+                    e2._check(e2.L.ps_get_state(e2.h, C.byref(vout)))   # D2H: poses + velocities + step counters (synchronous)
+                e2._check(e2.L.ps_set_state(e2.h, C.byref(vin)))          # H2D: poses + velocities of every body
+                e2._check(e2.L.ps_step(e2.h, STEP_INTERVAL))
+
+        def e2e_drain():
+            for e2, vin, vout, _, _ in halves:
+                e2._check(e2.L.ps_get_state(e2.h, C.byref(vout)))
+
+        e2e_round(True)
+        for _ in range(warm_steps - 1):
+            e2e_round(False)
+        e2e_drain()
+        barrier()
+        t0 = time.perf_counter()
+        e2e_round(True)
+        for _ in range(timed_steps_n - 1):
+            e2e_round(False)
+        e2e_drain()                       # the last step's results are on the host when the clock stops
+        torch.cuda.synchronize()
+        ms = max_over_ranks((time.perf_counter() - t0) * 1000.0)
+        for e2, *_ in halves:
+            e2.sync()
+            e2.close()
+        return {"value": world * n_arenas * N_ROBOTS * STEP_INTERVAL * timed_steps_n / (ms / 1000.0), "unit": UNIT,
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "call": "per step and per handle: ps_set_state(body) + ps_step(3) + ps_get_state(body, arena), pinned host buffers; "
+                        "%d handle(s) served round-robin; host wall clock" % n_handles}
+
+    import ctypes as C
+    eng = make_engine(A, lo)
+
+    # ---- device-resident throughput ("value"): W warm-up steps after the reset, then K timed steps ----
     for _ in range(args.warmup):
         eng.step(STEP_INTERVAL, sync=False)
-    eng.sync()
-    eng.profile(True)
-    eng.kernel_ms()
-    sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
-    launches0 = eng.kernel_launches
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    for _ in range(args.steps):
-        eng.step(STEP_INTERVAL, sync=False)
-    eng.join()
-    ev1.record(stream)
-    eng.sync()
+    ms_max, launches, kms, kcnt, clocks = timed_steps(eng, args.steps, sample_clocks=True)
     local_stats = eng.compute_stats()
-    total_stats = psd.allreduce_stats(local_stats, device=torch.device("cuda", local_rank)) if world > 1 else local_stats
-    barrier()
-    clocks = sampler.stop()
-    ms = ev0.elapsed_time(ev1)
-    launches = eng.kernel_launches - launches0
-    kms, kcnt = eng.kernel_ms()
-    eng.profile(False)
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    total_stats = psd.allreduce_stats(local_stats, device=dev) if world > 1 else local_stats
     robot_steps = world * A * N_ROBOTS * STEP_INTERVAL * args.steps
     value = robot_steps / (ms_max / 1000.0)
+    main_regime = "steady" if args.warmup * STEP_INTERVAL >= 300 else "early"
+    roofline, roofline_sense = rooflines(eng, kms, kcnt, total_stats, clocks, main_regime)
+    ticks_done = (args.warmup + args.steps) * STEP_INTERVAL
 
-    # ---- end to end through the C-ABI with host buffers ("e2e") ----
-    # Every step uploads the bodies' poses / velocities from pinned memory, steps, and downloads them with the step counters.
-    # PS_E2E_HANDLES > 1 splits the arenas over several handles served round-robin, so that one handle's copies overlap the
-    # others' stepping; measured in the steady state the copies (2 x 21 MB per step) cost less than what kernels of several
-    # handles running side by side lose: 5.64 / 5.37 / 5.22 M robot-steps/s with 1 / 2 / 4 handles. One handle is the default.
-    sense_dbg = eng.sense_stats().reshape(-1, 8).astype(np.float64)
-    n_groups = eng.num_groups
-    import ctypes as C
-    halves = []
-    old_groups = os.environ.get("PS_GROUPS")
-    n_handles = int(os.environ.get("PS_E2E_HANDLES", "1"))
-    os.environ["PS_GROUPS"] = str(max(1, n_groups // n_handles))
-    h2d = d2h = 0
-    for hi in range(n_handles):
-        a0, a1 = lo + hi * A // n_handles, lo + (hi + 1) * A // n_handles
-        c2 = abi.config_defaults(n_arenas=a1 - a0, n_robots=N_ROBOTS, n_pucks=N_PUCKS, controller=abi.PS_CTRL_CACHECONS,
-                                 rng_mode=abi.PS_RNG_JAVA_SHARED)
-        e2 = engine.Engine(c2, device=local_rank)
-        e2.reset(np.arange(a0, a1))
-        st = e2.new_state()
-        pinned_body = torch.empty(st.body.shape, dtype=torch.float32).pin_memory()
-        pinned_arena = torch.empty(st.arena.nbytes, dtype=torch.uint8).pin_memory()
-        body, arena = pinned_body.numpy(), pinned_arena.numpy().view(abi.ARENA_DTYPE)
-        vin, vout = abi.ps_state_view(), abi.ps_state_view()
-        vin.body = body.ctypes.data_as(C.POINTER(C.c_float))
-        vout.body = body.ctypes.data_as(C.POINTER(C.c_float))
-        vout.arena = arena.ctypes.data_as(C.POINTER(abi.ps_arena_state))
-        e2._check(e2.L.ps_get_state(e2.h, C.byref(vout)))
-        h2d += body.nbytes
-        d2h += body.nbytes + arena.nbytes
-        halves.append((e2, vin, vout, pinned_body, pinned_arena))
-    if old_groups is None:
-        os.environ.pop("PS_GROUPS", None)
-    else:
-        os.environ["PS_GROUPS"] = old_groups
-
-    def e2e_round(first):
-        for e2, vin, vout, _, _ in halves:
-            if not first:
-                e2._check(e2.L.ps_get_state(e2.h, C.byref(vout)))   # D2H: poses + velocities + step counters (synchronous)
-            e2._check(e2.L.ps_set_state(e2.h, C.byref(vin)))          # H2D: poses + velocities of every body
-            e2._check(e2.L.ps_step(e2.h, STEP_INTERVAL))
-
-    def e2e_drain():
-        for e2, vin, vout, _, _ in halves:
-            e2._check(e2.L.ps_get_state(e2.h, C.byref(vout)))
-
-    # the same simulated interval as the device-resident run: W warm-up steps after the reset, then K timed steps
-    e2e_round(True)
-    for _ in range(args.warmup - 1):
-        e2e_round(False)
-    e2e_drain()
-    barrier()
-    t0 = time.perf_counter()
-    e2e_round(True)
-    for _ in range(args.steps - 1):
-        e2e_round(False)
-    e2e_drain()                       # the last step's results are on the host when the clock stops
-    torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) * 1000.0
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = robot_steps / (float(t.item()) / 1000.0)
-    for e2, *_ in halves:
-        e2.close()
-
-    # ---- the same batch with the sensors on every tick (stepInterval = 1 beside the reference's 3) ----
+    # ---- the steady state the metric is defined on (SURVEY 8(d): >= 300 warm-up ticks, then >= 600 timed ticks), whatever
+    #      --steps / --warmup were: the same engine keeps running until tick 300, then STEADY_STEPS think steps are timed ----
     also = {}
+    if args.warmup * STEP_INTERVAL >= 300 and args.steps * STEP_INTERVAL >= 600:
+        steady = {"value": value, "unit": UNIT, "ms_per_step": ms_max / args.steps, "warmup_ticks": args.warmup * STEP_INTERVAL,
+                  "timed_ticks": args.steps * STEP_INTERVAL, "same_as": "main line", "roofline": roofline, "roofline_sense": roofline_sense}
+    elif not args.no_steady:
+        while ticks_done < 300:
+            eng.step(STEP_INTERVAL, sync=False)
+            ticks_done += STEP_INTERVAL
+        warm_ticks = ticks_done
+        s_ms, s_launches, s_kms, s_kcnt, s_clocks = timed_steps(eng, STEADY_STEPS, sample_clocks=True)
+        ticks_done += STEADY_STEPS * STEP_INTERVAL
+        s_local = eng.compute_stats()
+        s_stats = psd.allreduce_stats(s_local, device=dev) if world > 1 else s_local
+        s_roof, s_roof_sense = rooflines(eng, s_kms, s_kcnt, s_stats, s_clocks, "steady")
+        steady = {"value": world * A * N_ROBOTS * STEP_INTERVAL * STEADY_STEPS / (s_ms / 1000.0), "unit": UNIT, "ms_per_step": s_ms / STEADY_STEPS,
+                  "warmup_ticks": warm_ticks, "timed_ticks": STEADY_STEPS * STEP_INTERVAL, "gpu_launches": int(s_launches), "clocks": s_clocks,
+                  "roofline": s_roof, "roofline_sense": s_roof_sense,
+                  "stats": {"mean_percent_completion": psd.mean_completion(s_stats), "cached_contacts_per_arena": s_stats.n_contacts / max(1, s_stats.n_arenas)}}
+    else:
+        steady = None
+    if steady is not None:
+        also["steady_state"] = steady
+
+    # ---- no arena of the timed batch may have raised a capacity flag (ps_sync would have failed the run above; this is the count) ----
+    err_flags, err_arenas = eng.error_flags()
+    if err_flags:
+        raise SystemExit("bench.py: %d arena(s) raised capacity flags 0x%x: the batch left the reference's trajectory" % (err_arenas, err_flags))
+
+    # ---- parity of the timed batch: the first PARITY_ARENAS arenas of this rank against the oracle on the same seeds, same ticks ----
+    parity_check = None
+    n_par = 0 if (args.no_parity or rank != 0) else min(PARITY_ARENAS, A)
+    if n_par:
+        body = np.zeros((A, 6, eng.NB), np.float32)
+        robots = np.zeros((A, N_ROBOTS), abi.ROBOT_DTYPE)
+        arenas = np.zeros((A,), abi.ARENA_DTYPE)
+        v = abi.ps_state_view()
+        v.body = body.ctypes.data_as(C.POINTER(C.c_float))
+        v.robot = robots.ctypes.data_as(C.POINTER(abi.ps_robot_state))
+        v.arena = arenas.ctypes.data_as(C.POINTER(abi.ps_arena_state))
+        eng._check(eng.L.ps_get_state(eng.h, C.byref(v)))
+    eng.close()
+
+    # ---- end to end through the C-ABI with host buffers ("e2e"): same W and K as the main line ----
+    e2e = e2e_run(A, lo, args.warmup, args.steps)
+    if steady is not None and "same_as" not in steady and not args.no_extras:
+        steady["e2e"] = e2e_run(A, lo, 100, STEADY_STEPS)
+    elif steady is not None and "same_as" in steady:
+        steady["e2e"] = e2e
+
     if not args.no_extras:
-        cfg1 = abi.config_defaults(n_arenas=A, n_robots=N_ROBOTS, n_pucks=N_PUCKS, controller=abi.PS_CTRL_CACHECONS,
-                                   rng_mode=abi.PS_RNG_JAVA_SHARED, step_interval=1)
-        eng1 = engine.Engine(cfg1, device=local_rank)
-        eng1.reset(np.arange(lo, lo + A))
-        s1 = torch.cuda.ExternalStream(eng1.stream, device=local_rank)
+        # ---- the same batch with the sensors on every tick (SURVEY 8(d): stepInterval = 1 beside the reference's 3) ----
+        eng1 = make_engine(A, lo, step_interval=1)
         for _ in range(9):
             eng1.step(1, sync=False)
-        eng1.sync()
         n1 = 15
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(s1)
-        for _ in range(n1):
-            eng1.step(1, sync=False)
-        eng1.join()
-        e1.record(s1)
-        eng1.sync()
-        t1 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t1, op=dist.ReduceOp.MAX)
-        also["step_interval_1"] = {"value": world * A * N_ROBOTS * n1 / (float(t1.item()) / 1000.0), "unit": UNIT,
-                                   "ms_per_tick": float(t1.item()) / n1, "ticks": n1, "warmup_ticks": 9}
+        t1, *_ = timed_steps(eng1, n1, ticks_per_step=1)
+        also["step_interval_1"] = {"value": world * A * N_ROBOTS * n1 / (t1 / 1000.0), "unit": UNIT, "ms_per_tick": t1 / n1, "ticks": n1, "warmup_ticks": 9}
         eng1.close()
 
-    # ---- roofline of the dominant kernel (k_physics: World.step) ----
-    peak, peak_src = measured_peaks()
-    c_hat = total_stats.n_touching_points / max(1, total_stats.n_arenas)   # live touching manifold points per arena
-    bytes_per_arena_tick = 2.0 * (24.0 * (N_ROBOTS + N_PUCKS) + 24.0 * c_hat + 96.0 * N_ROBOTS)
-    # one World.step launch sequence of one arena group = k_phys_pre + island kernels + k_phys_post, each timed by its own
-    # event pair on the group's stream (the turn-taking wait between the island phase and k_phys_post is outside all three)
-    ticks_per_launch = STEP_INTERVAL
-    phys_ms = ticks_per_launch * sum(kms[k] / max(1, kcnt[k]) for k in ("phys_pre", "phys_islands", "phys_post"))
-    arenas_per_launch = A / max(1, eng.num_groups)   # every arena group launches its own kernel sequence
-    alg_bytes_per_launch = bytes_per_arena_tick * arenas_per_launch * ticks_per_launch
-    achieved = alg_bytes_per_launch / (phys_ms / 1000.0) / 1e9 if phys_ms > 0 else 0.0
-    top = ("sense", "think", "physics", "other")
-    total_k = sum(kms[k] for k in top)
-    roofline = {
-        "kernel": "World.step pipeline (k_phys_pre + k_island_big | k_island_warp | k_island_batch + k_phys_post) x %d ticks" % ticks_per_launch,
-        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-        "traffic": None,
-        "algorithmic_bytes_per_arena_tick": bytes_per_arena_tick, "touching_points_per_arena": c_hat,
-        "kernel_ms_per_launch": phys_ms, "arenas_per_launch": arenas_per_launch, "arena_groups": eng.num_groups,
-        "kernel_share_of_step": {k: (kms[k] / total_k if total_k > 0 else 0.0) for k in top},
-        "world_step_stage_ms_per_tick": {k: kms[k] / max(1, kcnt[k]) for k in ("phys_pre", "phys_islands", "phys_post")},
-        "kernel_ms_total": kms, "kernel_launch_counts": kcnt,
-    }
-    # ---- shared-memory roofline of the camera stage (algorithmic smem bytes per robot-sense) ----
-    p_act = 4556.0
-    k_bar = float(sense_dbg[:, 4].mean()) / p_act            # candidate bodies examined per pixel (measured)
-    smem_bytes_per_sense = p_act * 9.0 + p_act * k_bar * 12.0 + 3825.0 + 2294.0 * 3.0 + 19040.0
-    sense_ms = kms["sense"] / max(1, kcnt["sense"])             # k_sense + k_localmap of one arena group
-    robots_per_launch = arenas_per_launch * N_ROBOTS
-    smem_peak = 148 * 128 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e9   # GB/s: 148 SMs x 128 B/clk x SM clock
-    smem_achieved = smem_bytes_per_sense * robots_per_launch / (sense_ms / 1000.0) / 1e9 if sense_ms > 0 else 0.0
-    roofline_sense = {
-        "kernel": "k_sense + k_localmap (camera, occupancy, blobs, local map) per arena group", "bound": "smem",
-        "achieved": smem_achieved, "peak": smem_peak, "unit": "GB/s", "frac": smem_achieved / smem_peak,
-        "peak_source": "148 SMs x 128 B/clk x sampled SM clock", "candidates_per_pixel": k_bar,
-        "algorithmic_bytes_per_robot_sense": smem_bytes_per_sense, "kernel_ms_per_launch": sense_ms, "robots_per_launch": robots_per_launch,
-        "note": "candidate binning cuts K from the ~12 the survey assumed to the measured value, so the algorithmic byte count (and this fraction) "
-                "shrinks with it; the stage is issue/latency bound (profiles/)",
-    }
-    ncu_traffic = os.path.join(ROOT, "profiles", "k_physics_traffic.json")
-    if os.path.exists(ncu_traffic):
-        try:
-            # per launch like `achieved`: the ncu capture's DRAM bytes per arena-tick x the arenas and ticks of one launch sequence
-            per_arena_tick = json.load(open(ncu_traffic)).get("dram_bytes_per_arena_tick")
-            roofline["traffic"] = per_arena_tick * arenas_per_launch * ticks_per_launch
-            roofline["traffic_bytes_per_arena_tick"] = per_arena_tick
-        except Exception:
-            pass
+        # ---- north_star: "a batched per-tick JNI callback remains for arbitrary Java controllers, reported separately".
+        #      One think interval = ps_sense + ps_get_observations (local map, occupancy, pose into pinned host memory) + a host
+        #      controller over the whole batch + ps_step_external (commands up, 3 ticks). The host controller here is a vectorised
+        #      stand-in (steer towards the nearest perceived puck): the number is the round trip, not the controller. ----
+        engx = make_engine(A, lo, controller=abi.PS_CTRL_EXTERNAL)
+        obs = engx.new_observations(camera=False)
+        pin = {k: torch.empty(getattr(obs, k).nbytes, dtype=torch.uint8).pin_memory() for k in ("occupancy", "localmap", "pose")}
+        obs.occupancy = pin["occupancy"].numpy().view(np.uint8).reshape(obs.occupancy.shape)
+        obs.localmap = pin["localmap"].numpy().view(abi.LOCALMAP_DTYPE).reshape(obs.localmap.shape)
+        obs.pose = pin["pose"].numpy().view(np.float32).reshape(obs.pose.shape)
+        d2h_x = obs.occupancy.nbytes + obs.localmap.nbytes + obs.pose.nbytes
+
+        def external_step():
+            engx._check(engx.L.ps_sense(engx.h))
+            engx.get_observations(obs, camera=False)
+            lm = obs.localmap
+            has = lm["n_pucks"] > 0
+            ang = np.where(has, np.arctan2(lm["puck_y"][..., 0], np.maximum(lm["puck_x"][..., 0], 1e-3)), 0.3).astype(np.float32)
+            fwd = np.full((A, N_ROBOTS), 375000.0, np.float32)
+            tq = (np.clip(ang, -1.0, 1.0) * 2375000.0).astype(np.float32)
+            engx.step_external(fwd, tq, sync=False)
+
+        for _ in range(3):
+            external_step()
+        engx.sync()
+        barrier()
+        nx = 10
+        t0 = time.perf_counter()
+        for _ in range(nx):
+            external_step()
+        engx.sync()
+        tx = max_over_ranks((time.perf_counter() - t0) * 1000.0)
+        also["external_controller"] = {
+            "value": world * A * N_ROBOTS * STEP_INTERVAL * nx / (tx / 1000.0), "unit": UNIT, "ms_per_step": tx / nx, "steps": nx,
+            "d2h_bytes_per_step": int(d2h_x), "h2d_bytes_per_step": int(2 * A * N_ROBOTS * 4),
+            "call": "per think step: ps_sense + ps_get_observations(localmap, occupancy, pose; pinned) + host controller (vectorised numpy stand-in) "
+                    "+ ps_step_external; host wall clock; controllers.Controller seam (Controller.java:9-31), reported separately from the on-device path"}
+        engx.close()
+
+        # ---- BASELINE configs[3]: 65 536 arenas x 16 x 200 sharded over the GPUs of the job (named for 2 / 4 / 8 GPUs) ----
+        if world > 1 and 65536 % world == 0:
+            A3 = 65536 // world
+            eng3 = make_engine(A3, rank * A3)
+            for _ in range(3):
+                eng3.step(STEP_INTERVAL, sync=False)
+            n3 = 6
+            t3, *_ = timed_steps(eng3, n3)
+            s3 = psd.allreduce_stats(eng3.compute_stats(), device=dev)
+            also["config3"] = {"workload": "BASELINE configs[3]: 65536 arenas x 16 robots x 200 pucks over %d GPUs (%d per GPU), NCCL statistics reduce" % (world, A3),
+                               "value": 65536 * N_ROBOTS * STEP_INTERVAL * n3 / (t3 / 1000.0), "unit": UNIT, "ms_per_step": t3 / n3, "steps": n3, "warmup": 3,
+                               "arenas_reduced": int(s3.n_arenas), "regime": "early (ticks 9-27)"}
+            eng3.close()
+
+        # ---- BASELINE configs[4]: 1024 large arenas x 256 robots x 4000 pucks, enclosure scale 6 (sharded like the rest) ----
+        if 1024 % world == 0 and not args.no_config4:
+            A4 = 1024 // world
+            eng4 = make_engine(A4, rank * A4, n_robots=256, n_pucks=4000, enclosure_scale=6.0)
+            for _ in range(2):
+                eng4.step(STEP_INTERVAL, sync=False)
+            n4 = 4
+            t4, *_ = timed_steps(eng4, n4)
+            also["config4"] = {"workload": "BASELINE configs[4]: 1024 arenas x 256 robots x 4000 pucks, RoundedRectangleEnclosure.scale = 6, CacheCons on device, "
+                                           "local map on; %d arenas per GPU" % A4,
+                               "value": 1024 * 256 * STEP_INTERVAL * n4 / (t4 / 1000.0), "unit": UNIT, "ms_per_step": t4 / n4, "steps": n4, "warmup": 2,
+                               "regime": "early (ticks 6-18)"}
+            eng4.close()
+
+    # ---- parity_check, continued: the oracle replays the sampled arenas (clocks are stopped; one arena per host thread) ----
+    if n_par:
+        g.build_oracle()
+        import oracle_binding
+        ocfg = abi.config_defaults(n_arenas=n_par, n_robots=N_ROBOTS, n_pucks=N_PUCKS, controller=abi.PS_CTRL_CACHECONS, rng_mode=abi.PS_RNG_JAVA_SHARED)
+        orc = oracle_binding.Oracle(ocfg, threads=min(n_par, os.cpu_count() or 1))
+        orc.reset(np.arange(lo, lo + n_par))
+        t0 = time.perf_counter()
+        orc.step(ticks_done)
+        ost = orc.get_state()
+        ref, got = ost.body, body[:n_par]
+        rel = np.abs(got - ref) / np.maximum(1.0, np.abs(ref))
+        per_arena_bad = (rel.reshape(n_par, -1).max(axis=1) > 1e-5) | (robots[:n_par]["ctrl_state"] != ost.robot["ctrl_state"]).any(axis=1) \
+            | (arenas[:n_par]["n_contacts"] != ost.arena["n_contacts"]) | (arenas[:n_par]["update_count"] != ost.arena["update_count"])
+        parity_check = {"arenas": int(n_par), "ticks": int(ticks_done), "mismatches": int(per_arena_bad.sum()),
+                        "bit_exact_arenas": int((got.view(np.uint32).reshape(n_par, -1) == ref.view(np.uint32).reshape(n_par, -1)).all(axis=1).sum()),
+                        "max_rel_err": float(rel.max()), "compared": "body poses + velocities (1e-5 relative), controller states, cached-contact counts, tick counters",
+                        "error_flag_arenas": int(err_arenas), "oracle_seconds": time.perf_counter() - t0,
+                        "what": "arenas %d..%d of the timed batch (rank 0), free-running since the reset, against the CPU oracle on the same seeds" % (lo, lo + n_par - 1)}
+        orc.close()
 
     if rank == 0:
         cpu = None
@@ -411,11 +552,8 @@ def main():
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": workload_config(A * world, "arenas sharded by index, %d per GPU, one process per GPU" % A),
-            "clocks": clocks, "gpu_launches": int(launches),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "call": "per step and per handle: ps_set_state(body) + ps_step(3) + ps_get_state(body, arena), pinned host buffers; "
-                            "%d handle(s) served round-robin; host wall clock" % n_handles},
-            "roofline": roofline, "roofline_sense": roofline_sense, "also": also, "cpu_baseline": cpu,
+            "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
+            "roofline": roofline, "roofline_sense": roofline_sense, "parity_check": parity_check, "also": also, "cpu_baseline": cpu,
             "stats": {"mean_percent_completion": psd.mean_completion(total_stats), "arenas": int(total_stats.n_arenas),
                       "robots_carrying": int(total_stats.n_carrying), "cache_points": int(total_stats.n_caches),
                       "cached_contacts_per_arena": total_stats.n_contacts / max(1, total_stats.n_arenas)},
@@ -424,6 +562,8 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if parity_check and parity_check["mismatches"]:
+        raise SystemExit("bench.py: parity_check failed: %r" % (parity_check,))
     return 0
 
 

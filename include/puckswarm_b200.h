@@ -166,7 +166,9 @@ typedef struct ps_arena_state {
     int32_t  step_count;          /* Arena.stepCount (think steps done) */
     int32_t  n_contacts;          /* live entries of the contact cache */
     float    inv_dt0;             /* World.m_inv_dt0 */
-    int32_t  error_flags;         /* bit0 contact capacity, bit1 perceived-puck capacity, bit2 island scratch */
+    int32_t  error_flags;         /* capacity overflows (the arena has left the reference's trajectory): bit0 contact cache (max_contacts),
+                                     bit1 perceived pucks (PS_MAX_LM_PUCKS; reported by ps_sync / ps_get_error_flags from the local maps),
+                                     bit2 touching constraints (max_contacts / 4), bit3 broad-phase pair buffer, bit4 wall-contact list */
 } ps_arena_state;
 
 /*
@@ -250,13 +252,26 @@ int ps_load_calibration(ps_handle h, const float* XrYr, const uint16_t* xy, cons
 /* Spawn every arena from its seed exactly as new Experiment(seed) + new Arena(...) would (a24). */
 int ps_reset(ps_handle h, const int64_t* seeds);
 
+/* Partial views (NULL pointers) are allowed within these rules, enforced with PS_E_INVALID:
+ *   - contact_key, contact_info, contact_impulse and arena (for n_contacts) travel together; n_contacts <= max_contacts and every
+ *     key must name two different proxies of the arena;
+ *   - update_count must be the same in every arena (the batch steps in lock step; the host owns the think schedule);
+ *   - the first upload into a handle that was never reset must carry every component.
+ * Not checkable, so the caller's duty: the cache must equal the set of filtered proxy pairs whose fat AABBs overlap (JBox2D's
+ * invariant between steps; the solver's "new pair iff the boxes overlap now and did not before" relies on it). Uploading `body`
+ * alone is therefore only valid for poses that still lie inside the uploaded / resident fat AABBs (e.g. the state just downloaded,
+ * or velocity edits); to teleport a body upload body + sense_aabb + fat_aabb + the contact group of a consistent state. */
 int ps_set_state(ps_handle h, const ps_state_view* v);
 int ps_get_state(ps_handle h, ps_state_view* v);
 
 /* n_ticks iterations of RunOffline.step(): {Arena.step | Arena.coast} then World.step. Asynchronous on the
  * handle's stream; ps_sync waits and reports device-side capacity errors. */
 int ps_step(ps_handle h, int n_ticks);
+/* Waits for the handle's work. Returns PS_E_CAPACITY (after waiting; the state stays readable) when any arena raised a capacity
+ * flag: such an arena dropped a contact / constraint / pair / perceived puck and no longer follows the reference. */
 int ps_sync(ps_handle h);
+/* OR of all arenas' error_flags (bit1 also from the robots' last local maps) and the number of flagged arenas. */
+int ps_get_error_flags(ps_handle h, int32_t* flags, int32_t* n_flagged);
 /* Order the handle's main stream (ps_stream) after everything ps_step has queued so far, without waiting on the host:
  * an event recorded on that stream afterwards completes when the steps have. */
 int ps_join(ps_handle h);

@@ -329,6 +329,24 @@ __global__ void __launch_bounds__(128, 6) k_phys_post(KParams p) {
     if (threadIdx.x < 8) p.stepStats[a * 8 + threadIdx.x] = wk.stats[threadIdx.x];
 }
 
+// OR of every arena's error_flags (+ bit1 for a robot whose last local map overflowed) and the number of flagged arenas
+__global__ void k_error_scan(const ps_arena_state* arena, const ps_localmap* lm, int nArenas, int R, int* out) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    int f = 0;
+    if (a < nArenas) {
+        f = arena[a].error_flags;
+        if (lm)
+            for (int r = 0; r < R; ++r)
+                if (lm[(size_t)a * R + r].overflow) f |= ERR_LM_CAP;
+    }
+    unsigned any = __ballot_sync(0xFFFFFFFFu, f != 0);
+    for (int o = 16; o > 0; o >>= 1) f |= __shfl_xor_sync(0xFFFFFFFFu, f, o);
+    if ((threadIdx.x & 31) == 0 && any) {
+        atomicOr(&out[0], f);
+        atomicAdd(&out[1], __popc(any));
+    }
+}
+
 // The MathUtils sin table (228 KB) is the same for every handle: one device copy per GPU, shared by the handles of the
 // process, so that several engines on one GPU do not multiply its L1 / L2 footprint (it sits on the solver's critical path).
 struct SharedLut {
@@ -398,6 +416,7 @@ struct ps_engine {
     StatsDev* dStatsDev = nullptr;
     ps_stats* dStats = nullptr;
     float* dCmd = nullptr;
+    int* dErr = nullptr;     // [2]: OR of the arenas' error flags, flagged arenas (k_error_scan)
     bool isReset = false;
     // optional per-kernel timing (CUDA events on the engine's stream): classes 0 sense, 1 think, 2 physics, 3 other
     bool profiling = false;
@@ -537,6 +556,7 @@ int ps_destroy(ps_handle h) {
     cudaFree(h->dStatsDev);
     cudaFree(h->dStats);
     cudaFree(h->dCmd);
+    cudaFree(h->dErr);
     h->sd.release();
     for (auto& g : h->groups) {
         if (g.evPre) cudaEventDestroy(g.evPre);
@@ -624,6 +644,7 @@ int ps_create(const ps_config* cfg, int device, ps_handle* out) {
     TRY_OR_FREE(cudaMalloc(&e->dStats, sizeof(ps_stats)));
     TRY_OR_FREE(cudaMemset(e->dStats, 0, sizeof(ps_stats)));
     TRY_OR_FREE(cudaMalloc(&e->dCmd, 2 * A * pc.d.R * sizeof(float) + 16));
+    TRY_OR_FREE(cudaMalloc(&e->dErr, 2 * sizeof(int)));
     // working memory: shared memory up to the budget, the rest per slot in HBM
     e->threads = (int)envSize("PS_THREADS", 128);
     if (e->threads < 32 || e->threads > 256 || (e->threads & 31)) e->threads = 128;
@@ -716,11 +737,51 @@ int ps_load_calibration(ps_handle h, const float* XrYr, const uint16_t* xy, cons
     return PS_OK;
 }
 
+// OR of the arenas' capacity flags and the number of flagged arenas, on the main stream (the caller has joined the groups)
+static int scanErrors(ps_handle h, int* flags, int* nFlagged) {
+    int host[2] = {0, 0};
+    CUDA_TRY(cudaMemsetAsync(h->dErr, 0, 2 * sizeof(int), h->stream));
+    const ps_localmap* lm = h->sd.ready ? h->sd.kp.obs.lm : nullptr;
+    k_error_scan<<<(h->kp.nArenas + 127) / 128, 128, 0, h->stream>>>(h->kp.sp.arena, lm, h->kp.nArenas, h->hs.phys.d.R, h->dErr);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(host, h->dErr, sizeof(host), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    *flags = host[0];
+    *nFlagged = host[1];
+    return PS_OK;
+}
+
+int ps_get_error_flags(ps_handle h, int32_t* flags, int32_t* n_flagged) {
+    if (!h) return setError(PS_E_INVALID, "null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    { int jr = joinGroups(h); if (jr != PS_OK) return jr; }
+    int f = 0, n = 0;
+    int rc = scanErrors(h, &f, &n);
+    if (rc != PS_OK) return rc;
+    if (flags) *flags = f;
+    if (n_flagged) *n_flagged = n;
+    return PS_OK;
+}
+
 int ps_sync(ps_handle h) {
     if (!h) return setError(PS_E_INVALID, "null handle");
     CUDA_TRY(cudaSetDevice(h->device));
     { int jr = joinGroups(h); if (jr != PS_OK) return jr; }
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (!h->isReset) {
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        return PS_OK;
+    }
+    // a capacity overflow drops a contact / constraint / pair / perceived puck: the arena has left the reference's trajectory
+    int f = 0, n = 0;
+    int rc = scanErrors(h, &f, &n);
+    if (rc != PS_OK) return rc;
+    if (f != 0) {
+        char msg[256];
+        snprintf(msg, sizeof(msg), "capacity overflow in %d arena(s), flags 0x%x (bit0 contact cache, bit1 perceived pucks, bit2 touching "
+                 "constraints, bit3 pair buffer, bit4 wall-contact list): raise ps_config.max_contacts; ps_get_state shows the arenas", n, f);
+        return setError(PS_E_CAPACITY, msg);
+    }
     return PS_OK;
 }
 
@@ -996,6 +1057,30 @@ int ps_get_state(ps_handle h, ps_state_view* v) {
 int ps_set_state(ps_handle h, const ps_state_view* v) {
     if (!h || !v) return setError(PS_E_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(h->device));
+    const PhysCfg& pc = h->hs.phys;
+    int nA = h->kp.nArenas;
+    if (!h->isReset && !(v->body && v->sense_aabb && v->fat_aabb && v->contact_key && v->contact_info && v->contact_impulse && v->robot && v->arena))
+        return setError(PS_E_INVALID, "the first ps_set_state of a handle that was never reset must carry every component");
+    // the contact arrays are one group: the cache must stay the set of overlapping fat pairs (see the header)
+    if ((v->contact_key || v->contact_info || v->contact_impulse) && !(v->contact_key && v->contact_info && v->contact_impulse && v->arena))
+        return setError(PS_E_INVALID, "contact_key, contact_info, contact_impulse and arena (n_contacts) must be set together");
+    if (v->arena) {
+        // all arenas advance in lock step (the think scheduler is the host's): one update_count for the batch
+        int uc = v->arena[0].update_count;
+        unsigned maxProxy = (unsigned)(kWallFixtures + pc.d.NP);
+        for (int a = 0; a < nA; ++a) {
+            const ps_arena_state& as = v->arena[a];
+            if (as.update_count != uc) return setError(PS_E_INVALID, "ps_set_state: update_count differs between arenas (arenas step in lock step)");
+            if (as.n_contacts < 0 || as.n_contacts > pc.MC) return setError(PS_E_INVALID, "ps_set_state: n_contacts outside [0, max_contacts]");
+            if (v->contact_key) {
+                const uint32_t* key = v->contact_key + (size_t)a * pc.MC;
+                for (int i = 0; i < as.n_contacts; ++i) {
+                    unsigned pa = key[i] >> 16, pb = key[i] & 0xFFFFu;
+                    if (pa >= maxProxy || pb >= maxProxy || pa == pb) return setError(PS_E_INVALID, "ps_set_state: contact_key names a proxy outside the arena");
+                }
+            }
+        }
+    }
     int rc = copyState(h, v, false);
     if (rc != PS_OK) return rc;
     if (v->arena) h->updateCount = v->arena[0].update_count;
@@ -1034,7 +1119,7 @@ int ps_compute_stats(ps_handle h, float cluster_threshold, ps_stats* out) {
     for (int i = 0; i < 8; i++) out->ctrl_state_hist[i] = (int64_t)sd.ctrlState[i];
     out->n_carrying = (int64_t)sd.nCarrying;
     out->n_caches = (int64_t)sd.nCaches;
-    out->sum_completion = P > 0 ? 100.0 * (double)sd.sumMax / (double)P : 0.0;
+    out->sum_completion = h->hs.cfg.n_pucks > 0 ? 100.0 * (double)sd.sumMax / (double)h->hs.cfg.n_pucks : 0.0;   // Analyze.java:90,197: / the Arena.nPucks property
     out->n_touching_points = (int64_t)sd.nTouching;
     out->n_contacts = (int64_t)sd.nContacts;
     CUDA_TRY(cudaMemcpyAsync(h->dStats, out, sizeof(*out), cudaMemcpyHostToDevice, h->stream));

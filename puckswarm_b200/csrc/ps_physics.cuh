@@ -98,7 +98,7 @@ struct PhysWork {
     int* stats;                                          // [8] per-step diagnostics: 0 max position iterations, 1 TOI events, 2 islands
 };
 
-enum { ERR_CONTACT_CAP = 1, ERR_LM_CAP = 2, ERR_TOUCH_CAP = 4, ERR_PAIR_CAP = 8 };
+enum { ERR_CONTACT_CAP = 1, ERR_LM_CAP = 2, ERR_TOUCH_CAP = 4, ERR_PAIR_CAP = 8, ERR_WALL_CAP = 16 };
 
 // The handful of scene constants the solver loops read on every step, carried by value (kernel parameter /
 // constant bank) so that the Gauss-Seidel dependency chain does not wait on loads through the scene pointer.
@@ -1233,7 +1233,7 @@ PS_HD void physSolveTOI(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const Ar
                 wk.wallNeed[pos] = 1;
                 wk.bodyFlag[body] = 1;
             } else {
-                *st.errorFlags |= ERR_CONTACT_CAP;
+                *st.errorFlags |= ERR_WALL_CAP;
             }
         }
         nWall += total;

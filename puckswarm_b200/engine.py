@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("PS_ENGINE_LIB") or os.path.join(_HERE, "csrc", "libpu
 
 EXPORTS = [
     "ps_last_error", "ps_abi_version", "ps_struct_size", "ps_config_defaults", "ps_create", "ps_destroy", "ps_load_calibration",
-    "ps_reset", "ps_set_state", "ps_get_state", "ps_step", "ps_sync", "ps_join", "ps_sense", "ps_step_external",
+    "ps_reset", "ps_set_state", "ps_get_state", "ps_step", "ps_sync", "ps_get_error_flags", "ps_join", "ps_sense", "ps_step_external",
     "ps_get_observations", "ps_compute_stats", "ps_stats_device_ptr", "ps_get_dims", "ps_get_step_stats", "ps_get_sense_stats", "ps_get_island_hist",
     "ps_profile", "ps_get_kernel_ms", "ps_num_groups", "ps_kernel_launches", "ps_stream",
 ]
@@ -60,6 +60,7 @@ def load_library(path=None):
     L.ps_step.argtypes = [C.c_void_p, C.c_int]
     L.ps_sync.argtypes = [C.c_void_p]
     L.ps_join.argtypes = [C.c_void_p]
+    L.ps_get_error_flags.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.ps_sense.argtypes = [C.c_void_p]
     L.ps_step_external.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.ps_get_observations.argtypes = [C.c_void_p, C.POINTER(abi.ps_obs_view)]
@@ -131,6 +132,12 @@ class Engine:
 
     def sync(self):
         self._check(self.L.ps_sync(self.h))
+
+    def error_flags(self):
+        """(OR of the arenas' capacity flags, number of flagged arenas); ps_sync raises EngineError(PS_E_CAPACITY) on the same condition."""
+        f, n = C.c_int32(), C.c_int32()
+        self._check(self.L.ps_get_error_flags(self.h, C.byref(f), C.byref(n)))
+        return f.value, n.value
 
     def join(self):
         """Order the main stream after all queued steps (no host wait): events recorded on `stream` then cover them."""

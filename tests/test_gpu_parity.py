@@ -20,9 +20,10 @@ def _engine(cfg, **kw):
     return engine.Engine(cfg, device=0, **kw)
 
 
-def _oracle(cfg, threads=8):
+def _oracle(cfg, threads=None):
+    import os
     import oracle_binding
-    return oracle_binding.Oracle(cfg, threads=threads)
+    return oracle_binding.Oracle(cfg, threads=threads or min(64, max(8, os.cpu_count() or 8)))
 
 
 @pytest.mark.parametrize("shape", [(1, 2, 10, 2), (3, 4, 40, 2), (2, 16, 200, 2), (2, 5, 21, 3)])
@@ -179,6 +180,32 @@ def test_c3_shape_against_oracle():
     o.step(60)
     bad = parity.compare_states(e.get_state(), o.get_state(), A, tol=TOL)
     assert bad == [], bad[:5]
+
+
+def test_c3_shape_steady_state_free_running():
+    """The regime the benchmark is defined on (after >= 300 warm-up ticks): 16 robots / 200 pucks, CacheCons on
+    device, 900 ticks free-running with no re-synchronisation -- puck caches form, islands outgrow the lane and warp slots and
+    run into the 100-sweep cap. Compared with the oracle at ticks 300, 600 and 900 (contact cache, bodies, controllers)."""
+    import os
+    import parity
+    A = int(os.environ.get("PS_TEST_STEADY_ARENAS", "8"))
+    cfg = abi.config_defaults(n_arenas=A, n_robots=16, n_pucks=200, controller=abi.PS_CTRL_CACHECONS)
+    e, o = _engine(cfg), _oracle(cfg)
+    seeds = np.arange(7, 7 + A)
+    e.reset(seeds)
+    o.reset(seeds)
+    e.island_hist()
+    capped = 0
+    for k in range(3):
+        e.step(300)
+        o.step(300)
+        bad = parity.compare_states(e.get_state(), o.get_state(), A, tol=TOL)
+        assert bad == [], "tick %d: %s" % (300 * (k + 1), bad[:5])
+        capped += int(max(o.step_info(a)["pos_iters"] for a in range(A)) >= 100)
+    assert e.error_flags() == (0, 0)
+    hist = e.island_hist(reset=False)
+    assert hist[7, :7].sum() > 0, "no lane island ever ran into the 100-sweep cap: not the steady-state regime"
+    assert capped > 0
 
 
 def test_batch_position_independence_and_determinism():
@@ -354,6 +381,31 @@ def test_ensemble_statistics_match():
         assert list(se.ctrl_state_hist) == list(so.ctrl_state_hist)
         assert se.n_carrying == so.n_carrying and se.n_caches == so.n_caches
         assert abs(se.sum_completion - so.sum_completion) < 1e-9 * max(1.0, so.sum_completion)
+
+
+def test_ensemble_1000_episodes():
+    """north_star: ensemble statistics over 1 000 seeded episodes must match the reference's distributions. Here 1 000 episodes
+    (4 robots / 40 pucks / 2 colours, CacheCons, seeds 0..999) x 150 think steps are compared exactly: per-episode percent
+    completion and controller states, and the ensemble's cluster-size histograms."""
+    import os
+    n = int(os.environ.get("PS_TEST_EPISODES", "1000"))
+    cfg = abi.config_defaults(n_arenas=n, n_robots=4, n_pucks=40, controller=abi.PS_CTRL_CACHECONS)
+    e, o = _engine(cfg), _oracle(cfg)
+    e.reset(np.arange(n))
+    o.reset(np.arange(n))
+    e.step(450)
+    o.step(450)
+    se, so = e.compute_stats(9.45), o.compute_stats(9.45)
+    assert np.array_equal(np.ctypeslib.as_array(se.cluster_size_hist), np.ctypeslib.as_array(so.cluster_size_hist))
+    assert list(se.ctrl_state_hist) == list(so.ctrl_state_hist)
+    assert se.n_carrying == so.n_carrying and se.n_caches == so.n_caches
+    assert abs(se.sum_completion - so.sum_completion) < 1e-9 * max(1.0, so.sum_completion)
+    ge, go = e.get_state(), o.get_state()
+    # per episode: every puck and robot pose within TOL (bit-exact in practice), same controller states
+    assert np.array_equal(ge.robot["ctrl_state"], go.robot["ctrl_state"])
+    err = np.abs(ge.body - go.body) / np.maximum(1.0, np.abs(go.body))
+    assert err.max() <= TOL, "worst episode %d" % int(np.unravel_index(err.argmax(), err.shape)[0])
+    assert e.error_flags() == (0, 0)
 
 
 @pytest.mark.parametrize("controller,shift,shuffle,shape", [(abi.PS_CTRL_EXTERNAL, 4, 6, (3, 4, 60)), (abi.PS_CTRL_CACHECONS, 5, -1, (5, 4, 60)),
