@@ -584,7 +584,10 @@ struct SlotCtx {
 };
 
 // Returns false if the island does not fit the slot (the caller falls back to the sequential path).
-template <class Slot>
+// POS = false: the velocity half only (warm start, velocity sweeps, impulses, integration); the bodies are written back and
+// the row schedule is left in wk.tcPair[lo + q] = constraint (index into wk.tc) | row << 16, q in row-major solve order, for
+// the position-sweep kernel (k_island_pos) that follows on the same stream.
+template <class Slot, bool POS = true>
 __device__ __forceinline__ bool islandSolveSlot(const PhysEnv& e, const PhysWork& wk, const ArenaState& st, int k, Slot& s, int* itersOut) {
     const unsigned FULL = 0xFFFFFFFFu;
     int lane = threadIdx.x & 31;
@@ -712,10 +715,15 @@ __device__ __forceinline__ bool islandSolveSlot(const PhysEnv& e, const PhysWork
     // integrate the island's bodies
     for (int b = lane; b < nb; b += 32) lkIntegrate(e, wk, L, b);
     __syncwarp();
+    if (!POS)
+        for (int q = lane; q < nc; q += 32) {
+            int ci = s.sched[q];
+            wk.tcPair[lo + q] = (uint32_t)wk.order[lo + ci] | ((uint32_t)s.row[ci] << 16);
+        }
     // ---- position sweeps
     int posIters = e.cfg.posIters;
     int iters = 0;
-    bool done = posIters <= 0;
+    bool done = !POS || posIters <= 0;
     while (!done) {
         float minSep = 0.0f;
         bool changed = false;
@@ -773,6 +781,113 @@ __device__ __forceinline__ bool islandSolveSlot(const PhysEnv& e, const PhysWork
 }
 __device__ __forceinline__ bool islandSolveWarp(const PhysEnv& e, const PhysWork& wk, const ArenaState& st, int k, WarpSlot& s, int* itersOut) {
     return islandSolveSlot(e, wk, st, k, s, itersOut);
+}
+__device__ __forceinline__ bool islandVelocityWarp(const PhysEnv& e, const PhysWork& wk, const ArenaState& st, int k, WarpSlot& s, int* itersOut) {
+    return islandSolveSlot<WarpSlot, false>(e, wk, st, k, s, itersOut);
+}
+
+// ---- Position sweeps of the warp-bucket islands, G lanes per island and 32 / G islands per warp (k_island_pos) ----
+// The velocity half ran in k_island_vel (one warp per island); what is left is the long part: up to 100 Gauss-Seidel
+// sweeps whose corrections depend on each other, so a warp that holds ONE island issues from ~3 lanes. Here a warp holds
+// 32 / G islands in G-lane groups: every group walks its own row schedule (a lane pair per constraint, as in
+// lkCorrectPointPair), one pass per loop iteration, all groups through the same instructions. A group that finishes is
+// written back and refilled from the queue by the whole warp (staging is warp-cooperative and short), so the groups never
+// wait for each other's islands.
+struct PosSlot {
+    static constexpr int NBX = kWarpBodies + 1;
+    float cx[NBX], cy[NBX], a[NBX];
+    float px[NBX], py[NBX], c[NBX], s[NBX], pm[NBX], pi[NBX];
+    uint16_t gidx[NBX];
+    uint8_t kind[NBX];
+    float pc[kWarpContacts][9];            // row-major solve order: localNormal, localPoint, two manifold points, radius
+    uint32_t pcHead[kWarpContacts];        // bodyA | bodyB << 8 | type << 16 | points << 24
+    uint8_t rowStart[kWarpContacts + 2];
+    int nRows;
+};
+
+// Stage island `entry` (arena * NB + island) into T with all 32 lanes. Returns false when the island is not this kernel's
+// (it outgrew the slot, so the velocity kernel's fallback has already solved it completely).
+__device__ __forceinline__ bool posStage(const PhysEnv& e, const PhysWork& wk, int k, PosSlot& T, int lane) {
+    int lo = wk.islandStart[k], nc = wk.islandStart[k + 1] - lo;
+    int blo = wk.islandBodyStart[k], nb = wk.islandBodyStart[k + 1] - blo;
+    int P = e.cfg.d.P;
+    if (nb > kWarpBodies || nc > kWarpContacts) return false;
+    for (int i = lane; i <= nb; i += 32) {
+        if (i < nb) {
+            int g = wk.ibody[blo + i];
+            T.gidx[i] = (uint16_t)g;
+            T.cx[i] = wk.cx[g];
+            T.cy[i] = wk.cy[g];
+            T.a[i] = wk.a[g];
+            if (g >= P) {
+                int r = g - P;
+                T.kind[i] = LK_ROBOT;
+                T.pm[i] = e.hot.pmRobot;
+                T.pi[i] = e.hot.piRobot;
+                T.px[i] = wk.rpx[r];
+                T.py[i] = wk.rpy[r];
+                T.c[i] = wk.rc[r];
+                T.s[i] = wk.rs[r];
+            } else {
+                T.kind[i] = LK_PUCK;
+                T.pm[i] = e.hot.pmPuck;
+                T.pi[i] = e.hot.piPuck;
+                T.px[i] = T.cx[i];
+                T.py[i] = T.cy[i];
+                T.c[i] = 1.0f;
+                T.s[i] = 0.0f;
+            }
+        } else {
+            T.gidx[i] = 0xFFFF;
+            T.kind[i] = LK_WALL;
+            T.cx[i] = T.cy[i] = T.a[i] = 0.0f;
+            T.pm[i] = T.pi[i] = 0.0f;
+            T.px[i] = e.hot.wallXf.px;
+            T.py[i] = e.hot.wallXf.py;
+            T.c[i] = e.hot.wallXf.c;
+            T.s[i] = e.hot.wallXf.s;
+        }
+    }
+    for (int q = lane; q < nc; q += 32) {
+        uint32_t v = wk.tcPair[lo + q];
+        int row = (int)(v >> 16);
+        const TC& t = wk.tc[v & 0xFFFFu];
+        T.pc[q][0] = t.localNormal.x;
+        T.pc[q][1] = t.localNormal.y;
+        T.pc[q][2] = t.localPoint.x;
+        T.pc[q][3] = t.localPoint.y;
+        T.pc[q][4] = t.lp[0].x;
+        T.pc[q][5] = t.lp[0].y;
+        T.pc[q][6] = t.lp[1].x;
+        T.pc[q][7] = t.lp[1].y;
+        T.pc[q][8] = t.radius;
+        T.pcHead[q] = (uint32_t)t.bodyA | ((uint32_t)t.bodyB << 8) | ((uint32_t)t.type << 16) | ((uint32_t)t.solverPoints << 24);
+        // rows are contiguous in q: a constraint whose predecessor sits in another row starts its row
+        int prevRow = q > 0 ? (int)(wk.tcPair[lo + q - 1] >> 16) : -1;
+        if (row != prevRow) T.rowStart[row] = (uint8_t)q;
+        if (q == nc - 1) {
+            T.rowStart[row + 1] = (uint8_t)nc;
+            T.nRows = row + 1;
+        }
+    }
+    return true;
+}
+__device__ __forceinline__ void posFinish(const PhysEnv& e, const PhysWork& wk, int k, const PosSlot& T, int lane) {
+    int nb = wk.islandBodyStart[k + 1] - wk.islandBodyStart[k];
+    int P = e.cfg.d.P;
+    for (int i = lane; i < nb; i += 32) {
+        int g = T.gidx[i];
+        wk.cx[g] = T.cx[i];
+        wk.cy[g] = T.cy[i];
+        wk.a[g] = T.a[i];
+        if (g >= P) {
+            int r = g - P;
+            wk.rpx[r] = T.px[i];
+            wk.rpy[r] = T.py[i];
+            wk.rc[r] = T.c[i];
+            wk.rs[r] = T.s[i];
+        }
+    }
 }
 __device__ __forceinline__ bool islandSolveBig(const PhysEnv& e, const PhysWork& wk, const ArenaState& st, int k, BigSlot& s, int* itersOut) {
     return islandSolveSlot(e, wk, st, k, s, itersOut);
