@@ -189,6 +189,7 @@ def main():
     ap.add_argument("--no-steady", action="store_true", help="skip also.steady_state (the >= 300 warm-up ticks regime) when W / K are shorter")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle replay of arenas of the timed batch")
     ap.add_argument("--no-config4", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="A/B runs only: skip the end-to-end leg (the line then carries e2e = null and is not a bench line)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     claim_stdout()
@@ -435,8 +436,8 @@ def main():
     eng.close()
 
     # ---- end to end through the C-ABI with host buffers ("e2e"): same W and K as the main line ----
-    e2e = e2e_run(A, lo, args.warmup, args.steps)
-    if steady is not None and "same_as" not in steady and not args.no_extras:
+    e2e = None if args.no_e2e else e2e_run(A, lo, args.warmup, args.steps)
+    if steady is not None and "same_as" not in steady and not args.no_extras and not args.no_e2e:
         steady["e2e"] = e2e_run(A, lo, 100, STEADY_STEPS)
     elif steady is not None and "same_as" in steady:
         steady["e2e"] = e2e

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define PS_ABI_VERSION 2
+#define PS_ABI_VERSION 3
 
 /* ---- fixed sizes of the scene ---- */
 #define PS_MAX_COLOURS      8    /* SensedType.NPUCK_COLOURS, src/sensors/SensedType.java:39 */
@@ -220,17 +220,53 @@ typedef struct ps_obs_view {
     float*       pose;       /* [n_arenas][n_robots][3]: SimAPS pose x, y, theta (SimAPS.java:14-18) */
 } ps_obs_view;
 
-/* Per-arena experiment statistics (PositionList.getClusterStats, Analyze.java:187-218). */
+/* Experiment statistics reduced over the arenas of the handle (PositionList.getClusterStats, src/arena/PositionList.java:85-96;
+ * Analyze.java:176-259). The fields are grouped by the reduction that combines ranks, in this order, so that a multi-GPU reduce
+ * is one collective per group: int64 sums | double sums | int64 minima | int64 maxima | double minima | double maxima. */
 typedef struct ps_stats {
+    /* --- int64, summed */
     int64_t n_arenas;
     int64_t cluster_size_hist[PS_MAX_COLOURS][64]; /* count of clusters by size (sizes >= 63 in the last bin) */
     int64_t ctrl_state_hist[8];                    /* robots per controller state */
     int64_t n_carrying;                            /* robots with LocalMap.carrying */
     int64_t n_caches;                              /* CacheCons: valid cache points over all robots */
-    double  sum_completion;                        /* sum over arenas of 100 * sum_k max cluster size_k / n_pucks */
     int64_t n_touching_points;                     /* live touching manifold points (C-hat of SURVEY 8d) */
     int64_t n_contacts;                            /* live cached contacts */
+    int64_t n_completed;                           /* arenas whose stepsToCompletion != -1 (Analyze.java:247-256) */
+    int64_t sum_steps_to_completion;               /* over the completed arenas */
+    int64_t n_snapshots;                           /* storage-step records analysed, over all arenas */
+    /* --- double, summed */
+    double  sum_completion;                        /* sum over arenas of the CURRENT 100 * sum_k max cluster size_k / Arena.nPucks */
+    double  sum_twc;                               /* sum over arenas of timeWeightedCompletion (Analyze.java:206-216) */
+    /* --- int64 minimum / maximum over the completed arenas (INT64_MAX / -1 when none completed) */
+    int64_t min_steps_to_completion;
+    int64_t max_steps_to_completion;
+    /* --- double minima, then maxima, over the arenas */
+    double  min_completion, min_twc;
+    double  max_completion, max_twc;
 } ps_stats;
+
+/* The reference's periodic record, kept for the latest storage step (Arena.stepCount % 100 == 0) of every arena: what Arena.step
+ * writes to step%07d_robots.txt / _<COLOUR>_pucks.txt (Arena.java:223-243; poses after the perturbations, before World.step) and
+ * what the on-device controllers would write to _R<i>_cachePoints.txt / _R<i>_stateCounts.txt (CacheConsController.java:313-333,
+ * 531-551, BHDController.java:103-123). All pointers are HOST arrays of the caller; NULL skips a component. */
+typedef struct ps_snapshot_view {
+    int32_t* step_count;     /* [n_arenas]: Arena.stepCount of the record, -1 = none yet */
+    float*   robot_pose;     /* [n_arenas][n_robots][3]: body.m_xf.position.x, .y, body.getAngle() */
+    float*   puck_xy;        /* [n_arenas][P][2], pucks in creation order (colour k = pucks k*P/n_puck_types ..) */
+    float*   cache_xy;       /* [n_arenas][n_robots][PS_MAX_COLOURS][2]: (float)cachePoints[k], NaN = null (CacheCons only) */
+    int32_t* state_counts;   /* [n_arenas][n_robots][8]: recentStateCounts as saved, before they are cleared */
+} ps_snapshot_view;
+
+/* analysis.Analyze.computeEnsembleData for one repetition (Analyze.java:176-218), accumulated on the device at every storage
+ * step: percent completion = 100 * sum_k max cluster size_k / Arena.nPucks over the recorded puck positions. */
+typedef struct ps_arena_analysis {
+    int32_t n_snapshots;          /* rows so far (storage steps 0, 100, 200, ...) */
+    int32_t steps_to_completion;  /* first stepCount with completion >= target (TARGET_PERCENT_COMPLETION = 50), -1 = not reached */
+    double  twc_num;              /* sum over rows of stepCount * completion / 100 */
+    double  twc_den;              /* sum over rows of stepCount; timeWeightedCompletion = twc_num / twc_den */
+    double  completion;           /* percent completion of the latest row */
+} ps_arena_analysis;
 
 typedef struct ps_engine* ps_handle;
 
@@ -287,6 +323,17 @@ int ps_get_observations(ps_handle h, ps_obs_view* v);
  * (ps_stats_device_ptr, sizeof(ps_stats) bytes of int64/double) is what the host all-reduces over NCCL. */
 int ps_compute_stats(ps_handle h, float cluster_threshold, ps_stats* out);
 int ps_stats_device_ptr(ps_handle h, void** dptr, int64_t* n_bytes);
+/* The same, reduced over the ranks of an NCCL communicator (ps_get_stats(h, out, allreduce)): nccl_comm is the
+ * caller's ncclComm_t for this handle's device (NULL = this process only). One ncclAllReduce per reduction group of ps_stats
+ * (sum / min / max over int64 and double) on the handle's stream, straight on the device copy; libnccl.so.2 is loaded on first use. */
+int ps_get_stats(ps_handle h, float cluster_threshold, ps_stats* out, void* nccl_comm);
+
+/* Latest storage-step record of every arena / the per-arena Analyze accumulators (see the structs). The clustering threshold and
+ * the completion target default to ps_config.cluster_distance_threshold and 50 (Analyze.java:32); ps_analysis_config overrides them
+ * and clears the accumulators. */
+int ps_get_snapshot(ps_handle h, ps_snapshot_view* v);
+int ps_get_analysis(ps_handle h, ps_arena_analysis* out /* [n_arenas] */);
+int ps_analysis_config(ps_handle h, float cluster_threshold, float target_percent);
 
 /* Engine introspection */
 int ps_get_dims(ps_handle h, int32_t* n_bodies, int32_t* n_proxies, int32_t* max_contacts,

@@ -7,6 +7,8 @@
 // PARITY IS UNPINNED (see the headers): this is a restatement, not the JVM reference.
 #include "puckswarm.h"
 #include <thread>
+#include <climits>
+#include <limits>
 #include <functional>
 #include <atomic>
 #include <map>
@@ -19,6 +21,7 @@ struct orc_batch {
     bool haveCalib = false;
     std::vector<std::unique_ptr<Arena>> arenas;
     int NB = 0, NP = 0, maxContacts = 0;
+    float analysisThreshold = -1.0f, analysisTarget = 50.0f;   // < 0: cfg.cluster_distance_threshold
 };
 
 static int deriveMaxContacts(const ps_config& c) {
@@ -87,6 +90,8 @@ int orc_reset(orc_batch* b, const int64_t* seeds) {
     b->arenas.clear();
     for (int i = 0; i < b->cfg.n_arenas; i++) {
         b->arenas.emplace_back(new Arena(b->cfg, &b->calib));
+        if (b->analysisThreshold >= 0.0f) b->arenas.back()->analysisThreshold = b->analysisThreshold;
+        b->arenas.back()->analysisTarget = b->analysisTarget;
         b->arenas.back()->reset(seeds[i]);
         flushNewFixtures(*b->arenas.back());
     }
@@ -133,6 +138,7 @@ int orc_step_external(orc_batch* b, const float* fwd, const float* torque, int n
             a.robots[r].controller->movement.torque = torque[(size_t)i * R + r];
         }
         a.perturb();
+        if (a.stepCount % 100 == 0) a.storeRecord();
         a.stepCount++;
         for (int t = 0; t < a.cfg.step_interval; t++) {
             a.coast();
@@ -466,6 +472,9 @@ int orc_get_observations(orc_batch* b, ps_obs_view* v) {
 int orc_compute_stats(orc_batch* b, float threshold, ps_stats* out) {
     std::memset(out, 0, sizeof(*out));
     out->n_arenas = (int64_t)b->arenas.size();
+    out->min_steps_to_completion = INT64_MAX;
+    out->max_steps_to_completion = -1;
+    bool first = true;
     for (auto& ap : b->arenas) {
         Arena& a = *ap;
         double sumMax = 0;
@@ -482,7 +491,28 @@ int orc_compute_stats(orc_batch* b, float threshold, ps_stats* out) {
             }
             sumMax += mx;
         }
-        out->sum_completion += 100.0 * sumMax / (double)a.pucks.size();
+        // Analyze.java:90,197 divides by the configured Arena.nPucks property (not by the number of pucks spawned)
+        double pc = a.cfg.n_pucks > 0 ? 100.0 * sumMax / (double)a.cfg.n_pucks : 0.0;
+        out->sum_completion += pc;
+        double twc = a.analysis.twc_den > 0.0 ? a.analysis.twc_num / a.analysis.twc_den : 0.0;
+        out->sum_twc += twc;
+        out->n_snapshots += a.analysis.n_snapshots;
+        if (a.analysis.steps_to_completion >= 0) {
+            out->n_completed++;
+            out->sum_steps_to_completion += a.analysis.steps_to_completion;
+            out->min_steps_to_completion = std::min<int64_t>(out->min_steps_to_completion, a.analysis.steps_to_completion);
+            out->max_steps_to_completion = std::max<int64_t>(out->max_steps_to_completion, a.analysis.steps_to_completion);
+        }
+        if (first) {
+            out->min_completion = out->max_completion = pc;
+            out->min_twc = out->max_twc = twc;
+            first = false;
+        } else {
+            out->min_completion = std::min(out->min_completion, pc);
+            out->max_completion = std::max(out->max_completion, pc);
+            out->min_twc = std::min(out->min_twc, twc);
+            out->max_twc = std::max(out->max_twc, twc);
+        }
         for (Robot& r : a.robots) {
             out->ctrl_state_hist[r.controller->state & 7]++;
             if (r.localMap.carrying) out->n_carrying++;
@@ -496,6 +526,50 @@ int orc_compute_stats(orc_batch* b, float threshold, ps_stats* out) {
             out->n_contacts++;
             out->n_touching_points += c->manifold.pointCount;
         }
+    }
+    return PS_OK;
+}
+
+// The record the reference writes at the latest storage step (Arena.java:223-243 and the controllers' dumps), same layout as ps_get_snapshot
+int orc_get_snapshot(orc_batch* b, ps_snapshot_view* v) {
+    int R = b->cfg.n_robots;
+    for (size_t i = 0; i < b->arenas.size(); i++) {
+        Arena& a = *b->arenas[i];
+        size_t P = a.pucks.size();
+        if (v->step_count) v->step_count[i] = a.savedStep;
+        if (a.savedStep < 0) continue;
+        if (v->robot_pose) std::memcpy(v->robot_pose + i * R * 3, a.savedPoses.data(), sizeof(float) * R * 3);
+        if (v->puck_xy && P) std::memcpy(v->puck_xy + i * P * 2, a.savedPucks.data(), sizeof(float) * P * 2);
+        for (int r = 0; r < R; r++) {
+            const Controller* c = a.robots[r].controller.get();
+            if (!c || a.cfg.controller == PS_CTRL_EXTERNAL) continue;
+            for (int k = 0; k < PS_MAX_COLOURS; k++) {
+                bool cc = a.cfg.controller == PS_CTRL_CACHECONS;
+                if (v->cache_xy) {
+                    v->cache_xy[((i * R + r) * PS_MAX_COLOURS + k) * 2] = cc ? c->savedCache[k][0] : std::numeric_limits<float>::quiet_NaN();
+                    v->cache_xy[((i * R + r) * PS_MAX_COLOURS + k) * 2 + 1] = cc ? c->savedCache[k][1] : std::numeric_limits<float>::quiet_NaN();
+                }
+            }
+            if (v->state_counts)
+                for (int k = 0; k < 8; k++) v->state_counts[(i * R + r) * 8 + k] = c->savedStateCounts[k];
+        }
+    }
+    return PS_OK;
+}
+
+int orc_get_analysis(orc_batch* b, ps_arena_analysis* out) {
+    for (size_t i = 0; i < b->arenas.size(); i++) out[i] = b->arenas[i]->analysis;
+    return PS_OK;
+}
+
+int orc_analysis_config(orc_batch* b, float threshold, float target) {
+    b->analysisThreshold = threshold;
+    b->analysisTarget = target;
+    for (auto& ap : b->arenas) {
+        ap->analysisThreshold = threshold;
+        ap->analysisTarget = target;
+        ap->analysis = ps_arena_analysis{0, -1, 0.0, 0.0, 0.0};
+        ap->savedStep = -1;
     }
     return PS_OK;
 }

@@ -5,6 +5,7 @@
 // Each function cites the reference file:line it follows. PARITY IS UNPINNED: the reference has no
 // tests or golden vectors and cannot be executed here (no JVM).
 #pragma once
+#include <limits>
 #include "jb2d.h"
 #include "jrandom.h"
 #include "../include/puckswarm_b200.h"
@@ -725,12 +726,20 @@ struct Controller {
     MovementCommand movement;
     int state = 0, startCount = 0;
     int stateCounts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // what the controller wrote at the latest storage step: _R<i>_stateCounts.txt (FileUtils.saveArray of recentStateCounts,
+    // CacheConsController.java:313-333 / BHDController.java:103-123) and _R<i>_cachePoints.txt (8 lines, NaN for null, :531-551)
+    int savedStateCounts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float savedCache[PS_MAX_COLOURS][2] = {};
+    int savedStep = -1;
     VFHPlus vfh;
     JavaRandom* random = nullptr;
-    void updateStateCounts(int stepCount) {  // CacheConsController.java:313-333 (file output skipped)
+    void updateStateCounts(int stepCount) {  // CacheConsController.java:313-333: the file output becomes savedStateCounts
         stateCounts[state]++;
-        if (stepCount % 100 == 0)
+        if (stepCount % 100 == 0) {
+            for (int i = 0; i < 8; i++) savedStateCounts[i] = stateCounts[i];
+            savedStep = stepCount;
             for (int i = 0; i < 8; i++) stateCounts[i] = 0;
+        }
     }
 };
 
@@ -1015,6 +1024,11 @@ struct CacheConsController : Controller {  // src/controllers/CacheConsControlle
             movement = MovementCommand(-1, randomTurn);
         }
         if (carrying) lastCarriedType = carriedType;
+        if (stepCount % 100 == 0)   // :531-551 "Periodically save cache points to disk"
+            for (int k = 0; k < PS_MAX_COLOURS; k++) {
+                savedCache[k][0] = cacheValid[k] ? (float)cachePoints[k].x : std::numeric_limits<float>::quiet_NaN();
+                savedCache[k][1] = cacheValid[k] ? (float)cachePoints[k].y : std::numeric_limits<float>::quiet_NaN();
+            }
         updateStateCounts(stepCount);
     }
 };
@@ -1207,8 +1221,49 @@ struct Arena {
     std::vector<Robot> robots;
     std::vector<Puck> pucks;
     int stepCount = 0, updateCount = 0;
+    // the record Arena.step stores every STORAGE_INTERVAL think steps (Arena.java:223-243) and analysis.Analyze's per-repetition
+    // statistics over those records (Analyze.java:176-218)
+    int savedStep = -1;
+    std::vector<float> savedPoses, savedPucks;
+    ps_arena_analysis analysis = {0, -1, 0.0, 0.0, 0.0};
+    float analysisThreshold = 1.5f, analysisTarget = 50.0f;
 
-    Arena(const ps_config& c, const Calibration* cal) : cfg(c), calib(cal) {}
+    Arena(const ps_config& c, const Calibration* cal) : cfg(c), calib(cal), analysisThreshold(c.cluster_distance_threshold) {}
+    // PositionList.getClusterStats per colour (PositionList.java:85-96) -> Analyze's percent completion (Analyze.java:190-197)
+    double percentCompletion(float threshold) {
+        double sumMax = 0;
+        for (int k = 0; k < cfg.n_puck_types; k++) {
+            std::vector<Vec2> pos;
+            for (const Puck& p : pucks)
+                if (p.colour == k) pos.push_back(p.body->xf.position);
+            std::vector<Cluster> cl;
+            LocalMap::extractClusters(pos, 0, cl, threshold);
+            int mx = 0;
+            for (const Cluster& c : cl) mx = std::max(mx, c.size);
+            sumMax += mx;
+        }
+        return cfg.n_pucks > 0 ? 100.0 * sumMax / (double)cfg.n_pucks : 0.0;
+    }
+    void storeRecord() {  // Arena.java:223-243, then one row of Analyze.computeEnsembleData
+        savedStep = stepCount;
+        savedPoses.clear();
+        savedPucks.clear();
+        for (Robot& r : robots) {
+            savedPoses.push_back(r.body->xf.position.x);
+            savedPoses.push_back(r.body->xf.position.y);
+            savedPoses.push_back(r.body->sweep.a);
+        }
+        for (const Puck& p : pucks) {
+            savedPucks.push_back(p.body->xf.position.x);
+            savedPucks.push_back(p.body->xf.position.y);
+        }
+        double pc = percentCompletion(analysisThreshold);
+        analysis.n_snapshots++;
+        analysis.completion = pc;
+        if (analysis.steps_to_completion == -1 && pc >= (double)analysisTarget) analysis.steps_to_completion = stepCount;
+        analysis.twc_num += stepCount * pc / 100.0;
+        analysis.twc_den += stepCount;
+    }
 
     void createPuck(int colour, float minX, float maxX) {  // Arena.java:143-161
         Vec2 pos;
@@ -1302,6 +1357,10 @@ struct Arena {
         pucks.clear();
         stepCount = 0;
         updateCount = 0;
+        savedStep = -1;
+        savedPoses.clear();
+        savedPucks.clear();
+        analysis = ps_arena_analysis{0, -1, 0.0, 0.0, 0.0};
     }
     // RunOffline.recreateArena (:97-113) + new Arena(world, null, false) (Arena.java:45-120) for Experiment(seed)
     void reset(int64_t seed) {
@@ -1421,6 +1480,7 @@ struct Arena {
             if (cfg.controller != PS_CTRL_EXTERNAL) r.controller->computeDesired(r.localMap, getPose(r), stepCount);
             move(r);
         }
+        if (stepCount % 100 == 0) storeRecord();   // Arena.STORAGE_INTERVAL
         stepCount++;
     }
     void coast() {  // Arena.java:310-316

@@ -6,7 +6,7 @@ arrays the ABI exchanges. Nothing in this module computes simulation results.
 import ctypes as C
 import numpy as np
 
-PS_ABI_VERSION = 2
+PS_ABI_VERSION = 3
 PS_MAX_COLOURS = 8
 PS_ROBOT_FIXTURES = 14
 PS_PUCK_FIXTURES = 2
@@ -154,10 +154,37 @@ class ps_obs_view(C.Structure):
 
 
 class ps_stats(C.Structure):
+    """Grouped by the reduction that combines ranks: int64 sums | double sums | int64 min | int64 max | double minima | double maxima."""
     _fields_ = [
         ("n_arenas", C.c_int64), ("cluster_size_hist", (C.c_int64 * 64) * PS_MAX_COLOURS),
         ("ctrl_state_hist", C.c_int64 * 8), ("n_carrying", C.c_int64), ("n_caches", C.c_int64),
-        ("sum_completion", C.c_double), ("n_touching_points", C.c_int64), ("n_contacts", C.c_int64),
+        ("n_touching_points", C.c_int64), ("n_contacts", C.c_int64), ("n_completed", C.c_int64),
+        ("sum_steps_to_completion", C.c_int64), ("n_snapshots", C.c_int64),
+        ("sum_completion", C.c_double), ("sum_twc", C.c_double),
+        ("min_steps_to_completion", C.c_int64), ("max_steps_to_completion", C.c_int64),
+        ("min_completion", C.c_double), ("min_twc", C.c_double),
+        ("max_completion", C.c_double), ("max_twc", C.c_double),
+    ]
+
+
+STATS_SEGMENTS = [   # (first field, last field, dtype, reduction): one collective each
+    ("n_arenas", "n_snapshots", np.int64, "sum"), ("sum_completion", "sum_twc", np.float64, "sum"),
+    ("min_steps_to_completion", "min_steps_to_completion", np.int64, "min"), ("max_steps_to_completion", "max_steps_to_completion", np.int64, "max"),
+    ("min_completion", "min_twc", np.float64, "min"), ("max_completion", "max_twc", np.float64, "max"),
+]
+
+
+class ps_snapshot_view(C.Structure):
+    _fields_ = [
+        ("step_count", C.POINTER(C.c_int32)), ("robot_pose", C.POINTER(C.c_float)), ("puck_xy", C.POINTER(C.c_float)),
+        ("cache_xy", C.POINTER(C.c_float)), ("state_counts", C.POINTER(C.c_int32)),
+    ]
+
+
+class ps_arena_analysis(C.Structure):
+    _fields_ = [
+        ("n_snapshots", C.c_int32), ("steps_to_completion", C.c_int32), ("twc_num", C.c_double), ("twc_den", C.c_double),
+        ("completion", C.c_double),
     ]
 
 
@@ -165,6 +192,7 @@ ROBOT_DTYPE = np.dtype(ps_robot_state)
 ARENA_DTYPE = np.dtype(ps_arena_state)
 LOCALMAP_DTYPE = np.dtype(ps_localmap)
 STATS_DTYPE = np.dtype(ps_stats)
+ANALYSIS_DTYPE = np.dtype(ps_arena_analysis)
 
 
 def _ptr(a, ctype):
@@ -201,6 +229,27 @@ class State:
         """(key, info, impulse[4]) of the live cached contacts of arena a, creation order."""
         n = int(self.arena[a]["n_contacts"])
         return self.contact_key[a, :n], self.contact_info[a, :n], self.contact_impulse[a, :n]
+
+
+class Snapshot:
+    """Caller-allocated host arrays of one ps_snapshot_view (the reference's periodic record of the latest storage step)."""
+
+    def __init__(self, n_arenas, n_robots, n_pucks_spawned):
+        self.step_count = np.full((n_arenas,), -1, np.int32)
+        self.robot_pose = np.zeros((n_arenas, n_robots, 3), np.float32)
+        self.puck_xy = np.zeros((n_arenas, max(1, n_pucks_spawned), 2), np.float32)[:, :n_pucks_spawned]
+        self.cache_xy = np.zeros((n_arenas, n_robots, PS_MAX_COLOURS, 2), np.float32)
+        self.state_counts = np.zeros((n_arenas, n_robots, 8), np.int32)
+
+    def view(self):
+        v = ps_snapshot_view()
+        v.step_count = _ptr(self.step_count, C.c_int32)
+        v.robot_pose = _ptr(self.robot_pose, C.c_float)
+        if self.puck_xy.size:
+            v.puck_xy = _ptr(self.puck_xy, C.c_float)
+        v.cache_xy = _ptr(self.cache_xy, C.c_float)
+        v.state_counts = _ptr(self.state_counts, C.c_int32)
+        return v
 
 
 class Observations:

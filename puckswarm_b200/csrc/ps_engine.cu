@@ -11,6 +11,8 @@
 #include <vector>
 #include <map>
 #include <mutex>
+#include <dlfcn.h>
+#include <climits>
 #include "ps_host.hpp"
 #include "ps_sense_dev.cuh"
 #include "ps_pipeline.cuh"
@@ -178,8 +180,10 @@ __global__ void __launch_bounds__(128) k_phys_pre(KParams p) {
     physPre(ctx, p.env, wk, st, wk.fx, wk.fy, p.queue, a);
 }
 
-// stage B1: islands too large for a lane slot (queue bucket 0): one warp per island, staged in shared memory
-__global__ void __launch_bounds__(128) k_island_warp(KParams p) {
+// stage B1: islands too large for a lane slot (queue bucket 0): one warp per island, staged in shared memory.
+// VEL_ONLY: the velocity half only (k_island_vel); the position sweeps follow in k_island_pos on the same stream.
+template <bool VEL_ONLY>
+__device__ __forceinline__ void islandWarpKernel(const KParams& p) {
     extern __shared__ __align__(16) char smem[];
     WarpSlot* slot = reinterpret_cast<WarpSlot*>(smem) + (threadIdx.x >> 5);
     // the islands with the most contacts (bucket kBucketLarge) are handed out first, then bucket 0
@@ -198,7 +202,7 @@ __global__ void __launch_bounds__(128) k_island_warp(KParams p) {
         ArenaState st = arenaState(p.sp, p.env.cfg, a);
         int iters = 0;
         long long tw0 = clock64();
-        bool ok = islandSolveWarp(p.env, wk, st, k, *slot, &iters);
+        bool ok = VEL_ONLY ? islandVelocityWarp(p.env, wk, st, k, *slot, &iters) : islandSolveWarp(p.env, wk, st, k, *slot, &iters);
         if (!ok && lane == 0) {
             atomicAdd(&p.islandHist[62], 1ULL);   // diagnostic: islands that did not fit a slot
             // too large for a slot: lane 0 runs the island straight from HBM / L2
@@ -216,6 +220,125 @@ __global__ void __launch_bounds__(128) k_island_warp(KParams p) {
             atomicMax(&p.islandHist[63], (kc << 32) | ((nc & 0xFFF) << 20) | ((nb & 0x3FF) << 10) | (unsigned long long)(iters & 0x3FF) | (ok ? 0ULL : (1ULL << 31)));
         }
         __syncwarp();
+    }
+}
+__global__ void __launch_bounds__(128) k_island_warp(KParams p) { islandWarpKernel<false>(p); }
+__global__ void __launch_bounds__(128) k_island_vel(KParams p) { islandWarpKernel<true>(p); }
+
+// stage B1b: the position sweeps of the islands k_island_vel prepared: G lanes per island, 32 / G islands per warp (one warp
+// per CTA), every group on its own row schedule, finished groups written back and refilled by the whole warp.
+template <int G>
+__global__ void __launch_bounds__(32) k_island_pos(KParams p) {
+    extern __shared__ __align__(16) char smem[];
+    constexpr int NG = 32 / G;
+    constexpr unsigned GMASK = G == 32 ? 0xFFFFFFFFu : ((1u << G) - 1u);
+    const unsigned FULL = 0xFFFFFFFFu;
+    PosSlot* slots = reinterpret_cast<PosSlot*>(smem);
+    int lane = threadIdx.x & 31, grp = lane / G, sub = lane % G;
+    PosSlot& S = slots[grp];
+    SlotCtx<PosSlot> L;
+    L.S = &S;
+    int posIters = p.env.cfg.posIters;
+    if (posIters <= 0) return;
+    int nLarge = min(p.queue.counts[kBucketLarge], p.queue.cap);
+    int total = nLarge + min(p.queue.counts[0], p.queue.cap);
+    unsigned NB = (unsigned)p.env.cfg.d.NB;
+    bool running = false, exhausted = false;
+    int myEntry = -1;                  // arena * NB + island of this group's island
+    int nRows = 0, r = 0, base = 0, rowEnd = 0, iters = 0;
+    float minSep = 0.0f;
+    bool changed = false;
+    for (;;) {
+        // ---- finish + refill, by the whole warp, for every group that has no island
+        unsigned need = __ballot_sync(FULL, !running && !exhausted);
+        while (need) {
+            int g = (__ffs(need) - 1) / G;
+            need &= ~(GMASK << (g * G));
+            int ent = __shfl_sync(FULL, myEntry, g * G);
+            int its = __shfl_sync(FULL, iters, g * G);
+            PosSlot& T = slots[g];
+            if (ent >= 0) {
+                int a = (int)((unsigned)ent / NB), k = (int)((unsigned)ent % NB);
+                PhysWork wk = arenaWork(p, a);
+                posFinish(p.env, wk, k, T, lane);
+                if (lane == 0) atomicMax(&wk.stats[0], its);
+            }
+            bool mine = grp == g;
+            if (mine) myEntry = -1;
+            bool staged = false;
+            unsigned entry = 0;
+            while (!staged) {   // islands that outgrew the slot were solved by k_island_vel's fallback: skip them
+                int idx = 0;
+                if (lane == 0) idx = atomicAdd(&p.queue.counts[kQueueBuckets + 1], 1);
+                idx = __shfl_sync(FULL, idx, 0);
+                if (idx >= total) break;
+                entry = idx < nLarge ? p.queue.entries[(size_t)kBucketLarge * p.queue.cap + idx] : p.queue.entries[idx - nLarge];
+                int a = (int)(entry / NB), k = (int)(entry % NB);
+                PhysWork wk = arenaWork(p, a);
+                __syncwarp();
+                staged = posStage(p.env, wk, k, T, lane);
+            }
+            __syncwarp();
+            if (mine) {
+                if (staged) {
+                    myEntry = (int)entry;
+                    running = true;
+                    iters = 0;
+                    nRows = T.nRows;
+                    r = 0;
+                    base = 0;
+                    rowEnd = T.rowStart[1];
+                    minSep = 0.0f;
+                    changed = false;
+                } else {
+                    exhausted = true;
+                }
+            }
+        }
+        if (__all_sync(FULL, !running)) break;
+        // ---- one pass of every running group's current row: a lane pair per constraint, G / 2 constraints per pass
+        {
+            int q = base + (sub >> 1);
+            bool on = running && q < rowEnd;
+            int ci = on ? q : 0;
+            uint32_t hd = on ? S.pcHead[ci] : 0u;
+            int bA = (int)(hd & 255u), bB = (int)((hd >> 8) & 255u), type = (int)((hd >> 16) & 255u), np = (int)(hd >> 24);
+            V2 ln = mk(S.pc[ci][0], S.pc[ci][1]), lp = mk(S.pc[ci][2], S.pc[ci][3]);
+            float radius = S.pc[ci][8];
+            float sep0 = lkCorrectPointPair(p.env, L, on && np > 0, sub & 1, bA, bB, type, ln, lp, mk(S.pc[ci][4], S.pc[ci][5]), radius, &changed);
+            minSep = fminf_(minSep, sep0);
+            if (__any_sync(FULL, np > 1)) {
+                float sep1 = lkCorrectPointPair(p.env, L, on && np > 1, sub & 1, bA, bB, type, ln, lp, mk(S.pc[ci][6], S.pc[ci][7]), radius, &changed);
+                minSep = fminf_(minSep, sep1);
+            }
+        }
+        // ---- advance the cursors; at the end of a sweep the group decides like ContactSolver.solvePositionConstraints' caller
+        float m = minSep;
+        for (int o = 1; o < G; o <<= 1) m = fminf_(m, __shfl_xor_sync(FULL, m, o));
+        unsigned chg = __ballot_sync(FULL, changed);
+        if (running) {
+            base += G / 2;
+            if (base >= rowEnd) {
+                ++r;
+                if (r < nRows) {
+                    base = rowEnd;
+                    rowEnd = S.rowStart[r + 1];
+                } else {
+                    ++iters;
+                    bool anyChanged = ((chg >> (grp * G)) & GMASK) != 0u;
+                    if (m >= -1.5f * kLinearSlop || iters >= posIters) running = false;
+                    else if (!anyChanged) {   // fixed point: every later sweep repeats this one
+                        iters = posIters;
+                        running = false;
+                    }
+                    r = 0;
+                    base = 0;
+                    rowEnd = S.rowStart[1];
+                    minSep = 0.0f;
+                    changed = false;
+                }
+            }
+        }
     }
 }
 
@@ -407,7 +530,10 @@ struct ps_engine {
     int* dStepStats = nullptr;
     int nSlots = 0, threads = 128;
     bool fused = false;      // PS_FUSED=1: the single-kernel World.step (kept for comparison)
-    int workerBlocks = 0, batchBlocks = 0, bigBlocks = 0;
+    int workerBlocks = 0, batchBlocks = 0, bigBlocks = 0, posBlocks = 0;
+    int islandG = 0;         // PS_ISLAND_G = 2 / 4 / 8: split solver (k_island_vel + k_island_pos with G lanes per island); 0 (default): the one-kernel
+                             // warp-per-island solver. The split solver issues 4-5x fewer instructions but every island's sweeps take longer (the groups
+                             // of a warp share each other's divergent paths), and the tick waits for the longest island: measured slower (profiles/r02_summary.md)
     bool mergeBatch = true;    // one launch for all lane buckets (PS_MERGE_BATCH=0: one launch and stream per bucket)
     size_t smemBytes = 0;
     int64_t launches = 0;
@@ -417,6 +543,9 @@ struct ps_engine {
     ps_stats* dStats = nullptr;
     float* dCmd = nullptr;
     int* dErr = nullptr;     // [2]: OR of the arenas' error flags, flagged arenas (k_error_scan)
+    SnapPtrs snap = {};      // the reference's periodic record + Analyze accumulators (ps_sense_dev.cuh)
+    int stepCount = 0;       // Arena.stepCount of the batch (think steps done; all arenas in lock step)
+    float analysisThreshold = 1.5f, analysisTarget = 50.0f;
     bool isReset = false;
     // optional per-kernel timing (CUDA events on the engine's stream): classes 0 sense, 1 think, 2 physics, 3 other
     bool profiling = false;
@@ -473,6 +602,8 @@ int ps_struct_size(int which) {
         case 4: return (int)sizeof(ps_stats);
         case 5: return (int)sizeof(ps_state_view);
         case 6: return (int)sizeof(ps_obs_view);
+        case 7: return (int)sizeof(ps_snapshot_view);
+        case 8: return (int)sizeof(ps_arena_analysis);
         default: return -1;
     }
 }
@@ -557,6 +688,12 @@ int ps_destroy(ps_handle h) {
     cudaFree(h->dStats);
     cudaFree(h->dCmd);
     cudaFree(h->dErr);
+    cudaFree(h->snap.step);
+    cudaFree(h->snap.pose);
+    cudaFree(h->snap.puck);
+    cudaFree(h->snap.cache);
+    cudaFree(h->snap.counts);
+    cudaFree(h->snap.an);
     h->sd.release();
     for (auto& g : h->groups) {
         if (g.evPre) cudaEventDestroy(g.evPre);
@@ -645,6 +782,13 @@ int ps_create(const ps_config* cfg, int device, ps_handle* out) {
     TRY_OR_FREE(cudaMemset(e->dStats, 0, sizeof(ps_stats)));
     TRY_OR_FREE(cudaMalloc(&e->dCmd, 2 * A * pc.d.R * sizeof(float) + 16));
     TRY_OR_FREE(cudaMalloc(&e->dErr, 2 * sizeof(int)));
+    TRY_OR_FREE(cudaMalloc(&e->snap.step, A * sizeof(int)));
+    TRY_OR_FREE(cudaMalloc(&e->snap.pose, A * pc.d.R * 3 * sizeof(float)));
+    TRY_OR_FREE(cudaMalloc(&e->snap.puck, (A * pc.d.P * 2 + 4) * sizeof(float)));
+    TRY_OR_FREE(cudaMalloc(&e->snap.cache, A * pc.d.R * PS_MAX_COLOURS * 2 * sizeof(float)));
+    TRY_OR_FREE(cudaMalloc(&e->snap.counts, A * pc.d.R * 8 * sizeof(int)));
+    TRY_OR_FREE(cudaMalloc(&e->snap.an, A * sizeof(ps_arena_analysis)));
+    e->analysisThreshold = cfg->cluster_distance_threshold;
     // working memory: shared memory up to the budget, the rest per slot in HBM
     e->threads = (int)envSize("PS_THREADS", 128);
     if (e->threads < 32 || e->threads > 256 || (e->threads & 31)) e->threads = 128;
@@ -678,7 +822,7 @@ int ps_create(const ps_config* cfg, int device, ps_handle* out) {
         size_t perGroup = (A + nGroups - 1) / nGroups;
         int qcap = (int)std::min<size_t>(perGroup * (size_t)pc.d.NB, (size_t)1 << 27);
         TRY_OR_FREE(cudaMalloc(&e->kp.queue.entries, (size_t)nGroups * kQueueBuckets * qcap * sizeof(unsigned)));
-        TRY_OR_FREE(cudaMalloc(&e->kp.queue.counts, (size_t)nGroups * (kQueueBuckets + 1) * sizeof(int)));
+        TRY_OR_FREE(cudaMalloc(&e->kp.queue.counts, (size_t)nGroups * (kQueueBuckets + 2) * sizeof(int)));
         e->kp.queue.cap = qcap;
         e->groups.resize(nGroups);
         for (int g = 0; g < nGroups; g++) {
@@ -686,7 +830,7 @@ int ps_create(const ps_config* cfg, int device, ps_handle* out) {
             G.a0 = (int)std::min<size_t>(A, g * perGroup);
             G.n = (int)(std::min<size_t>(A, (g + 1) * perGroup) - G.a0);
             G.q.entries = e->kp.queue.entries + (size_t)g * kQueueBuckets * qcap;
-            G.q.counts = e->kp.queue.counts + (size_t)g * (kQueueBuckets + 1);
+            G.q.counts = e->kp.queue.counts + (size_t)g * (kQueueBuckets + 2);
             G.q.cap = qcap;
             TRY_OR_FREE(cudaStreamCreateWithFlags(&G.s, cudaStreamNonBlocking));
             // the island kernels are small and latency-bound: their CTAs go ahead of the other groups' wide kernels
@@ -703,6 +847,13 @@ int ps_create(const ps_config* cfg, int device, ps_handle* out) {
         TRY_OR_FREE(cudaMemset(e->kp.islandHist, 0, 64 * sizeof(unsigned long long)));
         e->workerBlocks = prop.multiProcessorCount * (int)envSize("PS_WORKER_BLOCKS_PER_SM", 4);
         TRY_OR_FREE(cudaFuncSetAttribute(k_island_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(WarpSlot))));
+        TRY_OR_FREE(cudaFuncSetAttribute(k_island_vel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(WarpSlot))));
+        e->islandG = (int)envSize("PS_ISLAND_G", 0);
+        if (e->islandG != 0 && e->islandG != 2 && e->islandG != 4 && e->islandG != 8) e->islandG = 0;
+        TRY_OR_FREE(cudaFuncSetAttribute(k_island_pos<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(16 * sizeof(PosSlot))));
+        TRY_OR_FREE(cudaFuncSetAttribute(k_island_pos<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(PosSlot))));
+        TRY_OR_FREE(cudaFuncSetAttribute(k_island_pos<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(PosSlot))));
+        e->posBlocks = prop.multiProcessorCount * (int)envSize("PS_POS_BLOCKS_PER_SM", 4);
         TRY_OR_FREE(cudaFuncSetAttribute(k_island_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((kBatchThreads / 32) * sizeof(LaneSlotsU))));
         e->mergeBatch = envSize("PS_MERGE_BATCH", 1) != 0;
         e->bigBlocks = prop.multiProcessorCount * 4;
@@ -785,6 +936,30 @@ int ps_sync(ps_handle h) {
     return PS_OK;
 }
 
+__global__ void k_snap_clear(SnapPtrs sn, int nArenas, int R) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= nArenas) return;
+    sn.step[a] = -1;
+    ps_arena_analysis z;
+    z.n_snapshots = 0;
+    z.steps_to_completion = -1;
+    z.twc_num = z.twc_den = z.completion = 0.0;
+    sn.an[a] = z;
+}
+// forget the periodic records and the Analyze accumulators (a new episode starts)
+static int clearRecords(ps_handle h) {
+    const PhysCfg& pc = h->hs.phys;
+    size_t A = (size_t)h->kp.nArenas;
+    CUDA_TRY(cudaMemsetAsync(h->snap.pose, 0, A * pc.d.R * 3 * sizeof(float), h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->snap.puck, 0, (A * pc.d.P * 2 + 4) * sizeof(float), h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->snap.cache, 0, A * pc.d.R * PS_MAX_COLOURS * 2 * sizeof(float), h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->snap.counts, 0, A * pc.d.R * 8 * sizeof(int), h->stream));
+    k_snap_clear<<<(unsigned)((A + 127) / 128), 128, 0, h->stream>>>(h->snap, (int)A, pc.d.R);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PS_OK;
+}
+
 int ps_reset(ps_handle h, const int64_t* seeds) {
     if (!h || !seeds) return setError(PS_E_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(h->device));
@@ -793,8 +968,10 @@ int ps_reset(ps_handle h, const int64_t* seeds) {
     k_reset<<<h->nSlots, h->threads, h->smemBytes, h->stream>>>(h->kp);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
+    { int cr = clearRecords(h); if (cr != PS_OK) return cr; }
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     h->updateCount = 0;
+    h->stepCount = 0;
     h->isReset = true;
     return PS_OK;
 }
@@ -809,16 +986,23 @@ static int launchPerturb(ps_handle h, int a0, int n, cudaStream_t s) {
 }
 
 // Arena.step of one group on a think tick: perturbations, then on-device sense + think (think == 1) or the step counter alone
-static int launchThinkStage(ps_handle h, ps_engine::Group& G, int think) {
+static constexpr int kStorageInterval = 100;   // Arena.STORAGE_INTERVAL (Arena.java:39)
+static int launchThinkStage(ps_handle h, ps_engine::Group& G, int think, int stepCount) {
     int rc = launchPerturb(h, G.a0, G.n, G.s);
     if (rc != PS_OK) return rc;
     int R = h->hs.phys.d.R;
+    // the reference's periodic record is due when Arena.stepCount is a multiple of the storage interval (Arena.java:223)
+    bool storage = stepCount % kStorageInterval == 0;
     if (think == 1) {
         {
             ScopedTimer timer(h, 0, G.s);
             rc = h->sd.launchSense(h->kp.env, h->kp.sp, G.s, &h->launches, false, G.a0 * R, G.n * R);
         }
         if (rc != PS_OK) return setError(rc, h->sd.error);
+        if (storage) {
+            k_snap_pre<<<(G.n * R + 127) / 128, 128, 0, G.s>>>(h->kp.sp, h->snap, G.a0, G.n, R, kStorageInterval);
+            h->launches++;
+        }
         {
             ScopedTimer timer(h, 1, G.s);
             rc = h->sd.launchThink(G.a0, G.n, G.s, &h->launches);
@@ -826,6 +1010,15 @@ static int launchThinkStage(ps_handle h, ps_engine::Group& G, int think) {
         if (rc != PS_OK) return setError(rc, h->sd.error);
     } else {
         k_count_step<<<(G.n + 127) / 128, 128, 0, G.s>>>(h->kp.sp.arena + G.a0, G.n);
+        h->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (storage && (think == 1 || h->sd.ready)) {
+        // host controllers (think == 2): the poses are those of the ps_sense the caller has just run for this step
+        int P = h->hs.phys.d.P;
+        size_t sh = (size_t)2 * (P > 0 ? P : 1) * sizeof(int);
+        k_snap_post<<<G.n, 128, sh, G.s>>>(h->kp.env, h->kp.sp, h->snap, h->sd.kp.obs.pose, G.a0, kStorageInterval, think == 1 ? 1 : 0, h->hs.cfg.controller,
+                                           h->hs.cfg.n_puck_types, h->hs.cfg.n_pucks, h->analysisThreshold, h->analysisTarget);
         h->launches++;
         CUDA_TRY(cudaGetLastError());
     }
@@ -839,7 +1032,7 @@ static int enqueuePreIslands(ps_handle h, ps_engine::Group& G) {
     KParams kp = h->kp;
     kp.a0 = G.a0;
     kp.queue = G.q;
-    CUDA_TRY(cudaMemsetAsync(G.q.counts, 0, (kQueueBuckets + 1) * sizeof(int), G.s));
+    CUDA_TRY(cudaMemsetAsync(G.q.counts, 0, (kQueueBuckets + 2) * sizeof(int), G.s));
     {
         ScopedTimer t4(h, 4, G.s);
         k_phys_pre<<<G.n, 128, 0, G.s>>>(kp);
@@ -854,7 +1047,18 @@ static int enqueuePreIslands(ps_handle h, ps_engine::Group& G) {
         k_island_big<<<std::max(1, std::min(h->bigBlocks, G.n)), 32, sizeof(BigSlot), G.sb[kBucketBig]>>>(kp);
         CUDA_TRY(cudaEventRecord(G.evb[kBucketBig], G.sb[kBucketBig]));
         int wb = std::max(1, std::min(h->workerBlocks, G.n * 3));
-        k_island_warp<<<wb, 128, 4 * sizeof(WarpSlot), G.s2>>>(kp);
+        if (h->islandG == 0) {
+            k_island_warp<<<wb, 128, 4 * sizeof(WarpSlot), G.s2>>>(kp);
+        } else {
+            // velocity half one warp per island, then the position sweeps G lanes per island (32 / G islands per warp)
+            k_island_vel<<<wb, 128, 4 * sizeof(WarpSlot), G.s2>>>(kp);
+            int pb = std::max(1, std::min(h->posBlocks, (G.n * 2 * h->islandG + 31) / 32));
+            size_t sm = (size_t)(32 / h->islandG) * sizeof(PosSlot);
+            if (h->islandG == 2) k_island_pos<2><<<pb, 32, sm, G.s2>>>(kp);
+            else if (h->islandG == 4) k_island_pos<4><<<pb, 32, sm, G.s2>>>(kp);
+            else k_island_pos<8><<<pb, 32, sm, G.s2>>>(kp);
+            h->launches++;
+        }
         CUDA_TRY(cudaEventRecord(G.evBig, G.s2));
         int bb = std::max(1, std::min(h->batchBlocks, (G.n * 12 + kBatchThreads - 1) / kBatchThreads));
         if (h->mergeBatch) {
@@ -902,9 +1106,10 @@ static int enqueueTicks(ps_handle h, int nTicks, int think) {
     if (h->fused) {
         ps_engine::Group& G = h->groups[0];
         int uc = h->updateCount, interval = h->hs.cfg.step_interval, t = 0;
+        int sc = h->stepCount;
         while (t < nTicks) {
             if (think && uc % interval == 0) {
-                int rc = launchThinkStage(h, G, think);
+                int rc = launchThinkStage(h, G, think, sc++);
                 if (rc != PS_OK) return rc;
             }
             int run = think ? interval - uc % interval : nTicks;
@@ -924,9 +1129,10 @@ static int enqueueTicks(ps_handle h, int nTicks, int think) {
     int interval = h->hs.cfg.step_interval;
     for (auto& G : h->groups) {
         if (G.n == 0) continue;
+        int sc = h->stepCount;
         for (int t = 0; t < nTicks; ++t) {
             int uc = h->updateCount + t, rc;
-            if (think && uc % interval == 0 && (rc = launchThinkStage(h, G, think)) != PS_OK) return rc;
+            if (think && uc % interval == 0 && (rc = launchThinkStage(h, G, think, sc++)) != PS_OK) return rc;
             if ((rc = enqueuePreIslands(h, G)) != PS_OK) return rc;
             if ((rc = enqueuePost(h, G)) != PS_OK) return rc;
         }
@@ -965,6 +1171,11 @@ int ps_step(ps_handle h, int n_ticks) {
     if (rc != PS_OK) return rc;
     rc = enqueueTicks(h, n_ticks, onDevice ? 1 : 2);
     if (rc != PS_OK) return rc;
+    {
+        int interval = h->hs.cfg.step_interval, uc = h->updateCount;
+        for (int t = 0; t < n_ticks; ++t)
+            if ((uc + t) % interval == 0) h->stepCount++;
+    }
     h->updateCount += n_ticks;
     h->groupsDirty = true;
     return PS_OK;
@@ -993,6 +1204,16 @@ int ps_step_external(ps_handle h, const float* forwards, const float* torque) {
     k_count_step<<<(h->kp.nArenas + 127) / 128, 128, 0, h->stream>>>(h->kp.sp.arena, h->kp.nArenas);
     h->launches += 2;
     CUDA_TRY(cudaGetLastError());
+    if (h->stepCount % kStorageInterval == 0 && h->sd.ready) {
+        // the periodic record of a host-controller run: poses of the ps_sense the caller ran for this step, pucks, Analyze row
+        int P = h->hs.phys.d.P;
+        size_t sh = (size_t)2 * (P > 0 ? P : 1) * sizeof(int);
+        k_snap_post<<<h->kp.nArenas, 128, sh, h->stream>>>(h->kp.env, h->kp.sp, h->snap, h->sd.kp.obs.pose, 0, kStorageInterval, 0, h->hs.cfg.controller,
+                                                          h->hs.cfg.n_puck_types, h->hs.cfg.n_pucks, h->analysisThreshold, h->analysisTarget);
+        h->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    h->stepCount++;
     // the caller may reuse its arrays as soon as we return
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     int rc = forkGroups(h);
@@ -1070,7 +1291,8 @@ int ps_set_state(ps_handle h, const ps_state_view* v) {
         unsigned maxProxy = (unsigned)(kWallFixtures + pc.d.NP);
         for (int a = 0; a < nA; ++a) {
             const ps_arena_state& as = v->arena[a];
-            if (as.update_count != uc) return setError(PS_E_INVALID, "ps_set_state: update_count differs between arenas (arenas step in lock step)");
+            if (as.update_count != uc || as.step_count != v->arena[0].step_count)
+                return setError(PS_E_INVALID, "ps_set_state: update_count / step_count differ between arenas (arenas step in lock step)");
             if (as.n_contacts < 0 || as.n_contacts > pc.MC) return setError(PS_E_INVALID, "ps_set_state: n_contacts outside [0, max_contacts]");
             if (v->contact_key) {
                 const uint32_t* key = v->contact_key + (size_t)a * pc.MC;
@@ -1083,7 +1305,10 @@ int ps_set_state(ps_handle h, const ps_state_view* v) {
     }
     int rc = copyState(h, v, false);
     if (rc != PS_OK) return rc;
-    if (v->arena) h->updateCount = v->arena[0].update_count;
+    if (v->arena) {
+        h->updateCount = v->arena[0].update_count;
+        h->stepCount = v->arena[0].step_count;
+    }
     h->isReset = true;
     return PS_OK;
 }
@@ -1098,15 +1323,21 @@ int ps_get_observations(ps_handle h, ps_obs_view* v) {
     return PS_OK;
 }
 
-int ps_compute_stats(ps_handle h, float cluster_threshold, ps_stats* out) {
-    if (!h || !out) return setError(PS_E_INVALID, "null argument");
-    CUDA_TRY(cudaSetDevice(h->device));
+// ps_stats of this handle's arenas into h->dStats (device) and *out (host)
+static int computeStatsLocal(ps_handle h, float cluster_threshold, ps_stats* out) {
     { int jr = joinGroups(h); if (jr != PS_OK) return jr; }
-    CUDA_TRY(cudaMemsetAsync(h->dStatsDev, 0, sizeof(StatsDev), h->stream));
+    StatsDev init;
+    std::memset(&init, 0, sizeof(init));
+    init.minStc = ~0ULL;
+    init.minSumMax = INT_MAX;
+    init.maxSumMax = 0;
+    init.minTwcBits = ~0ULL;
+    CUDA_TRY(cudaMemcpyAsync(h->dStatsDev, &init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));   // `init` is a stack object
     int P = h->hs.phys.d.P;
     size_t sh = (size_t)2 * (P > 0 ? P : 1) * sizeof(int);
     if (sh > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-    k_stats<<<h->kp.nArenas, 128, sh, h->stream>>>(h->kp.env, h->kp.sp, h->hs.cfg.n_puck_types, h->hs.cfg.controller, cluster_threshold, h->dStatsDev);
+    k_stats<<<h->kp.nArenas, 128, sh, h->stream>>>(h->kp.env, h->kp.sp, h->hs.cfg.n_puck_types, h->hs.cfg.controller, cluster_threshold, h->dStatsDev, h->snap.an);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     StatsDev sd;
@@ -1119,10 +1350,112 @@ int ps_compute_stats(ps_handle h, float cluster_threshold, ps_stats* out) {
     for (int i = 0; i < 8; i++) out->ctrl_state_hist[i] = (int64_t)sd.ctrlState[i];
     out->n_carrying = (int64_t)sd.nCarrying;
     out->n_caches = (int64_t)sd.nCaches;
-    out->sum_completion = h->hs.cfg.n_pucks > 0 ? 100.0 * (double)sd.sumMax / (double)h->hs.cfg.n_pucks : 0.0;   // Analyze.java:90,197: / the Arena.nPucks property
+    double perPuck = h->hs.cfg.n_pucks > 0 ? 100.0 / (double)h->hs.cfg.n_pucks : 0.0;   // Analyze.java:90,197: / the Arena.nPucks property
+    out->sum_completion = (double)sd.sumMax * perPuck;
+    out->min_completion = (double)sd.minSumMax * perPuck;
+    out->max_completion = (double)sd.maxSumMax * perPuck;
     out->n_touching_points = (int64_t)sd.nTouching;
     out->n_contacts = (int64_t)sd.nContacts;
+    out->n_completed = (int64_t)sd.nCompleted;
+    out->sum_steps_to_completion = (int64_t)sd.sumStc;
+    out->n_snapshots = (int64_t)sd.nSnapshots;
+    out->min_steps_to_completion = sd.nCompleted ? (int64_t)sd.minStc : INT64_MAX;
+    out->max_steps_to_completion = sd.nCompleted ? (int64_t)sd.maxStcPlus1 - 1 : -1;
+    out->sum_twc = sd.sumTwc;
+    std::memcpy(&out->min_twc, &sd.minTwcBits, sizeof(double));
+    std::memcpy(&out->max_twc, &sd.maxTwcBits, sizeof(double));
     CUDA_TRY(cudaMemcpyAsync(h->dStats, out, sizeof(*out), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return PS_OK;
+}
+
+int ps_compute_stats(ps_handle h, float cluster_threshold, ps_stats* out) {
+    if (!h || !out) return setError(PS_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    return computeStatsLocal(h, cluster_threshold, out);
+}
+
+// NCCL is the caller's (the communicator comes from the host process): resolve ncclAllReduce from libnccl.so.2 on first use
+typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef const char* (*nccl_errstr_fn)(int);
+static nccl_allreduce_fn g_ncclAllReduce = nullptr;
+static nccl_errstr_fn g_ncclErrStr = nullptr;
+static bool loadNccl() {
+    static std::mutex m;
+    std::lock_guard<std::mutex> lock(m);
+    if (g_ncclAllReduce) return true;
+    void* lib = dlopen(nullptr, RTLD_NOW);   // already in the process (torch loads its bundled copy)?
+    void* sym = lib ? dlsym(lib, "ncclAllReduce") : nullptr;
+    if (!sym) {
+        const char* env = getenv("PS_NCCL_LIB");
+        lib = dlopen(env && *env ? env : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        sym = lib ? dlsym(lib, "ncclAllReduce") : nullptr;
+    }
+    if (!sym) return false;
+    g_ncclErrStr = (nccl_errstr_fn)dlsym(lib, "ncclGetErrorString");
+    g_ncclAllReduce = (nccl_allreduce_fn)sym;
+    return true;
+}
+
+int ps_get_stats(ps_handle h, float cluster_threshold, ps_stats* out, void* nccl_comm) {
+    if (!h || !out) return setError(PS_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = computeStatsLocal(h, cluster_threshold, out);
+    if (rc != PS_OK || !nccl_comm) return rc;
+    if (!loadNccl()) return setError(PS_E_INVALID, "ps_get_stats: ncclAllReduce not found (libnccl.so.2; PS_NCCL_LIB overrides the path)");
+    // one collective per reduction group of ps_stats, in place on the device copy, on the handle's stream
+    enum { kInt64 = 4, kFloat64 = 8, kSum = 0, kMax = 2, kMin = 3 };
+    struct Seg { size_t off, count; int type, op; };
+    const Seg segs[] = {
+        {offsetof(ps_stats, n_arenas), (offsetof(ps_stats, sum_completion) - offsetof(ps_stats, n_arenas)) / 8, kInt64, kSum},
+        {offsetof(ps_stats, sum_completion), 2, kFloat64, kSum},
+        {offsetof(ps_stats, min_steps_to_completion), 1, kInt64, kMin},
+        {offsetof(ps_stats, max_steps_to_completion), 1, kInt64, kMax},
+        {offsetof(ps_stats, min_completion), 2, kFloat64, kMin},
+        {offsetof(ps_stats, max_completion), 2, kFloat64, kMax},
+    };
+    for (const Seg& sg : segs) {
+        char* p = (char*)h->dStats + sg.off;
+        int nr = g_ncclAllReduce(p, p, sg.count, sg.type, sg.op, nccl_comm, h->stream);
+        if (nr != 0) return setError(PS_E_CUDA, std::string("ncclAllReduce: ") + (g_ncclErrStr ? g_ncclErrStr(nr) : "error"));
+    }
+    CUDA_TRY(cudaMemcpyAsync(out, h->dStats, sizeof(*out), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return PS_OK;
+}
+
+int ps_get_snapshot(ps_handle h, ps_snapshot_view* v) {
+    if (!h || !v) return setError(PS_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    { int jr = joinGroups(h); if (jr != PS_OK) return jr; }
+    const PhysCfg& pc = h->hs.phys;
+    size_t A = (size_t)h->kp.nArenas;
+    if (v->step_count) CUDA_TRY(cudaMemcpyAsync(v->step_count, h->snap.step, A * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (v->robot_pose) CUDA_TRY(cudaMemcpyAsync(v->robot_pose, h->snap.pose, A * pc.d.R * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (v->puck_xy && pc.d.P > 0) CUDA_TRY(cudaMemcpyAsync(v->puck_xy, h->snap.puck, A * pc.d.P * 2 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (v->cache_xy) CUDA_TRY(cudaMemcpyAsync(v->cache_xy, h->snap.cache, A * pc.d.R * PS_MAX_COLOURS * 2 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (v->state_counts) CUDA_TRY(cudaMemcpyAsync(v->state_counts, h->snap.counts, A * pc.d.R * 8 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return PS_OK;
+}
+
+int ps_get_analysis(ps_handle h, ps_arena_analysis* out) {
+    if (!h || !out) return setError(PS_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    { int jr = joinGroups(h); if (jr != PS_OK) return jr; }
+    CUDA_TRY(cudaMemcpyAsync(out, h->snap.an, (size_t)h->kp.nArenas * sizeof(ps_arena_analysis), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return PS_OK;
+}
+
+int ps_analysis_config(ps_handle h, float cluster_threshold, float target_percent) {
+    if (!h || !(cluster_threshold >= 0.0f)) return setError(PS_E_INVALID, "bad argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    { int jr = joinGroups(h); if (jr != PS_OK) return jr; }
+    h->analysisThreshold = cluster_threshold;
+    h->analysisTarget = target_percent;
+    int rc = clearRecords(h);
+    if (rc != PS_OK) return rc;
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return PS_OK;
 }

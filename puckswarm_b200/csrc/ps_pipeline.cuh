@@ -21,7 +21,7 @@ struct IslandQueue {
     unsigned* entries;     // [kQueueBuckets][cap]: arena * NB + island. Bucket 0: islands that do not fit a lane slot or have
                            // >= PhysCfg::warpMinContacts contacts (one warp each, level-parallel sweeps); buckets 1..4: lane batches of
                            // islands with 1-2, 3-5, 6-12, 13+ contacts (like with like, so that the lanes of a warp finish together)
-    int* counts;           // [kQueueBuckets + 1]: entries per bucket, last = consumer head of bucket 0
+    int* counts;           // [kQueueBuckets + 2]: entries per bucket, then the consumer heads of the warp-bucket kernels (k_island_vel / k_island_warp, k_island_pos)
     int cap;
 };
 static constexpr int kQueueWarpBodies = 48, kQueueWarpContacts = 64;   // = kWarpBodies, kWarpContacts of ps_island_lanes.cuh

@@ -116,8 +116,13 @@ struct StatsDev {
     unsigned long long clusterHist[PS_MAX_COLOURS][64];
     unsigned long long ctrlState[8];
     unsigned long long nCarrying, nCaches, sumMax, nTouching, nContacts;
+    unsigned long long nCompleted, sumStc, nSnapshots;
+    unsigned long long minStc, maxStcPlus1;          // over the completed arenas; maxStcPlus1 = 0 when none
+    int minSumMax, maxSumMax;                        // extrema of sum_k max cluster size_k
+    double sumTwc;
+    unsigned long long minTwcBits, maxTwcBits;       // time-weighted completion is >= 0: its bit pattern orders like the value
 };
-__global__ void __launch_bounds__(128) k_stats(PhysEnv env, StatePtrs sp, int nTypes, int controller, float threshold, StatsDev* out) {
+__global__ void __launch_bounds__(128) k_stats(PhysEnv env, StatePtrs sp, int nTypes, int controller, float threshold, StatsDev* out, const ps_arena_analysis* an) {
     extern __shared__ int sh[];   // parent[P], size[P]
     const Dims& d = env.cfg.d;
     int a = blockIdx.x;
@@ -161,6 +166,21 @@ __global__ void __launch_bounds__(128) k_stats(PhysEnv env, StatePtrs sp, int nT
         int sum = 0;
         for (int k = 0; k < nTypes; ++k) sum += maxOfType[k];
         atomicAdd(&out->sumMax, (unsigned long long)sum);
+        atomicMin(&out->minSumMax, sum);
+        atomicMax(&out->maxSumMax, sum);
+        // analysis.Analyze's per-repetition results (accumulated by k_snap_post)
+        const ps_arena_analysis& A = an[a];
+        atomicAdd(&out->nSnapshots, (unsigned long long)A.n_snapshots);
+        if (A.steps_to_completion >= 0) {
+            atomicAdd(&out->nCompleted, 1ULL);
+            atomicAdd(&out->sumStc, (unsigned long long)A.steps_to_completion);
+            atomicMin(&out->minStc, (unsigned long long)A.steps_to_completion);
+            atomicMax(&out->maxStcPlus1, (unsigned long long)A.steps_to_completion + 1ULL);
+        }
+        double twc = A.twc_den > 0.0 ? A.twc_num / A.twc_den : 0.0;   // Analyze.java:212-216
+        atomicAdd(&out->sumTwc, twc);
+        atomicMin(&out->minTwcBits, (unsigned long long)__double_as_longlong(twc));
+        atomicMax(&out->maxTwcBits, (unsigned long long)__double_as_longlong(twc));
     }
     const ps_robot_state* rs = sp.robot + (size_t)a * d.R;
     for (int r = threadIdx.x; r < d.R; r += blockDim.x) {
@@ -177,6 +197,101 @@ __global__ void __launch_bounds__(128) k_stats(PhysEnv env, StatePtrs sp, int nT
     for (int i = threadIdx.x; i < nc; i += blockDim.x) touching += (int)(st.cinfo[i] & 3u);
     if (touching) atomicAdd(&out->nTouching, (unsigned long long)touching);
     if (threadIdx.x == 0) atomicAdd(&out->nContacts, (unsigned long long)nc);
+}
+
+// ---- the reference's periodic record (Arena.java:223-243, CacheConsController.java:313-333,531-551, BHDController.java:103-123)
+// and analysis.Analyze's per-repetition statistics (Analyze.java:176-218), kept per arena on the device.
+// At a think step whose Arena.stepCount is a multiple of the storage interval the reference writes robot poses and puck positions
+// (after the perturbations, before World.step), every robot's cache points after this step's think, and its recentStateCounts
+// (counted up to and including this step, then cleared). k_snap_pre runs before the think kernel (it saves the counters the
+// controllers are about to clear), k_snap_post after it.
+struct SnapPtrs {
+    int* step;            // [A] Arena.stepCount of the record, -1 = none yet
+    float* pose;          // [A][R][3]
+    float* puck;          // [A][P][2]
+    float* cache;         // [A][R][PS_MAX_COLOURS][2], NaN = null
+    int* counts;          // [A][R][8]
+    ps_arena_analysis* an;   // [A]
+};
+
+__global__ void k_snap_pre(StatePtrs sp, SnapPtrs sn, int a0, int nArenas, int R, int interval) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nArenas * R) return;
+    int a = a0 + i / R;
+    if (sp.arena[a].step_count % interval != 0) return;
+    const ps_robot_state& rs = sp.robot[(size_t)a0 * R + i];
+    int* out = sn.counts + ((size_t)a0 * R + i) * 8;
+    for (int k = 0; k < 8; ++k) out[k] = rs.state_counts[k];
+}
+
+// One CTA per arena. onDevice: the controllers ran on the device (cache points and state counters are theirs); otherwise only
+// the arena-level record and the analysis are kept (a host controller owns its own dumps).
+__global__ void __launch_bounds__(128) k_snap_post(PhysEnv env, StatePtrs sp, SnapPtrs sn, const float* obsPose, int a0, int interval, int onDevice,
+                                                   int controller, int nTypes, int nPucksCfg, float threshold, float targetPercent) {
+    extern __shared__ int sh[];   // parent[P], size[P]
+    const Dims& d = env.cfg.d;
+    int a = a0 + blockIdx.x;
+    int stepCount = sp.arena[a].step_count - 1;   // the think step that has just run
+    if (stepCount < 0 || stepCount % interval != 0) return;
+    ArenaState st = arenaState(sp, env.cfg, a);
+    int P = d.P, NB = d.NB, R = d.R;
+    if (threadIdx.x == 0) sn.step[a] = stepCount;
+    for (int i = threadIdx.x; i < R * 3; i += blockDim.x) sn.pose[(size_t)a * R * 3 + i] = obsPose[(size_t)a * R * 3 + i];
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        sn.puck[((size_t)a * P + i) * 2] = st.body[i];
+        sn.puck[((size_t)a * P + i) * 2 + 1] = st.body[NB + i];
+    }
+    if (onDevice) {
+        for (int i = threadIdx.x; i < R * PS_MAX_COLOURS; i += blockDim.x) {
+            int r = i / PS_MAX_COLOURS, k = i % PS_MAX_COLOURS;
+            const ps_robot_state& rs = sp.robot[(size_t)a * R + r];
+            bool valid = controller == PS_CTRL_CACHECONS && rs.cache_valid[k];
+            float* out = sn.cache + (((size_t)a * R + r) * PS_MAX_COLOURS + k) * 2;
+            out[0] = valid ? (float)rs.cache_x[k] : __int_as_float(0x7fc00000);
+            out[1] = valid ? (float)rs.cache_y[k] : __int_as_float(0x7fc00000);
+        }
+        for (int r = threadIdx.x; r < R; r += blockDim.x) sn.counts[((size_t)a * R + r) * 8 + (sp.robot[(size_t)a * R + r].ctrl_state & 7)] += 1;
+    }
+    // percent completion of this record: PositionList.getClusterStats per colour over the true puck positions
+    int* parent = sh;
+    int* size = sh + P;
+    int perType = nTypes > 0 ? P / nTypes : P;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        parent[i] = i;
+        size[i] = 0;
+    }
+    __syncthreads();
+    CtaCtx ctx;
+    ctx.scanScratch = nullptr;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        V2 pi = mk(st.body[i], st.body[NB + i]);
+        int k = i / perType;
+        for (int j = k * perType; j < i; ++j) {
+            V2 pj = mk(st.body[j], st.body[NB + j]);
+            bool same = pi.x == pj.x && pi.y == pj.y;
+            if (!same && dist(pi, pj) < threshold) ufUnion(ctx, parent, i, j);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < P; i += blockDim.x) atomicAdd(&size[ufFind(parent, i)], 1);
+    __syncthreads();
+    __shared__ int maxOfType[PS_MAX_COLOURS];
+    if (threadIdx.x < PS_MAX_COLOURS) maxOfType[threadIdx.x] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < P; i += blockDim.x)
+        if (size[i] > 0) atomicMax(&maxOfType[i / perType], size[i]);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int sum = 0;
+        for (int k = 0; k < nTypes; ++k) sum += maxOfType[k];
+        double pc = nPucksCfg > 0 ? 100.0 * (double)sum / (double)nPucksCfg : 0.0;   // Analyze.java:197
+        ps_arena_analysis& an = sn.an[a];
+        an.n_snapshots += 1;
+        an.completion = pc;
+        if (an.steps_to_completion == -1 && pc >= (double)targetPercent) an.steps_to_completion = stepCount;   // :202-204
+        an.twc_num += (double)stepCount * pc / 100.0;                                                          // :206
+        an.twc_den += (double)stepCount;                                                                       // :212-216
+    }
 }
 
 struct SenseDevice {

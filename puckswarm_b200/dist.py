@@ -19,49 +19,55 @@ def shard_range(n_arenas, rank, world_size):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def _segment(s, first, last, dtype):
+    """The bytes of ps_stats from field `first` to field `last` as a numpy view of `dtype` (fields of a segment are contiguous)."""
+    lo = getattr(abi.ps_stats, first).offset
+    hi = getattr(abi.ps_stats, last).offset + getattr(abi.ps_stats, last).size
+    buf = (C.c_char * C.sizeof(s)).from_address(C.addressof(s))
+    return np.frombuffer(buf, dtype=np.uint8)[lo:hi].view(dtype)
+
+
 def stats_to_arrays(s):
-    """ps_stats -> (int64 vector, float64 vector) in a fixed field order."""
-    ints = np.concatenate([
-        np.array([s.n_arenas], np.int64),
-        np.ctypeslib.as_array(s.cluster_size_hist).astype(np.int64).ravel(),
-        np.ctypeslib.as_array(s.ctrl_state_hist).astype(np.int64).ravel(),
-        np.array([s.n_carrying, s.n_caches, s.n_touching_points, s.n_contacts], np.int64),
-    ])
-    return ints, np.array([s.sum_completion], np.float64)
+    """ps_stats -> one array per reduction segment (abi.STATS_SEGMENTS: sums, minima, maxima over int64 and float64)."""
+    return [_segment(s, a, b, dt).copy() for a, b, dt, _ in abi.STATS_SEGMENTS]
 
 
-def arrays_to_stats(ints, floats):
+def arrays_to_stats(arrays):
     s = abi.ps_stats()
-    ints = np.asarray(ints, np.int64)
-    s.n_arenas = int(ints[0])
-    h = ints[1:1 + abi.PS_MAX_COLOURS * 64].reshape(abi.PS_MAX_COLOURS, 64)
-    for k in range(abi.PS_MAX_COLOURS):
-        for i in range(64):
-            s.cluster_size_hist[k][i] = int(h[k, i])
-    o = 1 + abi.PS_MAX_COLOURS * 64
-    for i in range(8):
-        s.ctrl_state_hist[i] = int(ints[o + i])
-    s.n_carrying, s.n_caches, s.n_touching_points, s.n_contacts = [int(x) for x in ints[o + 8:o + 12]]
-    s.sum_completion = float(np.asarray(floats)[0])
+    for (a, b, dt, _), arr in zip(abi.STATS_SEGMENTS, arrays):
+        _segment(s, a, b, dt)[:] = np.asarray(arr, dt)
     return s
 
 
 def allreduce_stats(stats, device=None, group=None):
-    """Sum ps_stats over all ranks. `device` is a torch device ('cuda:N' for NCCL, None / 'cpu' for gloo)."""
+    """Reduce ps_stats over all ranks with torch.distributed (one collective per segment: SUM / MIN / MAX). `device` is a torch
+    device ('cuda:N' for NCCL, None / 'cpu' for gloo). The C-ABI's ps_get_stats(h, thr, out, nccl_comm) does the same on the
+    device copy with ncclAllReduce for hosts without torch (the Java shim)."""
     import torch
     import torch.distributed as dist
-    ints, floats = stats_to_arrays(stats)
+    arrays = stats_to_arrays(stats)
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return arrays_to_stats(ints, floats)
-    ti = torch.from_numpy(ints.copy())
-    tf = torch.from_numpy(floats.copy())
-    if device is not None:
-        ti, tf = ti.to(device), tf.to(device)
-    dist.all_reduce(ti, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(tf, op=dist.ReduceOp.SUM, group=group)
-    return arrays_to_stats(ti.cpu().numpy(), tf.cpu().numpy())
+        return arrays_to_stats(arrays)
+    ops = {"sum": dist.ReduceOp.SUM, "min": dist.ReduceOp.MIN, "max": dist.ReduceOp.MAX}
+    out = []
+    for (_, _, _, red), arr in zip(abi.STATS_SEGMENTS, arrays):
+        t = torch.from_numpy(arr.copy())
+        if device is not None:
+            t = t.to(device)
+        dist.all_reduce(t, op=ops[red], group=group)
+        out.append(t.cpu().numpy())
+    return arrays_to_stats(out)
 
 
 def mean_completion(stats):
     """Analyze.java's ensemble average of percent completion over the arenas of the (reduced) statistics."""
     return stats.sum_completion / max(1, stats.n_arenas)
+
+
+def ensemble_summary(stats):
+    """What Analyze.computeEnsembleData prints for an experiment code (Analyze.java:240-258): avgTWC, and avgSTC or the number of
+    incompletions, from the (reduced) statistics."""
+    n = max(1, stats.n_arenas)
+    incompletions = int(stats.n_arenas - stats.n_completed)
+    return {"avgTWC": stats.sum_twc / n, "avgSTC": (stats.sum_steps_to_completion / n) if incompletions == 0 else None,
+            "incompletions": incompletions, "repetitions": int(stats.n_arenas)}

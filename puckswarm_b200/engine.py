@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("PS_ENGINE_LIB") or os.path.join(_HERE, "csrc", "libpu
 EXPORTS = [
     "ps_last_error", "ps_abi_version", "ps_struct_size", "ps_config_defaults", "ps_create", "ps_destroy", "ps_load_calibration",
     "ps_reset", "ps_set_state", "ps_get_state", "ps_step", "ps_sync", "ps_get_error_flags", "ps_join", "ps_sense", "ps_step_external",
-    "ps_get_observations", "ps_compute_stats", "ps_stats_device_ptr", "ps_get_dims", "ps_get_step_stats", "ps_get_sense_stats", "ps_get_island_hist",
+    "ps_get_observations", "ps_compute_stats", "ps_stats_device_ptr", "ps_get_stats", "ps_get_snapshot", "ps_get_analysis", "ps_analysis_config", "ps_get_dims", "ps_get_step_stats", "ps_get_sense_stats", "ps_get_island_hist",
     "ps_profile", "ps_get_kernel_ms", "ps_num_groups", "ps_kernel_launches", "ps_stream",
 ]
 
@@ -46,7 +46,8 @@ def load_library(path=None):
     L.ps_last_error.restype = C.c_char_p
     L.ps_abi_version.restype = C.c_int
     L.ps_struct_size.argtypes = [C.c_int]
-    structs = [abi.ps_config, abi.ps_robot_state, abi.ps_arena_state, abi.ps_localmap, abi.ps_stats, abi.ps_state_view, abi.ps_obs_view]
+    structs = [abi.ps_config, abi.ps_robot_state, abi.ps_arena_state, abi.ps_localmap, abi.ps_stats, abi.ps_state_view, abi.ps_obs_view,
+               abi.ps_snapshot_view, abi.ps_arena_analysis]
     for i, t in enumerate(structs):
         if L.ps_struct_size(i) != C.sizeof(t):
             raise EngineUnavailable("ABI layout mismatch for %s: library %d bytes, abi.py %d bytes" % (t.__name__, L.ps_struct_size(i), C.sizeof(t)))
@@ -66,6 +67,10 @@ def load_library(path=None):
     L.ps_get_observations.argtypes = [C.c_void_p, C.POINTER(abi.ps_obs_view)]
     L.ps_compute_stats.argtypes = [C.c_void_p, C.c_float, C.POINTER(abi.ps_stats)]
     L.ps_stats_device_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    L.ps_get_stats.argtypes = [C.c_void_p, C.c_float, C.POINTER(abi.ps_stats), C.c_void_p]
+    L.ps_get_snapshot.argtypes = [C.c_void_p, C.POINTER(abi.ps_snapshot_view)]
+    L.ps_get_analysis.argtypes = [C.c_void_p, C.c_void_p]
+    L.ps_analysis_config.argtypes = [C.c_void_p, C.c_float, C.c_float]
     L.ps_get_dims.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 5
     L.ps_get_step_stats.argtypes = [C.c_void_p, C.c_void_p]
     L.ps_get_sense_stats.argtypes = [C.c_void_p, C.c_void_p]
@@ -185,6 +190,29 @@ class Engine:
         thr = self.cfg.cluster_distance_threshold if threshold is None else threshold
         self._check(self.L.ps_compute_stats(self.h, thr, C.byref(s)))
         return s
+
+    def get_stats(self, threshold=None, nccl_comm=None):
+        """ps_stats of this handle's arenas, reduced over the ranks of `nccl_comm` (an ncclComm_t as an integer / c_void_p) on the device."""
+        s = abi.ps_stats()
+        thr = self.cfg.cluster_distance_threshold if threshold is None else threshold
+        self._check(self.L.ps_get_stats(self.h, thr, C.byref(s), C.c_void_p(nccl_comm) if nccl_comm else None))
+        return s
+
+    def get_snapshot(self, snap=None):
+        """The reference's periodic record (Arena.java:223-243 and the controllers' dumps) of the latest storage step."""
+        snap = snap or abi.Snapshot(self.cfg.n_arenas, self.cfg.n_robots, self.NB - self.cfg.n_robots)
+        v = snap.view()
+        self._check(self.L.ps_get_snapshot(self.h, C.byref(v)))
+        return snap
+
+    def get_analysis(self):
+        """Per-arena Analyze accumulators (numpy structured array of ps_arena_analysis)."""
+        out = np.zeros((self.cfg.n_arenas,), abi.ANALYSIS_DTYPE)
+        self._check(self.L.ps_get_analysis(self.h, out.ctypes.data))
+        return out
+
+    def analysis_config(self, cluster_threshold, target_percent=50.0):
+        self._check(self.L.ps_analysis_config(self.h, cluster_threshold, target_percent))
 
     def step_info(self, arena=0):
         out = np.zeros((self.cfg.n_arenas, 8), np.int32)

@@ -258,16 +258,23 @@ class Arena:
         self._obs_cache = None
         self._obs_has_camera = False
         self._ticks_in_interval = 0
+        self._step_count = 0
 
     # ---- Arena.step / coast ----
-    def step(self, allowThinking=True, allowForwards=True, allowTurning=True, forcedMarch=False, forcedTurn=0, showCamera=False):
+    def step(self, allowThinking=True, allowForwards=True, allowTurning=True, forcedMarch=False, forcedTurn=0, showCamera=False, ticks=None):
+        """One think step and the World.step calls that follow it (`ticks`, default stepInterval: RunOffline's coast ticks are
+        folded in). The periodic record of a storage step (stepCount % 100 == 0) is kept on the device: save_snapshot()."""
         if forcedMarch or forcedTurn or not (allowThinking and allowForwards and allowTurning):
             raise NotImplementedError("only the RunOffline call Arena.step(true, true, true, false, 0, false) is on the hot path")
         self._obs_cache = None
-        interval = self.cfg.step_interval
+        interval = self.cfg.step_interval if ticks is None else int(ticks)
+        if not (1 <= interval <= self.cfg.step_interval):
+            raise ValueError("ticks must be in [1, stepInterval]")
         if self.controllers is None:
             self.engine.step(interval)
         else:
+            if interval != self.cfg.step_interval:
+                raise NotImplementedError("host controllers advance whole think intervals (ps_step_external)")
             self.engine.sense()
             fwd = np.zeros((self.cfg.n_arenas, self.cfg.n_robots), np.float32)
             tq = np.zeros_like(fwd)
@@ -279,13 +286,15 @@ class Arena:
                     fwd[a, r], tq[a, r] = c.getForwards(), c.getTorque()
             self._obs_cache = None
             self.engine.step_external(fwd, tq)
+        self._step_count += 1
 
     def coast(self, allowThinking=True, allowForwards=True, allowTurning=True):
         """One tick with the previous commands; only valid between think steps of an on-device controller."""
         raise NotImplementedError("RunOffline's coast ticks are folded into step(): call step() once per think interval")
 
     def getStepCount(self):
-        return int(self.engine.get_state().arena["step_count"][0])
+        """Arena.stepCount (think steps done), tracked on the host: every arena of the batch is at the same count."""
+        return self._step_count
 
     def getWorld(self):
         return self.engine
@@ -333,25 +342,31 @@ class Arena:
         P = self.engine.NB - self.cfg.n_robots
         return np.stack([st.body[:, 0, :P], st.body[:, 1, :P]], axis=-1)
 
-    # ---- the reference's snapshot files (Arena.java:223-243) ----
+    # ---- the reference's snapshot files ----
     def save_snapshot(self, output_dir):
-        """Write stepNNNNNNN_robots.txt and stepNNNNNNN_<COLOUR>_pucks.txt per arena under
-        <output_dir>/<code>/<seed>/ in the reference's text formats, so analysis.Analyze can read GPU runs."""
-        step = self.getStepCount()
-        poses = self.robot_poses()
-        pucks = self.puck_positions()
-        per_type = max(1, pucks.shape[1] // max(1, self.cfg.n_puck_types))
+        """Write the files the reference stores at a storage step (stepCount % STORAGE_INTERVAL == 0), from the record the engine
+        kept on the device for the latest such step (ps_get_snapshot), under <output_dir>/<code>/<seed>/:
+          stepNNNNNNN_robots.txt, stepNNNNNNN_<COLOUR>_pucks.txt   Arena.java:223-243 (poses after the perturbations, before World.step)
+          stepNNNNNNN_R<i>_cachePoints.txt                         CacheConsController.java:531-551 (8 lines, `NaN, NaN` = null)
+          stepNNNNNNN_R<i>_stateCounts.txt                         CacheConsController.java:313-333, BHDController.java:103-123
+        in the reference's text formats, so that the unmodified analysis.Analyze can read a GPU run. Returns the file names."""
+        snap = self.engine.get_snapshot()
+        per_type = max(1, snap.puck_xy.shape[1] // max(1, self.cfg.n_puck_types))
+        n_states = {abi.PS_CTRL_CACHECONS: len(abi.CC_STATES), abi.PS_CTRL_BHD: len(abi.BHD_STATES)}.get(self.cfg.controller, 0)
         written = []
         for a, seed in enumerate(self.seeds):
+            step = int(snap.step_count[a])
+            if step < 0:
+                continue
             d = os.path.join(output_dir, self.experiment.code, str(int(seed)))
             os.makedirs(d, exist_ok=True)
             base = os.path.join(d, "step%07d" % step)
             with open(base + "_robots.txt", "w") as f:
-                for x, y, t in poses[a]:
+                for x, y, t in snap.robot_pose[a]:
                     f.write("%s, %s, %s\n" % (java_double_str(np.float32(x)), java_double_str(np.float32(y)), java_double_str(np.float32(t))))
             written.append(base + "_robots.txt")
             for k in range(self.cfg.n_puck_types):
-                sel = pucks[a, k * per_type:(k + 1) * per_type]
+                sel = snap.puck_xy[a, k * per_type:(k + 1) * per_type]
                 if len(sel) == 0:
                     continue
                 name = base + "_" + COLOUR_NAMES[k] + "_pucks.txt"
@@ -359,28 +374,60 @@ class Arena:
                     for x, y in sel:
                         f.write("%s, %s\n" % (java_float_str(x), java_float_str(y)))
                 written.append(name)
+            if self.controllers is not None:
+                continue      # a host controller writes its own dumps
+            for r in range(self.cfg.n_robots):
+                if self.cfg.controller == abi.PS_CTRL_CACHECONS:
+                    name = base + "_R%d_cachePoints.txt" % r
+                    with open(name, "w") as f:
+                        for x, y in snap.cache_xy[a, r]:
+                            f.write("%s, %s\n" % (java_float_str(x), java_float_str(y)))
+                    written.append(name)
+                if n_states:
+                    name = base + "_R%d_stateCounts.txt" % r
+                    with open(name, "w") as f:
+                        for v in snap.state_counts[a, r, :n_states]:
+                            f.write("%d\n" % int(v))       # FileUtils.saveArray (FileUtils.java:40-54)
+                    written.append(name)
         return written
+
+    def analysis(self):
+        """analysis.Analyze's per-repetition statistics, accumulated on the device at every storage step (ps_get_analysis):
+        per arena n_snapshots, steps_to_completion (-1 = target not reached), time-weighted completion, latest completion."""
+        an = self.engine.get_analysis()
+        twc = np.where(an["twc_den"] > 0, an["twc_num"] / np.maximum(an["twc_den"], 1e-300), 0.0)
+        return {"n_snapshots": an["n_snapshots"].copy(), "stepsToCompletion": an["steps_to_completion"].copy(),
+                "timeWeightedCompletion": twc, "percentCompletion": an["completion"].copy()}
 
 
 class RunOffline:
     """arena.RunOffline's loop (RunOffline.java:61-62,72-95) over a batch: every call of step() is one physics tick of the
-    reference's driver; think steps happen on every stepInterval-th tick."""
+    reference's driver; think steps happen on every stepInterval-th tick and carry the interval's World.step calls with them."""
 
-    def __init__(self, arena, output_dir=None):
+    def __init__(self, arena, output_dir=None, max_step_count=None):
         self.arena = arena
         self.output_dir = output_dir
         self.updateCount = 0
+        self.maxStepCount = Arena.maxStepCount if max_step_count is None else int(max_step_count)   # Arena.maxStepCount property
+        self.active = True
 
     def step(self):
+        """RunOffline.step(): stop check first (:75-86), then Arena.step on think ticks. The reference runs ONE World.step after the
+        last think step (stepCount == maxStepCount) before the check ends the episode; so does this."""
+        if self.arena.getStepCount() > self.maxStepCount:
+            self.active = False
+            return
         interval = self.arena.cfg.step_interval
         if self.updateCount % interval == 0:
-            if self.output_dir and self.arena.getStepCount() % Arena.STORAGE_INTERVAL == 0:
+            storage = self.arena.getStepCount() % Arena.STORAGE_INTERVAL == 0
+            last = self.arena.getStepCount() == self.maxStepCount
+            self.arena.step(ticks=1 if (last and self.arena.controllers is None) else None)
+            if storage and self.output_dir:
                 self.arena.save_snapshot(self.output_dir)
-            self.arena.step()          # Arena.step + the interval's World.step calls, fused on the device
         self.updateCount += 1
 
     def run(self, max_step_count=None):
-        limit = Arena.maxStepCount if max_step_count is None else max_step_count
-        while self.arena.getStepCount() <= limit:
-            for _ in range(self.arena.cfg.step_interval):
-                self.step()
+        if max_step_count is not None:
+            self.maxStepCount = int(max_step_count)
+        while self.active:
+            self.step()

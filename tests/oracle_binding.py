@@ -42,6 +42,9 @@ def lib():
         L.orc_get_observations.argtypes = [C.c_void_p, C.POINTER(abi.ps_obs_view)]
         L.orc_compute_stats.argtypes = [C.c_void_p, C.c_float, C.POINTER(abi.ps_stats)]
         L.orc_step_info.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_get_snapshot.argtypes = [C.c_void_p, C.POINTER(abi.ps_snapshot_view)]
+        L.orc_get_analysis.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_analysis_config.argtypes = [C.c_void_p, C.c_float, C.c_float]
         L.orc_solve_order.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.orc_manifold.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float,
                                    C.c_float, C.c_void_p]
@@ -128,6 +131,20 @@ class Oracle:
         thr = self.cfg.cluster_distance_threshold if threshold is None else threshold
         assert self.L.orc_compute_stats(self.h, thr, C.byref(s)) == 0
         return s
+
+    def get_snapshot(self, snap=None):
+        snap = snap or abi.Snapshot(self.cfg.n_arenas, self.cfg.n_robots, self.NB - self.cfg.n_robots)
+        v = snap.view()
+        assert self.L.orc_get_snapshot(self.h, C.byref(v)) == 0
+        return snap
+
+    def get_analysis(self):
+        out = np.zeros((self.cfg.n_arenas,), abi.ANALYSIS_DTYPE)
+        assert self.L.orc_get_analysis(self.h, out.ctypes.data) == 0
+        return out
+
+    def analysis_config(self, cluster_threshold, target_percent=50.0):
+        assert self.L.orc_analysis_config(self.h, cluster_threshold, target_percent) == 0
 
     def step_info(self, arena=0):
         out = np.zeros(8, np.int32)

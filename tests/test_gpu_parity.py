@@ -383,6 +383,44 @@ def test_ensemble_statistics_match():
         assert abs(se.sum_completion - so.sum_completion) < 1e-9 * max(1.0, so.sum_completion)
 
 
+@pytest.mark.parametrize("controller,extra", [(abi.PS_CTRL_CACHECONS, {}), (abi.PS_CTRL_BHD, {}), (abi.PS_CTRL_CACHECONS, dict(puck_shuffle_step=100)),
+                                              (abi.PS_CTRL_PROBSEEK, dict(n_pucks=41))])
+def test_periodic_record_and_analysis_match_oracle(controller, extra):
+    """The record the reference writes every 100 think steps (Arena.java:223-243, CacheConsController.java:313-333,531-551) and
+    analysis.Analyze's per-repetition statistics (Analyze.java:176-218), kept on the device, against the oracle's restatement:
+    storage steps 0, 100 and 200; poses and pucks after the perturbation of the same step; counters before they are cleared."""
+    A = 6
+    kw = dict(n_arenas=A, n_robots=4, n_pucks=40, controller=controller)
+    kw.update(extra)
+    cfg = abi.config_defaults(**kw)
+    e, o = _engine(cfg), _oracle(cfg)
+    for x in (e, o):
+        x.analysis_config(9.45, 12.0)
+        x.reset(np.arange(A))
+    for ticks in (1, 300, 300):       # just past think steps 0, 100, 200
+        e.step(ticks)
+        o.step(ticks)
+        se, so = e.get_snapshot(), o.get_snapshot()
+        assert np.array_equal(se.step_count, so.step_count) and se.step_count[0] in (0, 100, 200)
+        assert np.array_equal(se.robot_pose.view(np.uint32), so.robot_pose.view(np.uint32))
+        assert np.array_equal(se.puck_xy.view(np.uint32), so.puck_xy.view(np.uint32))
+        assert np.array_equal(se.state_counts, so.state_counts)
+        assert np.array_equal(np.isnan(se.cache_xy), np.isnan(so.cache_xy))
+        assert np.allclose(np.nan_to_num(se.cache_xy), np.nan_to_num(so.cache_xy), rtol=TOL, atol=0)
+        ae, ao = e.get_analysis(), o.get_analysis()
+        for f in ("n_snapshots", "steps_to_completion"):
+            assert np.array_equal(ae[f], ao[f]), f
+        for f in ("twc_num", "twc_den", "completion"):
+            assert np.allclose(ae[f], ao[f], rtol=1e-12, atol=0), f
+    assert (ae["n_snapshots"] == 3).all() and (se.state_counts.sum(axis=-1) == 100).all()
+    te, to = e.compute_stats(9.45), o.compute_stats(9.45)
+    for f in ("n_completed", "sum_steps_to_completion", "n_snapshots", "min_steps_to_completion", "max_steps_to_completion"):
+        assert getattr(te, f) == getattr(to, f), f
+    for f in ("sum_completion", "sum_twc", "min_completion", "max_completion", "min_twc", "max_twc"):
+        assert abs(getattr(te, f) - getattr(to, f)) <= 1e-9 * max(1.0, abs(getattr(to, f))), f
+    assert to.n_completed > 0
+
+
 def test_ensemble_1000_episodes():
     """north_star: ensemble statistics over 1 000 seeded episodes must match the reference's distributions. Here 1 000 episodes
     (4 robots / 40 pucks / 2 colours, CacheCons, seeds 0..999) x 150 think steps are compared exactly: per-episode percent

@@ -54,7 +54,13 @@ def test_arena_runoffline_snapshot_and_host_controllers(tmp_path):
         run.step()
     assert arena.getStepCount() == 10
     files = sorted(p.name for p in (tmp_path / "T" / "0").iterdir())
-    assert files == ["step0000000_GREEN_pucks.txt", "step0000000_RED_pucks.txt", "step0000000_robots.txt"]
+    per_robot = ["step0000000_R%d_%s.txt" % (r, what) for r in range(3) for what in ("cachePoints", "stateCounts")]
+    assert files == sorted(["step0000000_GREEN_pucks.txt", "step0000000_RED_pucks.txt", "step0000000_robots.txt"] + per_robot)
+    # CacheConsController.java:531-551: 8 lines, "NaN, NaN" for a null cache point; :313-333: one count per State, the step's own state counted
+    cp = (tmp_path / "T" / "0" / "step0000000_R1_cachePoints.txt").read_text().strip().split("\n")
+    assert len(cp) == 8 and cp[2:] == ["NaN, NaN"] * 6
+    sc = [int(x) for x in (tmp_path / "T" / "0" / "step0000000_R1_stateCounts.txt").read_text().split()]
+    assert len(sc) == len(abi.CC_STATES) and sum(sc) == 1
     rows = (tmp_path / "T" / "1" / "step0000000_robots.txt").read_text().strip().split("\n")
     assert len(rows) == 3 and all(len(r.split(", ")) == 3 for r in rows)
     # the poses of the snapshot are the spawn poses (Arena.java:231-233 stores them at the head of the first Arena.step)

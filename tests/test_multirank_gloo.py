@@ -24,11 +24,11 @@ def _worker(rank, world, port, q):
     lo, hi = psd.shard_range(n_total, rank, world)
     cfg = abi.config_defaults(n_arenas=hi - lo, n_robots=2, n_pucks=10)
     o = oracle.Oracle(cfg)
+    o.analysis_config(9.45, 10.0)
     o.reset(np.arange(lo, hi))
-    o.step(30)
+    o.step(330)   # storage steps 0 and 100: two Analyze rows per arena
     total = psd.allreduce_stats(o.compute_stats(9.45))
-    ints, floats = psd.stats_to_arrays(total)
-    q.put((rank, lo, hi, ints.tolist(), floats.tolist()))
+    q.put((rank, lo, hi, [a.tolist() for a in psd.stats_to_arrays(total)]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -56,12 +56,20 @@ def test_shard_and_reduce_two_ranks():
     cfg = abi.config_defaults(n_arenas=5, n_robots=2, n_pucks=10)
     o = oracle.Oracle(cfg)
     o.reset(np.arange(5))
-    o.step(30)
-    ints, floats = psd.stats_to_arrays(o.compute_stats(9.45))
-    for rank, lo, hi, ri, rf in res:
-        assert ri == ints.tolist()
-        assert abs(rf[0] - floats[0]) < 1e-9
+    o.analysis_config(9.45, 10.0)
+    o.reset(np.arange(5))
+    o.step(330)
+    truth = o.compute_stats(9.45)
+    arrays = psd.stats_to_arrays(truth)
+    assert truth.n_snapshots == 10 and truth.max_steps_to_completion >= 0 and truth.min_completion <= truth.max_completion
+    for rank, lo, hi, got in res:
+        for (first, last, dt, red), g, t in zip(abi.STATS_SEGMENTS, got, arrays):
+            if dt == np.int64:
+                assert g == t.tolist(), (first, red)            # sums, minimum and maximum of integers: exact
+            else:
+                assert np.allclose(g, t, rtol=1e-12, atol=1e-12), (first, red)
     # round trip of the struct <-> array mapping
-    s = psd.arrays_to_stats(ints, floats)
-    i2, f2 = psd.stats_to_arrays(s)
-    assert np.array_equal(i2, ints) and f2[0] == floats[0]
+    s = psd.arrays_to_stats(arrays)
+    for a, b in zip(psd.stats_to_arrays(s), arrays):
+        assert np.array_equal(a, b)
+    assert psd.ensemble_summary(truth)["repetitions"] == 5

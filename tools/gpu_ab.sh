@@ -1,6 +1,7 @@
+# A/B of engine builds / environments (run on the GPU box): every argument is one variant's env assignments.
+# AB_WARMUP / AB_STEPS choose the regime (default: steady state, 100 warm-up + 60 timed think steps), device-resident only.
 cd $GRAFT_REPO_ROOT
-run() { python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extras | python -c "import json,sys; d=json.loads(sys.stdin.read()); r=d['roofline']; print(d['value'], d['ms_per_step'], d['e2e']['value'], r['world_step_stage_ms_per_tick'], {k: r['kernel_ms_total'][k]/max(1,r['kernel_launch_counts'][k]) for k in ('sense','think','physics')})"; }
-echo "A: $A_ENV"; env $A_ENV bash -c "$(declare -f run); run"
-echo "B: $B_ENV"; env $B_ENV bash -c "$(declare -f run); run"
-echo "A: $A_ENV"; env $A_ENV bash -c "$(declare -f run); run"
-echo "B: $B_ENV"; env $B_ENV bash -c "$(declare -f run); run"
+run() { python bench.py --steps ${AB_STEPS:-60} --warmup ${AB_WARMUP:-100} --no-cpu-baseline --no-extras --no-parity --no-steady --no-e2e | python -c "import json,sys; d=json.loads(sys.stdin.read()); r=d['roofline']; print(round(d['value']), round(d['ms_per_step'],2), {k: round(v,2) for k,v in r['world_step_stage_ms_per_tick'].items()}, {k: round(r['kernel_ms_total'][k]/max(1,r['kernel_launch_counts'][k]),2) for k in ('sense','think','physics')})"; }
+for e in "$@"; do
+  echo "variant: $e"; env $e bash -c "$(declare -f run); run"
+done
