@@ -59,3 +59,26 @@ JNIEXPORT jint JNICALL FN(psGetBodies)(JNIEnv* env, jclass c, jlong h, jobject b
 JNIEXPORT jint JNICALL FN(psComputeStats)(JNIEnv* env, jclass c, jlong h, jfloat thr, jobject stats) {
     return ps_compute_stats((ps_handle)(intptr_t)h, thr, (ps_stats*)BUF(env, stats));
 }
+JNIEXPORT jint JNICALL FN(psGetStats)(JNIEnv* env, jclass c, jlong h, jfloat thr, jobject stats, jlong comm) {
+    return ps_get_stats((ps_handle)(intptr_t)h, thr, (ps_stats*)BUF(env, stats), (void*)(intptr_t)comm);
+}
+JNIEXPORT jint JNICALL FN(psGetSnapshot)(JNIEnv* env, jclass c, jlong h, jobject step, jobject pose, jobject puck, jobject cache, jobject counts) {
+    ps_snapshot_view v;
+    v.step_count = (int32_t*)BUF(env, step);
+    v.robot_pose = (float*)BUF(env, pose);
+    v.puck_xy = (float*)BUF(env, puck);
+    v.cache_xy = (float*)BUF(env, cache);
+    v.state_counts = (int32_t*)BUF(env, counts);
+    return ps_get_snapshot((ps_handle)(intptr_t)h, &v);
+}
+JNIEXPORT jint JNICALL FN(psGetAnalysis)(JNIEnv* env, jclass c, jlong h, jobject out) {
+    return ps_get_analysis((ps_handle)(intptr_t)h, (ps_arena_analysis*)BUF(env, out));
+}
+JNIEXPORT jint JNICALL FN(psGetErrorFlags)(JNIEnv* env, jclass c, jlong h, jintArray out) {
+    int32_t v[2] = {0, 0};
+    int rc = ps_get_error_flags((ps_handle)(intptr_t)h, &v[0], &v[1]);
+    jint j[2] = {v[0], v[1]};
+    (*env)->SetIntArrayRegion(env, out, 0, 2, j);
+    return rc;
+}
+JNIEXPORT jint JNICALL FN(psStructSize)(JNIEnv* env, jclass c, jint which) { return ps_struct_size(which); }

@@ -17,6 +17,8 @@ public final class NativeEngine implements AutoCloseable {
 
     /** cfg: a ps_config image laid out as in the header (use {@link Config#toBuffer()}). */
     public NativeEngine(ByteBuffer cfg, int device) {
+        if (psStructSize(0) != cfg.capacity())
+            throw new IllegalStateException("ps_config layout mismatch: library " + psStructSize(0) + " bytes, Java image " + cfg.capacity());
         long[] out = new long[1];
         check(psCreate(cfg, device, out));
         handle = out[0];
@@ -34,6 +36,16 @@ public final class NativeEngine implements AutoCloseable {
     public void getObservations(ByteBuffer camera, ByteBuffer occupancy, ByteBuffer localmap, ByteBuffer pose) { check(psGetObservations(handle, camera, occupancy, localmap, pose)); }
     public void getBodies(ByteBuffer body, ByteBuffer arena) { check(psGetBodies(handle, body, arena)); }
     public void computeStats(float clusterThreshold, ByteBuffer stats) { check(psComputeStats(handle, clusterThreshold, stats)); }
+    /** ps_stats reduced over the ranks of an NCCL communicator (ncclComm_t as a long; 0 = this process only). */
+    public void getStats(float clusterThreshold, ByteBuffer stats, long ncclComm) { check(psGetStats(handle, clusterThreshold, stats, ncclComm)); }
+    /** The reference's periodic record of the latest storage step (ps_snapshot_view; null = skip a component). */
+    public void getSnapshot(ByteBuffer stepCount, ByteBuffer robotPose, ByteBuffer puckXy, ByteBuffer cacheXy, ByteBuffer stateCounts) {
+        check(psGetSnapshot(handle, stepCount, robotPose, puckXy, cacheXy, stateCounts));
+    }
+    /** ps_arena_analysis[nArenas]: Analyze's stepsToCompletion / timeWeightedCompletion accumulators. */
+    public void getAnalysis(ByteBuffer out) { check(psGetAnalysis(handle, out)); }
+    /** {OR of the arenas' capacity flags, flagged arenas}; sync() throws on the same condition. */
+    public int[] getErrorFlags() { int[] o = new int[2]; check(psGetErrorFlags(handle, o)); return o; }
     @Override public void close() { if (handle != 0) { psDestroy(handle); handle = 0; } }
 
     public static native String lastError();
@@ -50,4 +62,9 @@ public final class NativeEngine implements AutoCloseable {
     private static native int psGetObservations(long h, ByteBuffer camera, ByteBuffer occupancy, ByteBuffer localmap, ByteBuffer pose);
     private static native int psGetBodies(long h, ByteBuffer body, ByteBuffer arena);
     private static native int psComputeStats(long h, float clusterThreshold, ByteBuffer stats);
+    private static native int psGetStats(long h, float clusterThreshold, ByteBuffer stats, long ncclComm);
+    private static native int psGetSnapshot(long h, ByteBuffer stepCount, ByteBuffer robotPose, ByteBuffer puckXy, ByteBuffer cacheXy, ByteBuffer stateCounts);
+    private static native int psGetAnalysis(long h, ByteBuffer out);
+    private static native int psGetErrorFlags(long h, int[] out);
+    private static native int psStructSize(int which);
 }

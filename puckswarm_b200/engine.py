@@ -107,6 +107,7 @@ class Engine:
         d = [C.c_int32() for _ in range(5)]
         self._check(self.L.ps_get_dims(self.h, *[C.byref(x) for x in d]))
         self.NB, self.NP, self.max_contacts, self.occ_w, self.occ_h = [x.value for x in d]
+        self.analysis_threshold = float(cfg.cluster_distance_threshold)   # Analyze clusters with LocalMap's threshold
 
     def _check(self, rc):
         if rc != abi.PS_OK:
@@ -213,6 +214,7 @@ class Engine:
 
     def analysis_config(self, cluster_threshold, target_percent=50.0):
         self._check(self.L.ps_analysis_config(self.h, cluster_threshold, target_percent))
+        self.analysis_threshold = float(cluster_threshold)
 
     def step_info(self, arena=0):
         out = np.zeros((self.cfg.n_arenas, 8), np.int32)

@@ -133,6 +133,74 @@ class Experiment:
         return cfg
 
 
+class ExperimentBlock:
+    """experiment.ExperimentBlock (ExperimentBlock.java:15-28): one experiment code repeated for seeds startIndex .. repetitions-1;
+    Experiment i of the block has index (= seed) i."""
+
+    def __init__(self, size, start_index, output_dir, code):
+        self.code, self.output_dir = code, output_dir
+        self.seeds = list(range(int(start_index), int(size)))
+
+    def experiments(self):
+        return [Experiment.from_files(self.output_dir, self.code, seed) for seed in self.seeds]
+
+
+class ExperimentManager:
+    """experiment.ExperimentManager's view of an existing sweep directory (ExperimentManager.java:397-428): every <code>.properties
+    beside common.properties is one experiment block; `repetitions` and the optional `startIndex` come from common.properties."""
+
+    @staticmethod
+    def readExistingExperiments(output_dir):
+        names = sorted(f for f in os.listdir(output_dir) if f.endswith(".properties") and f != "common.properties")
+        common = load_properties(os.path.join(output_dir, "common.properties"))
+        if "repetitions" not in common:
+            raise ValueError("ExperimentManager: Problem loading common properties (no `repetitions`)")
+        repetitions = int(common["repetitions"])                 # Integer.valueOf: NumberFormatException -> ValueError
+        start_index = int(common.get("startIndex", "0"))
+        return [ExperimentBlock(repetitions, start_index, output_dir, n[:-len(".properties")]) for n in names]
+
+
+class Sweep:
+    """A whole sweep directory on the GPU: one arena per (code, seed). A handle carries one ps_config, so every experiment block
+    (one code, its repetitions) is one batch; up to `concurrent` batches are stepped side by side (their kernels overlap on the
+    device). Snapshot files go to <output_dir>/<code>/<seed>/ exactly where RunOffline puts them, so analysis.Analyze reads them."""
+
+    def __init__(self, output_dir, device=0, concurrent=4, write_files=True):
+        self.output_dir, self.device, self.concurrent, self.write_files = output_dir, device, max(1, int(concurrent)), write_files
+        self.blocks = ExperimentManager.readExistingExperiments(output_dir)
+
+    def pairs(self):
+        """[(code, seed)] in the reference's execution order (block after block, repetition after repetition)."""
+        return [(b.code, seed) for b in self.blocks for seed in b.seeds]
+
+    def run(self, max_step_count=None):
+        """Runs every block to Arena.maxStepCount (property, default 10000; RunOffline.java:75-76). Returns {code: summary} with
+        Analyze's avgTWC / avgSTC / incompletions (Analyze.java:240-258) and the per-repetition arrays."""
+        from . import dist as psd
+        results = {}
+        pending = [b for b in self.blocks if b.seeds]
+        while pending:
+            wave, pending = pending[:self.concurrent], pending[self.concurrent:]
+            runs = []
+            for b in wave:
+                exp = Experiment.from_files(self.output_dir, b.code, b.seeds[0])
+                arena = Arena(exp, b.seeds, device=self.device)
+                limit = exp.getProperty("Arena.maxStepCount", Arena.maxStepCount) if max_step_count is None else max_step_count
+                runs.append((b, arena, RunOffline(arena, self.output_dir if self.write_files else None, limit)))
+            while any(r.active for _, _, r in runs):
+                for _, _, r in runs:                      # round-robin: ps_step is asynchronous, the handles overlap on the GPU
+                    if r.active:
+                        r.step()
+            for b, arena, _ in runs:
+                stats = arena.engine.get_stats(arena.engine.analysis_threshold)
+                summary = psd.ensemble_summary(stats)
+                summary.update(arena.analysis())
+                summary["seeds"] = list(b.seeds)
+                results[b.code] = summary
+                arena.dispose()
+        return results
+
+
 def java_float_str(x):
     """Float.toString(float): shortest decimal that round-trips, with Java's 1.0E-4 / 1.0E7 switch to E notation."""
     x = np.float32(x)

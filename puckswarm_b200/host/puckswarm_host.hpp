@@ -312,14 +312,17 @@ public:
     Arena(const Arena&) = delete;
     Arena& operator=(const Arena&) = delete;
 
+    // ticks: World.step calls that follow the think step (default: the whole interval; RunOffline's last step runs one)
     void step(bool allowThinking = true, bool allowForwards = true, bool allowTurning = true, bool forcedMarch = false, int forcedTurn = 0,
-              bool showCamera = false) {
+              bool showCamera = false, int ticks = 0) {
         (void)showCamera;
+        if (ticks < 0 || ticks > cfg_.step_interval) throw std::invalid_argument("ticks must be in [1, step_interval]");
         if (forcedMarch || forcedTurn || !(allowThinking && allowForwards && allowTurning))
             throw std::logic_error("only the RunOffline call Arena.step(true, true, true, false, 0, false) is on the hot path");
         obsValid_ = false;
         if (controllers_.empty()) {
-            check(ps_step(h_, cfg_.step_interval));
+            check(ps_step(h_, ticks > 0 ? ticks : cfg_.step_interval));
+            ++stepCount_;
             return;
         }
         check(ps_sense(h_));
@@ -337,17 +340,18 @@ public:
             }
         obsValid_ = false;
         check(ps_step_external(h_, fwd.data(), tq.data()));
+        ++stepCount_;
     }
     void coast(bool = true, bool = true, bool = true) {
         throw std::logic_error("RunOffline's coast ticks are folded into step(): call step() once per think interval");
     }
-    int getStepCount() {   // Arena.getStepCount (Arena.java:392-394); all arenas of the batch advance in lock step
-        std::vector<ps_arena_state> as((size_t)cfg_.n_arenas);
-        ps_state_view v = {};
-        v.arena = as.data();
-        check(ps_get_state(h_, &v));
-        return as[0].step_count;
-    }
+    int getStepCount() const { return stepCount_; }   // Arena.getStepCount (Arena.java:392-394), tracked on the host: the batch is in lock step
+    bool hasHostControllers() const { return !controllers_.empty(); }
+    ps_handle getWorld() const { return h_; }          // Arena.getWorld (Arena.java:396-398): the engine handle stands for the World
+    struct Enclosure {                                 // Arena.getEnclosure (Arena.java:400-402): RoundedRectangleEnclosure.java:37-44
+        float WIDTH, HEIGHT, R;
+    };
+    Enclosure getEnclosure() const { return {187.0f * cfg_.enclosure_scale, 187.0f * cfg_.enclosure_scale, 15.5f * cfg_.enclosure_scale}; }
     void dispose() {
         if (h_) ps_destroy(h_);
         h_ = nullptr;
@@ -392,43 +396,78 @@ public:
         obsValid_ = false;
         return pose;
     }
-    // The reference's snapshot files (Arena.java:223-243): step%07d_robots.txt ("x, y, theta" as doubles) and
-    // step%07d_<COLOUR>_pucks.txt ("x, y" as floats) per arena under <outputDir>/<code>/<seed>/, so that analysis.Analyze
-    // reads GPU runs unchanged. Returns the files written.
+    // The files the reference stores at a storage step (stepCount % 100 == 0), from the record the engine kept on the device for
+    // the latest such step (ps_get_snapshot), per arena under <outputDir>/<code>/<seed>/:
+    //   step%07d_robots.txt ("x, y, theta" as doubles), step%07d_<COLOUR>_pucks.txt ("x, y" as floats)      Arena.java:223-243
+    //   step%07d_R<i>_cachePoints.txt (8 lines, "NaN, NaN" = null)                                         CacheConsController.java:531-551
+    //   step%07d_R<i>_stateCounts.txt (one count per State)                           CacheConsController.java:313-333, BHDController.java:103-123
+    // so that analysis.Analyze reads GPU runs unchanged. Returns the files written.
     std::vector<std::string> saveSnapshot(const std::string& outputDir) {
         static const char* kColours[PS_MAX_COLOURS] = {"RED", "GREEN", "MAGENTA", "CYAN", "ORANGE", "GRAY", "YELLOW", "PINK"};   // SensedType.java:9-23
-        int step = getStepCount();
-        std::vector<float> pose = robotPoses(), body = bodies();
-        int R = cfg_.n_robots, NB = nBodies_, P = NB - R, K = cfg_.n_puck_types;
+        int R = cfg_.n_robots, P = nBodies_ - R, K = cfg_.n_puck_types;
+        size_t A = (size_t)cfg_.n_arenas;
+        std::vector<int32_t> step(A), counts(A * R * 8);
+        std::vector<float> pose(A * R * 3), puck(A * (size_t)std::max(1, P) * 2), cache(A * R * PS_MAX_COLOURS * 2);
+        ps_snapshot_view sv = {};
+        sv.step_count = step.data();
+        sv.robot_pose = pose.data();
+        sv.puck_xy = puck.data();
+        sv.cache_xy = cache.data();
+        sv.state_counts = counts.data();
+        check(ps_get_snapshot(h_, &sv));
         int perType = std::max(1, P / std::max(1, K));
+        int nStates = cfg_.controller == PS_CTRL_CACHECONS ? 7 : (cfg_.controller == PS_CTRL_BHD ? 4 : 0);   // State.values().length
         std::vector<std::string> written;
-        char name[32];
-        std::snprintf(name, sizeof(name), "step%07d", step);
         ::mkdir(outputDir.c_str(), 0777);
         ::mkdir((outputDir + "/" + code_).c_str(), 0777);
-        for (int a = 0; a < cfg_.n_arenas; ++a) {
+        for (size_t a = 0; a < A; ++a) {
+            if (step[a] < 0) continue;
+            char name[32];
+            std::snprintf(name, sizeof(name), "step%07d", step[a]);
             std::string d = outputDir + "/" + code_ + "/" + std::to_string(seeds_[a]);
             ::mkdir(d.c_str(), 0777);
             std::string base = d + "/" + name;
             {
                 std::ofstream f(base + "_robots.txt");
                 for (int r = 0; r < R; ++r) {
-                    const float* p = pose.data() + ((size_t)a * R + r) * 3;
+                    const float* p = pose.data() + (a * R + r) * 3;
                     f << javaDoubleStr(p[0]) << ", " << javaDoubleStr(p[1]) << ", " << javaDoubleStr(p[2]) << "\n";
                 }
                 written.push_back(base + "_robots.txt");
             }
-            const float* b = body.data() + (size_t)a * 6 * NB;
             for (int k = 0; k < K; ++k) {
                 int lo = k * perType, hi = std::min(P, (k + 1) * perType);
                 if (hi <= lo) continue;
                 std::string fn = base + "_" + kColours[k] + "_pucks.txt";
                 std::ofstream f(fn);
-                for (int p = lo; p < hi; ++p) f << javaFloatStr(b[0 * NB + p]) << ", " << javaFloatStr(b[1 * NB + p]) << "\n";
+                for (int p = lo; p < hi; ++p) f << javaFloatStr(puck[(a * P + p) * 2]) << ", " << javaFloatStr(puck[(a * P + p) * 2 + 1]) << "\n";
                 written.push_back(fn);
+            }
+            if (!controllers_.empty()) continue;   // a host controller writes its own dumps
+            for (int r = 0; r < R; ++r) {
+                std::string rb = base + "_R" + std::to_string(r);
+                if (cfg_.controller == PS_CTRL_CACHECONS) {
+                    std::ofstream f(rb + "_cachePoints.txt");
+                    for (int k = 0; k < PS_MAX_COLOURS; ++k) {
+                        const float* c = cache.data() + ((a * R + r) * PS_MAX_COLOURS + k) * 2;
+                        f << javaFloatStr(c[0]) << ", " << javaFloatStr(c[1]) << "\n";
+                    }
+                    written.push_back(rb + "_cachePoints.txt");
+                }
+                if (nStates) {
+                    std::ofstream f(rb + "_stateCounts.txt");
+                    for (int k = 0; k < nStates; ++k) f << counts[(a * R + r) * 8 + k] << "\n";   // FileUtils.saveArray (FileUtils.java:40-54)
+                    written.push_back(rb + "_stateCounts.txt");
+                }
             }
         }
         return written;
+    }
+    // analysis.Analyze's per-repetition statistics (Analyze.java:176-218), accumulated on the device at every storage step
+    std::vector<ps_arena_analysis> analysis() {
+        std::vector<ps_arena_analysis> an((size_t)cfg_.n_arenas);
+        check(ps_get_analysis(h_, an.data()));
+        return an;
     }
 
 private:
@@ -457,6 +496,7 @@ private:
     int32_t nBodies_ = 0, nProxies_ = 0, maxContacts_ = 0, occW_ = 0, occH_ = 0;
     int imgW_ = 0, imgH_ = 0;
     bool obsValid_ = false, obsCamera_ = false;
+    int stepCount_ = 0;
     std::vector<ps_localmap> lm_;
     std::vector<uint8_t> occ_, cam_;
     std::vector<float> pose_;
@@ -486,19 +526,66 @@ inline Pose Suite::getPose() const {
 
 // arena.RunOffline's loop (RunOffline.java:61-62,72-95) over a batch: every call of step() is one physics tick of the
 // reference's driver; think steps (and with them the interval's World.step calls, fused on the device) happen on every
-// step_interval-th tick.
+// step_interval-th tick. The stop check comes first (:75-86); the reference runs ONE World.step after the last think step
+// (stepCount == maxStepCount) before the check ends the episode, and so does this.
 class RunOffline {
 public:
-    explicit RunOffline(Arena& arena) : arena_(arena) {}
+    explicit RunOffline(Arena& arena, std::string outputDir = "", int maxStepCount = 10000)
+        : arena_(arena), outputDir_(std::move(outputDir)), maxStepCount_(maxStepCount) {}
     void step() {
-        if (updateCount_ % arena_.config().step_interval == 0) arena_.step();
+        if (arena_.getStepCount() > maxStepCount_) {
+            active_ = false;
+            return;
+        }
+        if (updateCount_ % arena_.config().step_interval == 0) {
+            bool storage = arena_.getStepCount() % 100 == 0;   // Arena.STORAGE_INTERVAL
+            bool last = arena_.getStepCount() == maxStepCount_ && !arena_.hasHostControllers();
+            arena_.step(true, true, true, false, 0, false, last ? 1 : 0);
+            if (storage && !outputDir_.empty()) arena_.saveSnapshot(outputDir_);
+        }
         ++updateCount_;
     }
+    void run() {
+        while (active_) step();
+    }
+    bool isActive() const { return active_; }
     int getUpdateCount() const { return updateCount_; }
 
 private:
     Arena& arena_;
+    std::string outputDir_;
+    int maxStepCount_;
     int updateCount_ = 0;
+    bool active_ = true;
 };
+
+// experiment.ExperimentBlock (ExperimentBlock.java:15-28) and ExperimentManager.readExistingExperiments (ExperimentManager.java:397-428):
+// every <code>.properties beside common.properties is one block of `repetitions` experiments, seeds startIndex .. repetitions - 1.
+// One arena = one (code, seed); a handle carries one ps_config, so a block is one batch.
+struct ExperimentBlock {
+    std::string code;
+    std::vector<int64_t> seeds;
+};
+inline std::vector<ExperimentBlock> readExistingExperiments(const std::string& outputDir, const std::vector<std::string>& propertyFiles) {
+    auto common = loadProperties(outputDir + "/common.properties");
+    auto rep = common.find("repetitions");
+    if (rep == common.end()) throw std::invalid_argument("ExperimentManager: Problem loading common properties (no `repetitions`)");
+    int repetitions = std::stoi(rep->second), startIndex = common.count("startIndex") ? std::stoi(common["startIndex"]) : 0;
+    std::vector<std::string> names;
+    for (const std::string& f : propertyFiles) {
+        const std::string suffix = ".properties";
+        if (f == "common.properties" || f.size() <= suffix.size() || f.compare(f.size() - suffix.size(), suffix.size(), suffix) != 0) continue;
+        names.push_back(f.substr(0, f.size() - suffix.size()));
+    }
+    std::sort(names.begin(), names.end());
+    std::vector<ExperimentBlock> blocks;
+    for (const std::string& n : names) {
+        ExperimentBlock b;
+        b.code = n;
+        for (int i = startIndex; i < repetitions; ++i) b.seeds.push_back(i);
+        blocks.push_back(b);
+    }
+    return blocks;
+}
 
 }  // namespace puckswarm

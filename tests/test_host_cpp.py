@@ -106,7 +106,7 @@ def test_cpp_host_matches_ctypes_binding(demo, tmp_path, external):
             arena.step()
         written = arena.save_snapshot(str(tmp_path / "snap_py"))
         arena.dispose()
-        assert len(written) == A * 3
+        assert len(written) == A * (3 + 3 * 2)     # robots + two colours + per robot cachePoints and stateCounts
         for f in written:
             rel = os.path.relpath(f, str(tmp_path / "snap_py"))
             assert open(f).read() == open(os.path.join(str(tmp_path / "snap_cpp"), rel)).read(), rel

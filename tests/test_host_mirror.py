@@ -40,6 +40,53 @@ def test_properties_to_config(tmp_path):
     assert (c2.puck_shift_step, c2.puck_shuffle_step, c2.n_informed_robots) == (5000, 2500, 2)
 
 
+def _write_sweep(d):
+    (d / "common.properties").write_text("repetitions=3\nstartIndex=1\nArena.nRobots=3\nArena.nPucks=20\nArena.nPuckTypes=2\nArena.maxStepCount=100\n")
+    (d / "K1_0.5.properties").write_text("code=K1_0.5\nCacheConsController.K1=0.5\n")
+    (d / "BHD.properties").write_text("code=BHD\ncontrollerType=BHD\n")
+
+
+def test_sweep_directory_enumeration(tmp_path):
+    """ExperimentManager.readExistingExperiments (ExperimentManager.java:397-428) + ExperimentBlock (ExperimentBlock.java:15-28):
+    one block per <code>.properties, repetitions / startIndex from common.properties, Experiment i has seed i."""
+    _write_sweep(tmp_path)
+    blocks = host.ExperimentManager.readExistingExperiments(str(tmp_path))
+    assert [(b.code, b.seeds) for b in blocks] == [("BHD", [1, 2]), ("K1_0.5", [1, 2])]
+    exps = blocks[1].experiments()
+    assert [e.getIndex() for e in exps] == [1, 2] and exps[0].getProperty("CacheConsController.K1", 1.0) == 0.5
+    assert exps[0].getProperty("Arena.maxStepCount", 10000) == 100
+    assert exps[0].to_config(n_arenas=2).n_robots == 3 and blocks[0].experiments()[0].to_config().controller == abi.PS_CTRL_BHD
+    (tmp_path / "common.properties").write_text("Arena.nRobots=3\n")
+    with pytest.raises(ValueError):
+        host.ExperimentManager.readExistingExperiments(str(tmp_path))
+
+
+@pytest.mark.gpu
+def test_sweep_runs_every_code_and_seed(tmp_path):
+    """A sweep directory end to end: every (code, seed) is one arena, the reference's files appear under <code>/<seed>/, and
+    Analyze's per-repetition numbers equal the oracle's restatement run on the same (code, seed) pairs."""
+    import oracle_binding as oracle
+    _write_sweep(tmp_path)
+    sweep = host.Sweep(str(tmp_path), concurrent=2)
+    assert sweep.pairs() == [("BHD", 1), ("BHD", 2), ("K1_0.5", 1), ("K1_0.5", 2)]
+    res = sweep.run()
+    for b in sweep.blocks:
+        for seed in b.seeds:
+            names = sorted(p.name for p in (tmp_path / b.code / str(seed)).iterdir())
+            assert "step0000000_robots.txt" in names and "step0000100_RED_pucks.txt" in names
+            assert ("step0000100_R2_cachePoints.txt" in names) == (b.code != "BHD")
+            n_state_lines = len((tmp_path / b.code / str(seed) / "step0000100_R0_stateCounts.txt").read_text().split())
+            assert n_state_lines == (4 if b.code == "BHD" else 7)
+        cfg = b.experiments()[0].to_config(n_arenas=len(b.seeds))
+        o = oracle.Oracle(cfg)
+        o.reset(b.seeds)
+        o.step(3 * 100 + 1)      # RunOffline: think steps 0..100, one World.step after the last
+        an = o.get_analysis()
+        assert np.array_equal(res[b.code]["stepsToCompletion"], an["steps_to_completion"])
+        assert np.allclose(res[b.code]["timeWeightedCompletion"], an["twc_num"] / an["twc_den"], rtol=1e-12)
+        assert (res[b.code]["n_snapshots"] == 2).all() and res[b.code]["repetitions"] == 2
+
+
 @pytest.mark.gpu
 def test_arena_runoffline_snapshot_and_host_controllers(tmp_path):
     """The mirror drives the engine like RunOffline drives Arena; snapshots come out in the reference's text format;

@@ -53,3 +53,17 @@ def test_no_device_is_a_loud_error():
     with pytest.raises(engine.EngineError) as ei:
         engine.Engine(abi.config_defaults())
     assert ei.value.code in (abi.PS_E_NODEVICE, abi.PS_E_CUDA)
+
+
+def test_java_config_image_matches_ps_config():
+    """java/puckswarm/b200/ArenaB200.java: Config.toBuffer() writes ps_config field by field; the sequence of putInt / putFloat
+    must be the header's sequence of int32 / float fields (no JDK here: checked on the source)."""
+    src = open(os.path.join(ROOT, "java", "puckswarm", "b200", "ArenaB200.java")).read()
+    body = src[src.index("public ByteBuffer toBuffer()"):src.index("b.rewind();")]
+    puts = re.findall(r"\.put(Int|Float)\(", body)
+    want = ["Float" if t is C.c_float else "Int" for _, t in abi.ps_config._fields_]
+    assert puts == want
+    assert "ABI_VERSION = %d" % abi.PS_ABI_VERSION in src
+    jni = open(os.path.join(ROOT, "java", "jni", "puckswarm_jni.c")).read()
+    native = set(re.findall(r"private static native \w+ (ps\w+)\(", open(os.path.join(ROOT, "java", "puckswarm", "b200", "NativeEngine.java")).read()))
+    assert native and all("FN(%s)" % n in jni for n in native)
