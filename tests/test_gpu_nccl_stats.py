@@ -14,11 +14,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 N_TOTAL, TICKS = 6, 301
 
 
+class NcclUniqueId(C.Structure):       # ncclUniqueId is passed BY VALUE to ncclCommInitRank
+    _fields_ = [("internal", C.c_char * 128)]
+
+
 def _nccl_lib():
     import torch  # noqa: F401  (its bundled libnccl.so.2 is then the copy both this test and the engine resolve by soname)
     lib = C.CDLL(os.environ.get("PS_NCCL_LIB", "libnccl.so.2"))
     lib.ncclGetUniqueId.argtypes = [C.c_void_p]
-    lib.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_char * 128, C.c_int]
+    lib.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, NcclUniqueId, C.c_int]
     lib.ncclCommDestroy.argtypes = [C.c_void_p]
     return lib
 
@@ -31,7 +35,7 @@ def _worker(rank, world, uid_bytes, q):
     from puckswarm_b200 import abi, engine, dist as psd
     torch.cuda.set_device(rank)
     lib = _nccl_lib()
-    uid = (C.c_char * 128).from_buffer_copy(uid_bytes)
+    uid = NcclUniqueId.from_buffer_copy(uid_bytes)
     comm = C.c_void_p()
     rc = lib.ncclCommInitRank(C.byref(comm), world, uid, rank)
     assert rc == 0, rc
@@ -55,14 +59,23 @@ def test_stats_allreduce_through_the_c_abi():
     import oracle_binding as oracle
     world = min(2, torch.cuda.device_count())
     lib = _nccl_lib()
-    uid = (C.c_char * 128)()
+    uid = NcclUniqueId()
     assert lib.ncclGetUniqueId(C.byref(uid)) == 0
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, world, bytes(uid), q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=300) for _ in procs]
+    res = []
+    import queue
+    import time
+    deadline = time.time() + 240
+    while len(res) < world:
+        try:
+            res.append(q.get(timeout=2))
+        except queue.Empty:
+            assert all(p.is_alive() or p.exitcode == 0 for p in procs), "a rank died: %r" % [p.exitcode for p in procs]
+            assert time.time() < deadline, "timed out"
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
