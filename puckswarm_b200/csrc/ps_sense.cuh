@@ -21,7 +21,7 @@ namespace ps {
 
 static constexpr int kMaxBlobs = 128;
 static constexpr int kMaxCand = 256;
-static constexpr int kMaxColPix = 4096;   // puck-coloured pixels listed per robot; beyond that the blob passes scan the whole rectangle
+static constexpr int kMaxColPix = 2048;   // puck-coloured pixels listed per robot (by the camera stage, as it finds them); beyond that the blob passes scan the whole rectangle
 static constexpr int kMaxBins = 64;       // robot-frame grid over the pixel footprint
 static constexpr int kBinCap = 30;        // candidates per bin; an overfull bin falls back to the full candidate list
 static constexpr int kSectors = PS_N_SECTORS;
@@ -35,7 +35,8 @@ struct SenseTables {
     const uint16_t* aRect;       // [nActive] index in the bounding rectangle, x-major: (x - x0) * RH + (y - y0)
     const uint16_t* aImg;        // [nActive] index in the camera image, y * imgW + x
     const uint8_t* aBin;         // [nActive] bin of the pixel's ground point in the robot-frame grid below
-    const struct PixRec* aPix;   // [nActive] the four tables above in one 16-byte record (what the camera stage reads)
+    const struct PixRec* aPix;   // [nActive] the four tables above in one 16-byte record, SORTED BY BIN (what the camera stage reads)
+    uint16_t binStart[65];       // [kMaxBins + 1] range of each bin's pixels in aPix
     float binSize;               // bins of binSize x binSize cm over [bbXmin, bbXmax] x [bbYmin, bbYmax]
     int binsX, binsY;
     int x0, y0, RW, RH;          // bounding rectangle of the active pixels
@@ -117,6 +118,8 @@ struct SenseWork {
     float* candRx;        // candidate origin in the sensing robot's frame (binning only, never decides a pixel)
     float* candRy;
     uint8_t* binCount;    // [kMaxBins]
+    uint8_t* binClass;    // [kMaxBins] 0 = general; 1 = no candidate can reach the bin and it lies inside the enclosure's central
+                          //   band with a margin: every pixel is NOTHING; 2 = inside the band, candidates present: skip inFreeSpace
     uint8_t* binList;     // [kMaxBins][kBinCap] candidate indices in body-list order
     int* blobArea;        // [kMaxBlobs]
     int* blobX0;
@@ -126,7 +129,7 @@ struct SenseWork {
     int* blobSeed;
     int* blobRoot;
     int* blobOrder;
-    uint16_t* colList;    // [kMaxColPix] (x - x0) << 8 | (y - y0) of the pixels that show a puck colour
+    uint16_t* colList;    // [kMaxColPix] the pixels that show a puck colour: rectangle index (camera stage), then (x - x0) << 8 | (y - y0)
     int* counters;        // [8]
     int* phase;           // [8] diagnostics: cycles / 16 of the phases of senseRobot (thread 0)
 };
@@ -140,8 +143,8 @@ inline SenseWork carveSense(const SenseTables& t, Carver& cv) {   // host only
     // the candidate / bin arrays (camera stage) and the blob / colour-pixel arrays (blob labelling, afterwards) share
     // one block: the two stages never overlap
     auto up16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
-    size_t szA = 11 * up16(kMaxCand * sizeof(float)) + up16(kMaxCand) + up16(kMaxBins) + up16(kMaxBins * kBinCap);
-    size_t szB = 8 * up16(kMaxBlobs * sizeof(int)) + up16(kMaxColPix * sizeof(uint16_t));
+    size_t szA = 11 * up16(kMaxCand * sizeof(float)) + up16(kMaxCand) + 2 * up16(kMaxBins) + up16(kMaxBins * kBinCap);
+    size_t szB = 8 * up16(kMaxBlobs * sizeof(int));
     char* blk = (char*)cv.take(szA > szB ? szA : szB);
     {
         char* q = blk;
@@ -159,6 +162,7 @@ inline SenseWork carveSense(const SenseTables& t, Carver& cv) {   // host only
         w.candRx = (float*)sub(kMaxCand * sizeof(float));
         w.candRy = (float*)sub(kMaxCand * sizeof(float));
         w.binCount = (uint8_t*)sub(kMaxBins);
+        w.binClass = (uint8_t*)sub(kMaxBins);
         w.binList = (uint8_t*)sub(kMaxBins * kBinCap);
     }
     {
@@ -172,8 +176,9 @@ inline SenseWork carveSense(const SenseTables& t, Carver& cv) {   // host only
         w.blobSeed = (int*)sub(kMaxBlobs * sizeof(int));
         w.blobRoot = (int*)sub(kMaxBlobs * sizeof(int));
         w.blobOrder = (int*)sub(kMaxBlobs * sizeof(int));
-        w.colList = (uint16_t*)sub(kMaxColPix * sizeof(uint16_t));
     }
+    // written by the camera stage, read by the blob labelling: outside the shared block
+    w.colList = (uint16_t*)cv.take(kMaxColPix * sizeof(uint16_t));
     return w;
 }
 
@@ -183,7 +188,7 @@ PS_HD SenseWork rebaseSense(const SenseWork& o, char* base) {
     size_t b = (size_t)base;
 #define RB(f) w.f = (decltype(w.f))((size_t)o.f + b);
     RB(img) RB(parent) RB(candX) RB(candY) RB(candBody) RB(candLx) RB(candLy) RB(candUx) RB(candUy) RB(candC) RB(candS) RB(candType) RB(candRx) RB(candRy)
-    RB(binCount) RB(binList) RB(blobArea) RB(blobX0) RB(blobX1) RB(blobY0) RB(blobY1) RB(blobSeed) RB(blobRoot) RB(blobOrder) RB(colList)
+    RB(binCount) RB(binClass) RB(binList) RB(blobArea) RB(blobX0) RB(blobX1) RB(blobY0) RB(blobY1) RB(blobSeed) RB(blobRoot) RB(blobOrder) RB(colList)
     RB(counters) RB(phase)
 #undef RB
     return w;
@@ -369,6 +374,36 @@ PS_HD void senseRobot(Ctx& ctx, const PhysEnv& e, const SenseTables& T, const Se
     }
 #endif
     ctx.sync();
+    // ---- classify the bins. RoundedRectangleEnclosure.inFreeSpace(g, 0) is true for every g with |g.x| < W/2 - R and
+    // |g.y| < H/2 (its first clause). A bin is a rectangle in the robot frame; if its four corners, mapped to the world, lie
+    // inside that band by a margin far above the rounding of the per-pixel transform (1e-2 cm vs ~1e-5), so does every pixel
+    // of the bin (the band is convex), and the per-pixel test can only say "free". With no candidate body listed either, and
+    // no sensable wall fixture within reach, PointSensor.pointSense returns NOTHING for all of the bin's pixels.
+    {
+        const float margin = 0.01f;
+        float bandX = scene.W / 2 - scene.R - margin, bandY = scene.H / 2 - margin;
+        PS_FOR(bin, nBins) {
+            int bxi = bin / T.binsY, byi = bin - bxi * T.binsY;
+            float x0 = T.bbXmin + bxi * T.binSize - margin, y0 = T.bbYmin + byi * T.binSize - margin;
+            float x1 = x0 + T.binSize + 2 * margin, y1 = y0 + T.binSize + 2 * margin;
+            bool inside = true;
+            for (int k = 0; k < 4; ++k) {
+                V2 g = mulX(xf, mk((k & 1) ? x1 : x0, (k & 2) ? y1 : y0));
+                inside = inside && fabsf(g.x) < bandX && fabsf(g.y) < bandY;
+            }
+            // (the wall body's own fixtures are sensed only within 22 cm of the world origin: leave such bins to the general path)
+            bool wallNear = false;
+            if (scene.wallSensable)
+                for (int k = 0; k < 4; ++k) {
+                    V2 g = mulX(xf, mk((k & 1) ? x1 : x0, (k & 2) ? y1 : y0));
+                    wallNear = wallNear || distSq(mk(0.0f, 0.0f), g) <= 40.0f * 40.0f;
+                }
+            int cls = 0;
+            if (inside && !wallNear) cls = wk.binCount[bin] == 0 ? 1 : 2;
+            wk.binClass[bin] = (uint8_t)cls;
+        }
+    }
+    ctx.sync();
     long long tc1 = phaseClock();
     // ---- PointSensor.pointSense for every active pixel
     const Shape& hull = scene.shapes[kShapeRobot0];
@@ -377,13 +412,19 @@ PS_HD void senseRobot(Ctx& ctx, const PhysEnv& e, const SenseTables& T, const Se
     FreeSpace fs = makeFreeSpace(scene, 0.0f);
     int visited = 0;   // candidate bodies examined by this thread's pixels (diagnostic: K of SURVEY 8(d))
     auto sensePixel = [&](const PixRec& px) {
+        int bin = (int)(px.rectBin >> 16);
+        int cls = wk.binClass[bin];
+        if (cls == 1) {   // nothing can be seen anywhere in this bin
+            wk.img[px.rectBin & 0xFFFFu] = (uint8_t)PS_T_NOTHING;
+            if (camOut) camOut[px.img] = (uint8_t)PS_T_NOTHING;
+            return;
+        }
         V2 g = mulX(xf, mk(px.xr, px.yr));
         int type = PS_T_NOTHING;
-        if (!inFreeSpaceFast(fs, g)) {
+        if (cls == 0 && !inFreeSpaceFast(fs, g)) {
             type = PS_T_WALL;
         } else {
             bool hit = false;
-            int bin = (int)(px.rectBin >> 16);
             int nList = wk.binCount[bin];
             bool full = nList == 255;   // overfull bin: walk the whole candidate list
             if (full) nList = nCand;
@@ -432,6 +473,10 @@ PS_HD void senseRobot(Ctx& ctx, const PhysEnv& e, const SenseTables& T, const Se
         }
         wk.img[px.rectBin & 0xFFFFu] = (uint8_t)type;
         if (camOut) camOut[px.img] = (uint8_t)type;
+        if (type < PS_MAX_COLOURS) {   // the blob labelling only ever looks at these
+            int pos = ctx.atomicAddI(&wk.counters[6], 1);
+            if (pos < kMaxColPix) wk.colList[pos] = (uint16_t)(px.rectBin & 0xFFFFu);
+        }
     };
     {
         // two pixels per trip: both table records are in flight before the first is used
@@ -467,27 +512,24 @@ PS_HD void senseRobot(Ctx& ctx, const PhysEnv& e, const SenseTables& T, const Se
     long long tq0 = phaseClock();
     // ---- BlobFinder: 8-connected components of equal puck colour.
     // (1) vertical runs: the rectangle is stored column-major, so a run of equal colour inside a column is a contiguous
-    //     index range; one thread per column labels every pixel with the index of its run's first pixel and appends the
-    //     coloured pixels to a list, so that the passes below touch those pixels only.
-    PS_FOR(cx, T.RW) {
-        int base = cx * T.RH;
-        int start = base;
-        uint8_t prev = 255;
-        for (int y = 0; y < T.RH; ++y) {
-            uint8_t t = wk.img[base + y];
-            if (t < PS_MAX_COLOURS) {
-                if (t != prev) start = base + y;
-                wk.parent[base + y] = start;
-                int pos = ctx.atomicAddI(&wk.counters[6], 1);
-                if (pos < kMaxColPix) wk.colList[pos] = (uint16_t)((cx << 8) | y);
-            }
-            prev = t < PS_MAX_COLOURS ? t : (uint8_t)255;
-        }
-    }
-    ctx.sync();
+    //     index range. Every coloured pixel (the camera stage listed them) walks up to its run's first pixel (runs are a
+    //     few pixels long) and labels itself with that index.
     int nCol = wk.counters[6];
     bool listed = nCol <= kMaxColPix;        // otherwise fall back to scanning the rectangle
     int nScan = listed ? nCol : nRect;
+    PS_FOR(n, nScan) {
+        int i = listed ? (int)wk.colList[n] : n;
+        uint8_t t = wk.img[i];
+        if (t >= PS_MAX_COLOURS) continue;
+        int cx = i / T.RH;
+        int colBase = cx * T.RH;
+        int start = i;
+        while (start > colBase && wk.img[start - 1] == t) --start;
+        wk.parent[i] = start;
+        if (listed) wk.colList[n] = (uint16_t)((cx << 8) | (i - colBase));
+    }
+    ctx.sync();
+    long long tb1 = phaseClock();
     // decode entry n of the scan into (i, x, y); returns false for pixels without a puck colour
 #define PS_COLPIX(n, i, x, y)                                   \
     int i, x, y;                                                \
@@ -520,6 +562,7 @@ PS_HD void senseRobot(Ctx& ctx, const PhysEnv& e, const SenseTables& T, const Se
         }
     }
     ctx.sync();
+    long long tb2 = phaseClock();
     // roots -> blob slots (any order: the local-map stage sorts the blobs by colour and seed)
     PS_FOR(n, nScan) {
         PS_COLPIX(n, i, x, y)
@@ -549,19 +592,26 @@ PS_HD void senseRobot(Ctx& ctx, const PhysEnv& e, const SenseTables& T, const Se
     ctx.sync();
     PS_FOR(s, nBlobs) wk.parent[wk.blobRoot[s]] = -(s + 1);
     ctx.sync();
+    long long tb3 = phaseClock();
+    // blob statistics, one update per vertical run (not per pixel): the run's first pixel walks down to its end
     PS_FOR(n, nScan) {
         PS_COLPIX(n, i, x, y)
+        uint8_t t = wk.img[i];
+        if (y > 0 && wk.img[i - 1] == t) continue;   // not the first pixel of its run
+        int yEnd = y;
+        while (yEnd + 1 < T.RH && wk.img[i + (yEnd + 1 - y)] == t) ++yEnd;
         int p = wk.parent[i];
         if (p >= 0) p = wk.parent[p];
         int s = -p - 1;
         if (s < 0 || s >= kMaxBlobs) continue;   // blob table overflow
-        int px = T.x0 + x, py = T.y0 + y;
-        ctx.atomicAddI(&wk.blobArea[s], 1);
+        int px = T.x0 + x, py = T.y0 + y, pyEnd = T.y0 + yEnd;
+        ctx.atomicAddI(&wk.blobArea[s], yEnd - y + 1);
         ctx.atomicMinI(&wk.blobX0[s], px);
         ctx.atomicMaxI(&wk.blobX1[s], px);
         ctx.atomicMinI(&wk.blobY0[s], py);
-        ctx.atomicMaxI(&wk.blobY1[s], py);
-        // BlobFinder seeds only at y < yMax (= imgH - 1); the seed fixes the blob's position in the list
+        ctx.atomicMaxI(&wk.blobY1[s], pyEnd);
+        // BlobFinder seeds only at y < yMax (= imgH - 1); the seed fixes the blob's position in the list. Within a run the
+        // smallest seed index is that of its first pixel
         if (py < T.imgH - 1) ctx.atomicMinI(&wk.blobSeed[s], (px * T.imgH + py));
     }
 #undef PS_COLPIX
@@ -596,6 +646,13 @@ PS_HD void senseRobot(Ctx& ctx, const PhysEnv& e, const SenseTables& T, const Se
         wk.phase[5] = wk.counters[6];            // puck-coloured pixels
         wk.phase[6] = nCand;
         wk.phase[7] = nBlobs;
+#if defined(PS_PHASE_CLOCKS)
+        // diagnostic build only: the blob labelling's passes instead of the counts
+        wk.phase[4] = (int)((tb1 - tq0) >> 4);   // vertical runs
+        wk.phase[5] = (int)((tb2 - tb1) >> 4);   // merge
+        wk.phase[6] = (int)((tb3 - tb2) >> 4);   // roots + flatten
+        wk.phase[7] = (int)((tc3 - tb3) >> 4);   // statistics
+#endif
     }
     ctx.sync();
 }
@@ -1941,6 +1998,16 @@ struct SenseSetup {
             aPix[k].yr = aYr[k];
             aPix[k].rectBin = (uint32_t)aRect[k] | ((uint32_t)aBin[k] << 16);
             aPix[k].img = aImg[k];
+        }
+        // the camera stage walks the pixels bin by bin (a warp then sees one bin class and one candidate list)
+        std::stable_sort(aPix.begin(), aPix.end(), [](const PixRec& a, const PixRec& b) { return (a.rectBin >> 16) < (b.rectBin >> 16); });
+        {
+            int nB = T.binsX * T.binsY;
+            size_t k = 0;
+            for (int b = 0; b <= kMaxBins; b++) {
+                while (b < nB && k < aPix.size() && (int)(aPix[k].rectBin >> 16) < b) k++;
+                T.binStart[b] = (uint16_t)(b < nB ? k : aPix.size());
+            }
         }
         T.aPix = aPix.data();
         cellRect.resize(cellSrc.size());
