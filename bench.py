@@ -36,6 +36,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 N_ROBOTS, N_PUCKS, ARENAS_PER_GPU, STEP_INTERVAL = 16, 200, 4096, 3
 STEADY_STEPS = 200      # think steps timed for also.steady_state (600 ticks) after >= 300 warm-up ticks
+FAST_POS_ITERS = 10     # also.fast_mode: position-iteration cap (the reference passes 100)
 PARITY_ARENAS = 8       # arenas of the timed batch replayed by the oracle after the clocks stop
 METRIC = "robot-steps/sec, 16 robots/200 pucks x N arenas"
 UNIT = "robot-steps/s"
@@ -490,6 +491,24 @@ def main():
             "call": "per think step: ps_sense + ps_get_observations(localmap, occupancy, pose; pinned) + host controller (vectorised numpy stand-in) "
                     "+ ps_step_external; host wall clock; controllers.Controller seam (Controller.java:9-31), reported separately from the on-device path"}
         engx.close()
+
+        # ---- FAST mode (north_star: "fixed-iteration order"): the same engine with JBox2D's position-iteration cap at 10 instead
+        #      of the 100 RunOffline passes. NOT the reference's configuration and never the headline: labelled, reported beside
+        #      it, gated by the ensemble KS test of tools/gpu_fast_mode_gate.py (profiles/r02_fast_mode_gate.json) ----
+        engf = make_engine(A, lo, pos_iters=FAST_POS_ITERS)
+        for _ in range(100):
+            engf.step(STEP_INTERVAL, sync=False)
+        nf = 60
+        tf, *_ = timed_steps(engf, nf)
+        gate = None
+        try:
+            gate = json.load(open(os.path.join(ROOT, "profiles", "r02_fast_mode_gate.json"))).get("gate")
+        except Exception:
+            pass
+        also["fast_mode"] = {"value": world * A * N_ROBOTS * STEP_INTERVAL * nf / (tf / 1000.0), "unit": UNIT, "ms_per_step": tf / nf, "steps": nf, "warmup": 100,
+                             "pos_iters": FAST_POS_ITERS, "parity": "NOT the reference configuration (World.step(1/14, 3, 100)); bit-exact against the oracle run "
+                             "with the same cap", "ensemble_ks_gate": gate, "gate_file": "profiles/r02_fast_mode_gate.json"}
+        engf.close()
 
         # ---- BASELINE configs[3]: 65 536 arenas x 16 x 200 sharded over the GPUs of the job (named for 2 / 4 / 8 GPUs) ----
         if world > 1 and 65536 % world == 0:

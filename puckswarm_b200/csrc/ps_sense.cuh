@@ -241,6 +241,135 @@ PS_HD bool lmReachable(float vx, float vy) {
     return sqrt(dXr * dXr + dYr * dYr) > radius;
 }
 
+// LocalMap.extractOccupancy (src/localmap/LocalMap.java:210-229): every cell takes the type of its last writer in (x, y)
+// scan order (a static table); getFreeerSide tallies on the way
+template <class Ctx>
+PS_HD void senseOccupancy(Ctx& ctx, const SenseTables& T, const SenseWork& wk, uint8_t* occOut) {
+    int nCells = T.occW * T.occH;
+    int leftSum = 0, rightSum = 0;
+    PS_FOR(c, nCells) {
+        int src = T.cellRect[c];
+        uint8_t t = src == 0xFFFF ? (uint8_t)PS_T_NOTHING : wk.img[src];
+        occOut[c] = t;
+        if (t == PS_T_ROBOT || t == PS_T_WALL) {
+            // LocalMap.getFreeerSide tallies (src/localmap/LocalMap.java:565-587)
+            if (c < (T.occW / 2) * T.occH) leftSum++;
+            else rightSum++;
+        }
+    }
+    if (leftSum) ctx.atomicAddI(&wk.counters[1], leftSum);
+    if (rightSum) ctx.atomicAddI(&wk.counters[2], rightSum);
+}
+
+// BlobFinder (src/sensors/BlobFinder.java:30-101): 8-connected components of equal puck colour over the coloured pixels the
+// camera stage listed; leaves the blob table in wk.blob* and the blob count in wk.counters[0]. `ctx` may be a whole CTA or
+// a single warp (the passes are short: a few hundred pixels).
+template <class Ctx>
+PS_HD void senseBlobs(Ctx& ctx, const SenseTables& T, const SenseWork& wk, int nRect) {
+    // ---- BlobFinder: 8-connected components of equal puck colour.
+    // (1) vertical runs: the rectangle is stored column-major, so a run of equal colour inside a column is a contiguous
+    //     index range. Every coloured pixel (the camera stage listed them) walks up to its run's first pixel (runs are a
+    //     few pixels long) and labels itself with that index.
+    int nCol = wk.counters[6];
+    bool listed = nCol <= kMaxColPix;        // otherwise fall back to scanning the rectangle
+    int nScan = listed ? nCol : nRect;
+    PS_FOR(n, nScan) {
+        int i = listed ? (int)wk.colList[n] : n;
+        uint8_t t = wk.img[i];
+        if (t >= PS_MAX_COLOURS) continue;
+        int cx = i / T.RH;
+        int colBase = cx * T.RH;
+        int start = i;
+        while (start > colBase && wk.img[start - 1] == t) --start;
+        wk.parent[i] = start;
+        if (listed) wk.colList[n] = (uint16_t)((cx << 8) | (i - colBase));
+    }
+    ctx.sync();
+    // decode entry n of the scan into (i, x, y); returns false for pixels without a puck colour
+#define PS_COLPIX(n, i, x, y)                                   \
+    int i, x, y;                                                \
+    if (listed) {                                               \
+        int xy_ = wk.colList[n];                                \
+        x = xy_ >> 8;                                           \
+        y = xy_ & 255;                                          \
+        i = x * T.RH + y;                                       \
+    } else {                                                    \
+        i = n;                                                  \
+        x = i / T.RH;                                           \
+        y = i - x * T.RH;                                       \
+        if (wk.img[i] >= PS_MAX_COLOURS) continue;              \
+    }
+    // (2) merge runs of neighbouring columns (8-connectivity: rows y-1, y, y+1 of column x-1). A pair of runs is united
+    //     once, by the first pixel at which the two runs face each other.
+    PS_FOR(n, nScan) {
+        PS_COLPIX(n, i, x, y)
+        uint8_t t = wk.img[i];
+        if (x == 0) continue;
+        bool upSame = y > 0 && wk.img[i - 1] == t;
+        int j0 = i - T.RH;
+        for (int dy = -1; dy <= 1; ++dy) {
+            int yy = y + dy;
+            if (yy < 0 || yy >= T.RH) continue;
+            if (wk.img[j0 + dy] != t) continue;
+            // the pixel above already joined these two runs if it saw the neighbour run one row up
+            if (upSame && yy - 1 >= 0 && wk.img[j0 + dy - 1] == t) continue;
+            ufUnion(ctx, wk.parent, wk.parent[i], wk.parent[j0 + dy]);
+        }
+    }
+    ctx.sync();
+    // roots -> blob slots (any order: the local-map stage sorts the blobs by colour and seed)
+    PS_FOR(n, nScan) {
+        PS_COLPIX(n, i, x, y)
+        if (wk.parent[i] == i) {
+            int pos = ctx.atomicAddI(&wk.counters[0], 1);
+            if (pos < kMaxBlobs) {
+                wk.blobRoot[pos] = i;
+                wk.blobArea[pos] = 0;
+                wk.blobX0[pos] = 1 << 30;
+                wk.blobX1[pos] = -(1 << 30);
+                wk.blobY0[pos] = 1 << 30;
+                wk.blobY1[pos] = -(1 << 30);
+                wk.blobSeed[pos] = 1 << 30;
+            } else {
+                wk.counters[5] = 1;
+            }
+        }
+    }
+    ctx.sync();
+    int nBlobs = wk.counters[0];
+    if (nBlobs > kMaxBlobs) nBlobs = kMaxBlobs;
+    // flatten every pixel to its root, then to "-(slot + 1)" via the root
+    PS_FOR(n, nScan) {
+        PS_COLPIX(n, i, x, y)
+        if (wk.parent[i] != i) wk.parent[i] = ufFind(wk.parent, wk.parent[i]);
+    }
+    ctx.sync();
+    PS_FOR(s, nBlobs) wk.parent[wk.blobRoot[s]] = -(s + 1);
+    ctx.sync();
+    // blob statistics, one update per vertical run (not per pixel): the run's first pixel walks down to its end
+    PS_FOR(n, nScan) {
+        PS_COLPIX(n, i, x, y)
+        uint8_t t = wk.img[i];
+        if (y > 0 && wk.img[i - 1] == t) continue;   // not the first pixel of its run
+        int yEnd = y;
+        while (yEnd + 1 < T.RH && wk.img[i + (yEnd + 1 - y)] == t) ++yEnd;
+        int p = wk.parent[i];
+        if (p >= 0) p = wk.parent[p];
+        int s = -p - 1;
+        if (s < 0 || s >= kMaxBlobs) continue;   // blob table overflow
+        int px = T.x0 + x, py = T.y0 + y, pyEnd = T.y0 + yEnd;
+        ctx.atomicAddI(&wk.blobArea[s], yEnd - y + 1);
+        ctx.atomicMinI(&wk.blobX0[s], px);
+        ctx.atomicMaxI(&wk.blobX1[s], px);
+        ctx.atomicMinI(&wk.blobY0[s], py);
+        ctx.atomicMaxI(&wk.blobY1[s], pyEnd);
+        // BlobFinder seeds only at y < yMax (= imgH - 1); the seed fixes the blob's position in the list. Within a run the
+        // smallest seed index is that of its first pixel
+        if (py < T.imgH - 1) ctx.atomicMinI(&wk.blobSeed[s], (px * T.imgH + py));
+    }
+#undef PS_COLPIX
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // senseRobot: camera image -> occupancy grid -> blobs -> perceived pucks -> clusters -> filtered clusters
 template <class Ctx>
@@ -493,129 +622,16 @@ PS_HD void senseRobot(Ctx& ctx, const PhysEnv& e, const SenseTables& T, const Se
     if (visited) ctx.atomicAddI(&wk.counters[7], visited);
     ctx.sync();
     long long tc2 = phaseClock();
-    // ---- LocalMap.extractOccupancy: every cell takes the type of its last writer in (x, y) scan order
-    int nCells = T.occW * T.occH;
-    int leftSum = 0, rightSum = 0;
-    PS_FOR(c, nCells) {
-        int src = T.cellRect[c];
-        uint8_t t = src == 0xFFFF ? (uint8_t)PS_T_NOTHING : wk.img[src];
-        occOut[c] = t;
-        if (t == PS_T_ROBOT || t == PS_T_WALL) {
-            // LocalMap.getFreeerSide tallies (src/localmap/LocalMap.java:565-587)
-            if (c < (T.occW / 2) * T.occH) leftSum++;
-            else rightSum++;
-        }
-    }
-    if (leftSum) ctx.atomicAddI(&wk.counters[1], leftSum);
-    if (rightSum) ctx.atomicAddI(&wk.counters[2], rightSum);
+    // ---- LocalMap.extractOccupancy and BlobFinder both only read the image: no barrier between them.
+    // (Measured: labelling the blobs on ONE warp with warp-level barriers while the other warps gather the occupancy grid
+    // more than doubles the stage, 6.8 -> 15.7 ms per 65 536 robots -- the passes are dependent shared-memory chains, and a
+    // single warp has nothing to hide their latency with while the CTA keeps its 56 KB of shared memory.)
+    senseOccupancy(ctx, T, wk, occOut);
+    senseBlobs(ctx, T, wk, nRect);
     ctx.sync();
-    long long tq0 = phaseClock();
-    // ---- BlobFinder: 8-connected components of equal puck colour.
-    // (1) vertical runs: the rectangle is stored column-major, so a run of equal colour inside a column is a contiguous
-    //     index range. Every coloured pixel (the camera stage listed them) walks up to its run's first pixel (runs are a
-    //     few pixels long) and labels itself with that index.
-    int nCol = wk.counters[6];
-    bool listed = nCol <= kMaxColPix;        // otherwise fall back to scanning the rectangle
-    int nScan = listed ? nCol : nRect;
-    PS_FOR(n, nScan) {
-        int i = listed ? (int)wk.colList[n] : n;
-        uint8_t t = wk.img[i];
-        if (t >= PS_MAX_COLOURS) continue;
-        int cx = i / T.RH;
-        int colBase = cx * T.RH;
-        int start = i;
-        while (start > colBase && wk.img[start - 1] == t) --start;
-        wk.parent[i] = start;
-        if (listed) wk.colList[n] = (uint16_t)((cx << 8) | (i - colBase));
-    }
-    ctx.sync();
-    long long tb1 = phaseClock();
-    // decode entry n of the scan into (i, x, y); returns false for pixels without a puck colour
-#define PS_COLPIX(n, i, x, y)                                   \
-    int i, x, y;                                                \
-    if (listed) {                                               \
-        int xy_ = wk.colList[n];                                \
-        x = xy_ >> 8;                                           \
-        y = xy_ & 255;                                          \
-        i = x * T.RH + y;                                       \
-    } else {                                                    \
-        i = n;                                                  \
-        x = i / T.RH;                                           \
-        y = i - x * T.RH;                                       \
-        if (wk.img[i] >= PS_MAX_COLOURS) continue;              \
-    }
-    // (2) merge runs of neighbouring columns (8-connectivity: rows y-1, y, y+1 of column x-1). A pair of runs is united
-    //     once, by the first pixel at which the two runs face each other.
-    PS_FOR(n, nScan) {
-        PS_COLPIX(n, i, x, y)
-        uint8_t t = wk.img[i];
-        if (x == 0) continue;
-        bool upSame = y > 0 && wk.img[i - 1] == t;
-        int j0 = i - T.RH;
-        for (int dy = -1; dy <= 1; ++dy) {
-            int yy = y + dy;
-            if (yy < 0 || yy >= T.RH) continue;
-            if (wk.img[j0 + dy] != t) continue;
-            // the pixel above already joined these two runs if it saw the neighbour run one row up
-            if (upSame && yy - 1 >= 0 && wk.img[j0 + dy - 1] == t) continue;
-            ufUnion(ctx, wk.parent, wk.parent[i], wk.parent[j0 + dy]);
-        }
-    }
-    ctx.sync();
-    long long tb2 = phaseClock();
-    // roots -> blob slots (any order: the local-map stage sorts the blobs by colour and seed)
-    PS_FOR(n, nScan) {
-        PS_COLPIX(n, i, x, y)
-        if (wk.parent[i] == i) {
-            int pos = ctx.atomicAddI(&wk.counters[0], 1);
-            if (pos < kMaxBlobs) {
-                wk.blobRoot[pos] = i;
-                wk.blobArea[pos] = 0;
-                wk.blobX0[pos] = 1 << 30;
-                wk.blobX1[pos] = -(1 << 30);
-                wk.blobY0[pos] = 1 << 30;
-                wk.blobY1[pos] = -(1 << 30);
-                wk.blobSeed[pos] = 1 << 30;
-            } else {
-                wk.counters[5] = 1;
-            }
-        }
-    }
-    ctx.sync();
+    long long tq0 = tc2;
     int nBlobs = wk.counters[0];
     if (nBlobs > kMaxBlobs) nBlobs = kMaxBlobs;
-    // flatten every pixel to its root, then to "-(slot + 1)" via the root
-    PS_FOR(n, nScan) {
-        PS_COLPIX(n, i, x, y)
-        if (wk.parent[i] != i) wk.parent[i] = ufFind(wk.parent, wk.parent[i]);
-    }
-    ctx.sync();
-    PS_FOR(s, nBlobs) wk.parent[wk.blobRoot[s]] = -(s + 1);
-    ctx.sync();
-    long long tb3 = phaseClock();
-    // blob statistics, one update per vertical run (not per pixel): the run's first pixel walks down to its end
-    PS_FOR(n, nScan) {
-        PS_COLPIX(n, i, x, y)
-        uint8_t t = wk.img[i];
-        if (y > 0 && wk.img[i - 1] == t) continue;   // not the first pixel of its run
-        int yEnd = y;
-        while (yEnd + 1 < T.RH && wk.img[i + (yEnd + 1 - y)] == t) ++yEnd;
-        int p = wk.parent[i];
-        if (p >= 0) p = wk.parent[p];
-        int s = -p - 1;
-        if (s < 0 || s >= kMaxBlobs) continue;   // blob table overflow
-        int px = T.x0 + x, py = T.y0 + y, pyEnd = T.y0 + yEnd;
-        ctx.atomicAddI(&wk.blobArea[s], yEnd - y + 1);
-        ctx.atomicMinI(&wk.blobX0[s], px);
-        ctx.atomicMaxI(&wk.blobX1[s], px);
-        ctx.atomicMinI(&wk.blobY0[s], py);
-        ctx.atomicMaxI(&wk.blobY1[s], pyEnd);
-        // BlobFinder seeds only at y < yMax (= imgH - 1); the seed fixes the blob's position in the list. Within a run the
-        // smallest seed index is that of its first pixel
-        if (py < T.imgH - 1) ctx.atomicMinI(&wk.blobSeed[s], (px * T.imgH + py));
-    }
-#undef PS_COLPIX
-    ctx.sync();
     long long tc3 = phaseClock();
     // ---- blob table for the local-map stage (one record per blob, in root order; sorted by (colour, seed) there)
     PS_FOR(b, nBlobs) {
@@ -646,13 +662,6 @@ PS_HD void senseRobot(Ctx& ctx, const PhysEnv& e, const SenseTables& T, const Se
         wk.phase[5] = wk.counters[6];            // puck-coloured pixels
         wk.phase[6] = nCand;
         wk.phase[7] = nBlobs;
-#if defined(PS_PHASE_CLOCKS)
-        // diagnostic build only: the blob labelling's passes instead of the counts
-        wk.phase[4] = (int)((tb1 - tq0) >> 4);   // vertical runs
-        wk.phase[5] = (int)((tb2 - tb1) >> 4);   // merge
-        wk.phase[6] = (int)((tb3 - tb2) >> 4);   // roots + flatten
-        wk.phase[7] = (int)((tc3 - tb3) >> 4);   // statistics
-#endif
     }
     ctx.sync();
 }

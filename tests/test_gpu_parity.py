@@ -167,6 +167,23 @@ def test_dense_arena_big_islands():
     assert most_bodies > 48 or most_contacts > 64, (most_bodies, most_contacts)
 
 
+def test_fast_mode_is_oracle_exact():
+    """FAST mode = a lower position-iteration cap (ps_config.pos_iters = 10; the reference passes 100). It is a different
+    experiment configuration, not a different engine: the oracle with the same cap must still be reproduced bit for bit."""
+    import parity
+    A = 6
+    cfg = abi.config_defaults(n_arenas=A, n_robots=8, n_pucks=120, controller=abi.PS_CTRL_CACHECONS, pos_iters=10)
+    e, o = _engine(cfg), _oracle(cfg)
+    e.reset(np.arange(A))
+    o.reset(np.arange(A))
+    for k in range(4):
+        e.step(90)
+        o.step(90)
+        bad = parity.compare_states(e.get_state(), o.get_state(), A, tol=TOL)
+        assert bad == [], "tick %d: %s" % (90 * (k + 1), bad[:5])
+    assert max(o.step_info(a)["pos_iters"] for a in range(A)) <= 10
+
+
 def test_c3_shape_against_oracle():
     """16 robots / 200 pucks (the shape of the headline config), CacheCons on device, 20 think steps free-running."""
     import parity

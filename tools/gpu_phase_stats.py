@@ -27,8 +27,8 @@ for a in w:
     print(int(a), int(st[a, 3]), int(st[a, 4]), int(st[a, 1]), st[a, 7] * 16 / 1e6)
 
 ss = e.sense_stats().reshape(-1, 8).astype(np.float64)
-for i, n in enumerate(['candidates', 'camera', 'occ+ccl', 'occupancy', 'blob runs', 'blob merge', 'blob roots', 'blob stats']):
-    sc = 16
+for i, n in enumerate(['candidates', 'camera', 'occupancy | blobs', '(unused)', 'bodies examined', 'coloured pixels', 'candidates', 'blobs']):
+    sc = 16 if i < 4 else 1
     print('sense %-15s mean %10.1f max %10.1f' % (n, ss[:, i].mean() * sc, ss[:, i].max() * sc))
 
 h = e.island_hist()
