@@ -351,9 +351,10 @@ int ps_get_island_hist(ps_handle h, int64_t* out /*[64]*/, int reset);
 /* Per-kernel device time, measured with CUDA events on the engine's stream while enabled. ps_get_kernel_ms waits for the
  * stream, returns the accumulated milliseconds and launch counts of 0 = sense, 1 = think, 2 = physics (World.step, all stages),
  * 3 = other, 4 / 5 / 6 = the three stages of World.step (collide + islands, island workers, broad phase + TOI), 7 unused,
- * and clears the accumulators. */
+ * 8 / 9 / 10 = the big-island, warp-per-island and lane-batch kernels of stage B, each from the end of stage A (they run side by
+ * side: the longest is what the tick waits for), 11 unused; and clears the accumulators. */
 int ps_profile(ps_handle h, int enable);
-int ps_get_kernel_ms(ps_handle h, double* ms /*[8]*/, int64_t* counts /*[8]*/);
+int ps_get_kernel_ms(ps_handle h, double* ms /*[12]*/, int64_t* counts /*[12]*/);
 int     ps_num_groups(ps_handle h);        /* arena groups (each runs its kernel sequence on its own stream) */
 int64_t ps_kernel_launches(ps_handle h);   /* kernels launched by this handle so far */
 void*   ps_stream(ps_handle h);            /* the cudaStream_t the engine launches on */

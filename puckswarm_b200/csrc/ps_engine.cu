@@ -180,23 +180,33 @@ __global__ void __launch_bounds__(128) k_phys_pre(KParams p) {
     physPre(ctx, p.env, wk, st, wk.fx, wk.fy, p.queue, a);
 }
 
+// entry `idx` of the warp-bucket islands in hand-out order: buckets kBucketXXL, kBucketXL, kBucketLarge, then bucket 0
+__device__ __forceinline__ unsigned warpBucketEntry(const IslandQueue& q, int idx, int n3, int n2, int nLarge) {
+    size_t cap = (size_t)q.cap;
+    if (idx < n3) return q.entries[kBucketXXL * cap + idx];
+    if (idx < n2) return q.entries[kBucketXL * cap + (idx - n3)];
+    if (idx < nLarge) return q.entries[kBucketLarge * cap + (idx - n2)];
+    return q.entries[idx - nLarge];
+}
+
 // stage B1: islands too large for a lane slot (queue bucket 0): one warp per island, staged in shared memory.
 // VEL_ONLY: the velocity half only (k_island_vel); the position sweeps follow in k_island_pos on the same stream.
 template <bool VEL_ONLY>
 __device__ __forceinline__ void islandWarpKernel(const KParams& p) {
     extern __shared__ __align__(16) char smem[];
     WarpSlot* slot = reinterpret_cast<WarpSlot*>(smem) + (threadIdx.x >> 5);
-    // the islands with the most contacts (bucket kBucketLarge) are handed out first, then bucket 0
-    int nLarge = min(p.queue.counts[kBucketLarge], p.queue.cap);
+    // the heaviest islands are handed out first (buckets kBucketXXL, kBucketXL, kBucketLarge), then bucket 0
+    int n3 = min(p.queue.counts[kBucketXXL], p.queue.cap), n2 = n3 + min(p.queue.counts[kBucketXL], p.queue.cap);
+    int nLarge = n2 + min(p.queue.counts[kBucketLarge], p.queue.cap);
     int total = nLarge + min(p.queue.counts[0], p.queue.cap);
     unsigned NB = (unsigned)p.env.cfg.d.NB;
     int lane = threadIdx.x & 31;
     for (;;) {
         int idx = 0;
-        if (lane == 0) idx = atomicAdd(&p.queue.counts[kQueueBuckets], 1);
+        if (lane == 0) idx = atomicAdd(&p.queue.counts[kQHeadWarp], 1);
         idx = __shfl_sync(0xFFFFFFFFu, idx, 0);
         if (idx >= total) break;
-        unsigned entry = idx < nLarge ? p.queue.entries[(size_t)kBucketLarge * p.queue.cap + idx] : p.queue.entries[idx - nLarge];
+        unsigned entry = warpBucketEntry(p.queue, idx, n3, n2, nLarge);
         int a = (int)(entry / NB), k = (int)(entry % NB);
         PhysWork wk = arenaWork(p, a);
         ArenaState st = arenaState(p.sp, p.env.cfg, a);
@@ -240,7 +250,8 @@ __global__ void __launch_bounds__(32) k_island_pos(KParams p) {
     L.S = &S;
     int posIters = p.env.cfg.posIters;
     if (posIters <= 0) return;
-    int nLarge = min(p.queue.counts[kBucketLarge], p.queue.cap);
+    int n3 = min(p.queue.counts[kBucketXXL], p.queue.cap), n2 = n3 + min(p.queue.counts[kBucketXL], p.queue.cap);
+    int nLarge = n2 + min(p.queue.counts[kBucketLarge], p.queue.cap);
     int total = nLarge + min(p.queue.counts[0], p.queue.cap);
     unsigned NB = (unsigned)p.env.cfg.d.NB;
     bool running = false, exhausted = false;
@@ -269,10 +280,10 @@ __global__ void __launch_bounds__(32) k_island_pos(KParams p) {
             unsigned entry = 0;
             while (!staged) {   // islands that outgrew the slot were solved by k_island_vel's fallback: skip them
                 int idx = 0;
-                if (lane == 0) idx = atomicAdd(&p.queue.counts[kQueueBuckets + 1], 1);
+                if (lane == 0) idx = atomicAdd(&p.queue.counts[kQHeadPos], 1);
                 idx = __shfl_sync(FULL, idx, 0);
                 if (idx >= total) break;
-                entry = idx < nLarge ? p.queue.entries[(size_t)kBucketLarge * p.queue.cap + idx] : p.queue.entries[idx - nLarge];
+                entry = warpBucketEntry(p.queue, idx, n3, n2, nLarge);
                 int a = (int)(entry / NB), k = (int)(entry % NB);
                 PhysWork wk = arenaWork(p, a);
                 __syncwarp();
@@ -554,8 +565,8 @@ struct ps_engine {
         int cls;
     };
     std::vector<Timed> timed;
-    double kernelMs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int64_t kernelCount[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double kernelMs[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int64_t kernelCount[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 struct ScopedTimer {   // records an event pair around the launches issued during its lifetime
@@ -572,11 +583,13 @@ struct ScopedTimer {   // records an event pair around the launches issued durin
         }
         cudaEventRecord(t.a, s);
     }
-    ~ScopedTimer() {
+    void stop() {
         if (!on) return;
         cudaEventRecord(t.b, s);
         e->timed.push_back(t);
+        on = false;
     }
+    ~ScopedTimer() { stop(); }
 };
 
 extern "C" {
@@ -822,7 +835,7 @@ int ps_create(const ps_config* cfg, int device, ps_handle* out) {
         size_t perGroup = (A + nGroups - 1) / nGroups;
         int qcap = (int)std::min<size_t>(perGroup * (size_t)pc.d.NB, (size_t)1 << 27);
         TRY_OR_FREE(cudaMalloc(&e->kp.queue.entries, (size_t)nGroups * kQueueBuckets * qcap * sizeof(unsigned)));
-        TRY_OR_FREE(cudaMalloc(&e->kp.queue.counts, (size_t)nGroups * (kQueueBuckets + 2) * sizeof(int)));
+        TRY_OR_FREE(cudaMalloc(&e->kp.queue.counts, (size_t)nGroups * kQueueSlots * sizeof(int)));
         e->kp.queue.cap = qcap;
         e->groups.resize(nGroups);
         for (int g = 0; g < nGroups; g++) {
@@ -830,7 +843,7 @@ int ps_create(const ps_config* cfg, int device, ps_handle* out) {
             G.a0 = (int)std::min<size_t>(A, g * perGroup);
             G.n = (int)(std::min<size_t>(A, (g + 1) * perGroup) - G.a0);
             G.q.entries = e->kp.queue.entries + (size_t)g * kQueueBuckets * qcap;
-            G.q.counts = e->kp.queue.counts + (size_t)g * (kQueueBuckets + 2);
+            G.q.counts = e->kp.queue.counts + (size_t)g * kQueueSlots;
             G.q.cap = qcap;
             TRY_OR_FREE(cudaStreamCreateWithFlags(&G.s, cudaStreamNonBlocking));
             // the island kernels are small and latency-bound: their CTAs go ahead of the other groups' wide kernels
@@ -1032,7 +1045,7 @@ static int enqueuePreIslands(ps_handle h, ps_engine::Group& G) {
     KParams kp = h->kp;
     kp.a0 = G.a0;
     kp.queue = G.q;
-    CUDA_TRY(cudaMemsetAsync(G.q.counts, 0, (kQueueBuckets + 2) * sizeof(int), G.s));
+    CUDA_TRY(cudaMemsetAsync(G.q.counts, 0, kQueueSlots * sizeof(int), G.s));
     {
         ScopedTimer t4(h, 4, G.s);
         k_phys_pre<<<G.n, 128, 0, G.s>>>(kp);
@@ -1044,9 +1057,12 @@ static int enqueuePreIslands(ps_handle h, ps_engine::Group& G) {
         CUDA_TRY(cudaStreamWaitEvent(G.s2, G.evPre, 0));
         // the largest islands start first, on a stream of their own
         CUDA_TRY(cudaStreamWaitEvent(G.sb[kBucketBig], G.evPre, 0));
+        ScopedTimer t8(h, 8, G.sb[kBucketBig]);   // each island kernel from the end of stage A: which one does the tick wait for?
         k_island_big<<<std::max(1, std::min(h->bigBlocks, G.n)), 32, sizeof(BigSlot), G.sb[kBucketBig]>>>(kp);
+        t8.stop();
         CUDA_TRY(cudaEventRecord(G.evb[kBucketBig], G.sb[kBucketBig]));
         int wb = std::max(1, std::min(h->workerBlocks, G.n * 3));
+        ScopedTimer t9(h, 9, G.s2);
         if (h->islandG == 0) {
             k_island_warp<<<wb, 128, 4 * sizeof(WarpSlot), G.s2>>>(kp);
         } else {
@@ -1059,9 +1075,11 @@ static int enqueuePreIslands(ps_handle h, ps_engine::Group& G) {
             else k_island_pos<8><<<pb, 32, sm, G.s2>>>(kp);
             h->launches++;
         }
+        t9.stop();
         CUDA_TRY(cudaEventRecord(G.evBig, G.s2));
         int bb = std::max(1, std::min(h->batchBlocks, (G.n * 12 + kBatchThreads - 1) / kBatchThreads));
         if (h->mergeBatch) {
+            ScopedTimer t10(h, 10, G.s);
             k_island_batch<<<bb * kLaneBuckets, kBatchThreads, (kBatchThreads / 32) * sizeof(LaneSlotsU), G.s>>>(kp, -1, bb);
         } else {
             for (int bucket = kLaneBuckets; bucket >= 2; --bucket) {
@@ -1527,7 +1545,7 @@ int ps_get_kernel_ms(ps_handle h, double* ms, int64_t* counts) {
         cudaEventDestroy(t.b);
     }
     h->timed.clear();
-    for (int i = 0; i < 8; i++) {
+    for (int i = 0; i < 12; i++) {
         ms[i] = h->kernelMs[i];
         counts[i] = h->kernelCount[i];
         h->kernelMs[i] = 0;

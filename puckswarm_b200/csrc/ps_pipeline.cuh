@@ -21,12 +21,15 @@ struct IslandQueue {
     unsigned* entries;     // [kQueueBuckets][cap]: arena * NB + island. Bucket 0: islands that do not fit a lane slot or have
                            // >= PhysCfg::warpMinContacts contacts (one warp each, level-parallel sweeps); buckets 1..4: lane batches of
                            // islands with 1-2, 3-5, 6-12, 13+ contacts (like with like, so that the lanes of a warp finish together)
-    int* counts;           // [kQueueBuckets + 2]: entries per bucket, then the consumer heads of the warp-bucket kernels (k_island_vel / k_island_warp, k_island_pos)
+    int* counts;           // [kQueueSlots]: entries per bucket, then kQHeadWarp / kQHeadPos (consumer heads of the warp-bucket kernels)
     int cap;
 };
 static constexpr int kQueueWarpBodies = 48, kQueueWarpContacts = 64;   // = kWarpBodies, kWarpContacts of ps_island_lanes.cuh
 static constexpr int kLaneBodies = 12, kLaneContacts = 16;   // what a lane slot of the lane-per-island solver holds
-static constexpr int kQueueBuckets = 7, kLaneBuckets = 4, kBucketBig = 5, kBucketLarge = 6, kWarpMinContactsDefault = 17;   // every island that fits a lane slot takes one (measured: 16 -> 17 shortens the island phase by 2 %, 10 lengthens it by 11 %)
+static constexpr int kQueueBuckets = 9, kLaneBuckets = 4, kBucketBig = 5, kBucketLarge = 6, kBucketXL = 7, kBucketXXL = 8, kWarpMinContactsDefault = 17;   // every island that fits a lane slot takes one (measured: 16 -> 17 shortens the island phase by 2 %, 10 lengthens it by 11 %)
+static constexpr int kQHeadWarp = kQueueBuckets, kQHeadPos = kQueueBuckets + 1, kQueueSlots = kQueueBuckets + 2;
+static constexpr int kXLPoints = 40, kXXLPoints = 56;   // manifold points of an island from which it is handed out before the other large ones: the tick ends when the
+                                                       // longest island ends, and an island's sweeps cost its points (robot jams: two per contact) x up to 100
 static constexpr int kLargeContacts = 28;   // warp-slot islands with at least this many contacts are handed out first (they are the tail)   // capacity of one lane's shared-memory slot (k_island_batch)
 
 template <class Ctx>
@@ -42,6 +45,8 @@ PS_HD void physPre(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaSt
     PS_FOR(b, d.NB) {
         if (wk.adjOff[b] == wk.adjOff[b + 1]) integrateBody(e, wk, b);
     }
+    if (ctx.tid() == 0 && e.cfg.posIters > 0) wk.stats[0] = 1;   // contact-free islands run the position loop once
+    ctx.sync();
     int nIsl = wk.counters[1];
     PS_FOR(k, nIsl) {
         int nb = wk.islandBodyStart[k + 1] - wk.islandBodyStart[k];
@@ -49,10 +54,16 @@ PS_HD void physPre(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaSt
         // 0: a warp each (WarpSlot); kBucketBig: what outgrows that (BigSlot); 1..4: a lane each, by contact count
         int bucket = (nc >= e.cfg.warpMinContacts || nc > kLaneContacts || nb > kLaneBodies) ? ((nb > kQueueWarpBodies || nc > kQueueWarpContacts) ? kBucketBig : (nc >= kLargeContacts ? kBucketLarge : 0))
                                                                                                : (nc <= 2 ? 1 : (nc <= 5 ? 2 : (nc <= 12 ? 3 : 4)));
+        if (bucket == kBucketLarge) {
+            // the heaviest warp-slot islands first: estimated by their manifold points
+            int lo = wk.islandStart[k], points = 0;
+            for (int i = 0; i < nc; ++i) points += wk.tc[wk.order[lo + i]].solverPoints;
+            if (points >= kXXLPoints) bucket = kBucketXXL;
+            else if (points >= kXLPoints) bucket = kBucketXL;
+        }
         int pos = ctx.atomicAddI(&q.counts[bucket], 1);
         if (pos < q.cap) q.entries[(size_t)bucket * q.cap + pos] = (unsigned)arena * (unsigned)d.NB + (unsigned)k;
     }
-    if (ctx.tid() == 0 && e.cfg.posIters > 0) wk.stats[0] = 1;   // contact-free islands run the position loop once
     ctx.sync();
 }
 

@@ -241,10 +241,10 @@ class Engine:
 
     def kernel_ms(self):
         """({'sense': ms, 'think': ms, 'physics': ms, 'other': ms}, counts) accumulated since the last call."""
-        ms = np.zeros(8, np.float64)
-        cnt = np.zeros(8, np.int64)
+        ms = np.zeros(12, np.float64)
+        cnt = np.zeros(12, np.int64)
         self._check(self.L.ps_get_kernel_ms(self.h, ms.ctypes.data, cnt.ctypes.data))
-        names = ("sense", "think", "physics", "other", "phys_pre", "phys_islands", "phys_post", "unused")
+        names = ("sense", "think", "physics", "other", "phys_pre", "phys_islands", "phys_post", "unused", "isl_big", "isl_warp", "isl_batch", "unused2")
         return dict(zip(names, ms.tolist())), dict(zip(names, cnt.tolist()))
 
     @property
