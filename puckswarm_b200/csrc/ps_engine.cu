@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(32) k_island_big(KParams p) {
     }
 }
 
-static constexpr int kBatchThreads = 64;   // two lane slots (2 x 32 islands) per CTA: a slot is ~41 KB of shared memory
+static constexpr int kBatchThreads = 64;   // at most two lane slots (2 x 32 islands) per CTA: a slot is ~41 KB of shared memory (run-time: ps_engine::batchThreads)
 // stage B2: all other islands (queue bucket 1): one lane per island, 32 islands per warp, bodies in shared memory
 // bucket < 0: one launch for all lane buckets, segBlocks CTAs each, the buckets of the largest islands first
 __global__ void __launch_bounds__(kBatchThreads) k_island_batch(KParams p, int bucket, int segBlocks) {
@@ -541,7 +541,7 @@ struct ps_engine {
     int* dStepStats = nullptr;
     int nSlots = 0, threads = 128;
     bool fused = false;      // PS_FUSED=1: the single-kernel World.step (kept for comparison)
-    int workerBlocks = 0, batchBlocks = 0, bigBlocks = 0, posBlocks = 0;
+    int workerBlocks = 0, batchBlocks = 0, bigBlocks = 0, posBlocks = 0, batchThreads = kBatchThreads;
     int islandG = 0;         // PS_ISLAND_G = 2 / 4 / 8: split solver (k_island_vel + k_island_pos with G lanes per island); 0 (default): the one-kernel
                              // warp-per-island solver. The split solver issues 4-5x fewer instructions but every island's sweeps take longer (the groups
                              // of a warp share each other's divergent paths), and the tick waits for the longest island: measured slower (profiles/r02_summary.md)
@@ -869,7 +869,8 @@ int ps_create(const ps_config* cfg, int device, ps_handle* out) {
         e->posBlocks = prop.multiProcessorCount * (int)envSize("PS_POS_BLOCKS_PER_SM", 4);
         TRY_OR_FREE(cudaFuncSetAttribute(k_island_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((kBatchThreads / 32) * sizeof(LaneSlotsU))));
         e->mergeBatch = envSize("PS_MERGE_BATCH", 1) != 0;
-        e->bigBlocks = prop.multiProcessorCount * 4;
+        e->bigBlocks = prop.multiProcessorCount * (int)envSize("PS_BIG_BLOCKS_PER_SM", 4);
+        e->batchThreads = envSize("PS_BATCH_THREADS", kBatchThreads) == 32 ? 32 : kBatchThreads;
         TRY_OR_FREE(cudaFuncSetAttribute(k_island_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BigSlot)));
         e->batchBlocks = prop.multiProcessorCount * (int)envSize("PS_BATCH_BLOCKS_PER_SM", 2);
     }
@@ -1077,17 +1078,18 @@ static int enqueuePreIslands(ps_handle h, ps_engine::Group& G) {
         }
         t9.stop();
         CUDA_TRY(cudaEventRecord(G.evBig, G.s2));
-        int bb = std::max(1, std::min(h->batchBlocks, (G.n * 12 + kBatchThreads - 1) / kBatchThreads));
+        int bt = h->batchThreads;
+        int bb = std::max(1, std::min(h->batchBlocks * (kBatchThreads / bt), (G.n * 12 + bt - 1) / bt));
         if (h->mergeBatch) {
             ScopedTimer t10(h, 10, G.s);
-            k_island_batch<<<bb * kLaneBuckets, kBatchThreads, (kBatchThreads / 32) * sizeof(LaneSlotsU), G.s>>>(kp, -1, bb);
+            k_island_batch<<<bb * kLaneBuckets, bt, (bt / 32) * sizeof(LaneSlotsU), G.s>>>(kp, -1, bb);
         } else {
             for (int bucket = kLaneBuckets; bucket >= 2; --bucket) {
                 CUDA_TRY(cudaStreamWaitEvent(G.sb[bucket], G.evPre, 0));
-                k_island_batch<<<bb, kBatchThreads, (kBatchThreads / 32) * sizeof(LaneSlotsU), G.sb[bucket]>>>(kp, bucket, bb);
+                k_island_batch<<<bb, bt, (bt / 32) * sizeof(LaneSlotsU), G.sb[bucket]>>>(kp, bucket, bb);
                 CUDA_TRY(cudaEventRecord(G.evb[bucket], G.sb[bucket]));
             }
-            k_island_batch<<<bb, kBatchThreads, (kBatchThreads / 32) * sizeof(LaneSlotsU), G.s>>>(kp, 1, bb);
+            k_island_batch<<<bb, bt, (bt / 32) * sizeof(LaneSlotsU), G.s>>>(kp, 1, bb);
             for (int bucket = 2; bucket <= kLaneBuckets; ++bucket) CUDA_TRY(cudaStreamWaitEvent(G.s, G.evb[bucket], 0));
         }
         CUDA_TRY(cudaStreamWaitEvent(G.s, G.evBig, 0));
