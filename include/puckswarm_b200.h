@@ -348,11 +348,17 @@ int ps_get_sense_stats(ps_handle h, int32_t* out);
 /* Diagnostics: islands with >= 3 contacts solved since the last reset, as an 8 x 8 histogram [position-iteration bucket][contact
  * bucket]; iterations <=1, <=3, <=6, <=12, <=25, <=50, <100, 100; contacts <=3, <=5, <=8, <=12, <=16, <=32, <=64, >64. */
 int ps_get_island_hist(ps_handle h, int64_t* out /*[64]*/, int reset);
+/* Diagnostics: census of stage B since the last reset. [0..9] islands per queue bucket (0 warp, 1-4 lane buckets, 5 big, 6 large,
+ * 7 XL, 8 XXL, 9 wide lane slot), [10] ticks (of arena group 0's first arena); [16..31] warp-slot islands by duration in bins of
+ * 2^18 cycles, [32..47] the same for the big islands; [48],[49] kilo-cycles and count of the warp-slot islands, [50],[51] of the
+ * big ones; [52 + 2 b],[53 + 2 b] kilo-cycles and warp rounds of lane bucket b + 1 ([62],[63]: of the wide lane slot); [60] sweeps
+ * summed over the lanes, [61] 32 x the warp's sweeps (their ratio is the lane occupancy of the lock-step position loop). */
+int ps_get_island_census(ps_handle h, int64_t* out /*[64]*/, int reset);
 /* Per-kernel device time, measured with CUDA events on the engine's stream while enabled. ps_get_kernel_ms waits for the
  * stream, returns the accumulated milliseconds and launch counts of 0 = sense, 1 = think, 2 = physics (World.step, all stages),
  * 3 = other, 4 / 5 / 6 = the three stages of World.step (collide + islands, island workers, broad phase + TOI), 7 unused,
  * 8 / 9 / 10 = the big-island, warp-per-island and lane-batch kernels of stage B, each from the end of stage A (they run side by
- * side: the longest is what the tick waits for), 11 unused; and clears the accumulators. */
+ * side: the longest is what the tick waits for), 11 = the wide-lane-slot kernel (same convention); and clears the accumulators. */
 int ps_profile(ps_handle h, int enable);
 int ps_get_kernel_ms(ps_handle h, double* ms /*[12]*/, int64_t* counts /*[12]*/);
 int     ps_num_groups(ps_handle h);        /* arena groups (each runs its kernel sequence on its own stream) */

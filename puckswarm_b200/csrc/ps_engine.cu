@@ -191,8 +191,9 @@ __device__ __forceinline__ unsigned warpBucketEntry(const IslandQueue& q, int id
 
 // stage B1: islands too large for a lane slot (queue bucket 0): one warp per island, staged in shared memory.
 // VEL_ONLY: the velocity half only (k_island_vel); the position sweeps follow in k_island_pos on the same stream.
+// mode 0: every warp-bucket island; 1: the heavy ones only (buckets kBucketXXL, kBucketXL); 2: the others (kBucketLarge, bucket 0)
 template <bool VEL_ONLY>
-__device__ __forceinline__ void islandWarpKernel(const KParams& p) {
+__device__ __forceinline__ void islandWarpKernel(const KParams& p, int mode) {
     extern __shared__ __align__(16) char smem[];
     WarpSlot* slot = reinterpret_cast<WarpSlot*>(smem) + (threadIdx.x >> 5);
     // the heaviest islands are handed out first (buckets kBucketXXL, kBucketXL, kBucketLarge), then bucket 0
@@ -201,11 +202,13 @@ __device__ __forceinline__ void islandWarpKernel(const KParams& p) {
     int total = nLarge + min(p.queue.counts[0], p.queue.cap);
     unsigned NB = (unsigned)p.env.cfg.d.NB;
     int lane = threadIdx.x & 31;
+    int first = mode == 2 ? n2 : 0, last = mode == 1 ? n2 : total;
+    int* head = &p.queue.counts[VEL_ONLY ? kQHeadVel : kQHeadWarp];
     for (;;) {
         int idx = 0;
-        if (lane == 0) idx = atomicAdd(&p.queue.counts[kQHeadWarp], 1);
+        if (lane == 0) idx = first + atomicAdd(head, 1);
         idx = __shfl_sync(0xFFFFFFFFu, idx, 0);
-        if (idx >= total) break;
+        if (idx >= last) break;
         unsigned entry = warpBucketEntry(p.queue, idx, n3, n2, nLarge);
         int a = (int)(entry / NB), k = (int)(entry % NB);
         PhysWork wk = arenaWork(p, a);
@@ -228,17 +231,21 @@ __device__ __forceinline__ void islandWarpKernel(const KParams& p) {
             unsigned long long nc = (unsigned long long)(wk.islandStart[k + 1] - wk.islandStart[k]);
             unsigned long long nb = (unsigned long long)(wk.islandBodyStart[k + 1] - wk.islandBodyStart[k]);
             atomicMax(&p.islandHist[63], (kc << 32) | ((nc & 0xFFF) << 20) | ((nb & 0x3FF) << 10) | (unsigned long long)(iters & 0x3FF) | (ok ? 0ULL : (1ULL << 31)));
+            // census: warp-slot islands by duration (bins of 2^18 cycles), their total kilo-cycles and count
+            atomicAdd(&p.islandHist[64 + 16 + (int)min(15ULL, kc >> 8)], 1ULL);
+            atomicAdd(&p.islandHist[64 + 48], kc);
+            atomicAdd(&p.islandHist[64 + 49], 1ULL);
         }
         __syncwarp();
     }
 }
-__global__ void __launch_bounds__(128) k_island_warp(KParams p) { islandWarpKernel<false>(p); }
-__global__ void __launch_bounds__(128) k_island_vel(KParams p) { islandWarpKernel<true>(p); }
+__global__ void __launch_bounds__(128) k_island_warp(KParams p, int mode) { islandWarpKernel<false>(p, mode); }
+__global__ void __launch_bounds__(128) k_island_vel(KParams p, int mode) { islandWarpKernel<true>(p, mode); }
 
 // stage B1b: the position sweeps of the islands k_island_vel prepared: G lanes per island, 32 / G islands per warp (one warp
 // per CTA), every group on its own row schedule, finished groups written back and refilled by the whole warp.
 template <int G>
-__global__ void __launch_bounds__(32) k_island_pos(KParams p) {
+__global__ void __launch_bounds__(32) k_island_pos(KParams p, int mode) {
     extern __shared__ __align__(16) char smem[];
     constexpr int NG = 32 / G;
     constexpr unsigned GMASK = G == 32 ? 0xFFFFFFFFu : ((1u << G) - 1u);
@@ -254,6 +261,7 @@ __global__ void __launch_bounds__(32) k_island_pos(KParams p) {
     int nLarge = n2 + min(p.queue.counts[kBucketLarge], p.queue.cap);
     int total = nLarge + min(p.queue.counts[0], p.queue.cap);
     unsigned NB = (unsigned)p.env.cfg.d.NB;
+    int first = mode == 2 ? n2 : 0;
     bool running = false, exhausted = false;
     int myEntry = -1;                  // arena * NB + island of this group's island
     int nRows = 0, r = 0, base = 0, rowEnd = 0, iters = 0;
@@ -280,7 +288,7 @@ __global__ void __launch_bounds__(32) k_island_pos(KParams p) {
             unsigned entry = 0;
             while (!staged) {   // islands that outgrew the slot were solved by k_island_vel's fallback: skip them
                 int idx = 0;
-                if (lane == 0) idx = atomicAdd(&p.queue.counts[kQHeadPos], 1);
+                if (lane == 0) idx = first + atomicAdd(&p.queue.counts[kQHeadPos], 1);
                 idx = __shfl_sync(FULL, idx, 0);
                 if (idx >= total) break;
                 entry = warpBucketEntry(p.queue, idx, n3, n2, nLarge);
@@ -383,6 +391,9 @@ __global__ void __launch_bounds__(32) k_island_big(KParams p) {
             unsigned long long nc = (unsigned long long)(wk.islandStart[k + 1] - wk.islandStart[k]);
             unsigned long long nb = (unsigned long long)(wk.islandBodyStart[k + 1] - wk.islandBodyStart[k]);
             atomicMax(&p.islandHist[63], (kc << 32) | ((nc & 0xFFF) << 20) | ((nb & 0x3FF) << 10) | (unsigned long long)(iters & 0x3FF) | (ok ? 0ULL : (1ULL << 31)));
+            atomicAdd(&p.islandHist[64 + 32 + (int)min(15ULL, kc >> 8)], 1ULL);   // census: big islands by duration
+            atomicAdd(&p.islandHist[64 + 50], kc);
+            atomicAdd(&p.islandHist[64 + 51], 1ULL);
         }
         __syncwarp();
     }
@@ -391,10 +402,15 @@ __global__ void __launch_bounds__(32) k_island_big(KParams p) {
 static constexpr int kBatchThreads = 64;   // at most two lane slots (2 x 32 islands) per CTA: a slot is ~41 KB of shared memory (run-time: ps_engine::batchThreads)
 // stage B2: all other islands (queue bucket 1): one lane per island, 32 islands per warp, bodies in shared memory
 // bucket < 0: one launch for all lane buckets, segBlocks CTAs each, the buckets of the largest islands first
-__global__ void __launch_bounds__(kBatchThreads) k_island_batch(KParams p, int bucket, int segBlocks) {
+template <class Slots>
+__device__ __forceinline__ void islandBatchKernel(const KParams& p, int bucket, int segBlocks) {
     extern __shared__ __align__(16) char smem[];
-    LaneCtx L;
-    L.S = reinterpret_cast<LaneSlotsU*>(smem) + (threadIdx.x >> 5);
+    LaneCtxT<Slots> L;
+    L.S = reinterpret_cast<Slots*>(smem) + (threadIdx.x >> 5);
+    L.pmPuck = p.env.hot.pmPuck;
+    L.piPuck = p.env.hot.piPuck;
+    L.pmRobot = p.env.hot.pmRobot;
+    L.piRobot = p.env.hot.piRobot;
     L.lane = threadIdx.x & 31;
     L.nb = L.lo = L.nc = 0;
     int cap = p.queue.cap;
@@ -423,7 +439,24 @@ __global__ void __launch_bounds__(kBatchThreads) k_island_batch(KParams p, int b
             lkStage(p.env, wk, k, L);
         }
         __syncwarp();
+        long long tb0 = clock64();
         int iters = lkSolve(p.env, wk, st, L, active);
+        if (L.lane == 0) {   // census: warp rounds of the lane batches per bucket, their kilo-cycles, and the lanes' summed sweeps vs the warp's
+            int cb = bucket == kBucketLaneX ? 5 : bucket - 1;   // the wide lane slot's rounds go to [62], [63]
+            atomicAdd(&p.islandHist[64 + 52 + 2 * cb], (unsigned long long)((clock64() - tb0) >> 10));
+            atomicAdd(&p.islandHist[64 + 53 + 2 * cb], 1ULL);
+        }
+        {
+            int sum = active ? iters : 0, mx = sum;
+            for (int o = 16; o > 0; o >>= 1) {
+                sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+                mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+            }
+            if (L.lane == 0) {
+                atomicAdd(&p.islandHist[64 + 60], (unsigned long long)sum);
+                atomicAdd(&p.islandHist[64 + 61], (unsigned long long)(32 * mx));
+            }
+        }
         if (active) {
             lkFinish(p.env, wk, L);
             atomicMax(&wk.stats[0], iters);
@@ -437,6 +470,9 @@ __global__ void __launch_bounds__(kBatchThreads) k_island_batch(KParams p, int b
         __syncwarp();
     }
 }
+__global__ void __launch_bounds__(kBatchThreads) k_island_batch(KParams p, int bucket, int segBlocks) { islandBatchKernel<LaneSlotsU>(p, bucket, segBlocks); }
+// the wide lane slot (queue bucket kBucketLaneX): one warp per CTA
+__global__ void __launch_bounds__(32) k_island_batch_x(KParams p, int segBlocks) { islandBatchKernel<LaneSlotsX>(p, kBucketLaneX, segBlocks); }
 
 // stage C: one CTA per arena
 __global__ void __launch_bounds__(128, 6) k_phys_post(KParams p) {
@@ -459,6 +495,8 @@ __global__ void __launch_bounds__(128, 6) k_phys_post(KParams p) {
     }
     __syncthreads();
     physPost(ctx, p.env, wk, st);
+    if (blockIdx.x == 0 && threadIdx.x <= kQueueBuckets)   // census: islands per queue bucket, ticks
+        atomicAdd(&p.islandHist[64 + threadIdx.x], threadIdx.x < kQueueBuckets ? (unsigned long long)p.queue.counts[threadIdx.x] : 1ULL);
     if (threadIdx.x == 0) p.sp.arena[a].update_count += 1;
     if (threadIdx.x < 8) p.stepStats[a * 8 + threadIdx.x] = wk.stats[threadIdx.x];
 }
@@ -541,12 +579,13 @@ struct ps_engine {
     int* dStepStats = nullptr;
     int nSlots = 0, threads = 128;
     bool fused = false;      // PS_FUSED=1: the single-kernel World.step (kept for comparison)
-    int workerBlocks = 0, batchBlocks = 0, bigBlocks = 0, posBlocks = 0, batchThreads = kBatchThreads;
+    int workerBlocks = 0, batchBlocks = 0, batchXBlocks = 0, bigBlocks = 0, posBlocks = 0, batchThreads = kBatchThreads;
+    bool islandSplit = false;   // PS_ISLAND_SPLIT=1 with PS_ISLAND_G: only the lighter warp-bucket islands go through the split solver
     int islandG = 0;         // PS_ISLAND_G = 2 / 4 / 8: split solver (k_island_vel + k_island_pos with G lanes per island); 0 (default): the one-kernel
                              // warp-per-island solver. The split solver issues 4-5x fewer instructions but every island's sweeps take longer (the groups
                              // of a warp share each other's divergent paths), and the tick waits for the longest island: measured slower (profiles/r02_summary.md)
     bool mergeBatch = true;    // one launch for all lane buckets (PS_MERGE_BATCH=0: one launch and stream per bucket)
-    size_t smemBytes = 0;
+    size_t smemBytes = 0, bigSmem = 0;
     int64_t launches = 0;
     int updateCount = 0;     // all arenas advance in lock step
     SenseDevice sd;
@@ -856,22 +895,27 @@ int ps_create(const ps_config* cfg, int device, ps_handle* out) {
             TRY_OR_FREE(cudaEventCreateWithFlags(&G.evBig, cudaEventDisableTiming));
             TRY_OR_FREE(cudaEventCreateWithFlags(&G.done, cudaEventDisableTiming));
         }
-        TRY_OR_FREE(cudaMalloc(&e->kp.islandHist, 64 * sizeof(unsigned long long)));
-        TRY_OR_FREE(cudaMemset(e->kp.islandHist, 0, 64 * sizeof(unsigned long long)));
+        TRY_OR_FREE(cudaMalloc(&e->kp.islandHist, 128 * sizeof(unsigned long long)));   // [64..127]: island census (ps_get_island_census)
+        TRY_OR_FREE(cudaMemset(e->kp.islandHist, 0, 128 * sizeof(unsigned long long)));
         e->workerBlocks = prop.multiProcessorCount * (int)envSize("PS_WORKER_BLOCKS_PER_SM", 4);
         TRY_OR_FREE(cudaFuncSetAttribute(k_island_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(WarpSlot))));
         TRY_OR_FREE(cudaFuncSetAttribute(k_island_vel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(WarpSlot))));
         e->islandG = (int)envSize("PS_ISLAND_G", 0);
         if (e->islandG != 0 && e->islandG != 2 && e->islandG != 4 && e->islandG != 8) e->islandG = 0;
+        e->islandSplit = envSize("PS_ISLAND_SPLIT", 0) != 0;
         TRY_OR_FREE(cudaFuncSetAttribute(k_island_pos<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(16 * sizeof(PosSlot))));
         TRY_OR_FREE(cudaFuncSetAttribute(k_island_pos<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(PosSlot))));
         TRY_OR_FREE(cudaFuncSetAttribute(k_island_pos<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(PosSlot))));
         e->posBlocks = prop.multiProcessorCount * (int)envSize("PS_POS_BLOCKS_PER_SM", 4);
         TRY_OR_FREE(cudaFuncSetAttribute(k_island_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((kBatchThreads / 32) * sizeof(LaneSlotsU))));
+        TRY_OR_FREE(cudaFuncSetAttribute(k_island_batch_x, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LaneSlotsX)));
+        e->batchXBlocks = prop.multiProcessorCount * (int)envSize("PS_BATCHX_BLOCKS_PER_SM", 1);
         e->mergeBatch = envSize("PS_MERGE_BATCH", 1) != 0;
         e->bigBlocks = prop.multiProcessorCount * (int)envSize("PS_BIG_BLOCKS_PER_SM", 4);
         e->batchThreads = envSize("PS_BATCH_THREADS", kBatchThreads) == 32 ? 32 : kBatchThreads;
-        TRY_OR_FREE(cudaFuncSetAttribute(k_island_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BigSlot)));
+        // PS_BIG_SMEM_KB: shared memory a big-island CTA asks for beyond its slot: the SM then holds fewer warps beside the tick's longest chains
+        e->bigSmem = std::min<size_t>(std::max<size_t>(sizeof(BigSlot), envSize("PS_BIG_SMEM_KB", 0) * 1024), 227 * 1024);
+        TRY_OR_FREE(cudaFuncSetAttribute(k_island_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->bigSmem));
         e->batchBlocks = prop.multiProcessorCount * (int)envSize("PS_BATCH_BLOCKS_PER_SM", 2);
     }
     e->kp.env.scene = e->dScene;
@@ -1059,21 +1103,45 @@ static int enqueuePreIslands(ps_handle h, ps_engine::Group& G) {
         // the largest islands start first, on a stream of their own
         CUDA_TRY(cudaStreamWaitEvent(G.sb[kBucketBig], G.evPre, 0));
         ScopedTimer t8(h, 8, G.sb[kBucketBig]);   // each island kernel from the end of stage A: which one does the tick wait for?
-        k_island_big<<<std::max(1, std::min(h->bigBlocks, G.n)), 32, sizeof(BigSlot), G.sb[kBucketBig]>>>(kp);
+        k_island_big<<<std::max(1, std::min(h->bigBlocks, G.n)), 32, h->bigSmem, G.sb[kBucketBig]>>>(kp);
         t8.stop();
         CUDA_TRY(cudaEventRecord(G.evb[kBucketBig], G.sb[kBucketBig]));
+        if (h->hs.phys.laneXMaxContacts > 0) {
+            // the wide lane slots next: their lanes run the longest lane chains (up to 28 contacts x 100 sweeps)
+            CUDA_TRY(cudaStreamWaitEvent(G.sb[kBucketLaneX], G.evPre, 0));
+            ScopedTimer t11(h, 11, G.sb[kBucketLaneX]);
+            int xb = std::max(1, std::min(h->batchXBlocks, (G.n + 31) / 32 * 2));
+            k_island_batch_x<<<xb, 32, sizeof(LaneSlotsX), G.sb[kBucketLaneX]>>>(kp, xb);
+            t11.stop();
+            CUDA_TRY(cudaEventRecord(G.evb[kBucketLaneX], G.sb[kBucketLaneX]));
+            h->launches++;
+        }
         int wb = std::max(1, std::min(h->workerBlocks, G.n * 3));
         ScopedTimer t9(h, 9, G.s2);
         if (h->islandG == 0) {
-            k_island_warp<<<wb, 128, 4 * sizeof(WarpSlot), G.s2>>>(kp);
-        } else {
-            // velocity half one warp per island, then the position sweeps G lanes per island (32 / G islands per warp)
-            k_island_vel<<<wb, 128, 4 * sizeof(WarpSlot), G.s2>>>(kp);
+            k_island_warp<<<wb, 128, 4 * sizeof(WarpSlot), G.s2>>>(kp, 0);
+        } else if (h->islandSplit) {
+            // the heavy islands (the tick's longest chains) a warp each; the others G lanes each: fewer instructions beside the chains
+            k_island_warp<<<std::max(1, wb / 2), 128, 4 * sizeof(WarpSlot), G.s2>>>(kp, 1);
+            cudaStream_t sl = G.sb[kBucketLarge];
+            CUDA_TRY(cudaStreamWaitEvent(sl, G.evPre, 0));
+            k_island_vel<<<wb, 128, 4 * sizeof(WarpSlot), sl>>>(kp, 2);
             int pb = std::max(1, std::min(h->posBlocks, (G.n * 2 * h->islandG + 31) / 32));
             size_t sm = (size_t)(32 / h->islandG) * sizeof(PosSlot);
-            if (h->islandG == 2) k_island_pos<2><<<pb, 32, sm, G.s2>>>(kp);
-            else if (h->islandG == 4) k_island_pos<4><<<pb, 32, sm, G.s2>>>(kp);
-            else k_island_pos<8><<<pb, 32, sm, G.s2>>>(kp);
+            if (h->islandG == 2) k_island_pos<2><<<pb, 32, sm, sl>>>(kp, 2);
+            else if (h->islandG == 4) k_island_pos<4><<<pb, 32, sm, sl>>>(kp, 2);
+            else k_island_pos<8><<<pb, 32, sm, sl>>>(kp, 2);
+            CUDA_TRY(cudaEventRecord(G.evb[kBucketLarge], sl));
+            CUDA_TRY(cudaStreamWaitEvent(G.s2, G.evb[kBucketLarge], 0));
+            h->launches += 2;
+        } else {
+            // velocity half one warp per island, then the position sweeps G lanes per island (32 / G islands per warp)
+            k_island_vel<<<wb, 128, 4 * sizeof(WarpSlot), G.s2>>>(kp, 0);
+            int pb = std::max(1, std::min(h->posBlocks, (G.n * 2 * h->islandG + 31) / 32));
+            size_t sm = (size_t)(32 / h->islandG) * sizeof(PosSlot);
+            if (h->islandG == 2) k_island_pos<2><<<pb, 32, sm, G.s2>>>(kp, 0);
+            else if (h->islandG == 4) k_island_pos<4><<<pb, 32, sm, G.s2>>>(kp, 0);
+            else k_island_pos<8><<<pb, 32, sm, G.s2>>>(kp, 0);
             h->launches++;
         }
         t9.stop();
@@ -1094,6 +1162,7 @@ static int enqueuePreIslands(ps_handle h, ps_engine::Group& G) {
         }
         CUDA_TRY(cudaStreamWaitEvent(G.s, G.evBig, 0));
         CUDA_TRY(cudaStreamWaitEvent(G.s, G.evb[kBucketBig], 0));
+        if (h->hs.phys.laneXMaxContacts > 0) CUDA_TRY(cudaStreamWaitEvent(G.s, G.evb[kBucketLaneX], 0));
     }
     h->launches += 3 + (h->mergeBatch ? 1 : kLaneBuckets);
     CUDA_TRY(cudaGetLastError());
@@ -1522,6 +1591,16 @@ int ps_get_island_hist(ps_handle h, int64_t* out /*[64]*/, int reset) {
     { int jr = joinGroups(h); if (jr != PS_OK) return jr; }
     CUDA_TRY(cudaMemcpyAsync(out, h->kp.islandHist, 64 * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
     if (reset) CUDA_TRY(cudaMemsetAsync(h->kp.islandHist, 0, 64 * sizeof(int64_t), h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return PS_OK;
+}
+
+int ps_get_island_census(ps_handle h, int64_t* out /*[64]*/, int reset) {
+    if (!h || !out) return setError(PS_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    { int jr = joinGroups(h); if (jr != PS_OK) return jr; }
+    CUDA_TRY(cudaMemcpyAsync(out, h->kp.islandHist + 64, 64 * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    if (reset) CUDA_TRY(cudaMemsetAsync(h->kp.islandHist + 64, 0, 64 * sizeof(int64_t), h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return PS_OK;
 }

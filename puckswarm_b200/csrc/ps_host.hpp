@@ -49,6 +49,8 @@ struct HostSetup {
         {
             const char* wv = getenv("PS_WARP_MIN_CONTACTS");
             phys.warpMinContacts = wv && *wv ? atoi(wv) : kWarpMinContactsDefault;
+            const char* lx = getenv("PS_LANEX_MAX_CONTACTS");
+            phys.laneXMaxContacts = lx && *lx ? atoi(lx) : 0;   // off by default: a lane's chain of a 27-contact island is the longest of the tick (measured)
         }
         phys.velIters = c.vel_iters;
         phys.posIters = c.pos_iters;

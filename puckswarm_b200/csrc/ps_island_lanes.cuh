@@ -14,43 +14,52 @@
 #if defined(__CUDACC__)
 namespace ps {
 
-static constexpr int kLB = kLaneBodies + 1;   // staged bodies per lane + the wall
 enum { LK_PUCK = 0, LK_ROBOT = 1, LK_WALL = 2 };
 
-struct LaneSlotsU {
-    float cx[kLB][32], cy[kLB][32], a[kLB][32], vx[kLB][32], vy[kLB][32], w[kLB][32];
-    float px[kLB][32], py[kLB][32], c[kLB][32], s[kLB][32];
-    float pm[kLB][32], pi[kLB][32];   // position-solver inverse masses (mass * invMass, mass * invI; 0 for the wall)
-    uint16_t gidx[kLB][32];
-    uint8_t kind[kLB][32];
+// A warp's lane-interleaved slot: NBL dynamic bodies (+ the wall) and NCL constraints per lane. 31 bytes per body: the
+// velocity (used up to the integration) and the transform's px / py / c (used from the integration on) share storage, and the
+// position solver's inverse masses follow from the body kind -- the slot's size is what bounds how many islands an SM holds.
+template <int NBL, int NCL>
+struct LaneSlotsT {
+    static constexpr int kBodies = NBL, kContacts = NCL, kLBX = NBL + 1;   // staged bodies per lane + the wall
+    float cx[kLBX][32], cy[kLBX][32], a[kLBX][32];
+    float u0[kLBX][32], u1[kLBX][32], u2[kLBX][32];   // vx, vy, w until lkIntegrateLane; then px, py, c
+    float s[kLBX][32];
+    uint16_t gidx[kLBX][32];
+    uint8_t kind[kLBX][32];
     // what the position sweeps read of each constraint: localNormal, localPoint, the two manifold points, radius, and
     // bodyA | bodyB << 8 | type << 16 | points << 24 (up to 100 sweeps re-read these: shared memory instead of L2 latency)
-    float pc[kLaneContacts][9][32];
-    uint32_t pcHead[kLaneContacts][32];
+    float pc[NCL][9][32];
+    uint32_t pcHead[NCL][32];
 };
+typedef LaneSlotsT<kLaneBodies, kLaneContacts> LaneSlotsU;
+typedef LaneSlotsT<kLaneXBodies, kLaneXContacts> LaneSlotsX;
 
-struct LaneCtx {
-    LaneSlotsU* S;
+template <class Slots>
+struct LaneCtxT {
+    typedef Slots SlotsType;
+    Slots* S;
     int lane;
     int nb;          // staged dynamic bodies; local index nb is the wall
     int lo, nc;      // this island's range in wk.order
-    // body-table accessors (the solver routines below are written against these; WarpBodies in ps_pipeline.cuh is the
-    // other implementation)
+    float pmPuck, piPuck, pmRobot, piRobot;
+    // body-table accessors (the solver routines below are written against these; SlotCtx is the other implementation)
     __device__ __forceinline__ float& cx(int l) const { return S->cx[l][lane]; }
     __device__ __forceinline__ float& cy(int l) const { return S->cy[l][lane]; }
     __device__ __forceinline__ float& a(int l) const { return S->a[l][lane]; }
-    __device__ __forceinline__ float& vx(int l) const { return S->vx[l][lane]; }
-    __device__ __forceinline__ float& vy(int l) const { return S->vy[l][lane]; }
-    __device__ __forceinline__ float& w(int l) const { return S->w[l][lane]; }
-    __device__ __forceinline__ float& px(int l) const { return S->px[l][lane]; }
-    __device__ __forceinline__ float& py(int l) const { return S->py[l][lane]; }
-    __device__ __forceinline__ float& c(int l) const { return S->c[l][lane]; }
+    __device__ __forceinline__ float& vx(int l) const { return S->u0[l][lane]; }
+    __device__ __forceinline__ float& vy(int l) const { return S->u1[l][lane]; }
+    __device__ __forceinline__ float& w(int l) const { return S->u2[l][lane]; }
+    __device__ __forceinline__ float& px(int l) const { return S->u0[l][lane]; }
+    __device__ __forceinline__ float& py(int l) const { return S->u1[l][lane]; }
+    __device__ __forceinline__ float& c(int l) const { return S->u2[l][lane]; }
     __device__ __forceinline__ float& s(int l) const { return S->s[l][lane]; }
-    __device__ __forceinline__ float pm(int l) const { return S->pm[l][lane]; }
-    __device__ __forceinline__ float pi(int l) const { return S->pi[l][lane]; }
+    __device__ __forceinline__ float pm(int l) const { int k = kind(l); return k == LK_PUCK ? pmPuck : (k == LK_ROBOT ? pmRobot : 0.0f); }
+    __device__ __forceinline__ float pi(int l) const { int k = kind(l); return k == LK_PUCK ? piPuck : (k == LK_ROBOT ? piRobot : 0.0f); }
     __device__ __forceinline__ int kind(int l) const { return S->kind[l][lane]; }
     __device__ __forceinline__ int gidx(int l) const { return S->gidx[l][lane]; }
 };
+typedef LaneCtxT<LaneSlotsU> LaneCtx;
 
 __device__ __forceinline__ float lkInvMass(const HotConsts& h, int kind) { return kind == LK_PUCK ? h.puck.invMass : (kind == LK_ROBOT ? h.robot.invMass : 0.0f); }
 __device__ __forceinline__ float lkInvI(const HotConsts& h, int kind) { return kind == LK_PUCK ? h.puck.invI : (kind == LK_ROBOT ? h.robot.invI : 0.0f); }
@@ -70,9 +79,11 @@ __device__ __forceinline__ void lkSyncXf(const PhysEnv& e, const BT& L, int l) {
     }
 }
 
-// stage island k of the arena behind wk into this lane's slot; constraint body references become staged indices
-__device__ __forceinline__ void lkStage(const PhysEnv& e, const PhysWork& wk, int k, LaneCtx& L) {
-    LaneSlotsU& S = *L.S;
+// stage island k of the arena behind wk into this lane's slot; constraint body references become staged indices.
+// Up to the integration the slot holds poses and velocities; the transforms follow in lkIntegrateLane.
+template <class LC>
+__device__ __forceinline__ void lkStage(const PhysEnv& e, const PhysWork& wk, int k, LC& L) {
+    typename LC::SlotsType& S = *L.S;
     int ln = L.lane;
     int blo = wk.islandBodyStart[k];
     int nb = wk.islandBodyStart[k + 1] - blo;
@@ -86,42 +97,20 @@ __device__ __forceinline__ void lkStage(const PhysEnv& e, const PhysWork& wk, in
         S.cx[l][ln] = wk.cx[g];
         S.cy[l][ln] = wk.cy[g];
         S.a[l][ln] = wk.a[g];
-        S.vx[l][ln] = wk.vx[g];
-        S.vy[l][ln] = wk.vy[g];
-        S.w[l][ln] = wk.w[g];
-        if (g >= P) {
-            int r = g - P;
-            S.kind[l][ln] = LK_ROBOT;
-            S.pm[l][ln] = e.hot.pmRobot;
-            S.pi[l][ln] = e.hot.piRobot;
-            S.px[l][ln] = wk.rpx[r];
-            S.py[l][ln] = wk.rpy[r];
-            S.c[l][ln] = wk.rc[r];
-            S.s[l][ln] = wk.rs[r];
-        } else {
-            S.kind[l][ln] = LK_PUCK;
-            S.pm[l][ln] = e.hot.pmPuck;
-            S.pi[l][ln] = e.hot.piPuck;
-            S.px[l][ln] = wk.cx[g];
-            S.py[l][ln] = wk.cy[g];
-            S.c[l][ln] = 1.0f;
-            S.s[l][ln] = 0.0f;
-        }
+        S.u0[l][ln] = wk.vx[g];
+        S.u1[l][ln] = wk.vy[g];
+        S.u2[l][ln] = wk.w[g];
+        S.kind[l][ln] = g >= P ? LK_ROBOT : LK_PUCK;
     }
-    // the wall: a body that never moves (zero inverse masses), sweep.c = (0, 0), its transform from the scene
+    // the wall: a body that never moves (zero inverse masses), sweep.c = (0, 0); its transform follows at the integration
     S.kind[nb][ln] = LK_WALL;
-    S.pm[nb][ln] = 0.0f;
-    S.pi[nb][ln] = 0.0f;
+    S.gidx[nb][ln] = 0xFFFF;
     S.cx[nb][ln] = 0.0f;
     S.cy[nb][ln] = 0.0f;
     S.a[nb][ln] = 0.0f;
-    S.vx[nb][ln] = 0.0f;
-    S.vy[nb][ln] = 0.0f;
-    S.w[nb][ln] = 0.0f;
-    S.px[nb][ln] = e.hot.wallXf.px;
-    S.py[nb][ln] = e.hot.wallXf.py;
-    S.c[nb][ln] = e.hot.wallXf.c;
-    S.s[nb][ln] = e.hot.wallXf.s;
+    S.u0[nb][ln] = 0.0f;
+    S.u1[nb][ln] = 0.0f;
+    S.u2[nb][ln] = 0.0f;
     for (int i = 0; i < L.nc; ++i) {
         TC& t = wk.tc[wk.order[L.lo + i]];
         int a = t.bodyA, b = t.bodyB;
@@ -146,8 +135,10 @@ __device__ __forceinline__ void lkStage(const PhysEnv& e, const PhysWork& wk, in
     }
 }
 
-__device__ __forceinline__ void lkFinish(const PhysEnv& e, const PhysWork& wk, const LaneCtx& L) {
-    LaneSlotsU& S = *L.S;
+// the velocities went back at the integration (lkIntegrateLane); what is left are the poses and the robots' transforms
+template <class LC>
+__device__ __forceinline__ void lkFinish(const PhysEnv& e, const PhysWork& wk, const LC& L) {
+    typename LC::SlotsType& S = *L.S;
     int ln = L.lane;
     int P = e.cfg.d.P;
     for (int l = 0; l < L.nb; ++l) {
@@ -155,14 +146,11 @@ __device__ __forceinline__ void lkFinish(const PhysEnv& e, const PhysWork& wk, c
         wk.cx[g] = S.cx[l][ln];
         wk.cy[g] = S.cy[l][ln];
         wk.a[g] = S.a[l][ln];
-        wk.vx[g] = S.vx[l][ln];
-        wk.vy[g] = S.vy[l][ln];
-        wk.w[g] = S.w[l][ln];
         if (g >= P) {
             int r = g - P;
-            wk.rpx[r] = S.px[l][ln];
-            wk.rpy[r] = S.py[l][ln];
-            wk.rc[r] = S.c[l][ln];
+            wk.rpx[r] = S.u0[l][ln];
+            wk.rpy[r] = S.u1[l][ln];
+            wk.rc[r] = S.u2[l][ln];
             wk.rs[r] = S.s[l][ln];
         }
     }
@@ -467,8 +455,64 @@ __device__ __forceinline__ void lkIntegrate(const PhysEnv& e, const PhysWork& g,
     lkSyncXf(e, L, l);
 }
 
+// Island.solve step 6 for staged body l of a lane slot (= integrateBody). The clamped velocity goes back to the arena here (it
+// does not change afterwards), the start-of-step pose / transform go straight to HBM, and the slot's velocity storage
+// becomes the transform of the advanced pose.
+template <class LC>
+__device__ __forceinline__ void lkIntegrateLane(const PhysEnv& e, const PhysWork& g, const LC& L, int l) {
+    int gb = L.gidx(l);
+    int P = e.cfg.d.P;
+    float dt = e.cfg.dt;
+    float vx = L.vx(l), vy = L.vy(l), w = L.w(l);
+    V2 tr = mk(dt * vx, dt * vy);
+    if (dot(tr, tr) > kMaxTranslationSquared) {
+        float ratio = kMaxTranslation / len(tr);
+        vx *= ratio;
+        vy *= ratio;
+    }
+    float rot = dt * w;
+    if (rot * rot > kMaxRotationSquared) {
+        float ratio = kMaxRotation / fabsf(rot);
+        w *= ratio;
+    }
+    g.vx[gb] = vx;
+    g.vy[gb] = vy;
+    g.w[gb] = w;
+    g.c0x[gb] = L.cx(l);
+    g.c0y[gb] = L.cy(l);
+    g.a0[gb] = L.a(l);
+    L.cx(l) += dt * vx;
+    L.cy(l) += dt * vy;
+    L.a(l) += dt * w;
+    if (gb >= P) {
+        int r = gb - P;
+        g.r0px[r] = g.rpx[r];
+        g.r0py[r] = g.rpy[r];
+        g.r0c[r] = g.rc[r];
+        g.r0s[r] = g.rs[r];
+        Xf T = makeXf(e.trig, L.cx(l), L.cy(l), L.a(l), e.hot.robot.lcx, e.hot.robot.lcy);
+        L.px(l) = T.px;
+        L.py(l) = T.py;
+        L.c(l) = T.c;
+        L.s(l) = T.s;
+    } else {
+        L.px(l) = L.cx(l);
+        L.py(l) = L.cy(l);
+        L.c(l) = 1.0f;
+        L.s(l) = 0.0f;
+    }
+}
+template <class LC>
+__device__ __forceinline__ void lkWallXf(const PhysEnv& e, const LC& L) {
+    L.px(L.nb) = e.hot.wallXf.px;
+    L.py(L.nb) = e.hot.wallXf.py;
+    L.c(L.nb) = e.hot.wallXf.c;
+    L.s(L.nb) = e.hot.wallXf.s;
+}
+
 // Island.solve of up to 32 staged islands in lock step. `has`: this lane holds an island. Returns its position iterations.
-__device__ __forceinline__ int lkSolve(const PhysEnv& e, const PhysWork& wk, const ArenaState& st, const LaneCtx& L, bool has) {
+template <class LC>
+__device__ __forceinline__ int lkSolve(const PhysEnv& e, const PhysWork& wk, const ArenaState& st, const LC& L, bool has) {
     const unsigned FULL = 0xFFFFFFFFu;
     int nc = has ? L.nc : 0;
     int maxNc = nc;
@@ -490,7 +534,8 @@ __device__ __forceinline__ int lkSolve(const PhysEnv& e, const PhysWork& wk, con
                 st.cimp[4 * t.ci + 2 * j + 1] = t.tImp[j];
             }
         }
-        for (int l = 0; l < L.nb; ++l) lkIntegrate(e, wk, L, l);
+        for (int l = 0; l < L.nb; ++l) lkIntegrateLane(e, wk, L, l);
+        lkWallXf(e, L);
     }
     __syncwarp();
     int iters = 0;
@@ -500,7 +545,7 @@ __device__ __forceinline__ int lkSolve(const PhysEnv& e, const PhysWork& wk, con
         bool changed = false;
         for (int i = 0; i < maxNc; ++i) {
             if (running && i < nc) {
-                const LaneSlotsU& S = *L.S;
+                const typename LC::SlotsType& S = *L.S;
                 int ln = L.lane;
                 uint32_t hd = S.pcHead[i][ln];
                 int bA = (int)(hd & 255u), bB = (int)((hd >> 8) & 255u), type = (int)((hd >> 16) & 255u), np = (int)(hd >> 24);

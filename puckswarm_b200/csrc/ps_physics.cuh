@@ -23,6 +23,7 @@ struct PhysCfg {
     int MPAIR;       // new-pair buffer capacity (power of two)
     int MW;          // capacity of the wall-contact list
     int warpMinContacts;   // islands with at least this many contacts get a warp of their own (level-parallel sweeps)
+    int laneXMaxContacts;  // ... unless they have at most this many and fit the wide lane slot (0: the wide lane slot is not used)
     int velIters, posIters, toiEnabled;
     float dt;
     float damp;      // clamp(1 - dt * 10, 0, 1): linear and angular damping factor of pucks and robots

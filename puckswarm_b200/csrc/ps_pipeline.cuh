@@ -19,15 +19,16 @@ namespace ps {
 
 struct IslandQueue {
     unsigned* entries;     // [kQueueBuckets][cap]: arena * NB + island. Bucket 0: islands that do not fit a lane slot or have
-                           // >= PhysCfg::warpMinContacts contacts (one warp each, level-parallel sweeps); buckets 1..4: lane batches of
+                           // >= PhysCfg::warpMinContacts contacts (one warp each, level-parallel sweeps; those that fit the wide lane slot go to bucket kBucketLaneX); buckets 1..4: lane batches of
                            // islands with 1-2, 3-5, 6-12, 13+ contacts (like with like, so that the lanes of a warp finish together)
     int* counts;           // [kQueueSlots]: entries per bucket, then kQHeadWarp / kQHeadPos (consumer heads of the warp-bucket kernels)
     int cap;
 };
 static constexpr int kQueueWarpBodies = 48, kQueueWarpContacts = 64;   // = kWarpBodies, kWarpContacts of ps_island_lanes.cuh
 static constexpr int kLaneBodies = 12, kLaneContacts = 16;   // what a lane slot of the lane-per-island solver holds
-static constexpr int kQueueBuckets = 9, kLaneBuckets = 4, kBucketBig = 5, kBucketLarge = 6, kBucketXL = 7, kBucketXXL = 8, kWarpMinContactsDefault = 17;   // every island that fits a lane slot takes one (measured: 16 -> 17 shortens the island phase by 2 %, 10 lengthens it by 11 %)
-static constexpr int kQHeadWarp = kQueueBuckets, kQHeadPos = kQueueBuckets + 1, kQueueSlots = kQueueBuckets + 2;
+static constexpr int kLaneXBodies = 24, kLaneXContacts = 28;   // ... and the wide lane slot (bucket kBucketLaneX): the smaller half of what used to take a warp each
+static constexpr int kQueueBuckets = 10, kLaneBuckets = 4, kBucketBig = 5, kBucketLarge = 6, kBucketXL = 7, kBucketXXL = 8, kBucketLaneX = 9, kWarpMinContactsDefault = 17;   // every island that fits a lane slot takes one (measured: 16 -> 17 shortens the island phase by 2 %, 10 lengthens it by 11 %)
+static constexpr int kQHeadWarp = kQueueBuckets, kQHeadPos = kQueueBuckets + 1, kQHeadVel = kQueueBuckets + 2, kQueueSlots = kQueueBuckets + 3;
 static constexpr int kXLPoints = 40, kXXLPoints = 56;   // manifold points of an island from which it is handed out before the other large ones: the tick ends when the
                                                        // longest island ends, and an island's sweeps cost its points (robot jams: two per contact) x up to 100
 static constexpr int kLargeContacts = 28;   // warp-slot islands with at least this many contacts are handed out first (they are the tail)   // capacity of one lane's shared-memory slot (k_island_batch)
@@ -54,6 +55,8 @@ PS_HD void physPre(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaSt
         // 0: a warp each (WarpSlot); kBucketBig: what outgrows that (BigSlot); 1..4: a lane each, by contact count
         int bucket = (nc >= e.cfg.warpMinContacts || nc > kLaneContacts || nb > kLaneBodies) ? ((nb > kQueueWarpBodies || nc > kQueueWarpContacts) ? kBucketBig : (nc >= kLargeContacts ? kBucketLarge : 0))
                                                                                                : (nc <= 2 ? 1 : (nc <= 5 ? 2 : (nc <= 12 ? 3 : 4)));
+        // the smaller warp-bucket islands take a lane of a wide lane slot instead (32 islands per instruction stream)
+        if (bucket == 0 && nc <= e.cfg.laneXMaxContacts && nc <= kLaneXContacts && nb <= kLaneXBodies) bucket = kBucketLaneX;
         if (bucket == kBucketLarge) {
             // the heaviest warp-slot islands first: estimated by their manifold points
             int lo = wk.islandStart[k], points = 0;

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("PS_ENGINE_LIB") or os.path.join(_HERE, "csrc", "libpu
 EXPORTS = [
     "ps_last_error", "ps_abi_version", "ps_struct_size", "ps_config_defaults", "ps_create", "ps_destroy", "ps_load_calibration",
     "ps_reset", "ps_set_state", "ps_get_state", "ps_step", "ps_sync", "ps_get_error_flags", "ps_join", "ps_sense", "ps_step_external",
-    "ps_get_observations", "ps_compute_stats", "ps_stats_device_ptr", "ps_get_stats", "ps_get_snapshot", "ps_get_analysis", "ps_analysis_config", "ps_get_dims", "ps_get_step_stats", "ps_get_sense_stats", "ps_get_island_hist",
+    "ps_get_observations", "ps_compute_stats", "ps_stats_device_ptr", "ps_get_stats", "ps_get_snapshot", "ps_get_analysis", "ps_analysis_config", "ps_get_dims", "ps_get_step_stats", "ps_get_sense_stats", "ps_get_island_hist", "ps_get_island_census",
     "ps_profile", "ps_get_kernel_ms", "ps_num_groups", "ps_kernel_launches", "ps_stream",
 ]
 
@@ -75,6 +75,7 @@ def load_library(path=None):
     L.ps_get_step_stats.argtypes = [C.c_void_p, C.c_void_p]
     L.ps_get_sense_stats.argtypes = [C.c_void_p, C.c_void_p]
     L.ps_get_island_hist.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.ps_get_island_census.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.ps_profile.argtypes = [C.c_void_p, C.c_int]
     L.ps_get_kernel_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.ps_num_groups.argtypes = [C.c_void_p]
@@ -236,6 +237,12 @@ class Engine:
         self._check(self.L.ps_get_island_hist(self.h, out.ctypes.data, 1 if reset else 0))
         return out
 
+    def island_census(self, reset=True):
+        """Stage-B census since the last reset (include/puckswarm_b200.h: ps_get_island_census)."""
+        out = np.zeros(64, np.int64)
+        self._check(self.L.ps_get_island_census(self.h, out.ctypes.data, 1 if reset else 0))
+        return out
+
     def profile(self, enable=True):
         self._check(self.L.ps_profile(self.h, 1 if enable else 0))
 
@@ -244,7 +251,7 @@ class Engine:
         ms = np.zeros(12, np.float64)
         cnt = np.zeros(12, np.int64)
         self._check(self.L.ps_get_kernel_ms(self.h, ms.ctypes.data, cnt.ctypes.data))
-        names = ("sense", "think", "physics", "other", "phys_pre", "phys_islands", "phys_post", "unused", "isl_big", "isl_warp", "isl_batch", "unused2")
+        names = ("sense", "think", "physics", "other", "phys_pre", "phys_islands", "phys_post", "unused", "isl_big", "isl_warp", "isl_batch", "isl_lanex")
         return dict(zip(names, ms.tolist())), dict(zip(names, cnt.tolist()))
 
     @property
