@@ -127,7 +127,12 @@ __global__ void __launch_bounds__(256) k_physics(KParams p, int nTicks) {
 __device__ __forceinline__ PhysWork arenaWork(const KParams& p, int a) { return rebaseWork(p.workOff, p.arenaScratch + (size_t)a * p.arenaScratchStride); }
 // The same into one shared-memory copy per CTA ; the caller synchronises. As per-thread values the ~60 pointers spill to local memory, which is HBM traffic.
 __device__ __forceinline__ void arenaWorkShared(const KParams& p, int a, PhysWork& wk, ArenaState& st) {
-    if (threadIdx.x == 0) rebaseWorkInto(wk, p.workOff, p.arenaScratch + (size_t)a * p.arenaScratchStride);
+    // PhysWork is ~60 pointers: one per thread (offset from the kernel parameters + the arena's scratch block)
+    constexpr int kPtrs = (int)(sizeof(PhysWork) / sizeof(void*));
+    static_assert(sizeof(PhysWork) == kPtrs * sizeof(void*), "PhysWork holds pointers only");
+    const size_t base = (size_t)(p.arenaScratch + (size_t)a * p.arenaScratchStride);
+    constexpr int kFatNow = (int)(offsetof(PhysWork, fatNow) / sizeof(void*));   // not part of the scratch block: null = st.fat
+    for (int i = threadIdx.x; i < kPtrs; i += blockDim.x) reinterpret_cast<size_t*>(&wk)[i] = i == kFatNow ? 0 : reinterpret_cast<const size_t*>(&p.workOff)[i] + base;
     if (threadIdx.x == 32 % blockDim.x) {
         const PhysCfg& c = p.env.cfg;
         size_t A = (size_t)a;
@@ -143,8 +148,39 @@ __device__ __forceinline__ void arenaWorkShared(const KParams& p, int a, PhysWor
     }
 }
 
+// Shared memory of k_phys_pre beyond its static part: the contact graph and the DFS bookkeeping, sized for the configuration's
+// bodies and for up to `capT` touching contacts (an arena with more keeps those arrays in its scratch block for that tick).
+struct PreSmem {
+    int nb;        // bodies the shared arrays hold (0: none -- the arena is too large)
+    int capT;      // touching contacts the shared arrays hold
+    __host__ __device__ static size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+    __host__ __device__ size_t bytes() const {
+        if (nb <= 0) return 0;
+        return align16((size_t)(nb + 1) * 4) + align16((size_t)nb * 4) + align16((size_t)nb * 2) + align16((size_t)nb) + align16((size_t)capT * 4) + align16((size_t)capT * 4) +
+               align16((size_t)capT);
+    }
+};
+struct PreHook {
+    PhysWork* wk;
+    char* base;
+    int capT;
+    __device__ void operator()() const {
+        // (physCollide ended with a barrier; counters[0] = touching contacts of this tick)
+        if (base && threadIdx.x == 0 && wk->counters[0] <= capT) {
+            char* q = base;
+            wk->tcPair = (uint32_t*)q;
+            q += PreSmem::align16((size_t)capT * 4);
+            wk->adj = (uint16_t*)q;
+            q += PreSmem::align16((size_t)capT * 4);
+            wk->tcFlag = (uint8_t*)q;
+        }
+        __syncthreads();
+    }
+};
+
 // stage A: one CTA per arena
-__global__ void __launch_bounds__(128) k_phys_pre(KParams p) {
+__global__ void __launch_bounds__(128) k_phys_pre(KParams p, PreSmem sm) {
+    extern __shared__ __align__(16) char dsm[];
     __shared__ int scan[40];
     CtaCtx ctx;
     ctx.scanScratch = scan;
@@ -152,23 +188,28 @@ __global__ void __launch_bounds__(128) k_phys_pre(KParams p) {
     int R = p.env.cfg.d.R;
     __shared__ PhysWork wk;     // one copy per CTA (see k_phys_post)
     __shared__ ArenaState st;
-    // the contact graph and the DFS bookkeeping are used by this stage only and are walked by one thread with dependent
-    // loads: keep them in shared memory when the arena is small enough (the usual case)
-    constexpr int kSB = 512, kST = 2304;
-    __shared__ int sAdjOff[kSB + 1], sAdjFill[kSB];
-    __shared__ uint16_t sAdj[2 * kST], sStack[kSB];
-    __shared__ uint32_t sTcPair[kST];
-    __shared__ uint8_t sBodyFlag[kSB], sTcFlag[kST];
     arenaWorkShared(p, a, wk, st);
     __syncthreads();
-    if (threadIdx.x == 0 && p.env.cfg.d.NB <= kSB && p.env.cfg.MT <= kST) {
-        wk.adjOff = sAdjOff;
-        wk.adjFill = sAdjFill;
-        wk.adj = sAdj;
-        wk.stack = sStack;
-        wk.tcPair = sTcPair;
-        wk.bodyFlag = sBodyFlag;
-        wk.tcFlag = sTcFlag;
+    // the contact graph and the DFS bookkeeping are used by this stage only and are walked with dependent loads: they live in
+    // shared memory when the arena is small enough (the usual case)
+    PreHook hook = {&wk, nullptr, sm.capT};
+    if (sm.nb > 0) {
+        char* q = dsm;
+        int* adjOff = (int*)q;
+        q += PreSmem::align16((size_t)(sm.nb + 1) * 4);
+        int* adjFill = (int*)q;
+        q += PreSmem::align16((size_t)sm.nb * 4);
+        uint16_t* stack = (uint16_t*)q;
+        q += PreSmem::align16((size_t)sm.nb * 2);
+        uint8_t* bodyFlag = (uint8_t*)q;
+        q += PreSmem::align16((size_t)sm.nb);
+        hook.base = q;
+        if (threadIdx.x == 0) {
+            wk.adjOff = adjOff;
+            wk.adjFill = adjFill;
+            wk.stack = stack;
+            wk.bodyFlag = bodyFlag;
+        }
     }
     __syncthreads();
     const ps_robot_state* rs = p.sp.robot + (size_t)a * R;
@@ -177,7 +218,14 @@ __global__ void __launch_bounds__(128) k_phys_pre(KParams p) {
         wk.fy[r] = rs[r].cmd_torque;
     }
     __syncthreads();
-    physPre(ctx, p.env, wk, st, wk.fx, wk.fy, p.queue, a);
+    long long pc[4] = {0, 0, 0, 0};
+    physPre(ctx, p.env, wk, st, wk.fx, wk.fy, p.queue, a, pc, hook);
+#if defined(PS_PHASE_CLOCKS)
+    if (threadIdx.x == 0) {   // census [11..14]: cycles of the stage's phases, [15]: arena-ticks
+        for (int i = 0; i < 4; ++i) atomicAdd(&p.islandHist[64 + 11 + i], (unsigned long long)pc[i]);
+        atomicAdd(&p.islandHist[64 + 15], 1ULL);
+    }
+#endif
 }
 
 // entry `idx` of the warp-bucket islands in hand-out order: buckets kBucketXXL, kBucketXL, kBucketLarge, then bucket 0
@@ -474,8 +522,9 @@ __global__ void __launch_bounds__(kBatchThreads) k_island_batch(KParams p, int b
 // the wide lane slot (queue bucket kBucketLaneX): one warp per CTA
 __global__ void __launch_bounds__(32) k_island_batch_x(KParams p, int segBlocks) { islandBatchKernel<LaneSlotsX>(p, kBucketLaneX, segBlocks); }
 
-// stage C: one CTA per arena
-__global__ void __launch_bounds__(128, 6) k_phys_post(KParams p) {
+// stage C: one CTA per arena. Dynamic shared memory: nbFat bodies' box unions, then npFat proxies' fat boxes (0: not staged)
+__global__ void __launch_bounds__(128, 6) k_phys_post(KParams p, int nbFat, int npFat) {
+    extern __shared__ __align__(16) char dsm[];
     __shared__ int scan[40];
     CtaCtx ctx;
     ctx.scanScratch = scan;
@@ -484,14 +533,15 @@ __global__ void __launch_bounds__(128, 6) k_phys_post(KParams p) {
     // local memory, and local memory goes through L2 to HBM
     __shared__ PhysWork wk;
     __shared__ ArenaState st;
-    // the pair search reads every body's box union once per moved body: keep that table in shared memory when it fits
-    __shared__ float sBodyFat[4 * 512];
     arenaWorkShared(p, a, wk, st);
     __syncthreads();
-    __shared__ float sFatNow[4 * 1024];   // this step's fat boxes of every proxy (pair search)
+    // the pair search reads every body's box union once per moved body, and this step's fat boxes of every proxy: both tables
+    // are kept in shared memory when they fit
     if (threadIdx.x == 0) {
-        if (p.env.cfg.d.NB <= 512) wk.bodyFat = sBodyFat;
-        if (p.env.cfg.d.NP <= 1024) wk.fatNow = sFatNow;
+        float* sBodyFat = (float*)dsm;
+        float* sFatNow = sBodyFat + 4 * nbFat;
+        if (nbFat > 0) wk.bodyFat = sBodyFat;
+        if (npFat > 0) wk.fatNow = sFatNow;
     }
     __syncthreads();
     physPost(ctx, p.env, wk, st);
@@ -586,6 +636,8 @@ struct ps_engine {
                              // of a warp share each other's divergent paths), and the tick waits for the longest island: measured slower (profiles/r02_summary.md)
     bool mergeBatch = true;    // one launch for all lane buckets (PS_MERGE_BATCH=0: one launch and stream per bucket)
     size_t smemBytes = 0, bigSmem = 0;
+    PreSmem preSmem = {0, 0};   // k_phys_pre / k_phys_post: CTA width and what they keep in shared memory
+    int preThreads = 64, postThreads = 128, postNbFat = 0, postNpFat = 0;
     int64_t launches = 0;
     int updateCount = 0;     // all arenas advance in lock step
     SenseDevice sd;
@@ -910,6 +962,17 @@ int ps_create(const ps_config* cfg, int device, ps_handle* out) {
         TRY_OR_FREE(cudaFuncSetAttribute(k_island_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((kBatchThreads / 32) * sizeof(LaneSlotsU))));
         TRY_OR_FREE(cudaFuncSetAttribute(k_island_batch_x, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LaneSlotsX)));
         e->batchXBlocks = prop.multiProcessorCount * (int)envSize("PS_BATCHX_BLOCKS_PER_SM", 1);
+        // stage A / C shared memory by configuration (arenas beyond these sizes work from their scratch blocks)
+        e->preThreads = (int)envSize("PS_PRE_THREADS", 64);   // measured (profiles/r02_ab_prepost.log): stage A 1.18 ms per 4096 arenas with 128 threads, 1.08 with 64 (the stage waits on its serial parts; narrow CTAs put more arenas on an SM); stage C is faster with 128
+        e->postThreads = (int)envSize("PS_POST_THREADS", 128);
+        if (e->preThreads != 32 && e->preThreads != 128) e->preThreads = 64;
+        if (e->postThreads != 32 && e->postThreads != 64) e->postThreads = 128;
+        e->preSmem.nb = pc.d.NB <= 512 ? pc.d.NB : 0;
+        e->preSmem.capT = (int)std::min<size_t>((size_t)pc.MT, envSize("PS_PRE_SMEM_T", 512));
+        e->postNbFat = pc.d.NB <= 512 ? pc.d.NB : 0;
+        e->postNpFat = pc.d.NP <= 1024 ? pc.d.NP : 0;
+        TRY_OR_FREE(cudaFuncSetAttribute(k_phys_pre, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->preSmem.bytes()));
+        TRY_OR_FREE(cudaFuncSetAttribute(k_phys_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)4 * (e->postNbFat + e->postNpFat) * sizeof(float))));
         e->mergeBatch = envSize("PS_MERGE_BATCH", 1) != 0;
         e->bigBlocks = prop.multiProcessorCount * (int)envSize("PS_BIG_BLOCKS_PER_SM", 4);
         e->batchThreads = envSize("PS_BATCH_THREADS", kBatchThreads) == 32 ? 32 : kBatchThreads;
@@ -1093,7 +1156,7 @@ static int enqueuePreIslands(ps_handle h, ps_engine::Group& G) {
     CUDA_TRY(cudaMemsetAsync(G.q.counts, 0, kQueueSlots * sizeof(int), G.s));
     {
         ScopedTimer t4(h, 4, G.s);
-        k_phys_pre<<<G.n, 128, 0, G.s>>>(kp);
+        k_phys_pre<<<G.n, h->preThreads, h->preSmem.bytes(), G.s>>>(kp, h->preSmem);
     }
     CUDA_TRY(cudaEventRecord(G.evPre, G.s));
     {
@@ -1176,7 +1239,7 @@ static int enqueuePost(ps_handle h, ps_engine::Group& G) {
     {
         ScopedTimer timer(h, 2, G.s);
         ScopedTimer t6(h, 6, G.s);
-        k_phys_post<<<G.n, 128, 0, G.s>>>(kp);
+        k_phys_post<<<G.n, h->postThreads, (size_t)4 * (h->postNbFat + h->postNpFat) * sizeof(float), G.s>>>(kp, h->postNbFat, h->postNpFat);
     }
     h->launches++;
     CUDA_TRY(cudaGetLastError());

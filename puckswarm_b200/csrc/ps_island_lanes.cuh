@@ -584,21 +584,37 @@ __device__ __forceinline__ int lkSolve(const PhysEnv& e, const PhysWork& wk, con
 // real islands leaves ~2 independent corrections per step, less than the bookkeeping costs. The plain row schedule stays.)
 static constexpr int kWarpBodies = kQueueWarpBodies, kWarpContacts = kQueueWarpContacts;
 static constexpr int kBigBodies = 254, kBigContacts = 640;
+// A staged body as the position sweeps read it: two 16-byte loads give a correction everything it needs of a body (sweep.c,
+// the mass-scaled inverse masses, the transform); the angle and the kind are read by the lane that moves the body only.
+struct __align__(16) BodyRec {
+    float cx, cy, pm, pi;     // sweep.c; mass * invMass, mass * invI (0 for the wall)
+    float px, py, c, s;       // transform
+    float a;                  // sweep.a
+    uint32_t kind;            // LK_*
+    uint32_t gidx;            // body index in the arena (0xFFFF: the wall)
+    uint32_t bodyRow;         // row-schedule scratch
+};
+// What the position sweeps read of a constraint, in ROW-MAJOR solve order (three 16-byte loads, no index indirection)
+struct __align__(16) ConRec {
+    float lnx, lny, lpx, lpy;   // localNormal, localPoint
+    float p0x, p0y, p1x, p1y;   // the two manifold points
+    float radius;
+    uint32_t offs;              // byte offsets of bodyA | bodyB << 16 in IslandSlot::br
+    uint32_t typeNp;            // manifold type | points << 8
+    uint32_t pad;
+};
 template <int NB_, int NC_, bool STAGE_TC>
-struct IslandSlot {
+struct __align__(16) IslandSlot {
     static constexpr int NBX = NB_ + 1;
     static constexpr int kBodies = NB_, kContacts = NC_;
     static constexpr bool kStageTC = STAGE_TC;
-    float cx[NBX], cy[NBX], a[NBX], vx[NBX], vy[NBX], w[NBX];
-    float px[NBX], py[NBX], c[NBX], s[NBX], pm[NBX], pi[NBX];
-    uint16_t gidx[NBX], bodyRow[NBX];
-    uint8_t kind[NBX];
-    float pc[NC_][9];                      // localNormal, localPoint, two manifold points, radius
-    uint32_t pcHead[NC_];                  // bodyA | bodyB << 8 | type << 16 | points << 24
+    BodyRec br[NBX];
+    ConRec cr[NC_];
+    float vx[NBX], vy[NBX], w[NBX];
+    uint16_t pcHead[NC_];                  // bodyA | bodyB << 8 (staged indices) in solve order: input of the row schedule
     uint16_t row[NC_], sched[NC_], rowStart[NC_ + 2];
     int nRows;
     TC tc[STAGE_TC ? NC_ : 1];
-    __device__ __forceinline__ float& CX(int l) { return cx[l]; }
 };
 // The velocity-phase constraints (TC, 164 B each) stay in HBM / L2 for both slot sizes: staging them made a warp slot 17.7 KB
 // instead of 5.6 KB, and the shared memory the island kernels hold is what keeps the other arena groups' wide kernels off the
@@ -628,6 +644,119 @@ struct SlotCtx {
     __device__ __forceinline__ int gidx(int l) const { return S->gidx[l]; }
 };
 
+template <class Slot>
+struct RecCtx {   // the same accessors over IslandSlot's body records
+    Slot* S;
+    __device__ __forceinline__ float& cx(int l) const { return S->br[l].cx; }
+    __device__ __forceinline__ float& cy(int l) const { return S->br[l].cy; }
+    __device__ __forceinline__ float& a(int l) const { return S->br[l].a; }
+    __device__ __forceinline__ float& vx(int l) const { return S->vx[l]; }
+    __device__ __forceinline__ float& vy(int l) const { return S->vy[l]; }
+    __device__ __forceinline__ float& w(int l) const { return S->w[l]; }
+    __device__ __forceinline__ float& px(int l) const { return S->br[l].px; }
+    __device__ __forceinline__ float& py(int l) const { return S->br[l].py; }
+    __device__ __forceinline__ float& c(int l) const { return S->br[l].c; }
+    __device__ __forceinline__ float& s(int l) const { return S->br[l].s; }
+    __device__ __forceinline__ float pm(int l) const { return S->br[l].pm; }
+    __device__ __forceinline__ float pi(int l) const { return S->br[l].pi; }
+    __device__ __forceinline__ int kind(int l) const { return (int)S->br[l].kind; }
+    __device__ __forceinline__ int gidx(int l) const { return (int)S->br[l].gidx; }
+};
+
+// shared-memory accesses of the position sweeps, by 32-bit shared address
+__device__ __forceinline__ float4 lds128(unsigned a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float2 lds64(unsigned a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(unsigned a, float x, float y, float z, float w) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ void sts64(unsigned a, float x, float y) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory"); }
+__device__ __forceinline__ void sts32(unsigned a, float x) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(x) : "memory"); }
+
+// lkCorrectPointPair over body records: `br` is the shared address of IslandSlot::br, offA / offB the bodies' byte offsets.
+// The arithmetic is lkCorrectPointPair's, operation for operation.
+__device__ __forceinline__ float lkCorrectPointPairRec(const PhysEnv& e, unsigned br, bool on, int side, unsigned offA, unsigned offB, int type, V2 localNormal,
+                                                       V2 localPoint, V2 pointLocal, float radius, bool* changed) {
+    float separation = 0.0f;
+    bool write = false;
+    unsigned me = br + (side ? offB : offA);
+    V2 nc = mk(0.0f, 0.0f);
+    float na = 0.0f, pmM = 0.0f, piM = 0.0f;
+    bool robot = false;
+    if (on) {
+        float4 A0 = lds128(br + offA), A1 = lds128(br + offA + 16), B0 = lds128(br + offB), B1 = lds128(br + offB + 16);
+        Xf xfA, xfB;
+        xfA.px = A1.x;
+        xfA.py = A1.y;
+        xfA.c = A1.z;
+        xfA.s = A1.w;
+        xfB.px = B1.x;
+        xfB.py = B1.y;
+        xfB.c = B1.z;
+        xfB.s = B1.w;
+        bool faceB = type == MF_FACE_B;
+        Xf xfRef = faceB ? xfB : xfA, xfInc = faceB ? xfA : xfB;
+        V2 p1 = mulX(xfRef, localPoint), p2 = mulX(xfInc, pointLocal);
+        V2 normal, point;
+        if (type == MF_CIRCLES) {
+            if (distSq(p1, p2) > kEpsilon * kEpsilon) {
+                normal = p2 - p1;
+                normalize(normal);
+            } else {
+                normal = mk(1.0f, 0.0f);
+            }
+            point = 0.5f * (p1 + p2);
+            separation = dot(p2 - p1, normal) - radius;
+        } else {
+            normal = mulR(xfRef, localNormal);
+            separation = dot(p2 - p1, normal) - radius;
+            point = p2;
+            if (faceB) normal = -normal;
+        }
+        float C = clampf(kContactBaumgarte * (separation + kLinearSlop), -kMaxLinearCorrection, 0.0f);
+        if (C != 0.0f) {
+            float2 ak = lds64(me + 32);   // own angle, kind
+            V2 cA = mk(A0.x, A0.y), cB = mk(B0.x, B0.y);
+            V2 rA = point - cA, rB = point - cB;
+            float invMassA = A0.z, invIA = A0.w, invMassB = B0.z, invIB = B0.w;
+            float rnA = cross(rA, normal), rnB = cross(rB, normal);
+            float K = invMassA + invMassB + invIA * rnA * rnA + invIB * rnB * rnB;
+            float impulse = K > 0.0f ? -C / K : 0.0f;
+            V2 P = impulse * normal;
+            V2 cM = side ? cB : cA, rM = side ? rB : rA;
+            float sm = side ? invMassB : -invMassA, si = side ? invIB : -invIA;
+            float oa = ak.x;
+            nc = cM + sm * P;
+            na = oa + si * cross(rM, P);
+            write = nc.x != cM.x || nc.y != cM.y || na != oa;
+            pmM = side ? invMassB : invMassA;
+            piM = side ? invIB : invIA;
+            robot = __float_as_uint(ak.y) == (unsigned)LK_ROBOT;
+        }
+    }
+    __syncwarp();
+    if (write) {
+        sts128(me, nc.x, nc.y, pmM, piM);
+        sts32(me + 32, na);
+        if (robot) {   // Body.synchronizeTransform (lkSyncXf)
+            Xf T = makeXf(e.trig, nc.x, nc.y, na, e.hot.robot.lcx, e.hot.robot.lcy);
+            sts128(me + 16, T.px, T.py, T.c, T.s);
+        } else {
+            sts64(me + 16, nc.x, nc.y);
+        }
+        *changed = true;
+    }
+    __syncwarp();
+    return separation;
+}
+
 // Returns false if the island does not fit the slot (the caller falls back to the sequential path).
 // POS = false: the velocity half only (warm start, velocity sweeps, impulses, integration); the bodies are written back and
 // the row schedule is left in wk.tcPair[lo + q] = constraint (index into wk.tc) | row << 16, q in row-major solve order, for
@@ -643,90 +772,85 @@ __device__ __forceinline__ bool islandSolveSlot(const PhysEnv& e, const PhysWork
     if (nb > Slot::kBodies || nc > Slot::kContacts) return false;
     // ---- stage the bodies (island order) and the wall
     for (int i = lane; i <= nb; i += 32) {
+        BodyRec r;
         if (i < nb) {
             int g = wk.ibody[blo + i];
-            s.gidx[i] = (uint16_t)g;
-            s.cx[i] = wk.cx[g];
-            s.cy[i] = wk.cy[g];
-            s.a[i] = wk.a[g];
+            r.gidx = (uint32_t)g;
+            r.cx = wk.cx[g];
+            r.cy = wk.cy[g];
+            r.a = wk.a[g];
             s.vx[i] = wk.vx[g];
             s.vy[i] = wk.vy[g];
             s.w[i] = wk.w[g];
             if (g >= P) {
-                int r = g - P;
-                s.kind[i] = LK_ROBOT;
-                s.pm[i] = e.hot.pmRobot;
-                s.pi[i] = e.hot.piRobot;
-                s.px[i] = wk.rpx[r];
-                s.py[i] = wk.rpy[r];
-                s.c[i] = wk.rc[r];
-                s.s[i] = wk.rs[r];
+                int rr = g - P;
+                r.kind = LK_ROBOT;
+                r.pm = e.hot.pmRobot;
+                r.pi = e.hot.piRobot;
+                r.px = wk.rpx[rr];
+                r.py = wk.rpy[rr];
+                r.c = wk.rc[rr];
+                r.s = wk.rs[rr];
             } else {
-                s.kind[i] = LK_PUCK;
-                s.pm[i] = e.hot.pmPuck;
-                s.pi[i] = e.hot.piPuck;
-                s.px[i] = wk.cx[g];
-                s.py[i] = wk.cy[g];
-                s.c[i] = 1.0f;
-                s.s[i] = 0.0f;
+                r.kind = LK_PUCK;
+                r.pm = e.hot.pmPuck;
+                r.pi = e.hot.piPuck;
+                r.px = r.cx;
+                r.py = r.cy;
+                r.c = 1.0f;
+                r.s = 0.0f;
             }
         } else {
-            s.gidx[i] = 0xFFFF;
-            s.kind[i] = LK_WALL;
-            s.cx[i] = s.cy[i] = s.a[i] = s.vx[i] = s.vy[i] = s.w[i] = 0.0f;
-            s.pm[i] = s.pi[i] = 0.0f;
-            s.px[i] = e.hot.wallXf.px;
-            s.py[i] = e.hot.wallXf.py;
-            s.c[i] = e.hot.wallXf.c;
-            s.s[i] = e.hot.wallXf.s;
+            r.gidx = 0xFFFFu;
+            r.kind = LK_WALL;
+            r.cx = r.cy = r.a = 0.0f;
+            s.vx[i] = s.vy[i] = s.w[i] = 0.0f;
+            r.pm = r.pi = 0.0f;
+            r.px = e.hot.wallXf.px;
+            r.py = e.hot.wallXf.py;
+            r.c = e.hot.wallXf.c;
+            r.s = e.hot.wallXf.s;
         }
-        s.bodyRow[i] = 0;
+        r.bodyRow = 0;
+        s.br[i] = r;
     }
     for (int i = lane; i < nc + 2; i += 32) s.rowStart[i] = 0;
     __syncwarp();
-    // ---- constraints: body references -> staged indices (wall -> nb); position data -> shared memory
+    // ---- constraints: body references -> staged indices (wall -> nb)
     for (int i = lane; i < nc; i += 32) {
         TC& g = wk.tc[wk.order[lo + i]];
-        TC t = g;
+        int gA = g.bodyA, gB = g.bodyB;
         int la = nb, lb = nb;
         for (int j = 0; j < nb; ++j) {
-            int gi = s.gidx[j];
-            if (gi == t.bodyA) la = j;
-            if (gi == t.bodyB) lb = j;
+            int gi = (int)s.br[j].gidx;
+            if (gi == gA) la = j;
+            if (gi == gB) lb = j;
         }
-        t.bodyA = la;
-        t.bodyB = lb;
         if (Slot::kStageTC) {
+            TC t = g;
+            t.bodyA = la;
+            t.bodyB = lb;
             s.tc[i] = t;
         } else {
             g.bodyA = la;
             g.bodyB = lb;
         }
-        s.pc[i][0] = t.localNormal.x;
-        s.pc[i][1] = t.localNormal.y;
-        s.pc[i][2] = t.localPoint.x;
-        s.pc[i][3] = t.localPoint.y;
-        s.pc[i][4] = t.lp[0].x;
-        s.pc[i][5] = t.lp[0].y;
-        s.pc[i][6] = t.lp[1].x;
-        s.pc[i][7] = t.lp[1].y;
-        s.pc[i][8] = t.radius;
-        s.pcHead[i] = (uint32_t)la | ((uint32_t)lb << 8) | ((uint32_t)t.type << 16) | ((uint32_t)t.solverPoints << 24);
+        s.pcHead[i] = (uint16_t)(la | (lb << 8));
     }
     __syncwarp();
-    // ---- rows of one Gauss-Seidel sweep (CSR: rowStart / sched) and the sweep distance D
+    // ---- rows of one Gauss-Seidel sweep (CSR: rowStart / sched)
     if (lane == 0) {
         int nRows = 0;
         for (int i = 0; i < nc; ++i) {
-            uint32_t hd = s.pcHead[i];
-            int a = (int)(hd & 255u), b = (int)((hd >> 8) & 255u);
+            int hd = s.pcHead[i];
+            int a = hd & 255, b = hd >> 8;
             int r = 0;
-            if (a < nb) r = s.bodyRow[a];
-            if (b < nb && s.bodyRow[b] > r) r = s.bodyRow[b];
+            if (a < nb) r = (int)s.br[a].bodyRow;
+            if (b < nb && (int)s.br[b].bodyRow > r) r = (int)s.br[b].bodyRow;
             s.row[i] = (uint16_t)r;
             s.rowStart[r + 2]++;                       // counts, shifted by two for the in-place prefix sum below
-            if (a < nb) s.bodyRow[a] = (uint16_t)(r + 1);
-            if (b < nb) s.bodyRow[b] = (uint16_t)(r + 1);
+            if (a < nb) s.br[a].bodyRow = (uint32_t)(r + 1);
+            if (b < nb) s.br[b].bodyRow = (uint32_t)(r + 1);
             if (r + 1 > nRows) nRows = r + 1;
         }
         for (int r = 0; r < nRows; ++r) s.rowStart[r + 2] += s.rowStart[r + 1];             // rowStart[r + 1] = start of row r, for now
@@ -734,10 +858,29 @@ __device__ __forceinline__ bool islandSolveSlot(const PhysEnv& e, const PhysWork
         s.nRows = nRows;
     }
     __syncwarp();
-    SlotCtx<Slot> L;
+    RecCtx<Slot> L;
     L.S = &s;
     int nRows = s.nRows;
     auto constraint = [&](int ci) -> TC& { return Slot::kStageTC ? s.tc[ci] : wk.tc[wk.order[lo + ci]]; };
+    // ---- what the position sweeps read of each constraint, in row-major solve order
+    if (POS)
+        for (int q = lane; q < nc; q += 32) {
+            const TC& t = constraint(s.sched[q]);
+            ConRec c;
+            c.lnx = t.localNormal.x;
+            c.lny = t.localNormal.y;
+            c.lpx = t.localPoint.x;
+            c.lpy = t.localPoint.y;
+            c.p0x = t.lp[0].x;
+            c.p0y = t.lp[0].y;
+            c.p1x = t.lp[1].x;
+            c.p1y = t.lp[1].y;
+            c.radius = t.radius;
+            c.offs = (uint32_t)t.bodyA * (uint32_t)sizeof(BodyRec) | (((uint32_t)t.bodyB * (uint32_t)sizeof(BodyRec)) << 16);
+            c.typeNp = (uint32_t)t.type | ((uint32_t)t.solverPoints << 8);
+            c.pad = 0;
+            s.cr[q] = c;
+        }
     // ContactSolver.warmStart
     for (int r = 0; r < nRows; ++r) {
         for (int q = s.rowStart[r] + lane; q < s.rowStart[r + 1]; q += 32) lkWarmStart(e, L, constraint(s.sched[q]));
@@ -769,27 +912,31 @@ __device__ __forceinline__ bool islandSolveSlot(const PhysEnv& e, const PhysWork
     int posIters = e.cfg.posIters;
     int iters = 0;
     bool done = !POS || posIters <= 0;
+    const unsigned brAddr = (unsigned)__cvta_generic_to_shared(&s.br[0]), crAddr = (unsigned)__cvta_generic_to_shared(&s.cr[0]);
     while (!done) {
         float minSep = 0.0f;
         bool changed = false;
+        int rowBeg = 0;
         for (int r = 0; r < nRows; ++r) {
             // a lane pair per constraint of the row (16 constraints per pass; a row rarely holds more than three)
             int rowEnd = s.rowStart[r + 1];
-            for (int base = s.rowStart[r]; base < rowEnd; base += 16) {
+            for (int base = rowBeg; base < rowEnd; base += 16) {
                 int q = base + (lane >> 1);
                 bool on = q < rowEnd;
-                int ci = on ? s.sched[q] : 0;
-                uint32_t hd = on ? s.pcHead[ci] : 0u;
-                int bA = (int)(hd & 255u), bB = (int)((hd >> 8) & 255u), type = (int)((hd >> 16) & 255u), np = (int)(hd >> 24);
-                V2 ln = mk(s.pc[ci][0], s.pc[ci][1]), lp = mk(s.pc[ci][2], s.pc[ci][3]);
-                float radius = s.pc[ci][8];
-                float sep0 = lkCorrectPointPair(e, L, on && np > 0, lane & 1, bA, bB, type, ln, lp, mk(s.pc[ci][4], s.pc[ci][5]), radius, &changed);
+                unsigned ca = crAddr + (unsigned)(on ? q : 0) * (unsigned)sizeof(ConRec);
+                float4 c0 = lds128(ca), c1 = lds128(ca + 16), c2 = lds128(ca + 32);
+                unsigned offs = __float_as_uint(c2.y), tn = __float_as_uint(c2.z);
+                unsigned offA = offs & 0xFFFFu, offB = offs >> 16;
+                int type = (int)(tn & 255u), np = on ? (int)(tn >> 8) : 0;
+                V2 ln = mk(c0.x, c0.y), lp = mk(c0.z, c0.w);
+                float sep0 = lkCorrectPointPairRec(e, brAddr, np > 0, lane & 1, offA, offB, type, ln, lp, mk(c1.x, c1.y), c2.x, &changed);
                 minSep = fminf_(minSep, sep0);
                 if (__any_sync(FULL, np > 1)) {
-                    float sep1 = lkCorrectPointPair(e, L, on && np > 1, lane & 1, bA, bB, type, ln, lp, mk(s.pc[ci][6], s.pc[ci][7]), radius, &changed);
+                    float sep1 = lkCorrectPointPairRec(e, brAddr, np > 1, lane & 1, offA, offB, type, ln, lp, mk(c1.z, c1.w), c2.x, &changed);
                     minSep = fminf_(minSep, sep1);
                 }
             }
+            rowBeg = rowEnd;
         }
         for (int o = 16; o > 0; o >>= 1) {
             float other = __shfl_xor_sync(FULL, minSep, o);
@@ -806,19 +953,20 @@ __device__ __forceinline__ bool islandSolveSlot(const PhysEnv& e, const PhysWork
     if (lane == 0) *itersOut = iters;
     __syncwarp();
     for (int i = lane; i < nb; i += 32) {
-        int g = s.gidx[i];
-        wk.cx[g] = s.cx[i];
-        wk.cy[g] = s.cy[i];
-        wk.a[g] = s.a[i];
+        BodyRec r = s.br[i];
+        int g = (int)r.gidx;
+        wk.cx[g] = r.cx;
+        wk.cy[g] = r.cy;
+        wk.a[g] = r.a;
         wk.vx[g] = s.vx[i];
         wk.vy[g] = s.vy[i];
         wk.w[g] = s.w[i];
         if (g >= P) {
-            int r = g - P;
-            wk.rpx[r] = s.px[i];
-            wk.rpy[r] = s.py[i];
-            wk.rc[r] = s.c[i];
-            wk.rs[r] = s.s[i];
+            int rr = g - P;
+            wk.rpx[rr] = r.px;
+            wk.rpy[rr] = r.py;
+            wk.rc[rr] = r.c;
+            wk.rs[rr] = r.s;
         }
     }
     __syncwarp();

@@ -33,14 +33,24 @@ static constexpr int kXLPoints = 40, kXXLPoints = 56;   // manifold points of an
                                                        // longest island ends, and an island's sweeps cost its points (robot jams: two per contact) x up to 100
 static constexpr int kLargeContacts = 28;   // warp-slot islands with at least this many contacts are handed out first (they are the tail)   // capacity of one lane's shared-memory slot (k_island_batch)
 
-template <class Ctx>
+struct NoHook {
+    PS_HD void operator()() const {}
+};
+// afterCollide: called by every thread between ContactManager.collide and the island search (the device kernel points the
+// contact-graph arrays at shared memory there when the arena's touching contacts fit)
+template <class Ctx, class Hook = NoHook>
 PS_HD void physPre(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaState& st, const float* cmdFwd, const float* cmdTorque,
-                   const IslandQueue& q, int arena) {
+                   const IslandQueue& q, int arena, long long* preCycles = nullptr, const Hook& afterCollide = Hook()) {
     float dtRatio = *st.invDt0 * e.cfg.dt;
     ctx.sync();
+    long long t0 = phaseClock();
     physLoad(ctx, e, wk, st, cmdFwd, cmdTorque);
+    long long t1 = phaseClock();
     physCollide(ctx, e, wk, st, dtRatio);
+    long long t2 = phaseClock();
+    afterCollide();
     physIslands(ctx, e, wk);
+    long long t3 = phaseClock();
     const Dims& d = e.cfg.d;
     // bodies without touching contacts are islands of their own: Island.solve reduces to the position integration
     PS_FOR(b, d.NB) {
@@ -68,6 +78,13 @@ PS_HD void physPre(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaSt
         if (pos < q.cap) q.entries[(size_t)bucket * q.cap + pos] = (unsigned)arena * (unsigned)d.NB + (unsigned)k;
     }
     ctx.sync();
+    if (preCycles && ctx.tid() == 0) {   // diagnostics: cycles of load, collide, graph + islands, integration + queue
+        long long t4 = phaseClock();
+        preCycles[0] = t1 - t0;
+        preCycles[1] = t2 - t1;
+        preCycles[2] = t3 - t2;
+        preCycles[3] = t4 - t3;
+    }
 }
 
 // One island's Island.solve as a resumable state machine: each step handles one contact

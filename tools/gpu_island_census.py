@@ -27,3 +27,4 @@ print('big islands: mean kcycles', c[50] / max(1, c[51]), 'total Gcycles per tic
 for b in (0, 1, 2, 3, 5):
     print('lane bucket', b + 1 if b < 4 else 'X', ': warp rounds per tick', c[53 + 2 * b] / T, 'mean kcycles per round', c[52 + 2 * b] / max(1, c[53 + 2 * b]), 'warp-ms per tick', c[52 + 2 * b] * 1024 / T / 1.965e6)
 print('lane occupancy of the lock-step position loop (sum of lane sweeps / 32 x warp sweeps):', c[60] / max(1, c[61]))
+print('k_phys_pre cycles per arena-tick: load %.0f collide %.0f graph+islands %.0f integrate+queue %.0f' % tuple(c[11:15] / max(1, c[15])))
