@@ -352,8 +352,10 @@ int ps_get_island_hist(ps_handle h, int64_t* out /*[64]*/, int reset);
  * 7 XL, 8 XXL, 9 wide lane slot), [10] ticks (of arena group 0's first arena); [16..31] warp-slot islands by duration in bins of
  * 2^18 cycles, [32..47] the same for the big islands; [48],[49] kilo-cycles and count of the warp-slot islands, [50],[51] of the
  * big ones; [52 + 2 b],[53 + 2 b] kilo-cycles and warp rounds of lane bucket b + 1 ([62],[63]: of the wide lane slot); [60] sweeps
- * summed over the lanes, [61] 32 x the warp's sweeps (their ratio is the lane occupancy of the lock-step position loop). */
-int ps_get_island_census(ps_handle h, int64_t* out /*[64]*/, int reset);
+ * summed over the lanes, [61] 32 x the warp's sweeps (their ratio is the lane occupancy of the lock-step position loop);
+ * [11..14] cycles of stage A's phases and [15] its arena-ticks (diagnostic build only); [64..68] big islands: row passes, contact-sweeps,
+ * contacts, bodies, sweeps (sums); [70..74] the same for the warp-slot islands. */
+int ps_get_island_census(ps_handle h, int64_t* out /*[128]*/, int reset);
 /* Per-kernel device time, measured with CUDA events on the engine's stream while enabled. ps_get_kernel_ms waits for the
  * stream, returns the accumulated milliseconds and launch counts of 0 = sense, 1 = think, 2 = physics (World.step, all stages),
  * 3 = other, 4 / 5 / 6 = the three stages of World.step (collide + islands, island workers, broad phase + TOI), 7 unused,

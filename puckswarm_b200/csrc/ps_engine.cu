@@ -283,6 +283,13 @@ __device__ __forceinline__ void islandWarpKernel(const KParams& p, int mode) {
             atomicAdd(&p.islandHist[64 + 16 + (int)min(15ULL, kc >> 8)], 1ULL);
             atomicAdd(&p.islandHist[64 + 48], kc);
             atomicAdd(&p.islandHist[64 + 49], 1ULL);
+            if (ok) {
+                atomicAdd(&p.islandHist[64 + 70], (unsigned long long)slot->nRows * (unsigned long long)iters);
+                atomicAdd(&p.islandHist[64 + 71], nc * (unsigned long long)iters);
+                atomicAdd(&p.islandHist[64 + 72], nc);
+                atomicAdd(&p.islandHist[64 + 73], nb);
+                atomicAdd(&p.islandHist[64 + 74], (unsigned long long)iters);
+            }
         }
         __syncwarp();
     }
@@ -440,6 +447,13 @@ __global__ void __launch_bounds__(32) k_island_big(KParams p) {
             unsigned long long nb = (unsigned long long)(wk.islandBodyStart[k + 1] - wk.islandBodyStart[k]);
             atomicMax(&p.islandHist[63], (kc << 32) | ((nc & 0xFFF) << 20) | ((nb & 0x3FF) << 10) | (unsigned long long)(iters & 0x3FF) | (ok ? 0ULL : (1ULL << 31)));
             atomicAdd(&p.islandHist[64 + 32 + (int)min(15ULL, kc >> 8)], 1ULL);   // census: big islands by duration
+            if (ok) {   // ... and their row passes, contact-sweeps, contacts, bodies
+                atomicAdd(&p.islandHist[64 + 64], (unsigned long long)slot->nRows * (unsigned long long)iters);
+                atomicAdd(&p.islandHist[64 + 65], nc * (unsigned long long)iters);
+                atomicAdd(&p.islandHist[64 + 66], nc);
+                atomicAdd(&p.islandHist[64 + 67], nb);
+                atomicAdd(&p.islandHist[64 + 68], (unsigned long long)iters);
+            }
             atomicAdd(&p.islandHist[64 + 50], kc);
             atomicAdd(&p.islandHist[64 + 51], 1ULL);
         }
@@ -947,8 +961,8 @@ int ps_create(const ps_config* cfg, int device, ps_handle* out) {
             TRY_OR_FREE(cudaEventCreateWithFlags(&G.evBig, cudaEventDisableTiming));
             TRY_OR_FREE(cudaEventCreateWithFlags(&G.done, cudaEventDisableTiming));
         }
-        TRY_OR_FREE(cudaMalloc(&e->kp.islandHist, 128 * sizeof(unsigned long long)));   // [64..127]: island census (ps_get_island_census)
-        TRY_OR_FREE(cudaMemset(e->kp.islandHist, 0, 128 * sizeof(unsigned long long)));
+        TRY_OR_FREE(cudaMalloc(&e->kp.islandHist, 192 * sizeof(unsigned long long)));   // [64..191]: island census (ps_get_island_census)
+        TRY_OR_FREE(cudaMemset(e->kp.islandHist, 0, 192 * sizeof(unsigned long long)));
         e->workerBlocks = prop.multiProcessorCount * (int)envSize("PS_WORKER_BLOCKS_PER_SM", 4);
         TRY_OR_FREE(cudaFuncSetAttribute(k_island_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(WarpSlot))));
         TRY_OR_FREE(cudaFuncSetAttribute(k_island_vel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(WarpSlot))));
@@ -1658,12 +1672,12 @@ int ps_get_island_hist(ps_handle h, int64_t* out /*[64]*/, int reset) {
     return PS_OK;
 }
 
-int ps_get_island_census(ps_handle h, int64_t* out /*[64]*/, int reset) {
+int ps_get_island_census(ps_handle h, int64_t* out /*[128]*/, int reset) {
     if (!h || !out) return setError(PS_E_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(h->device));
     { int jr = joinGroups(h); if (jr != PS_OK) return jr; }
-    CUDA_TRY(cudaMemcpyAsync(out, h->kp.islandHist + 64, 64 * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
-    if (reset) CUDA_TRY(cudaMemsetAsync(h->kp.islandHist + 64, 0, 64 * sizeof(int64_t), h->stream));
+    CUDA_TRY(cudaMemcpyAsync(out, h->kp.islandHist + 64, 128 * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    if (reset) CUDA_TRY(cudaMemsetAsync(h->kp.islandHist + 64, 0, 128 * sizeof(int64_t), h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return PS_OK;
 }

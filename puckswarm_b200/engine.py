@@ -239,7 +239,7 @@ class Engine:
 
     def island_census(self, reset=True):
         """Stage-B census since the last reset (include/puckswarm_b200.h: ps_get_island_census)."""
-        out = np.zeros(64, np.int64)
+        out = np.zeros(128, np.int64)
         self._check(self.L.ps_get_island_census(self.h, out.ctypes.data, 1 if reset else 0))
         return out
 

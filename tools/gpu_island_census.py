@@ -28,3 +28,6 @@ for b in (0, 1, 2, 3, 5):
     print('lane bucket', b + 1 if b < 4 else 'X', ': warp rounds per tick', c[53 + 2 * b] / T, 'mean kcycles per round', c[52 + 2 * b] / max(1, c[53 + 2 * b]), 'warp-ms per tick', c[52 + 2 * b] * 1024 / T / 1.965e6)
 print('lane occupancy of the lock-step position loop (sum of lane sweeps / 32 x warp sweeps):', c[60] / max(1, c[61]))
 print('k_phys_pre cycles per arena-tick: load %.0f collide %.0f graph+islands %.0f integrate+queue %.0f' % tuple(c[11:15] / max(1, c[15])))
+for name, o, cyc, n in (('big', 64, c[50], c[51]), ('warp-slot', 70, c[48], c[49])):
+    print(name, 'islands: mean contacts %.1f bodies %.1f sweeps %.1f rows per sweep %.1f; cycles per row pass %.0f, per contact-sweep %.0f' % (
+        c[o + 2] / max(1, n), c[o + 3] / max(1, n), c[o + 4] / max(1, n), c[o] / max(1, c[o + 4]), cyc * 1024 / max(1, c[o]), cyc * 1024 / max(1, c[o + 1])))
