@@ -51,7 +51,9 @@ struct KParams {
     size_t arenaScratchStride;
     IslandQueue queue;
     unsigned long long* islandHist;   // [8][8] diagnostics: islands by (position iterations bucket, contact count bucket)
+    const int* perm;         // arena order (heavy / light arena split) or null = identity: slot a0 + i of a launch is arena perm[a0 + i]
 };
+__device__ __forceinline__ int arenaAt(const KParams& p, int i) { return p.perm ? p.perm[p.a0 + i] : p.a0 + i; }
 
 extern __shared__ __align__(16) char g_smem[];
 
@@ -90,7 +92,8 @@ __global__ void __launch_bounds__(256) k_perturb(KParams p, int a0, int n, int p
     // arena groups run this concurrently on their own streams, so the working arrays come from the arenas' own scratch
     // blocks (HBM / L2: the perturbations are rare); the fused single-stream mode has CTA slots only
     PhysWork slotWork = ctaWork(p);
-    for (int a = a0 + blockIdx.x; a < a0 + n; a += gridDim.x) {
+    for (int slot = a0 + blockIdx.x; slot < a0 + n; slot += gridDim.x) {
+        int a = p.perm ? p.perm[slot] : slot;
         ArenaState st = arenaState(p.sp, p.env.cfg, a);
         PhysWork wk = perArenaScratch ? rebaseWork(p.workOff, p.arenaScratch + (size_t)a * p.arenaScratchStride) : slotWork;
         arenaPerturb(ctx, p.env, wk, st, p.sp.arena + a, p.puckShiftStep, p.puckShuffleStep);
@@ -184,7 +187,7 @@ __global__ void __launch_bounds__(128) k_phys_pre(KParams p, PreSmem sm) {
     __shared__ int scan[40];
     CtaCtx ctx;
     ctx.scanScratch = scan;
-    int a = p.a0 + blockIdx.x;
+    int a = arenaAt(p, blockIdx.x);
     int R = p.env.cfg.d.R;
     __shared__ PhysWork wk;     // one copy per CTA (see k_phys_post)
     __shared__ ArenaState st;
@@ -461,6 +464,53 @@ __global__ void __launch_bounds__(32) k_island_big(KParams p) {
     }
 }
 
+// Heavy / light arena split: the nHeavy arenas with the highest scores (their longest islands lately) go first in `perm`, the
+// others follow, both in arena order (deterministic). One CTA; the scores decay so that an arena leaves the heavy group a few
+// think steps after its island is gone.
+__global__ void __launch_bounds__(1024) k_classify(int* score, int* perm, int nArenas, int nHeavy) {
+    __shared__ int scan[40];
+    __shared__ int hist[256];
+    __shared__ int sh[3];   // threshold bin, ties taken into the heavy group, -
+    CtaCtx ctx;
+    ctx.scanScratch = scan;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int a = threadIdx.x; a < nArenas; a += blockDim.x) atomicAdd(&hist[min(255, score[a])], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int above = 0, t = 255;
+        while (t > 0 && above + hist[t] <= nHeavy) above += hist[t--];
+        // bins > t are heavy as a whole (above <= nHeavy); bin t fills the rest in arena order (bin 0: arenas without any scored island)
+        sh[0] = t;
+        sh[1] = nHeavy - above;
+    }
+    __syncthreads();
+    int t = sh[0], tiesWanted = sh[1];
+    int nH = 0, nTie = 0, nL = 0;
+    for (int base = 0; base < nArenas; base += blockDim.x) {
+        int a = base + threadIdx.x;
+        int q = a < nArenas ? min(255, score[a]) : -1;
+        bool hv = q > t, tie = q == t, any = q >= 0;
+        int totH, totT, totA;
+        int pH = ctx.exscanFlag(hv, totH);
+        int pT = ctx.exscanFlag(tie, totT);
+        int pA = ctx.exscanFlag(any, totA);
+        if (any) {
+            bool heavy = hv || (tie && nTie + pT < tiesWanted);
+            // heavy rank: heavies before it; light rank: everything before it that is not heavy
+            int tiesBefore = min(nTie + pT, tiesWanted);
+            int heavyBefore = nH + pH + tiesBefore;
+            int pos = heavy ? heavyBefore : nHeavy + (base + pA) - heavyBefore;
+            perm[pos] = a;
+            score[a] = (score[a] * 3) >> 2;
+        }
+        nH += totH;
+        nTie += totT;
+        nL += totA;
+        __syncthreads();
+    }
+}
+
 static constexpr int kBatchThreads = 64;   // at most two lane slots (2 x 32 islands) per CTA: a slot is ~41 KB of shared memory (run-time: ps_engine::batchThreads)
 // stage B2: all other islands (queue bucket 1): one lane per island, 32 islands per warp, bodies in shared memory
 // bucket < 0: one launch for all lane buckets, segBlocks CTAs each, the buckets of the largest islands first
@@ -537,12 +587,15 @@ __global__ void __launch_bounds__(kBatchThreads) k_island_batch(KParams p, int b
 __global__ void __launch_bounds__(32) k_island_batch_x(KParams p, int segBlocks) { islandBatchKernel<LaneSlotsX>(p, kBucketLaneX, segBlocks); }
 
 // stage C: one CTA per arena. Dynamic shared memory: nbFat bodies' box unions, then npFat proxies' fat boxes (0: not staged)
-__global__ void __launch_bounds__(128, 6) k_phys_post(KParams p, int nbFat, int npFat) {
+#ifndef PS_POST_MIN_CTAS
+#define PS_POST_MIN_CTAS 6
+#endif
+__global__ void __launch_bounds__(128, PS_POST_MIN_CTAS) k_phys_post(KParams p, int nbFat, int npFat) {
     extern __shared__ __align__(16) char dsm[];
     __shared__ int scan[40];
     CtaCtx ctx;
     ctx.scanScratch = scan;
-    int a = p.a0 + blockIdx.x;
+    int a = arenaAt(p, blockIdx.x);
     // the ~60 array pointers of the arena live in shared memory, one copy per CTA: as per-thread values they spill to
     // local memory, and local memory goes through L2 to HBM
     __shared__ PhysWork wk;
@@ -644,6 +697,9 @@ struct ps_engine {
     int nSlots = 0, threads = 128;
     bool fused = false;      // PS_FUSED=1: the single-kernel World.step (kept for comparison)
     int workerBlocks = 0, batchBlocks = 0, batchXBlocks = 0, bigBlocks = 0, posBlocks = 0, batchThreads = kBatchThreads;
+    int* dPerm = nullptr;      // heavy / light arena split (PS_HEAVY_ARENAS): arena order, the nHeavy heaviest first; null = off
+    int* dScore = nullptr;     // [nArenas] heaviness scores (IslandQueue::score)
+    int nHeavy = 0;
     bool islandSplit = false;   // PS_ISLAND_SPLIT=1 with PS_ISLAND_G: only the lighter warp-bucket islands go through the split solver
     int islandG = 0;         // PS_ISLAND_G = 2 / 4 / 8: split solver (k_island_vel + k_island_pos with G lanes per island); 0 (default): the one-kernel
                              // warp-per-island solver. The split solver issues 4-5x fewer instructions but every island's sweeps take longer (the groups
@@ -797,6 +853,8 @@ int ps_destroy(ps_handle h) {
     cudaFree(h->kp.queue.entries);
     cudaFree(h->kp.queue.counts);
     cudaFree(h->kp.islandHist);
+    cudaFree(h->dPerm);
+    cudaFree(h->dScore);
     cudaFree(h->dScene);
     if (h->dLut) releaseSharedLut(h->device);
     cudaFree(h->dRobotInit);
@@ -937,8 +995,21 @@ int ps_create(const ps_config* cfg, int device, ps_handle* out) {
         int nGroups = (int)envSize("PS_GROUPS", 1);
         if (e->fused || nGroups < 1) nGroups = 1;
         if ((size_t)nGroups > A) nGroups = (int)A;
+        // heavy / light arena split: two groups over a device-side arena order, the nHeavy arenas with the longest islands first
+        e->nHeavy = (int)envSize("PS_HEAVY_ARENAS", 0);
+        if (e->fused || e->nHeavy < 0 || (size_t)e->nHeavy * 2 > A) e->nHeavy = 0;
+        if (e->nHeavy > 0) {
+            nGroups = 2;
+            std::vector<int> ident(A);
+            for (size_t i = 0; i < A; ++i) ident[i] = (int)i;
+            TRY_OR_FREE(cudaMalloc(&e->dPerm, A * sizeof(int)));
+            TRY_OR_FREE(cudaMemcpy(e->dPerm, ident.data(), A * sizeof(int), cudaMemcpyHostToDevice));
+            TRY_OR_FREE(cudaMalloc(&e->dScore, A * sizeof(int)));
+            TRY_OR_FREE(cudaMemset(e->dScore, 0, A * sizeof(int)));
+            e->kp.perm = e->dPerm;
+        }
         size_t perGroup = (A + nGroups - 1) / nGroups;
-        int qcap = (int)std::min<size_t>(perGroup * (size_t)pc.d.NB, (size_t)1 << 27);
+        int qcap = (int)std::min<size_t>((e->nHeavy > 0 ? A : perGroup) * (size_t)pc.d.NB, (size_t)1 << 27);
         TRY_OR_FREE(cudaMalloc(&e->kp.queue.entries, (size_t)nGroups * kQueueBuckets * qcap * sizeof(unsigned)));
         TRY_OR_FREE(cudaMalloc(&e->kp.queue.counts, (size_t)nGroups * kQueueSlots * sizeof(int)));
         e->kp.queue.cap = qcap;
@@ -947,9 +1018,14 @@ int ps_create(const ps_config* cfg, int device, ps_handle* out) {
             ps_engine::Group& G = e->groups[g];
             G.a0 = (int)std::min<size_t>(A, g * perGroup);
             G.n = (int)(std::min<size_t>(A, (g + 1) * perGroup) - G.a0);
+            if (e->nHeavy > 0) {   // group 0: the light arenas (slots nHeavy..A of the order), group 1: the heavy ones (slots 0..nHeavy)
+                G.a0 = g == 0 ? e->nHeavy : 0;
+                G.n = g == 0 ? (int)A - e->nHeavy : e->nHeavy;
+            }
             G.q.entries = e->kp.queue.entries + (size_t)g * kQueueBuckets * qcap;
             G.q.counts = e->kp.queue.counts + (size_t)g * kQueueSlots;
             G.q.cap = qcap;
+            G.q.score = e->dScore;
             TRY_OR_FREE(cudaStreamCreateWithFlags(&G.s, cudaStreamNonBlocking));
             // the island kernels are small and latency-bound: their CTAs go ahead of the other groups' wide kernels
             TRY_OR_FREE(cudaStreamCreateWithPriority(&G.s2, cudaStreamNonBlocking, prioHigh));
@@ -1131,20 +1207,20 @@ static int launchThinkStage(ps_handle h, ps_engine::Group& G, int think, int ste
     if (think == 1) {
         {
             ScopedTimer timer(h, 0, G.s);
-            rc = h->sd.launchSense(h->kp.env, h->kp.sp, G.s, &h->launches, false, G.a0 * R, G.n * R);
+            rc = h->sd.launchSense(h->kp.env, h->kp.sp, G.s, &h->launches, false, G.a0 * R, G.n * R, h->dPerm);
         }
         if (rc != PS_OK) return setError(rc, h->sd.error);
         if (storage) {
-            k_snap_pre<<<(G.n * R + 127) / 128, 128, 0, G.s>>>(h->kp.sp, h->snap, G.a0, G.n, R, kStorageInterval);
+            k_snap_pre<<<(G.n * R + 127) / 128, 128, 0, G.s>>>(h->kp.sp, h->snap, h->dPerm, G.a0, G.n, R, kStorageInterval);
             h->launches++;
         }
         {
             ScopedTimer timer(h, 1, G.s);
-            rc = h->sd.launchThink(G.a0, G.n, G.s, &h->launches);
+            rc = h->sd.launchThink(G.a0, G.n, G.s, &h->launches, h->dPerm);
         }
         if (rc != PS_OK) return setError(rc, h->sd.error);
     } else {
-        k_count_step<<<(G.n + 127) / 128, 128, 0, G.s>>>(h->kp.sp.arena + G.a0, G.n);
+        k_count_step<<<(G.n + 127) / 128, 128, 0, G.s>>>(h->kp.sp.arena, h->dPerm, G.a0, G.n);
         h->launches++;
         CUDA_TRY(cudaGetLastError());
     }
@@ -1152,7 +1228,7 @@ static int launchThinkStage(ps_handle h, ps_engine::Group& G, int think, int ste
         // host controllers (think == 2): the poses are those of the ps_sense the caller has just run for this step
         int P = h->hs.phys.d.P;
         size_t sh = (size_t)2 * (P > 0 ? P : 1) * sizeof(int);
-        k_snap_post<<<G.n, 128, sh, G.s>>>(h->kp.env, h->kp.sp, h->snap, h->sd.kp.obs.pose, G.a0, kStorageInterval, think == 1 ? 1 : 0, h->hs.cfg.controller,
+        k_snap_post<<<G.n, 128, sh, G.s>>>(h->kp.env, h->kp.sp, h->snap, h->sd.kp.obs.pose, h->dPerm, G.a0, kStorageInterval, think == 1 ? 1 : 0, h->hs.cfg.controller,
                                            h->hs.cfg.n_puck_types, h->hs.cfg.n_pucks, h->analysisThreshold, h->analysisTarget);
         h->launches++;
         CUDA_TRY(cudaGetLastError());
@@ -1293,6 +1369,38 @@ static int enqueueTicks(ps_handle h, int nTicks, int think) {
     // (all groups' tick t, then tick t + 1): 36.1 vs 39.8 ms per think step in the steady state -- the head start keeps the
     // groups out of phase, so one group's CTA-per-arena kernels run beside the other's island tail
     int interval = h->hs.cfg.step_interval;
+    if (h->nHeavy > 0) {
+        // heavy / light arena split: the groups' membership is redrawn at every think interval (all groups joined, k_classify on the
+        // main stream, fork); in between, the few heavy arenas run their long island chains on their own streams while the light
+        // ones go through their ticks without waiting for them
+        int t = 0, sc = h->stepCount;
+        while (t < nTicks) {
+            int uc = h->updateCount + t;
+            int run = interval - uc % interval;
+            if (run > nTicks - t) run = nTicks - t;
+            if (uc % interval == 0) {
+                h->groupsDirty = true;
+                int rc = joinGroups(h);
+                if (rc != PS_OK) return rc;
+                k_classify<<<1, 1024, 0, h->stream>>>(h->dScore, h->dPerm, h->kp.nArenas, h->nHeavy);
+                h->launches++;
+                CUDA_TRY(cudaGetLastError());
+                if ((rc = forkGroups(h)) != PS_OK) return rc;
+            }
+            for (auto& G : h->groups) {
+                if (G.n == 0) continue;
+                for (int k = 0; k < run; ++k) {
+                    int rc;
+                    if (think && (uc + k) % interval == 0 && (rc = launchThinkStage(h, G, think, sc)) != PS_OK) return rc;
+                    if ((rc = enqueuePreIslands(h, G)) != PS_OK) return rc;
+                    if ((rc = enqueuePost(h, G)) != PS_OK) return rc;
+                }
+            }
+            if (uc % interval == 0) ++sc;
+            t += run;
+        }
+        return PS_OK;
+    }
     for (auto& G : h->groups) {
         if (G.n == 0) continue;
         int sc = h->stepCount;
@@ -1367,14 +1475,14 @@ int ps_step_external(ps_handle h, const float* forwards, const float* torque) {
     CUDA_TRY(cudaMemcpyAsync(h->dCmd + n, torque, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     k_set_commands<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->kp.sp.robot, h->dCmd, h->dCmd + n, n);
     { int pr = launchPerturb(h, 0, h->kp.nArenas, h->stream); if (pr != PS_OK) return pr; }
-    k_count_step<<<(h->kp.nArenas + 127) / 128, 128, 0, h->stream>>>(h->kp.sp.arena, h->kp.nArenas);
+    k_count_step<<<(h->kp.nArenas + 127) / 128, 128, 0, h->stream>>>(h->kp.sp.arena, nullptr, 0, h->kp.nArenas);
     h->launches += 2;
     CUDA_TRY(cudaGetLastError());
     if (h->stepCount % kStorageInterval == 0 && h->sd.ready) {
         // the periodic record of a host-controller run: poses of the ps_sense the caller ran for this step, pucks, Analyze row
         int P = h->hs.phys.d.P;
         size_t sh = (size_t)2 * (P > 0 ? P : 1) * sizeof(int);
-        k_snap_post<<<h->kp.nArenas, 128, sh, h->stream>>>(h->kp.env, h->kp.sp, h->snap, h->sd.kp.obs.pose, 0, kStorageInterval, 0, h->hs.cfg.controller,
+        k_snap_post<<<h->kp.nArenas, 128, sh, h->stream>>>(h->kp.env, h->kp.sp, h->snap, h->sd.kp.obs.pose, nullptr, 0, kStorageInterval, 0, h->hs.cfg.controller,
                                                           h->hs.cfg.n_puck_types, h->hs.cfg.n_pucks, h->analysisThreshold, h->analysisTarget);
         h->launches++;
         CUDA_TRY(cudaGetLastError());
@@ -1396,7 +1504,7 @@ int ps_step_external(ps_handle h, const float* forwards, const float* torque) {
 static int copyState(ps_handle h, const ps_state_view* v, bool toHost) {
     const PhysCfg& pc = h->hs.phys;
     cudaMemcpyKind kind = toHost ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice;
-    bool grouped = !h->fused && !h->groups.empty();
+    bool grouped = !h->fused && !h->groups.empty() && !h->dPerm;   // (with the heavy / light split a group is not a slice of the arrays)
     if (grouped) {
         int rc = forkGroups(h);
         if (rc != PS_OK) return rc;

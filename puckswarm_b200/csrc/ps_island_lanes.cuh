@@ -16,15 +16,16 @@ namespace ps {
 
 enum { LK_PUCK = 0, LK_ROBOT = 1, LK_WALL = 2 };
 
-// A warp's lane-interleaved slot: NBL dynamic bodies (+ the wall) and NCL constraints per lane. 31 bytes per body: the
-// velocity (used up to the integration) and the transform's px / py / c (used from the integration on) share storage, and the
-// position solver's inverse masses follow from the body kind -- the slot's size is what bounds how many islands an SM holds.
+// A warp's lane-interleaved slot: NBL dynamic bodies (+ the wall) and NCL constraints per lane. 39 bytes per body: the
+// velocity (used up to the integration) and the transform's px / py / c (used from the integration on) share storage -- the
+// slot's size is what bounds how many islands an SM holds.
 template <int NBL, int NCL>
 struct LaneSlotsT {
     static constexpr int kBodies = NBL, kContacts = NCL, kLBX = NBL + 1;   // staged bodies per lane + the wall
     float cx[kLBX][32], cy[kLBX][32], a[kLBX][32];
     float u0[kLBX][32], u1[kLBX][32], u2[kLBX][32];   // vx, vy, w until lkIntegrateLane; then px, py, c
     float s[kLBX][32];
+    float pm[kLBX][32], pi[kLBX][32];   // position-solver inverse masses (mass * invMass, mass * invI; 0 for the wall): selecting them from the kind in the sweeps costs more than the 8 bytes
     uint16_t gidx[kLBX][32];
     uint8_t kind[kLBX][32];
     // what the position sweeps read of each constraint: localNormal, localPoint, the two manifold points, radius, and
@@ -54,8 +55,8 @@ struct LaneCtxT {
     __device__ __forceinline__ float& py(int l) const { return S->u1[l][lane]; }
     __device__ __forceinline__ float& c(int l) const { return S->u2[l][lane]; }
     __device__ __forceinline__ float& s(int l) const { return S->s[l][lane]; }
-    __device__ __forceinline__ float pm(int l) const { int k = kind(l); return k == LK_PUCK ? pmPuck : (k == LK_ROBOT ? pmRobot : 0.0f); }
-    __device__ __forceinline__ float pi(int l) const { int k = kind(l); return k == LK_PUCK ? piPuck : (k == LK_ROBOT ? piRobot : 0.0f); }
+    __device__ __forceinline__ float pm(int l) const { return S->pm[l][lane]; }
+    __device__ __forceinline__ float pi(int l) const { return S->pi[l][lane]; }
     __device__ __forceinline__ int kind(int l) const { return S->kind[l][lane]; }
     __device__ __forceinline__ int gidx(int l) const { return S->gidx[l][lane]; }
 };
@@ -101,9 +102,13 @@ __device__ __forceinline__ void lkStage(const PhysEnv& e, const PhysWork& wk, in
         S.u1[l][ln] = wk.vy[g];
         S.u2[l][ln] = wk.w[g];
         S.kind[l][ln] = g >= P ? LK_ROBOT : LK_PUCK;
+        S.pm[l][ln] = g >= P ? L.pmRobot : L.pmPuck;
+        S.pi[l][ln] = g >= P ? L.piRobot : L.piPuck;
     }
     // the wall: a body that never moves (zero inverse masses), sweep.c = (0, 0); its transform follows at the integration
     S.kind[nb][ln] = LK_WALL;
+    S.pm[nb][ln] = 0.0f;
+    S.pi[nb][ln] = 0.0f;
     S.gidx[nb][ln] = 0xFFFF;
     S.cx[nb][ln] = 0.0f;
     S.cy[nb][ln] = 0.0f;

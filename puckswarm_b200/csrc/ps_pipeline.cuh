@@ -23,6 +23,8 @@ struct IslandQueue {
                            // islands with 1-2, 3-5, 6-12, 13+ contacts (like with like, so that the lanes of a warp finish together)
     int* counts;           // [kQueueSlots]: entries per bucket, then kQHeadWarp / kQHeadPos (consumer heads of the warp-bucket kernels)
     int cap;
+    int* score;            // [nArenas] or null: heaviest island of the arena lately (contacts / manifold points of its warp-bucket and big islands),
+                           // written here, read and decayed by the heavy / light arena split (k_classify)
 };
 static constexpr int kQueueWarpBodies = 48, kQueueWarpContacts = 64;   // = kWarpBodies, kWarpContacts of ps_island_lanes.cuh
 static constexpr int kLaneBodies = 12, kLaneContacts = 16;   // what a lane slot of the lane-per-island solver holds
@@ -73,6 +75,11 @@ PS_HD void physPre(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaSt
             for (int i = 0; i < nc; ++i) points += wk.tc[wk.order[lo + i]].solverPoints;
             if (points >= kXXLPoints) bucket = kBucketXXL;
             else if (points >= kXLPoints) bucket = kBucketXL;
+        }
+        if (q.score && (bucket == 0 || bucket >= kBucketBig) && bucket != kBucketLaneX) {
+            // a sweep costs the island's manifold points; robots' contacts carry two (estimated for the buckets that did not count them)
+            int w = bucket == kBucketBig ? 2 * nc : (bucket == 0 ? nc : (bucket == kBucketLarge ? 32 : (bucket == kBucketXL ? 48 : 64)) + nc / 4);
+            ctx.atomicMaxI(&q.score[arena], w);
         }
         int pos = ctx.atomicAddI(&q.counts[bucket], 1);
         if (pos < q.cap) q.entries[(size_t)bucket * q.cap + pos] = (unsigned)arena * (unsigned)d.NB + (unsigned)k;

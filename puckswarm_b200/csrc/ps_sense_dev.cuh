@@ -17,6 +17,7 @@ struct SenseKParams {
     size_t fastCap;
     SenseWork workOff;   // byte offsets of the camera stage's shared-memory arrays
     int r0;            // first robot (k_sense, k_localmap) / first arena (k_think) of the launch
+    const int* perm;   // arena order of the launch (heavy / light arena split) or null = identity: slot i of the launch is arena perm[i]
     int* senseDbg;     // [nRobots][8] phase diagnostics of the last sense
     SenseHead* senseHead;   // [nRobots] camera stage -> local-map stage
     BlobRec* blobs;         // [nRobots][kMaxBlobs]
@@ -33,6 +34,10 @@ __global__ void __launch_bounds__(256) k_sense(SenseKParams p) {
     int R = p.env.cfg.d.R;
     int rg = p.r0 + (int)blockIdx.x;
     int a = rg / R, r = rg - a * R;
+    if (p.perm) {
+        a = p.perm[a];
+        rg = a * R + r;
+    }
     ArenaState st = arenaState(p.sp, p.env.cfg, a);
     size_t ri = (size_t)rg;
     int nCells = p.T.occW * p.T.occH;
@@ -57,6 +62,11 @@ __global__ void __launch_bounds__(128) k_localmap(SenseKParams p, int nRobots) {
     int idx = blockIdx.x * 4 + warp;
     if (idx >= nRobots) return;
     int ri = p.r0 + idx;
+    if (p.perm) {
+        int R = p.env.cfg.d.R;
+        int slot = ri / R;
+        ri = p.perm[slot] * R + (ri - slot * R);
+    }
     int nCells = p.T.occW * p.T.occH;
     ps_localmap& lm = lmS[warp];
     uint32_t* w = (uint32_t*)&lm;
@@ -91,14 +101,15 @@ __global__ void __launch_bounds__(128) k_think(SenseKParams p) {
     tw.flag = flag;
     int R = p.env.cfg.d.R;
     int a = p.r0 + (int)blockIdx.x;
+    if (p.perm) a = p.perm[a];
     size_t r0 = (size_t)a * R;
     int nCells = p.T.occW * p.T.occH;
     thinkArena(ctx, p.T, p.sc, tw, R, p.obs.occupancy + r0 * nCells, p.obs.lm + r0, p.obs.pose + r0 * 3, p.sp.robot + r0, p.sp.arena + a, &rng);
 }
 
-__global__ void k_count_step(ps_arena_state* arena, int nArenas) {
-    int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a < nArenas) arena[a].step_count += 1;
+__global__ void k_count_step(ps_arena_state* arena, const int* perm, int a0, int nArenas) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nArenas) arena[perm ? perm[a0 + i] : a0 + i].step_count += 1;
 }
 
 __global__ void k_set_commands(ps_robot_state* robot, const float* fwd, const float* tq, size_t n) {
@@ -214,23 +225,25 @@ struct SnapPtrs {
     ps_arena_analysis* an;   // [A]
 };
 
-__global__ void k_snap_pre(StatePtrs sp, SnapPtrs sn, int a0, int nArenas, int R, int interval) {
+__global__ void k_snap_pre(StatePtrs sp, SnapPtrs sn, const int* perm, int a0, int nArenas, int R, int interval) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nArenas * R) return;
-    int a = a0 + i / R;
+    int slot = a0 + i / R;
+    int a = perm ? perm[slot] : slot;
     if (sp.arena[a].step_count % interval != 0) return;
-    const ps_robot_state& rs = sp.robot[(size_t)a0 * R + i];
-    int* out = sn.counts + ((size_t)a0 * R + i) * 8;
+    size_t ri = (size_t)a * R + (size_t)(i % R);
+    const ps_robot_state& rs = sp.robot[ri];
+    int* out = sn.counts + ri * 8;
     for (int k = 0; k < 8; ++k) out[k] = rs.state_counts[k];
 }
 
 // One CTA per arena. onDevice: the controllers ran on the device (cache points and state counters are theirs); otherwise only
 // the arena-level record and the analysis are kept (a host controller owns its own dumps).
-__global__ void __launch_bounds__(128) k_snap_post(PhysEnv env, StatePtrs sp, SnapPtrs sn, const float* obsPose, int a0, int interval, int onDevice,
+__global__ void __launch_bounds__(128) k_snap_post(PhysEnv env, StatePtrs sp, SnapPtrs sn, const float* obsPose, const int* perm, int a0, int interval, int onDevice,
                                                    int controller, int nTypes, int nPucksCfg, float threshold, float targetPercent) {
     extern __shared__ int sh[];   // parent[P], size[P]
     const Dims& d = env.cfg.d;
-    int a = a0 + blockIdx.x;
+    int a = perm ? perm[a0 + blockIdx.x] : a0 + (int)blockIdx.x;
     int stepCount = sp.arena[a].step_count - 1;   // the think step that has just run
     if (stepCount < 0 || stepCount % interval != 0) return;
     ArenaState st = arenaState(sp, env.cfg, a);
@@ -389,9 +402,10 @@ struct SenseDevice {
         kp.env = env;
         kp.sp = sp;
     }
-    int launchSense(const PhysEnv& env, const StatePtrs& sp, cudaStream_t stream, int64_t* launches, bool camera, int firstRobot, int nRobots) {
+    int launchSense(const PhysEnv& env, const StatePtrs& sp, cudaStream_t stream, int64_t* launches, bool camera, int firstRobot, int nRobots, const int* perm = nullptr) {
         bind(env, sp);
         SenseKParams p = kp;
+        p.perm = perm;
         if (!camera) p.obs.camera = nullptr;
         p.r0 = firstRobot;
         k_sense<<<(unsigned)nRobots, threads, senseSmem, stream>>>(p);
@@ -400,8 +414,9 @@ struct SenseDevice {
         if (cudaGetLastError() != cudaSuccess) return fail(PS_E_CUDA, "k_sense / k_localmap launch failed");
         return PS_OK;
     }
-    int launchThink(int firstArena, int nArenas, cudaStream_t stream, int64_t* launches) {
+    int launchThink(int firstArena, int nArenas, cudaStream_t stream, int64_t* launches, const int* perm = nullptr) {
         SenseKParams p = kp;
+        p.perm = perm;
         p.r0 = firstArena;
         // CTA width by batch size. The stage is the robots' controllers one after the other (shared java.util.Random), with a
         // barrier between every parallel piece and the serial state machine. When the launch fills the GPU, one warp per arena
