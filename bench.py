@@ -321,6 +321,14 @@ def main():
             "note": "candidate binning cuts K from the ~12 the survey assumed to the measured value, so the algorithmic byte count (and this fraction) "
                     "shrinks with it; the stage is issue/latency bound (profiles/)",
         }
+        # issue-slot view of the same stage (the smem byte count shrank with K, so the smem fraction says little): executed warp
+        # instructions and issue utilisation cannot be counted outside a profiler; they come from the ncu capture profiles/k_sense_issue.json names
+        issue_json = os.path.join(ROOT, "profiles", "k_sense_issue.json")
+        if os.path.exists(issue_json):
+            try:
+                roofline_sense["issue_slots"] = json.load(open(issue_json))
+            except Exception:
+                pass
         return roofline, roofline_sense
 
     def e2e_run(n_arenas, first_seed, warm_steps, timed_steps_n):
