@@ -707,6 +707,7 @@ struct ps_engine {
     bool mergeBatch = true;    // one launch for all lane buckets (PS_MERGE_BATCH=0: one launch and stream per bucket)
     size_t smemBytes = 0, bigSmem = 0;
     PreSmem preSmem = {0, 0};   // k_phys_pre / k_phys_post: CTA width and what they keep in shared memory
+    bool preThreadsSet = false;
     int preThreads = 64, postThreads = 128, postNbFat = 0, postNpFat = 0;
     int64_t launches = 0;
     int updateCount = 0;     // all arenas advance in lock step
@@ -1056,6 +1057,7 @@ int ps_create(const ps_config* cfg, int device, ps_handle* out) {
         e->preThreads = (int)envSize("PS_PRE_THREADS", 64);   // measured (profiles/r02_ab_prepost.log): stage A 1.18 ms per 4096 arenas with 128 threads, 1.08 with 64 (the stage waits on its serial parts; narrow CTAs put more arenas on an SM); stage C is faster with 128
         e->postThreads = (int)envSize("PS_POST_THREADS", 128);
         if (e->preThreads != 32 && e->preThreads != 128) e->preThreads = 64;
+        e->preThreadsSet = getenv("PS_PRE_THREADS") != nullptr;
         if (e->postThreads != 32 && e->postThreads != 64) e->postThreads = 128;
         e->preSmem.nb = pc.d.NB <= 512 ? pc.d.NB : 0;
         e->preSmem.capT = (int)std::min<size_t>((size_t)pc.MT, envSize("PS_PRE_SMEM_T", 512));
@@ -1246,7 +1248,10 @@ static int enqueuePreIslands(ps_handle h, ps_engine::Group& G) {
     CUDA_TRY(cudaMemsetAsync(G.q.counts, 0, kQueueSlots * sizeof(int), G.s));
     {
         ScopedTimer t4(h, 4, G.s);
-        k_phys_pre<<<G.n, h->preThreads, h->preSmem.bytes(), G.s>>>(kp, h->preSmem);
+        // CTA width by batch size, like k_think: narrow CTAs put more arenas on an SM when the launch fills the GPU (1.08 against 1.18 ms
+        // per 4096 arenas), a small launch is one arena's latency (1024 arenas: 0.36 ms with 128 threads, 0.43 with 64)
+        int pt = h->preThreadsSet ? h->preThreads : (G.n >= 2368 ? 64 : 128);
+        k_phys_pre<<<G.n, pt, h->preSmem.bytes(), G.s>>>(kp, h->preSmem);
     }
     CUDA_TRY(cudaEventRecord(G.evPre, G.s));
     {

@@ -1,6 +1,6 @@
 # Round 2 evidence run (one B200): GPU parity suite, the driver-style bench line, the default (steady-state) bench line, the
-# reference arm, the launch list of a steady-state think step and full ncu captures of every kernel of a think step in both
-# regimes (1024 arenas, one arena group; each ncu run after a plain run of the same command).
+# reference arm, the launch list of a steady-state think step and one full ncu capture of every kernel of a steady-state think
+# step (1024 arenas, one arena group; each ncu run after a plain run of the same command). Part 2: tools/gpu_r2_final_early.sh.
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/r02_pytest_gpu.log 2>&1; tail -2 gpurun_out/r02_pytest_gpu.log
@@ -15,7 +15,3 @@ CMD2="python bench.py --steps 2 --warmup 100 --no-cpu-baseline --no-extras --no-
 PS_GROUPS=1 $CMD2 > gpurun_out/r02_plain2.log 2>&1 && \
 PS_GROUPS=1 ncu --set full --clock-control none --import-source on -k regex:'k_sense|k_localmap|k_think|k_phys_pre|k_island_big|k_island_warp|k_island_batch|k_phys_post' --launch-skip 1800 --launch-count 8 -f -o gpurun_out/r02_prof $CMD2 > gpurun_out/r02_ncu_full.log 2>&1
 echo "ncu full rc=$?"; ls -la gpurun_out/r02_prof.ncu-rep
-CMD3="python bench.py --steps 2 --warmup 12 --no-cpu-baseline --no-extras --no-parity --no-steady --no-e2e --arenas 1024"
-PS_GROUPS=1 $CMD3 > gpurun_out/r02_plain3.log 2>&1 && \
-PS_GROUPS=1 ncu --set full --clock-control none -k regex:'k_sense|k_localmap|k_think|k_phys_pre|k_island_big|k_island_warp|k_island_batch|k_phys_post' --launch-skip 216 --launch-count 8 -f -o gpurun_out/r02_prof_early $CMD3 > gpurun_out/r02_ncu_full_early.log 2>&1
-echo "ncu early rc=$?"; ls -la gpurun_out/r02_prof_early.ncu-rep
