@@ -527,6 +527,30 @@ def test_think_stage_cta_widths(threads, monkeypatch):
         assert bad == [], "think step %d: %s" % (k, bad[:4])
 
 
+@pytest.mark.parametrize("env", [{"PS_LANEX_MAX_CONTACTS": "27"}, {"PS_ISLAND_G": "8"}, {"PS_ISLAND_G": "4", "PS_ISLAND_SPLIT": "1"}, {"PS_HEAVY_ARENAS": "2"},
+                                 {"PS_GROUPS": "3"}, {"PS_BATCH_THREADS": "32", "PS_MERGE_BATCH": "0"}, {"PS_PRE_THREADS": "128", "PS_PRE_SMEM_T": "64"},
+                                 {"PS_PRE_THREADS": "32", "PS_POST_THREADS": "64"}])
+def test_scheduling_options_keep_parity(env, monkeypatch):
+    """The island / stage scheduling knobs only decide which kernel solves an island and which arenas share a stream; every
+    one of them -- the measured-and-off ones included (wide lane slots, split solver, heavy / light arena split) -- must leave the
+    trajectories bit-identical. 16 robots / 200 pucks, 240 ticks free-running (islands of every bucket form), compared every 60 ticks."""
+    import parity
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    A = 6
+    cfg = abi.config_defaults(n_arenas=A, n_robots=16, n_pucks=200, controller=abi.PS_CTRL_CACHECONS)
+    e, o = _engine(cfg), _oracle(cfg)
+    seeds = np.arange(11, 11 + A)
+    e.reset(seeds)
+    o.reset(seeds)
+    for k in range(4):
+        e.step(60)
+        o.step(60)
+        bad = parity.compare_states(e.get_state(), o.get_state(), A, tol=TOL)
+        assert bad == [], "%s, tick %d: %s" % (env, 60 * (k + 1), bad[:4])
+    assert e.error_flags() == (0, 0)
+
+
 @pytest.mark.parametrize("shape", [(1, 2, 0, 2, abi.PS_CTRL_BHD), (2, 3, 7, 2, abi.PS_CTRL_CACHECONS), (1, 1, 5, 5, abi.PS_CTRL_PROBSEEK),
                                    (1, 6, 3, 3, abi.PS_CTRL_CACHECONS), (1, 2, 16, 8, abi.PS_CTRL_CACHECONS)])
 def test_edge_shapes(shape):
