@@ -612,6 +612,10 @@ __global__ void __launch_bounds__(128, PS_POST_MIN_CTAS) k_phys_post(KParams p, 
     }
     __syncthreads();
     physPost(ctx, p.env, wk, st);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && p.queue.load) {   // this tick's count of warp-class islands becomes "the previous tick's"
+        p.queue.load[0] = p.queue.load[1];
+        p.queue.load[1] = 0;
+    }
     if (blockIdx.x == 0 && threadIdx.x <= kQueueBuckets)   // census: islands per queue bucket, ticks
         atomicAdd(&p.islandHist[64 + threadIdx.x], threadIdx.x < kQueueBuckets ? (unsigned long long)p.queue.counts[threadIdx.x] : 1ULL);
     if (threadIdx.x == 0) p.sp.arena[a].update_count += 1;
@@ -682,7 +686,7 @@ struct ps_engine {
         cudaEvent_t evb[kQueueBuckets] = {};
         cudaEvent_t evPre = nullptr, evBig = nullptr, done = nullptr;
         int a0 = 0, n = 0;
-        IslandQueue q;
+        IslandQueue q = {};
     };
     std::vector<Group> groups;
     cudaEvent_t evStart = nullptr;
@@ -873,6 +877,7 @@ int ps_destroy(ps_handle h) {
     cudaFree(h->snap.an);
     h->sd.release();
     for (auto& g : h->groups) {
+        if (g.q.load) cudaFree(g.q.load);
         if (g.evPre) cudaEventDestroy(g.evPre);
         if (g.evBig) cudaEventDestroy(g.evBig);
         if (g.done) cudaEventDestroy(g.done);
@@ -1027,6 +1032,15 @@ int ps_create(const ps_config* cfg, int device, ps_handle* out) {
             G.q.counts = e->kp.queue.counts + (size_t)g * kQueueSlots;
             G.q.cap = qcap;
             G.q.score = e->dScore;
+            // adaptive lane / warp boundary (unless PS_WARP_MIN_CONTACTS pins it): see IslandQueue::load
+            G.q.load = nullptr;
+            G.q.nArenasLoad = G.n;
+            G.q.adaptX100 = (int)envSize("PS_WARP_ADAPT_X100", 40);   // measured (profiles/r02_ab_adapt.log): 13 wins by 3.3 % at 0.13 such islands per arena (ticks 15-75), 17 by 2 % at 0.65 (ticks 105-165)
+            if (!getenv("PS_WARP_MIN_CONTACTS") && G.q.adaptX100 > 0) {
+                TRY_OR_FREE(cudaMalloc(&G.q.load, 2 * sizeof(int)));
+                int init[2] = {1 << 30, 0};   // no history yet: the default boundary
+                TRY_OR_FREE(cudaMemcpy(G.q.load, init, sizeof(init), cudaMemcpyHostToDevice));
+            }
             TRY_OR_FREE(cudaStreamCreateWithFlags(&G.s, cudaStreamNonBlocking));
             // the island kernels are small and latency-bound: their CTAs go ahead of the other groups' wide kernels
             TRY_OR_FREE(cudaStreamCreateWithPriority(&G.s2, cudaStreamNonBlocking, prioHigh));

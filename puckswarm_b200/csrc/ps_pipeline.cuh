@@ -23,13 +23,18 @@ struct IslandQueue {
                            // islands with 1-2, 3-5, 6-12, 13+ contacts (like with like, so that the lanes of a warp finish together)
     int* counts;           // [kQueueSlots]: entries per bucket, then kQHeadWarp / kQHeadPos (consumer heads of the warp-bucket kernels)
     int cap;
+    int* load;             // [2] or null: islands of >= kWarpMinContactsDefault contacts (or too many bodies for a lane) of the previous tick / counted so far
+                           // this tick; swapped by stage C. While the previous tick had few of them per arena (right after a reset) the warp kernel has
+                           // room, and islands of 13-16 contacts -- the lane batches' longest chains -- take a warp each as well
+    int nArenasLoad;       // arenas the load counts (the group's), times adaptPerArenaX100 / 100 = the switch-over
+    int adaptX100;
     int* score;            // [nArenas] or null: heaviest island of the arena lately (contacts / manifold points of its warp-bucket and big islands),
                            // written here, read and decayed by the heavy / light arena split (k_classify)
 };
 static constexpr int kQueueWarpBodies = 48, kQueueWarpContacts = 64;   // = kWarpBodies, kWarpContacts of ps_island_lanes.cuh
 static constexpr int kLaneBodies = 12, kLaneContacts = 16;   // what a lane slot of the lane-per-island solver holds
 static constexpr int kLaneXBodies = 24, kLaneXContacts = 28;   // ... and the wide lane slot (bucket kBucketLaneX): the smaller half of what used to take a warp each
-static constexpr int kQueueBuckets = 10, kLaneBuckets = 4, kBucketBig = 5, kBucketLarge = 6, kBucketXL = 7, kBucketXXL = 8, kBucketLaneX = 9, kWarpMinContactsDefault = 17;   // every island that fits a lane slot takes one (measured: 16 -> 17 shortens the island phase by 2 %, 10 lengthens it by 11 %)
+static constexpr int kQueueBuckets = 10, kLaneBuckets = 4, kBucketBig = 5, kBucketLarge = 6, kBucketXL = 7, kBucketXXL = 8, kBucketLaneX = 9, kWarpMinContactsDefault = 17, kWarpMinContactsLight = 13;   // every island that fits a lane slot takes one (measured: 16 -> 17 shortens the island phase by 2 %, 10 lengthens it by 11 %)
 static constexpr int kQHeadWarp = kQueueBuckets, kQHeadPos = kQueueBuckets + 1, kQHeadVel = kQueueBuckets + 2, kQueueSlots = kQueueBuckets + 3;
 static constexpr int kXLPoints = 40, kXXLPoints = 56;   // manifold points of an island from which it is handed out before the other large ones: the tick ends when the
                                                        // longest island ends, and an island's sweeps cost its points (robot jams: two per contact) x up to 100
@@ -61,11 +66,14 @@ PS_HD void physPre(Ctx& ctx, const PhysEnv& e, const PhysWork& wk, const ArenaSt
     if (ctx.tid() == 0 && e.cfg.posIters > 0) wk.stats[0] = 1;   // contact-free islands run the position loop once
     ctx.sync();
     int nIsl = wk.counters[1];
+    int warpMin = e.cfg.warpMinContacts;
+    if (q.load && (long long)q.load[0] * 100 < (long long)q.nArenasLoad * q.adaptX100 && warpMin > kWarpMinContactsLight) warpMin = kWarpMinContactsLight;
     PS_FOR(k, nIsl) {
         int nb = wk.islandBodyStart[k + 1] - wk.islandBodyStart[k];
         int nc = wk.islandStart[k + 1] - wk.islandStart[k];
+        if (q.load && (nc >= kWarpMinContactsDefault || nb > kLaneBodies)) ctx.atomicAddI(&q.load[1], 1);
         // 0: a warp each (WarpSlot); kBucketBig: what outgrows that (BigSlot); 1..4: a lane each, by contact count
-        int bucket = (nc >= e.cfg.warpMinContacts || nc > kLaneContacts || nb > kLaneBodies) ? ((nb > kQueueWarpBodies || nc > kQueueWarpContacts) ? kBucketBig : (nc >= kLargeContacts ? kBucketLarge : 0))
+        int bucket = (nc >= warpMin || nc > kLaneContacts || nb > kLaneBodies) ? ((nb > kQueueWarpBodies || nc > kQueueWarpContacts) ? kBucketBig : (nc >= kLargeContacts ? kBucketLarge : 0))
                                                                                                : (nc <= 2 ? 1 : (nc <= 5 ? 2 : (nc <= 12 ? 3 : 4)));
         // the smaller warp-bucket islands take a lane of a wide lane slot instead (32 islands per instruction stream)
         if (bucket == 0 && nc <= e.cfg.laneXMaxContacts && nc <= kLaneXContacts && nb <= kLaneXBodies) bucket = kBucketLaneX;
